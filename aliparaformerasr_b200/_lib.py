@@ -1,0 +1,122 @@
+"""ctypes binding of ``libpfasr.so`` (include/pf_abi.h).
+
+This is the same stub a C# maintainer writes with ``[DllImport("pfasr")]``; Python is used
+here because the build image has no dotnet.  Loading fails loudly when the CUDA library has not been built: there
+is no CPU fallback anywhere in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libpfasr.so"
+
+PF_OK = 0
+PF_ERR_BAD_ARG = -1
+PF_ERR_CUDA = -2
+PF_ERR_OOM = -3
+PF_ERR_SHAPE = -4
+PF_ERR_DISPOSED = -5
+PF_ERR_WEIGHTS = -6
+PF_ERR_UNSUPPORTED = -7
+
+PF_MODEL_PARAFORMER = 0
+PF_MODEL_SENSEVOICE_SMALL = 1
+PF_RUN_WANT_LOGITS = 1
+PF_RUN_WANT_CIF_PEAK = 2
+
+
+class PfConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("model_kind", C.c_int32), ("input_size", C.c_int32), ("d_model", C.c_int32),
+        ("heads", C.c_int32), ("ffn", C.c_int32), ("enc_layers", C.c_int32), ("tp_layers", C.c_int32),
+        ("enc_kernel", C.c_int32), ("dec_layers", C.c_int32), ("dec_ffn", C.c_int32), ("dec_kernel", C.c_int32),
+        ("vocab", C.c_int32), ("ln_eps", C.c_float), ("cif_threshold", C.c_float), ("cif_tail", C.c_float),
+        ("smooth_factor", C.c_float), ("noise_threshold", C.c_float), ("fs", C.c_int32), ("n_mels", C.c_int32),
+        ("lfr_m", C.c_int32), ("lfr_n", C.c_int32), ("snip_edges", C.c_int32), ("use_itn", C.c_int32),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+class PfResult(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("max_len", C.c_int32), ("vocab", C.c_int32), ("feat_frames", C.c_int32),
+        ("tokens", C.POINTER(C.c_int32)), ("token_num", C.POINTER(C.c_int32)),
+        ("logits", C.POINTER(C.c_float)), ("cif_peak", C.POINTER(C.c_float)),
+    ]
+
+
+class PfError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libpfasr error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_F = C.POINTER(C.c_float)
+_I = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); every symbol include/pf_abi.h declares
+SIGNATURES = {
+    "pf_offline_create": (C.c_int32, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_offline_create_from_memory": (C.c_int32, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_offline_destroy": (C.c_int32, [C.c_void_p]),
+    "pf_offline_set_cmvn": (C.c_int32, [C.c_void_p, _F, _F, C.c_int32]),
+    "pf_frontend_extract": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
+    "pf_frontend_fbank": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
+    "pf_frontend_num_frames": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pf_offline_run_pcm": (C.c_int32, [C.c_void_p, C.POINTER(_F), _I, C.c_int32, C.c_uint32, C.POINTER(PfResult)]),
+    "pf_offline_run_feats": (C.c_int32, [C.c_void_p, _F, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(PfResult)]),
+    "pf_offline_stage_pcm": (C.c_int32, [C.c_void_p, C.POINTER(_F), _I, C.c_int32]),
+    "pf_offline_run_staged": (C.c_int32, [C.c_void_p, C.c_uint32, C.POINTER(PfResult)]),
+    "pf_offline_get_tensor": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p, _F, C.c_size_t, _I, _I]),
+    "pf_offline_get_timings": (C.c_int32, [C.c_void_p, _F, C.c_int32]),
+    "pf_offline_get_launch_count": (C.c_int64, [C.c_void_p]),
+    "pf_offline_get_gemm_flops": (C.c_double, [C.c_void_p]),
+    "pf_offline_get_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "pf_last_error": (C.c_char_p, []),
+    "pf_abi_version": (C.c_int32, []),
+    "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),
+    "pf_dbg_layernorm": (C.c_int32, [C.c_int32, C.c_int32, _F, _F, _F, C.c_float, _F]),
+    "pf_dbg_embed_pe_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, C.c_float, _F, _F, C.c_float, _F]),
+    "pf_dbg_attention": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F]),
+    "pf_dbg_fsmn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _I, C.c_int32, _F]),
+    "pf_dbg_cif": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_float, C.c_int32, _F, _I, _I, _F]),
+    "pf_dbg_logsoftmax_argmax": (C.c_int32, [C.c_int32, C.c_int32, _F, _I]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libpfasr.so and attach the signatures.  Raises if the CUDA library is missing (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.environ.get("PFASR_LIB", str(LIB_PATH))
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -m aliparaformerasr_b200.build` "
+            "(nvcc, sm_100a). aliparaformerasr_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != PF_OK:
+        raise PfError(status, load().pf_last_error().decode(errors="replace"))
+
+
+def fptr(a):
+    return a.ctypes.data_as(_F)
+
+
+def iptr(a):
+    return a.ctypes.data_as(_I)

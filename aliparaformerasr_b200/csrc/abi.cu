@@ -1,0 +1,345 @@
+// extern "C" surface of libpfasr (include/pf_abi.h): handle lifecycle, batch sharding over devices, error mapping,
+// and the op-level test hooks.
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <thread>
+
+#include "engine.cuh"
+
+namespace pf {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+template <typename F>
+static pf_status guarded(F&& f) {
+    try {
+        f();
+        return PF_OK;
+    } catch (const StatusError& e) {
+        set_last_error(e.what);
+        return e.code;
+    } catch (const CudaError& e) {
+        set_last_error(e.what);
+        cudaGetLastError();
+        return PF_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        set_last_error("host allocation failed");
+        return PF_ERR_OOM;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return PF_ERR_BAD_ARG;
+    }
+}
+
+static void validate_config(const pf_config& c) {
+    if (c.struct_bytes != static_cast<int32_t>(sizeof(pf_config))) throw StatusError{PF_ERR_BAD_ARG, "pf_config.struct_bytes mismatch (ABI version skew)"};
+    if (c.model_kind != PF_MODEL_PARAFORMER && c.model_kind != PF_MODEL_SENSEVOICE_SMALL) throw StatusError{PF_ERR_UNSUPPORTED, "unsupported model_kind"};
+    if (c.n_mels != 80 || c.fs != 16000) throw StatusError{PF_ERR_UNSUPPORTED, "front-end supports fs=16000, n_mels=80 (the reference hard-codes 80, WavFrontend.cs:75)"};
+    if (c.lfr_m < 1 || c.lfr_n < 1 || 2 * c.lfr_n < c.lfr_m + 1) throw StatusError{PF_ERR_UNSUPPORTED, "LFR setting would reach the reference's tail-replicate branch; unsupported"};
+    if (c.input_size != c.lfr_m * c.n_mels) throw StatusError{PF_ERR_SHAPE, "input_size must equal lfr_m * n_mels"};
+    if (c.input_size % 8 || c.input_size > 640) throw StatusError{PF_ERR_SHAPE, "input_size must be a multiple of 8 and <= 640"};
+    if (c.d_model != 512 || c.heads != 4) throw StatusError{PF_ERR_UNSUPPORTED, "kernels are specialised for d_model=512, 4 heads (head dim 128)"};
+    if (c.ffn != 2048 && c.ffn != 1024 && c.ffn != 512) throw StatusError{PF_ERR_UNSUPPORTED, "ffn width must be 512/1024/2048"};
+    if (c.enc_layers < 1 || c.tp_layers < 0) throw StatusError{PF_ERR_BAD_ARG, "bad layer counts"};
+    if (c.enc_kernel != 11 && c.enc_kernel != 21) throw StatusError{PF_ERR_UNSUPPORTED, "FSMN kernel must be 11 or 21"};
+    if (c.model_kind == PF_MODEL_PARAFORMER) {
+        if (c.dec_layers < 1) throw StatusError{PF_ERR_BAD_ARG, "paraformer needs decoder layers"};
+        if (c.dec_ffn != 2048 && c.dec_ffn != 1024 && c.dec_ffn != 512) throw StatusError{PF_ERR_UNSUPPORTED, "decoder ffn width must be 512/1024/2048"};
+        if (c.dec_kernel != 11 && c.dec_kernel != 21) throw StatusError{PF_ERR_UNSUPPORTED, "decoder FSMN kernel must be 11 or 21"};
+    }
+    if (c.vocab < 8 || c.vocab % 4) throw StatusError{PF_ERR_SHAPE, "vocab must be a positive multiple of 4 (fp32 row alignment)"};
+}
+
+static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
+    if (!cfg || !blob) throw StatusError{PF_ERR_BAD_ARG, "null config or weights"};
+    validate_config(*cfg);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw StatusError{PF_ERR_CUDA, std::string("no CUDA device available (libpfasr has no CPU fallback): ") + cudaGetErrorString(e)};
+    }
+    std::vector<int> devs;
+    if (devices && ndev > 0) devs.assign(devices, devices + ndev);
+    else {
+        int cur = 0;
+        PF_CUDA(cudaGetDevice(&cur));
+        devs.push_back(cur);
+    }
+    for (int d : devs) if (d < 0 || d >= count) throw StatusError{PF_ERR_BAD_ARG, "device ordinal out of range"};
+    Blob b;
+    b.parse(blob, bytes);
+    std::unique_ptr<OfflineHandle> h(new OfflineHandle());
+    h->cfg = *cfg;
+    for (int d : devs) {
+        std::unique_ptr<DeviceCtx> ctx(new DeviceCtx(d, *cfg));
+        ctx->load_weights(b);
+        h->devs.push_back(std::move(ctx));
+    }
+    return h.release();
+}
+
+// contiguous split of B items over n shards
+static void split_batch(int B, int n, std::vector<int>& begin, std::vector<int>& count) {
+    begin.assign(n, 0);
+    count.assign(n, 0);
+    const int base = B / n, rem = B % n;
+    int pos = 0;
+    for (int i = 0; i < n; ++i) {
+        begin[i] = pos;
+        count[i] = base + (i < rem ? 1 : 0);
+        pos += count[i];
+    }
+}
+
+static void run_all(OfflineHandle* h, uint32_t flags, pf_result* out) {
+    if (!h->staged) throw StatusError{PF_ERR_BAD_ARG, "no batch staged"};
+    const int n = static_cast<int>(h->devs.size());
+    std::vector<int> active;
+    for (int i = 0; i < n; ++i) if (h->shard_count[i] > 0) active.push_back(i);
+    const int na = static_cast<int>(active.size());
+    if (na == 1) {
+        h->devs[active[0]]->run(flags, nullptr, 0);
+    } else {
+        SharedRun shared(na);
+        std::vector<std::thread> threads;
+        std::vector<std::pair<pf_status, std::string>> errs(na, {PF_OK, ""});
+        for (int k = 0; k < na; ++k) {
+            threads.emplace_back([&, k] {
+                try {
+                    h->devs[active[k]]->run(flags, &shared, k);
+                } catch (const StatusError& e) {
+                    errs[k] = {e.code, e.what};
+                } catch (const CudaError& e) {
+                    errs[k] = {PF_ERR_CUDA, e.what};
+                } catch (const std::exception& e) {
+                    errs[k] = {PF_ERR_BAD_ARG, e.what()};
+                }
+            });
+        }
+        for (auto& t : threads) t.join();
+        for (auto& er : errs) if (er.first != PF_OK) throw StatusError{er.first, er.second};
+        if (shared.failed) throw StatusError{PF_ERR_CUDA, "a device shard failed"};
+    }
+    // assemble [B, Lmax] across shards
+    int lmax = 0, T = 0;
+    for (int i : active) { lmax = std::max(lmax, h->devs[i]->Lmax_); T = std::max(T, h->devs[i]->T_); }
+    const int B = h->B, V = h->cfg.vocab;
+    h->Lmax = lmax;
+    h->T = T;
+    const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0 && lmax > 0;
+    const bool wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0 && lmax > 0 && h->cfg.model_kind == PF_MODEL_PARAFORMER;
+    out->batch = B;
+    out->max_len = lmax;
+    out->vocab = V;
+    out->feat_frames = T;
+    if (na == 1) {
+        DeviceCtx* d = h->devs[active[0]].get();
+        out->tokens = d->h_tokens;
+        out->token_num = d->h_token_num;
+        out->logits = wl ? d->h_logits : nullptr;
+        out->cif_peak = wp ? d->h_peaks : nullptr;
+        return;
+    }
+    h->tokens.assign(static_cast<size_t>(B) * lmax, 0);
+    h->token_num.assign(B, 0);
+    if (wl) h->logits.resize(static_cast<size_t>(B) * lmax * V);
+    if (wp) h->peaks.resize(static_cast<size_t>(B) * (T + 1));
+    for (int i : active) {
+        DeviceCtx* d = h->devs[i].get();
+        const int b0 = h->shard_begin[i], nb = h->shard_count[i];
+        if (lmax > 0) memcpy(h->tokens.data() + static_cast<size_t>(b0) * lmax, d->h_tokens, static_cast<size_t>(nb) * lmax * sizeof(int32_t));
+        memcpy(h->token_num.data() + b0, d->h_token_num, static_cast<size_t>(nb) * sizeof(int32_t));
+        if (wl) memcpy(h->logits.data() + static_cast<size_t>(b0) * lmax * V, d->h_logits, static_cast<size_t>(nb) * lmax * V * sizeof(float));
+        if (wp) memcpy(h->peaks.data() + static_cast<size_t>(b0) * (T + 1), d->h_peaks, static_cast<size_t>(nb) * (T + 1) * sizeof(float));
+    }
+    out->tokens = h->tokens.data();
+    out->token_num = h->token_num.data();
+    out->logits = wl ? h->logits.data() : nullptr;
+    out->cif_peak = wp ? h->peaks.data() : nullptr;
+}
+
+static void stage_pcm_all(OfflineHandle* h, const float* const* pcm, const int32_t* nsamp, int32_t B) {
+    if (!pcm || !nsamp || B <= 0) throw StatusError{PF_ERR_BAD_ARG, "pcm/nsamp null or empty batch"};
+    int tmax = 0;
+    for (int b = 0; b < B; ++b) {
+        if (nsamp[b] < 0 || (nsamp[b] > 0 && !pcm[b])) throw StatusError{PF_ERR_BAD_ARG, "null samples (ArgumentNullException 'source' in the reference, WavFrontend.cs:34)"};
+        tmax = std::max(tmax, frontend_num_frames(nsamp[b], h->cfg.snip_edges != 0) / h->cfg.lfr_n);
+    }
+    const int n = static_cast<int>(h->devs.size());
+    split_batch(B, n, h->shard_begin, h->shard_count);
+    for (int i = 0; i < n; ++i)
+        if (h->shard_count[i] > 0) h->devs[i]->stage_pcm(pcm + h->shard_begin[i], nsamp + h->shard_begin[i], h->shard_count[i], tmax);
+    h->B = B;
+    h->staged = true;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" {
+
+const char* pf_last_error(void) { return g_last_error.c_str(); }
+int32_t pf_abi_version(void) { return PF_ABI_VERSION; }
+
+pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes, const int32_t* devices,
+                                        int32_t ndev, pf_offline** out) {
+    return guarded([&] {
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        *out = nullptr;
+        *out = reinterpret_cast<pf_offline*>(create_handle(cfg, blob, blob_bytes, devices, ndev));
+    });
+}
+
+pf_status pf_offline_create(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev, pf_offline** out) {
+    return guarded([&] {
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        *out = nullptr;
+        if (!weights_path || !*weights_path) throw StatusError{PF_ERR_WEIGHTS, "weights path is empty"};
+        std::ifstream f(weights_path, std::ios::binary | std::ios::ate);
+        if (!f) throw StatusError{PF_ERR_WEIGHTS, std::string("cannot open weights file ") + weights_path};
+        const std::streamsize sz = f.tellg();
+        f.seekg(0);
+        std::vector<char> buf(static_cast<size_t>(sz));
+        if (!f.read(buf.data(), sz)) throw StatusError{PF_ERR_WEIGHTS, "short read on weights file"};
+        *out = reinterpret_cast<pf_offline*>(create_handle(cfg, buf.data(), buf.size(), devices, ndev));
+    });
+}
+
+pf_status pf_offline_destroy(pf_offline* hh) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null (ObjectDisposedException in the reference)"};
+        delete reinterpret_cast<OfflineHandle*>(hh);
+    });
+}
+
+pf_status pf_offline_set_cmvn(pf_offline* hh, const float* add_shift, const float* rescale, int32_t dim) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!add_shift || !rescale) throw StatusError{PF_ERR_BAD_ARG, "null cmvn vectors"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        for (auto& d : h->devs) d->set_cmvn(add_shift, rescale, dim);
+    });
+}
+
+static pf_status extract_common(pf_offline* hh, const float* samples, int32_t nsamp, float* out, int32_t cap, int32_t* out_frames, bool raw) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!samples) throw StatusError{PF_ERR_BAD_ARG, "samples is null (ArgumentNullException 'source' in the reference, WavFrontend.cs:34)"};
+        if (nsamp < 0 || !out_frames || (!out && cap > 0)) throw StatusError{PF_ERR_BAD_ARG, "bad arguments"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        *out_frames = h->devs[0]->extract(samples, nsamp, out, cap, raw);
+    });
+}
+
+pf_status pf_frontend_extract(pf_offline* hh, const float* samples, int32_t nsamp, float* feats, int32_t capacity_frames, int32_t* out_frames) {
+    return extract_common(hh, samples, nsamp, feats, capacity_frames, out_frames, false);
+}
+pf_status pf_frontend_fbank(pf_offline* hh, const float* samples, int32_t nsamp, float* fbank, int32_t capacity_frames, int32_t* out_frames) {
+    return extract_common(hh, samples, nsamp, fbank, capacity_frames, out_frames, true);
+}
+int32_t pf_frontend_num_frames(const pf_offline* hh, int32_t nsamp) {
+    if (!hh || nsamp < 0) return -1;
+    const OfflineHandle* h = reinterpret_cast<const OfflineHandle*>(hh);
+    return frontend_num_frames(nsamp, h->cfg.snip_edges != 0) / h->cfg.lfr_n;
+}
+
+pf_status pf_offline_stage_pcm(pf_offline* hh, const float* const* pcm, const int32_t* nsamp, int32_t batch) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        stage_pcm_all(h, pcm, nsamp, batch);
+    });
+}
+
+pf_status pf_offline_run_staged(pf_offline* hh, uint32_t flags, pf_result* out) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        memset(out, 0, sizeof(*out));
+        run_all(h, flags, out);
+    });
+}
+
+pf_status pf_offline_run_pcm(pf_offline* hh, const float* const* pcm, const int32_t* nsamp, int32_t batch, uint32_t flags, pf_result* out) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        memset(out, 0, sizeof(*out));
+        stage_pcm_all(h, pcm, nsamp, batch);
+        run_all(h, flags, out);
+    });
+}
+
+pf_status pf_offline_run_feats(pf_offline* hh, const float* speech, int32_t batch, int32_t frames, uint32_t flags, pf_result* out) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!out || !speech) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
+        if (batch <= 0 || frames <= 0) throw StatusError{PF_ERR_SHAPE, "speech must be [B>0, T>0, input_size]"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        memset(out, 0, sizeof(*out));
+        const int n = static_cast<int>(h->devs.size());
+        split_batch(batch, n, h->shard_begin, h->shard_count);
+        const size_t row = static_cast<size_t>(frames) * h->cfg.input_size;
+        for (int i = 0; i < n; ++i)
+            if (h->shard_count[i] > 0) h->devs[i]->stage_feats(speech + h->shard_begin[i] * row, h->shard_count[i], frames);
+        h->B = batch;
+        h->staged = true;
+        run_all(h, flags, out);
+    });
+}
+
+pf_status pf_offline_get_tensor(pf_offline* hh, int32_t dev_index, const char* name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim) {
+    return guarded([&] {
+        if (!hh || !name) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        if (dev_index < 0 || dev_index >= static_cast<int>(h->devs.size())) throw StatusError{PF_ERR_BAD_ARG, "dev_index out of range"};
+        h->devs[dev_index]->get_tensor(name, dst, capacity, dims4, ndim);
+    });
+}
+
+int32_t pf_offline_get_timings(pf_offline* hh, float* ms, int32_t capacity) {
+    if (!hh || !ms) return 0;
+    OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+    const int n = std::min(capacity, 6);
+    for (int i = 0; i < n; ++i) ms[i] = h->devs[0]->timings_ms[i];
+    return n;
+}
+
+int64_t pf_offline_get_launch_count(pf_offline* hh) {
+    if (!hh) return 0;
+    OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+    int64_t n = 0;
+    for (auto& d : h->devs) n += d->launches;
+    return n;
+}
+
+double pf_offline_get_gemm_flops(pf_offline* hh) {
+    if (!hh) return 0;
+    OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+    double n = 0;
+    for (auto& d : h->devs) n += d->gemm_flops;
+    return n;
+}
+
+void* pf_offline_get_stream(pf_offline* hh, int32_t dev_index) {
+    if (!hh) return nullptr;
+    OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+    if (dev_index < 0 || dev_index >= static_cast<int>(h->devs.size())) return nullptr;
+    return h->devs[dev_index]->stream();
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// Multi-head scaled-dot-product attention for SAN-M self-attention (encoder) and cross-attention (decoder):
+//   O[b, :, h] = softmax(Q[b,:,h] K[b,:,h]^T / sqrt(128)) V[b,:,h],  head dim 128, fp16 operands, fp32 softmax state.
+// Single pass over K/V in 64-row chunks with an online (running max / running sum) softmax reduced with warp
+// shuffles; QK^T and PV run on mma.sync m16n8k16 (the north-star keeps tcgen05 for the projection GEMMs).
+// Masks: the reference feeds speech_lengths = T for every item (OfflineProjOfParaformer.cs:53-63, Q3), so key
+// masks are all ones; only the chunk tail (kv >= Tk) is masked here.
+#include "attention.cuh"
+
+namespace pf {
+
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 64;
+constexpr int BKV = 64;
+constexpr int LDS = HD + 8;            // padded row: 272 B, conflict-free for ldmatrix
+constexpr int kThreads = 128;
+constexpr int kSmemBytes = (BQ + 4 * BKV) * LDS * 2;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Stage `rows` rows x 128 halfs from global (row pitch ld) into padded smem; rows >= valid are zero-filled.
+__device__ __forceinline__ void stage_tile(uint32_t smem_base, const __half* g, int ld, int valid_rows, int rows) {
+    for (int i = threadIdx.x; i < rows * (HD / 8); i += kThreads) {
+        const int r = i >> 4;
+        const int c = i & 15;
+        const bool ok = r < valid_rows;
+        const __half* src = g + static_cast<size_t>(ok ? r : 0) * ld + c * 8;
+        cp_async_16(smem_base + (r * LDS + c * 8) * 2, src, ok);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
+                  __half* __restrict__ O, int Tq, int Tk, int ldq, int ldk, int ldv, int ldo, float scale_log2e) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t sQ = smem_u32(smem);
+    const uint32_t sK = sQ + BQ * LDS * 2;
+    const uint32_t sV = sK + 2 * BKV * LDS * 2;
+
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int q0 = blockIdx.x * BQ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+
+    const __half* Qg = Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * HD;
+    const __half* Kg = K + static_cast<size_t>(b) * Tk * ldk + h * HD;
+    const __half* Vg = V + static_cast<size_t>(b) * Tk * ldv + h * HD;
+
+    const int nchunks = (Tk + BKV - 1) / BKV;
+    stage_tile(sQ, Qg, ldq, min(BQ, Tq - q0), BQ);
+    stage_tile(sK, Kg, ldk, min(BKV, Tk), BKV);
+    stage_tile(sV, Vg, ldv, min(BKV, Tk), BKV);
+    cp_async_commit();
+
+    uint32_t qf[HD / 16][4];
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+
+    for (int j = 0; j < nchunks; ++j) {
+        const int buf = j & 1;
+        if (j + 1 < nchunks) {
+            const int kv1 = (j + 1) * BKV;
+            stage_tile(sK + (buf ^ 1) * BKV * LDS * 2, Kg + static_cast<size_t>(kv1) * ldk, ldk, min(BKV, Tk - kv1), BKV);
+            stage_tile(sV + (buf ^ 1) * BKV * LDS * 2, Vg + static_cast<size_t>(kv1) * ldv, ldv, min(BKV, Tk - kv1), BKV);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (j == 0) {
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+                const uint32_t addr = sQ + ((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + kk * 16 + (lane >> 4) * 8) * 2;
+                ldmatrix_x4(addr, qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+            }
+        }
+        const uint32_t kb = sK + buf * BKV * LDS * 2;
+        const uint32_t vb = sV + buf * BKV * LDS * 2;
+
+        // S = Q K^T for this chunk: 16 x 64 per warp
+        float s[BKV / 8][4];
+#pragma unroll
+        for (int i = 0; i < BKV / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f; }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+            for (int np = 0; np < BKV / 16; ++np) {
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = kb + ((np * 16 + ((lane >> 4) & 1) * 8 + (lane & 7)) * LDS + kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+                ldmatrix_x4(addr, b0, b1, b2, b3);
+                mma_16816(s[2 * np], qf[kk], b0, b1);
+                mma_16816(s[2 * np + 1], qf[kk], b2, b3);
+            }
+        }
+        // scale into the log2 domain, mask the chunk tail, running max
+        const int kv0 = j * BKV;
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int nt = 0; nt < BKV / 8; ++nt) {
+            const int col = kv0 + nt * 8 + 2 * t4;
+            const bool v0 = col < Tk, v1 = col + 1 < Tk;
+            s[nt][0] = v0 ? s[nt][0] * scale_log2e : -INFINITY;
+            s[nt][1] = v1 ? s[nt][1] * scale_log2e : -INFINITY;
+            s[nt][2] = v0 ? s[nt][2] * scale_log2e : -INFINITY;
+            s[nt][3] = v1 ? s[nt][3] * scale_log2e : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);   // first chunk: exp2(-inf) = 0
+        m0 = mx0; m1 = mx1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < BKV / 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - m0);
+            s[nt][1] = exp2f(s[nt][1] - m0);
+            s[nt][2] = exp2f(s[nt][2] - m1);
+            s[nt][3] = exp2f(s[nt][3] - m1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+        // O += P V
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack_half2(s[2 * kk][0], s[2 * kk][1]);
+            pa[1] = pack_half2(s[2 * kk][2], s[2 * kk][3]);
+            pa[2] = pack_half2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            pa[3] = pack_half2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int dp = 0; dp < HD / 16; ++dp) {
+                uint32_t b0, b1, b2, b3;
+                const uint32_t addr = vb + ((kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + dp * 16 + ((lane >> 4) & 1) * 8) * 2;
+                ldmatrix_x4_trans(addr, b0, b1, b2, b3);
+                mma_16816(o[2 * dp], pa, b0, b1);
+                mma_16816(o[2 * dp + 1], pa, b2, b3);
+            }
+        }
+        __syncthreads();   // everyone done with this K/V buffer before it is refilled
+    }
+
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = q0 + warp * 16 + g;
+    const int r1 = r0 + 8;
+    __half* Og = O + static_cast<size_t>(b) * Tq * ldo + h * HD;
+#pragma unroll
+    for (int nt = 0; nt < HD / 8; ++nt) {
+        const int col = nt * 8 + 2 * t4;
+        if (r0 < Tq) *reinterpret_cast<uint32_t*>(Og + static_cast<size_t>(r0) * ldo + col) = pack_half2(o[nt][0] * inv0, o[nt][1] * inv0);
+        if (r1 < Tq) *reinterpret_cast<uint32_t*>(Og + static_cast<size_t>(r1) * ldo + col) = pack_half2(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+}
+
+}  // namespace
+
+void attention_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int Tq, int Tk, int ldq,
+                      int ldk, int ldv, int ldo, int head_dim, cudaStream_t s) {
+    if (head_dim != HD) throw CudaError{"attention: head dim must be 128"};
+    if (Tq <= 0 || Tk <= 0 || B <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int ndev = 0, cur = 0;
+        PF_CUDA(cudaGetDeviceCount(&ndev));
+        PF_CUDA(cudaGetDevice(&cur));
+        for (int d = 0; d < ndev; ++d) {
+            PF_CUDA(cudaSetDevice(d));
+            PF_CUDA(cudaFuncSetAttribute(pf_sanm_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        }
+        PF_CUDA(cudaSetDevice(cur));
+        attr_set = true;
+    }
+    const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+    dim3 grid(ceil_div(Tq, BQ), H, B);
+    pf_sanm_attention<<<grid, kThreads, kSmemBytes, s>>>(Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e);
+    PF_CUDA(cudaGetLastError());
+}
+
+}  // namespace pf

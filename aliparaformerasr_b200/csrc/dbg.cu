@@ -1,0 +1,223 @@
+// Op-level test hooks of the C-ABI (pf_dbg_*): run one kernel on the current device with host fp32 in/out so that
+// tests/ can compare each stage with the oracle.  Not on the product path.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/pf_abi.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace pf {
+void set_last_error(const std::string& msg);
+
+namespace {
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        cudaDeviceSynchronize();
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        PF_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    float* up(const float* h, size_t n) {
+        float* d = alloc<float>(n);
+        PF_CUDA(cudaMemcpy(d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+        return d;
+    }
+    __half* up_half(const float* h, size_t n) {
+        float* t = up(h, n);
+        __half* d = alloc<__half>(n);
+        f32_to_f16_launch(t, d, n, 0);
+        return d;
+    }
+};
+
+__global__ void pf_dbg_f16_to_f32(const __half* in, float* out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __half2float(in[i]);
+}
+
+template <typename F>
+pf_status guarded(F&& f) {
+    try {
+        f();
+        return PF_OK;
+    } catch (const CudaError& e) {
+        set_last_error(e.what);
+        cudaGetLastError();
+        return PF_ERR_CUDA;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return PF_ERR_BAD_ARG;
+    }
+}
+
+}  // namespace
+}  // namespace pf
+
+using namespace pf;
+
+extern "C" {
+
+pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, const float* resid,
+                      const float* addend, int32_t relu, int32_t out_half, int32_t tile_n, float* out, float* elapsed_ms,
+                      int32_t iters) {
+    return guarded([&] {
+        Scratch s;
+        __half* dA = s.up_half(A, static_cast<size_t>(M) * K);
+        __half* dW = s.up_half(W, static_cast<size_t>(N) * K);
+        GemmEpi e;
+        if (bias) e.bias = s.up(bias, N);
+        float* dres = nullptr;
+        if (resid) { dres = s.up(resid, static_cast<size_t>(M) * N); e.resid = dres; e.ld_resid = N; }
+        if (addend) { e.addend = s.up(addend, static_cast<size_t>(M) * N); e.ld_addend = N; }
+        e.relu = relu;
+        e.ld_out = N;
+        float* o32 = s.alloc<float>(static_cast<size_t>(M) * N);
+        __half* o16 = nullptr;
+        if (out_half) { o16 = s.alloc<__half>(static_cast<size_t>(M) * N); e.out_f16 = o16; }
+        else e.out_f32 = o32;
+        GemmOp op;
+        gemm_prepare(op, dA, K, dW, K, M, N, K, e, tile_n);
+        gemm_launch(op, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        if (out_half) {
+            pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, static_cast<size_t>(M) * N);
+            PF_CUDA(cudaGetLastError());
+        }
+        PF_CUDA(cudaMemcpy(out, o32, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
+        if (elapsed_ms && iters > 0) {
+            cudaEvent_t a, b;
+            PF_CUDA(cudaEventCreate(&a));
+            PF_CUDA(cudaEventCreate(&b));
+            for (int i = 0; i < 3; ++i) gemm_launch(op, 0);
+            PF_CUDA(cudaEventRecord(a, 0));
+            for (int i = 0; i < iters; ++i) gemm_launch(op, 0);
+            PF_CUDA(cudaEventRecord(b, 0));
+            PF_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            PF_CUDA(cudaEventElapsedTime(&ms, a, b));
+            *elapsed_ms = ms / iters;
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    });
+}
+
+pf_status pf_dbg_layernorm(int32_t M, int32_t D, const float* x, const float* gamma, const float* beta, float eps, float* out) {
+    return guarded([&] {
+        Scratch s;
+        float* dx = s.up(x, static_cast<size_t>(M) * D);
+        float* g = s.up(gamma, D);
+        float* b = s.up(beta, D);
+        float* o = s.alloc<float>(static_cast<size_t>(M) * D);
+        layernorm_f32_launch(dx, D, M, D, g, b, eps, nullptr, 0, o, D, 0);
+        PF_CUDA(cudaMemcpy(out, o, static_cast<size_t>(M) * D * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats, float scale, const float* gamma, const float* beta,
+                             float eps, float* out) {
+    return guarded([&] {
+        Scratch s;
+        const size_t n = static_cast<size_t>(B) * T * D;
+        float* dx = s.up(feats, n);
+        float* g = s.up(gamma, D);
+        float* b = s.up(beta, D);
+        const int half = D / 2;
+        std::vector<float> inv(half);
+        const float inc = static_cast<float>(log(10000.0) / (half - 1));
+        for (int i = 0; i < half; ++i) inv[i] = expf(static_cast<float>(i) * -inc);
+        float* dinv = s.up(inv.data(), half);
+        __half* o16 = s.alloc<__half>(n);
+        float* o32 = s.alloc<float>(n);
+        embed_pe_ln_launch(dx, B * T, T, D, scale, dinv, g, b, eps, o16, 0);
+        pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, n);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(out, o32, n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+pf_status pf_dbg_attention(int32_t B, int32_t H, int32_t Tq, int32_t Tk, const float* q, const float* k, const float* v, float* out) {
+    return guarded([&] {
+        Scratch s;
+        const int D = H * 128;
+        const size_t nq = static_cast<size_t>(B) * Tq * D, nk = static_cast<size_t>(B) * Tk * D;
+        __half* dq = s.up_half(q, nq);
+        __half* dk = s.up_half(k, nk);
+        __half* dv = s.up_half(v, nk);
+        __half* o16 = s.alloc<__half>(nq);
+        float* o32 = s.alloc<float>(nq);
+        attention_launch(dq, dk, dv, o16, B, H, Tq, Tk, D, D, D, D, 128, 0);
+        pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, nq);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(out, o32, nq * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+pf_status pf_dbg_fsmn(int32_t B, int32_t T, int32_t D, int32_t K, const float* x, const float* w, const float* resid,
+                      const int32_t* lens, int32_t half_input, float* out) {
+    return guarded([&] {
+        Scratch s;
+        const size_t n = static_cast<size_t>(B) * T * D;
+        float* dw = s.up(w, static_cast<size_t>(D) * K);
+        float* dres = resid ? s.up(resid, n) : nullptr;
+        int* dl = nullptr;
+        if (lens) {
+            dl = s.alloc<int>(B);
+            PF_CUDA(cudaMemcpy(dl, lens, B * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        float* o = s.alloc<float>(n);
+        if (half_input) fsmn_f16_launch(s.up_half(x, n), D, dw, K, o, D, dres, D, dl, B, T, D, 0);
+        else fsmn_f32_launch(s.up(x, n), D, dw, K, o, D, dres, D, dl, B, T, D, 0);
+        PF_CUDA(cudaMemcpy(out, o, n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+pf_status pf_dbg_cif(int32_t B, int32_t T, int32_t D, const float* hidden, const float* alphas_with_tail, float threshold,
+                     int32_t lcap, float* embeds, int32_t* token_num, int32_t* fires, float* peaks) {
+    return guarded([&] {
+        Scratch s;
+        const int T1 = T + 1;
+        float* dh = s.up(hidden, static_cast<size_t>(B) * T * D);
+        float* da = s.up(alphas_with_tail, static_cast<size_t>(B) * T1);
+        float* wc = s.alloc<float>(static_cast<size_t>(B) * T1);
+        float* wr = s.alloc<float>(static_cast<size_t>(B) * T1);
+        float* pk = s.alloc<float>(static_cast<size_t>(B) * T1);
+        int* fi = s.alloc<int>(static_cast<size_t>(B) * T1);
+        int* tn = s.alloc<int>(B);
+        int* fr = s.alloc<int>(B);
+        int* meta = s.alloc<int>(4);
+        PF_CUDA(cudaMemset(meta, 0, 4 * sizeof(int)));
+        float* emb = s.alloc<float>(static_cast<size_t>(B) * lcap * D);
+        PF_CUDA(cudaMemset(emb, 0, static_cast<size_t>(B) * lcap * D * sizeof(float)));
+        cif_scan_launch(da, B, T1, threshold, wc, wr, fi, pk, tn, fr, meta, 0);
+        cif_gather_launch(dh, B, T, D, wc, wr, fi, T1, emb, lcap, 0);
+        PF_CUDA(cudaMemcpy(embeds, emb, static_cast<size_t>(B) * lcap * D * sizeof(float), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(token_num, tn, B * sizeof(int), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(fires, fr, B * sizeof(int), cudaMemcpyDeviceToHost));
+        if (peaks) PF_CUDA(cudaMemcpy(peaks, pk, static_cast<size_t>(B) * T1 * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+pf_status pf_dbg_logsoftmax_argmax(int32_t M, int32_t V, float* logits_inout, int32_t* tokens) {
+    return guarded([&] {
+        Scratch s;
+        float* d = s.up(logits_inout, static_cast<size_t>(M) * V);
+        int* t = s.alloc<int>(M);
+        logsoftmax_argmax_launch(d, M, V, V, t, 1, 0);
+        PF_CUDA(cudaMemcpy(logits_inout, d, static_cast<size_t>(M) * V * sizeof(float), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(tokens, t, M * sizeof(int), cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

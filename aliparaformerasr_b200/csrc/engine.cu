@@ -1,0 +1,750 @@
+// Per-device offline engine: PFW1 blob -> device weights, workspace, cached TMA launch plans, forward passes.
+//
+// Replaces the InferenceSession the reference builds in OfflineModel.initModel
+// (/root/reference/AliParaformerAsr/OfflineModel.cs:35-70) and runs in IOfflineProj.ModelProj
+// (OfflineProjOfParaformer.cs:39-87, OfflineProjOfSenseVoiceSmall.cs:53-175).
+#include "engine.cuh"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace pf {
+
+// ------------------------------------------------------------------ blob
+// Layout (little endian): "PFW1" | u32 version | u32 count | u32 reserved |
+//   count x { char name[96]; u32 dtype(0=f32); u32 ndim; u64 dims[4]; u64 offset; u64 nbytes } | payload
+namespace {
+struct RawEntry {
+    char name[96];
+    uint32_t dtype;
+    uint32_t ndim;
+    uint64_t dims[4];
+    uint64_t offset;
+    uint64_t nbytes;
+};
+static_assert(sizeof(RawEntry) == 96 + 8 + 32 + 16, "PFW1 entry layout");
+}  // namespace
+
+void Blob::parse(const void* data, size_t bytes) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    if (bytes < 16 || memcmp(p, "PFW1", 4) != 0) throw StatusError{PF_ERR_WEIGHTS, "weights blob: bad magic (expected PFW1)"};
+    uint32_t version, count;
+    memcpy(&version, p + 4, 4);
+    memcpy(&count, p + 8, 4);
+    if (version != 1) throw StatusError{PF_ERR_WEIGHTS, "weights blob: unsupported version"};
+    if (16 + static_cast<size_t>(count) * sizeof(RawEntry) > bytes) throw StatusError{PF_ERR_WEIGHTS, "weights blob: truncated table"};
+    for (uint32_t i = 0; i < count; ++i) {
+        RawEntry e;
+        memcpy(&e, p + 16 + static_cast<size_t>(i) * sizeof(RawEntry), sizeof(RawEntry));
+        e.name[95] = 0;
+        if (e.dtype != 0 || e.ndim > 4) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad entry ") + e.name};
+        if (e.offset + e.nbytes > bytes || (e.offset & 3)) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad extent ") + e.name};
+        BlobEntry be;
+        be.name = e.name;
+        be.ndim = static_cast<int>(e.ndim);
+        size_t cnt = 1;
+        for (int d = 0; d < 4; ++d) {
+            be.dims[d] = d < be.ndim ? static_cast<int64_t>(e.dims[d]) : 1;
+            cnt *= static_cast<size_t>(be.dims[d]);
+        }
+        if (cnt * 4 != e.nbytes) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: size mismatch ") + e.name};
+        be.count = cnt;
+        be.data = reinterpret_cast<const float*>(p + e.offset);
+        entries_[be.name] = be;
+    }
+}
+
+const BlobEntry& Blob::get(const std::string& name) const {
+    auto it = entries_.find(name);
+    if (it == entries_.end()) throw StatusError{PF_ERR_WEIGHTS, "weights blob: missing tensor '" + name + "'"};
+    return it->second;
+}
+
+static void expect_shape(const BlobEntry& e, std::initializer_list<int64_t> dims) {
+    size_t n = 1;
+    for (auto d : dims) n *= static_cast<size_t>(d);
+    if (n != e.count) {
+        std::string want;
+        for (auto d : dims) want += std::to_string(d) + " ";
+        throw StatusError{PF_ERR_WEIGHTS, "weights blob: tensor '" + e.name + "' has " + std::to_string(e.count) +
+                                              " elements, expected [" + want + "]"};
+    }
+}
+
+// ------------------------------------------------------------------ DeviceCtx basics
+DeviceCtx::DeviceCtx(int dev, const pf_config& cfg) : dev_(dev), cfg_(cfg) {
+    PF_CUDA(cudaSetDevice(dev_));
+    cudaDeviceProp prop;
+    PF_CUDA(cudaGetDeviceProperties(&prop, dev_));
+    if (prop.major != 10)
+        throw StatusError{PF_ERR_CUDA, "device " + std::to_string(dev_) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
+                                           std::to_string(prop.minor) + ") is not sm_100: libpfasr has no fallback path"};
+    PF_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& e : ev_) PF_CUDA(cudaEventCreate(&e));
+    fe_tables_ = frontend_tables_create();
+    // FunASR SinusoidalPositionEncoder: inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1)), float32 arithmetic
+    const int half = cfg_.input_size / 2;
+    std::vector<float> inv(half);
+    const float inc = static_cast<float>(log(10000.0) / (half - 1));
+    for (int i = 0; i < half; ++i) inv[i] = expf(static_cast<float>(i) * -inc);
+    inv_ts_ = up_f32(inv.data(), inv.size());
+    PF_CUDA(cudaMallocHost(&h_meta_, 16 * sizeof(int)));
+    const int dim = cfg_.lfr_m * cfg_.n_mels;
+    std::vector<float> zeros(dim, 0.0f), ones(dim, 1.0f);
+    cmvn_shift_ = up_f32(zeros.data(), dim);
+    cmvn_scale_ = up_f32(ones.data(), dim);
+}
+
+void DeviceCtx::free_pool(std::vector<void*>& pool) {
+    for (void* p : pool) cudaFree(p);
+    pool.clear();
+}
+
+DeviceCtx::~DeviceCtx() {
+    cudaSetDevice(dev_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    free_pool(wpool_);
+    free_pool(apool_);
+    free_pool(tmp_);
+    frontend_tables_destroy(fe_tables_);
+    if (pcm_) cudaFree(pcm_);
+    if (d_off_) cudaFree(d_off_);
+    if (d_meta_) cudaFree(d_meta_);
+    if (h_stage_) cudaFreeHost(h_stage_);
+    if (h_meta_) cudaFreeHost(h_meta_);
+    if (h_tokens) cudaFreeHost(h_tokens);
+    if (h_token_num) cudaFreeHost(h_token_num);
+    if (h_logits) cudaFreeHost(h_logits);
+    if (h_peaks) cudaFreeHost(h_peaks);
+    for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+template <typename T>
+T* DeviceCtx::dalloc(size_t n, std::vector<void*>& pool) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw StatusError{PF_ERR_OOM, "cudaMalloc of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e)};
+    }
+    pool.push_back(p);
+    return static_cast<T*>(p);
+}
+
+float* DeviceCtx::up_f32(const float* host, size_t n) {
+    float* d = dalloc<float>(n, wpool_);
+    PF_CUDA(cudaMemcpyAsync(d, host, n * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    PF_CUDA(cudaStreamSynchronize(stream_));   // host buffer may be a temporary
+    return d;
+}
+float* DeviceCtx::up_f32(const BlobEntry& e) { return up_f32(e.data, e.count); }
+
+__half* DeviceCtx::up_f16(const float* host, size_t n) {
+    float* t = dalloc<float>(n, tmp_);
+    PF_CUDA(cudaMemcpyAsync(t, host, n * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    __half* d = dalloc<__half>(n, wpool_);
+    f32_to_f16_launch(t, d, n, stream_);
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    free_pool(tmp_);
+    return d;
+}
+
+LnW DeviceCtx::up_ln(const Blob& b, const std::string& prefix) {
+    LnW w;
+    w.g = up_f32(b.get(prefix + ".weight"));
+    w.b = up_f32(b.get(prefix + ".bias"));
+    return w;
+}
+
+void DeviceCtx::load_enc_layer(const Blob& b, const std::string& p, int in_size, EncLayerW& w) {
+    const int d = cfg_.d_model, f = cfg_.ffn, k = cfg_.enc_kernel;
+    w.in_size = in_size;
+    expect_shape(b.get(p + ".norm1.weight"), {in_size});
+    w.ln1 = up_ln(b, p + ".norm1");
+    const BlobEntry& qkv = b.get(p + ".self_attn.linear_q_k_v.weight");
+    expect_shape(qkv, {3 * d, in_size});
+    w.w_qkv = up_f16(qkv.data, qkv.count);
+    expect_shape(b.get(p + ".self_attn.linear_q_k_v.bias"), {3 * d});
+    w.b_qkv = up_f32(b.get(p + ".self_attn.linear_q_k_v.bias"));
+    expect_shape(b.get(p + ".self_attn.fsmn_block.weight"), {d, 1, k});
+    w.fsmn = up_f32(b.get(p + ".self_attn.fsmn_block.weight"));
+    const BlobEntry& wo = b.get(p + ".self_attn.linear_out.weight");
+    expect_shape(wo, {d, d});
+    w.w_out = up_f16(wo.data, wo.count);
+    w.b_out = up_f32(b.get(p + ".self_attn.linear_out.bias"));
+    expect_shape(b.get(p + ".norm2.weight"), {d});
+    w.ln2 = up_ln(b, p + ".norm2");
+    const BlobEntry& w1 = b.get(p + ".feed_forward.w_1.weight");
+    expect_shape(w1, {f, d});
+    w.w_ffn1 = up_f16(w1.data, w1.count);
+    w.b_ffn1 = up_f32(b.get(p + ".feed_forward.w_1.bias"));
+    const BlobEntry& w2 = b.get(p + ".feed_forward.w_2.weight");
+    expect_shape(w2, {d, f});
+    w.w_ffn2 = up_f16(w2.data, w2.count);
+    w.b_ffn2 = up_f32(b.get(p + ".feed_forward.w_2.bias"));
+}
+
+void DeviceCtx::load_dec_ffn(const Blob& b, const std::string& p, DecFfnW& w) {
+    const int d = cfg_.d_model, f = cfg_.dec_ffn;
+    w.ln_in = up_ln(b, p + ".norm1");
+    const BlobEntry& w1 = b.get(p + ".feed_forward.w_1.weight");
+    expect_shape(w1, {f, d});
+    w.w1 = up_f16(w1.data, w1.count);
+    w.b1 = up_f32(b.get(p + ".feed_forward.w_1.bias"));
+    expect_shape(b.get(p + ".feed_forward.norm.weight"), {f});
+    w.ln_mid = up_ln(b, p + ".feed_forward.norm");
+    const BlobEntry& w2 = b.get(p + ".feed_forward.w_2.weight");
+    expect_shape(w2, {d, f});
+    w.w2 = up_f16(w2.data, w2.count);
+}
+
+void DeviceCtx::load_weights(const Blob& b) {
+    PF_CUDA(cudaSetDevice(dev_));
+    const int d = cfg_.d_model;
+    enc_.resize(cfg_.enc_layers);
+    load_enc_layer(b, "encoder.encoders0.0", cfg_.input_size, enc_[0]);
+    for (int i = 1; i < cfg_.enc_layers; ++i) load_enc_layer(b, "encoder.encoders." + std::to_string(i - 1), d, enc_[i]);
+    after_norm_ = up_ln(b, "encoder.after_norm");
+    tp_.resize(cfg_.tp_layers);
+    for (int i = 0; i < cfg_.tp_layers; ++i) load_enc_layer(b, "encoder.tp_encoders." + std::to_string(i), d, tp_[i]);
+    if (cfg_.tp_layers) tp_norm_ = up_ln(b, "encoder.tp_norm");
+
+    if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
+        const BlobEntry& w = b.get("ctc.ctc_lo.weight");
+        expect_shape(w, {cfg_.vocab, d});
+        w_head_ = up_f16(w.data, w.count);
+        b_head_ = up_f32(b.get("ctc.ctc_lo.bias"));
+        const BlobEntry& tab = b.get("embed.weight");
+        expect_shape(tab, {16, cfg_.input_size});
+        embed_table_ = up_f32(tab);
+        return;
+    }
+    // CifPredictorV2: conv1d weight [out, in, 3] -> GEMM weight [out, 3*in] with k = tap*in + cin (im2col order)
+    {
+        const BlobEntry& cw = b.get("predictor.cif_conv1d.weight");
+        expect_shape(cw, {d, d, 3});
+        std::vector<float> re(static_cast<size_t>(d) * 3 * d);
+        for (int o = 0; o < d; ++o)
+            for (int c = 0; c < d; ++c)
+                for (int j = 0; j < 3; ++j) re[(static_cast<size_t>(o) * 3 + j) * d + c] = cw.data[(static_cast<size_t>(o) * d + c) * 3 + j];
+        w_conv_ = up_f16(re.data(), re.size());
+        b_conv_ = up_f32(b.get("predictor.cif_conv1d.bias"));
+        expect_shape(b.get("predictor.cif_output.weight"), {1, d});
+        w_alpha_ = up_f32(b.get("predictor.cif_output.weight"));
+        b_alpha_ = up_f32(b.get("predictor.cif_output.bias"));
+    }
+    dec_.resize(cfg_.dec_layers);
+    std::vector<float> kvw(static_cast<size_t>(cfg_.dec_layers) * 2 * d * d), kvb(static_cast<size_t>(cfg_.dec_layers) * 2 * d);
+    for (int i = 0; i < cfg_.dec_layers; ++i) {
+        const std::string p = "decoder.decoders." + std::to_string(i);
+        DecLayerW& w = dec_[i];
+        load_dec_ffn(b, p, w.ffn);
+        w.ln2 = up_ln(b, p + ".norm2");
+        expect_shape(b.get(p + ".self_attn.fsmn_block.weight"), {d, 1, cfg_.dec_kernel});
+        w.fsmn = up_f32(b.get(p + ".self_attn.fsmn_block.weight"));
+        w.ln3 = up_ln(b, p + ".norm3");
+        const BlobEntry& wq = b.get(p + ".src_attn.linear_q.weight");
+        expect_shape(wq, {d, d});
+        w.wq = up_f16(wq.data, wq.count);
+        w.bq = up_f32(b.get(p + ".src_attn.linear_q.bias"));
+        const BlobEntry& wkv = b.get(p + ".src_attn.linear_k_v.weight");
+        expect_shape(wkv, {2 * d, d});
+        memcpy(kvw.data() + static_cast<size_t>(i) * 2 * d * d, wkv.data, wkv.count * sizeof(float));
+        const BlobEntry& bkv = b.get(p + ".src_attn.linear_k_v.bias");
+        expect_shape(bkv, {2 * d});
+        memcpy(kvb.data() + static_cast<size_t>(i) * 2 * d, bkv.data, bkv.count * sizeof(float));
+        const BlobEntry& wo = b.get(p + ".src_attn.linear_out.weight");
+        expect_shape(wo, {d, d});
+        w.wo = up_f16(wo.data, wo.count);
+        w.bo = up_f32(b.get(p + ".src_attn.linear_out.bias"));
+    }
+    // the K/V projections of all decoder layers read the same encoder output: one [layers*2d, d] GEMM
+    w_kv_all_ = up_f16(kvw.data(), kvw.size());
+    b_kv_all_ = up_f32(kvb.data(), kvb.size());
+    load_dec_ffn(b, "decoder.decoders3.0", dec3_);
+    dec_after_ = up_ln(b, "decoder.after_norm");
+    const BlobEntry& wo = b.get("decoder.output_layer.weight");
+    expect_shape(wo, {cfg_.vocab, d});
+    w_head_ = up_f16(wo.data, wo.count);
+    expect_shape(b.get("decoder.output_layer.bias"), {cfg_.vocab});
+    b_head_ = up_f32(b.get("decoder.output_layer.bias"));
+}
+
+void DeviceCtx::set_cmvn(const float* shift, const float* scale, int dim) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (dim != cfg_.lfr_m * cfg_.n_mels) throw StatusError{PF_ERR_SHAPE, "cmvn dim must be lfr_m * n_mels"};
+    PF_CUDA(cudaMemcpyAsync(cmvn_shift_, shift, dim * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    PF_CUDA(cudaMemcpyAsync(cmvn_scale_, scale, dim * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    PF_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ------------------------------------------------------------------ workspace
+void DeviceCtx::ensure_workspace(int B, int T) {
+    if (B <= capB_ && T <= capT_) return;
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    free_pool(apool_);
+    enc_plans_.clear();
+    dec_plans_.clear();
+    capB_ = std::max(capB_, B);
+    capT_ = std::max(capT_, T);
+    const size_t M = static_cast<size_t>(capB_) * capT_;
+    const size_t Md = static_cast<size_t>(capB_) * (capT_ + 1);
+    const int d = cfg_.d_model, din = cfg_.input_size;
+    const bool sv = cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL;
+    feats_ = dalloc<float>(M * din, apool_);
+    feats_raw_ = sv ? dalloc<float>(M * din, apool_) : nullptr;
+    a16_ = dalloc<__half>(M * std::max(din, d), apool_);
+    qkv16_ = dalloc<__half>(M * 3 * d, apool_);
+    ctx16_ = dalloc<__half>(M * d, apool_);
+    h16_ = dalloc<__half>(M * cfg_.ffn, apool_);
+    mem32_ = dalloc<float>(M * d, apool_);
+    x32_ = dalloc<float>(M * d, apool_);
+    enc32_ = dalloc<float>(M * d, apool_);
+    enc16_ = dalloc<__half>(M * d, apool_);
+    prompt_ids_ = dalloc<int>(4, apool_);
+    if (sv) {
+        logits_ = dalloc<float>(M * cfg_.vocab, apool_);
+        tokens_ = dalloc<int>(M, apool_);
+        token_num_ = dalloc<int>(capB_, apool_);
+        return;
+    }
+    kv16_ = dalloc<__half>(M * cfg_.dec_layers * 2 * d, apool_);
+    const size_t A = static_cast<size_t>(capB_) * (capT_ + 1);
+    alphas_ = dalloc<float>(A, apool_);
+    wcur_ = dalloc<float>(A, apool_);
+    wrem_ = dalloc<float>(A, apool_);
+    peaks_ = dalloc<float>(A, apool_);
+    fire_idx_ = dalloc<int>(A, apool_);
+    token_num_ = dalloc<int>(capB_, apool_);
+    fires_ = dalloc<int>(capB_, apool_);
+    meta_ = dalloc<int>(4, apool_);
+    xd32_ = dalloc<float>(Md * d, apool_);
+    ad16_ = dalloc<__half>(Md * d, apool_);
+    hd32_ = dalloc<float>(Md * cfg_.dec_ffn, apool_);
+    hd16_ = dalloc<__half>(Md * cfg_.dec_ffn, apool_);
+    t32_ = dalloc<float>(Md * d, apool_);
+    tn32_ = dalloc<float>(Md * d, apool_);
+    q16_ = dalloc<__half>(Md * d, apool_);
+    ctxd16_ = dalloc<__half>(Md * d, apool_);
+    logits_ = dalloc<float>(Md * cfg_.vocab, apool_);
+    tokens_ = dalloc<int>(Md, apool_);
+}
+
+static void ensure_pinned(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *cap = 0;
+        throw StatusError{PF_ERR_OOM, "cudaMallocHost of " + std::to_string(bytes) + " bytes failed"};
+    }
+    *cap = bytes;
+}
+
+void DeviceCtx::ensure_host(size_t tokens, size_t logits, size_t peaks) {
+    ensure_pinned(reinterpret_cast<void**>(&h_tokens), &h_tokens_cap_, std::max<size_t>(tokens, 1) * sizeof(int32_t));
+    if (logits) ensure_pinned(reinterpret_cast<void**>(&h_logits), &h_logits_cap_, logits * sizeof(float));
+    if (peaks) ensure_pinned(reinterpret_cast<void**>(&h_peaks), &h_peaks_cap_, peaks * sizeof(float));
+}
+
+// ------------------------------------------------------------------ plans (TMA descriptors are baked per shape)
+EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
+    auto key = std::make_pair(B, T);
+    auto it = enc_plans_.find(key);
+    if (it != enc_plans_.end()) return it->second;
+    EncoderPlan plan;
+    const int M = B * T, d = cfg_.d_model, f = cfg_.ffn;
+    auto build_layer = [&](const EncLayerW& w, bool residual) {
+        EncLayerPlan lp;
+        GemmEpi e;
+        e = GemmEpi{}; e.bias = w.b_qkv; e.out_f16 = qkv16_; e.ld_out = 3 * d;
+        gemm_prepare(lp.qkv, a16_, w.in_size, w.w_qkv, w.in_size, M, 3 * d, w.in_size, e);
+        e = GemmEpi{}; e.bias = w.b_out; e.addend = mem32_; e.ld_addend = d; e.out_f32 = x32_; e.ld_out = d;
+        if (residual) { e.resid = x32_; e.ld_resid = d; }
+        gemm_prepare(lp.out, ctx16_, d, w.w_out, d, M, d, d, e);
+        e = GemmEpi{}; e.bias = w.b_ffn1; e.relu = 1; e.out_f16 = h16_; e.ld_out = f;
+        gemm_prepare(lp.ffn1, a16_, d, w.w_ffn1, d, M, f, d, e);
+        e = GemmEpi{}; e.bias = w.b_ffn2; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
+        gemm_prepare(lp.ffn2, h16_, f, w.w_ffn2, f, M, d, f, e);
+        plan.layers.push_back(lp);
+    };
+    for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], enc_[i].in_size == d);
+    for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i], true);
+    if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
+        GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = cfg_.vocab;
+        gemm_prepare(plan.ctc_head, enc16_, d, w_head_, d, M, cfg_.vocab, d, e);
+    } else {
+        GemmEpi e; e.bias = b_conv_; e.relu = 1; e.out_f32 = mem32_; e.ld_out = d;
+        gemm_prepare(plan.pred_conv, qkv16_, 3 * d, w_conv_, 3 * d, M, d, 3 * d, e);   // qkv16_ holds the im2col rows
+        GemmEpi k; k.bias = b_kv_all_; k.out_f16 = kv16_; k.ld_out = cfg_.dec_layers * 2 * d;
+        gemm_prepare(plan.kv_all, enc16_, d, w_kv_all_, d, M, cfg_.dec_layers * 2 * d, d, k);
+    }
+    return enc_plans_.emplace(key, std::move(plan)).first->second;
+}
+
+DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
+    if (dec_plan_T_ != T) { dec_plans_.clear(); dec_plan_T_ = T; }
+    auto key = std::make_pair(B, L);
+    auto it = dec_plans_.find(key);
+    if (it != dec_plans_.end()) return it->second;
+    DecoderPlan plan;
+    const int Md = B * L, d = cfg_.d_model, f = cfg_.dec_ffn;
+    auto ffn = [&](const DecFfnW& w, GemmOp& g1, GemmOp& g2) {
+        GemmEpi e; e.bias = w.b1; e.relu = 1; e.out_f32 = hd32_; e.ld_out = f;
+        gemm_prepare(g1, ad16_, d, w.w1, d, Md, f, d, e);
+        GemmEpi e2; e2.out_f32 = t32_; e2.ld_out = d;
+        gemm_prepare(g2, hd16_, f, w.w2, f, Md, d, f, e2);
+    };
+    for (const DecLayerW& w : dec_) {
+        DecLayerPlan lp;
+        ffn(w.ffn, lp.w1, lp.w2);
+        GemmEpi e; e.bias = w.bq; e.out_f16 = q16_; e.ld_out = d;
+        gemm_prepare(lp.q, ad16_, d, w.wq, d, Md, d, d, e);
+        GemmEpi o; o.bias = w.bo; o.resid = xd32_; o.ld_resid = d; o.out_f32 = xd32_; o.ld_out = d;
+        gemm_prepare(lp.out, ctxd16_, d, w.wo, d, Md, d, d, o);
+        plan.layers.push_back(lp);
+    }
+    ffn(dec3_, plan.d3_w1, plan.d3_w2);
+    GemmEpi h; h.bias = b_head_; h.out_f32 = logits_; h.ld_out = cfg_.vocab;
+    gemm_prepare(plan.head, ad16_, d, w_head_, d, Md, cfg_.vocab, d, h);
+    return dec_plans_.emplace(key, std::move(plan)).first->second;
+}
+
+void DeviceCtx::gemm(const GemmOp& op) {
+    gemm_launch(op, stream_);
+    ++launches;
+    gemm_flops += pf::gemm_flops(op);
+}
+
+// ------------------------------------------------------------------ staging
+void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr) {
+    PF_CUDA(cudaSetDevice(dev_));
+    const bool sv = cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL;
+    const int Tenc = tmax_lfr + (sv ? 4 : 0);
+    ensure_workspace(B, Tenc);
+    // per-utterance tables: offsets (pcm, feats) as int64, then nsamp / nframes / nlfr as int32
+    const size_t tab_bytes = static_cast<size_t>(B) * (2 * sizeof(long long) + 3 * sizeof(int));
+    ensure_pinned(&h_stage_, &h_stage_bytes_, tab_bytes);
+    if (B > meta_capB_) {
+        if (d_off_) cudaFree(d_off_);
+        if (d_meta_) cudaFree(d_meta_);
+        PF_CUDA(cudaMalloc(&d_off_, static_cast<size_t>(B) * 2 * sizeof(long long)));
+        PF_CUDA(cudaMalloc(&d_meta_, static_cast<size_t>(B) * 3 * sizeof(int)));
+        meta_capB_ = B;
+    }
+    long long* h_off = static_cast<long long*>(h_stage_);
+    int* h_m = reinterpret_cast<int*>(h_off + 2 * B);
+    size_t total = 0;
+    int maxframes = 0;
+    const int dim = cfg_.lfr_m * cfg_.n_mels;
+    for (int b = 0; b < B; ++b) {
+        h_off[b] = static_cast<long long>(total);
+        h_off[B + b] = static_cast<long long>(b) * tmax_lfr * dim;
+        const int nf = frontend_num_frames(nsamp[b], cfg_.snip_edges != 0);
+        h_m[b] = nsamp[b];
+        h_m[B + b] = nf;
+        h_m[2 * B + b] = nf / cfg_.lfr_n;
+        maxframes = std::max(maxframes, nf);
+        total += static_cast<size_t>(nsamp[b]);
+        total = (total + 3) & ~static_cast<size_t>(3);
+    }
+    if (total > pcm_cap_) {
+        if (pcm_) cudaFree(pcm_);
+        pcm_ = nullptr;
+        PF_CUDA(cudaMalloc(&pcm_, std::max<size_t>(total, 1) * sizeof(float)));
+        pcm_cap_ = total;
+    }
+    PF_CUDA(cudaEventRecord(ev_[0], stream_));
+    ev0_armed_ = true;
+    PF_CUDA(cudaMemcpyAsync(d_off_, h_off, static_cast<size_t>(B) * 2 * sizeof(long long), cudaMemcpyHostToDevice, stream_));
+    PF_CUDA(cudaMemcpyAsync(d_meta_, h_m, static_cast<size_t>(B) * 3 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    for (int b = 0; b < B; ++b)
+        if (nsamp[b] > 0)
+            PF_CUDA(cudaMemcpyAsync(pcm_ + h_off[b], pcm[b], static_cast<size_t>(nsamp[b]) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    staged_B_ = B;
+    staged_T_ = tmax_lfr;
+    staged_maxframes_ = maxframes;
+    staged_is_pcm_ = true;
+}
+
+void DeviceCtx::stage_feats(const float* speech, int B, int T) {
+    PF_CUDA(cudaSetDevice(dev_));
+    ensure_workspace(B, T);
+    PF_CUDA(cudaEventRecord(ev_[0], stream_));
+    ev0_armed_ = true;
+    PF_CUDA(cudaMemcpyAsync(feats_, speech, static_cast<size_t>(B) * T * cfg_.input_size * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    staged_B_ = B;
+    staged_T_ = T;
+    staged_is_pcm_ = false;
+}
+
+int DeviceCtx::extract(const float* samples, int nsamp, float* out, int capacity_frames, bool raw_fbank) {
+    PF_CUDA(cudaSetDevice(dev_));
+    const int nf = frontend_num_frames(nsamp, cfg_.snip_edges != 0);
+    const int nl = nf / cfg_.lfr_n;
+    const int rows = raw_fbank ? nf : nl;
+    const int width = raw_fbank ? cfg_.n_mels : cfg_.lfr_m * cfg_.n_mels;
+    if (rows > capacity_frames) throw StatusError{PF_ERR_SHAPE, "feature buffer too small: need " + std::to_string(rows) + " frames"};
+    if (rows == 0) return 0;
+    std::vector<void*> pool;
+    float* d_pcm = dalloc<float>(nsamp, pool);
+    float* d_out = dalloc<float>(static_cast<size_t>(rows) * width, pool);
+    long long* d_off = dalloc<long long>(2, pool);
+    int* d_m = dalloc<int>(3, pool);
+    try {
+        const long long off[2] = {0, 0};
+        const int m[3] = {nsamp, nf, nl};
+        PF_CUDA(cudaMemcpyAsync(d_pcm, samples, static_cast<size_t>(nsamp) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        PF_CUDA(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, stream_));
+        PF_CUDA(cudaMemcpyAsync(d_m, m, sizeof(m), cudaMemcpyHostToDevice, stream_));
+        FrontendLaunch a;
+        a.tables = fe_tables_; a.pcm = d_pcm; a.pcm_off = d_off; a.nsamp = d_m; a.nframes = d_m + 1; a.nlfr = d_m + 2;
+        a.add_shift = cmvn_shift_; a.rescale = cmvn_scale_;
+        if (raw_fbank) { a.fbank_out = d_out; a.fbank_off = d_off + 1; }
+        else { a.feats_out = d_out; a.feats_off = d_off + 1; }
+        a.batch = 1; a.max_frames = nf; a.tmax_lfr = nl; a.lfr_m = cfg_.lfr_m; a.lfr_n = cfg_.lfr_n;
+        a.snip_edges = cfg_.snip_edges != 0;
+        frontend_launch(a, stream_);
+        PF_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(rows) * width * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+    } catch (...) {
+        cudaStreamSynchronize(stream_);
+        free_pool(pool);
+        throw;
+    }
+    free_pool(pool);
+    return rows;
+}
+
+// ------------------------------------------------------------------ forward passes
+void DeviceCtx::encoder_forward(int B, int T) {
+    const int M = B * T, d = cfg_.d_model, H = cfg_.heads;
+    EncoderPlan& plan = encoder_plan(B, T);
+    embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), inv_ts_, enc_[0].ln1.g, enc_[0].ln1.b,
+                       cfg_.ln_eps, a16_, stream_);
+    ++launches;
+    auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool first) {
+        if (!first) { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); ++launches; }
+        gemm(lp.qkv);
+        fsmn_f16_launch(qkv16_ + 2 * d, 3 * d, w.fsmn, cfg_.enc_kernel, mem32_, d, nullptr, 0, nullptr, B, T, d, stream_);
+        attention_launch(qkv16_, qkv16_ + d, qkv16_ + 2 * d, ctx16_, B, H, T, T, 3 * d, 3 * d, 3 * d, d, d / H, stream_);
+        launches += 2;
+        gemm(lp.out);
+        layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_);
+        ++launches;
+        gemm(lp.ffn1);
+        gemm(lp.ffn2);
+    };
+    size_t li = 0;
+    for (size_t i = 0; i < enc_.size(); ++i, ++li) layer(enc_[i], plan.layers[li], i == 0);
+    if (tp_.empty()) {
+        layernorm_f32_launch(x32_, d, M, d, after_norm_.g, after_norm_.b, cfg_.ln_eps, enc16_, d, enc32_, d, stream_);
+        ++launches;
+    } else {
+        layernorm_f32_launch(x32_, d, M, d, after_norm_.g, after_norm_.b, cfg_.ln_eps, nullptr, 0, x32_, d, stream_);
+        ++launches;
+        for (size_t i = 0; i < tp_.size(); ++i, ++li) layer(tp_[i], plan.layers[li], false);
+        layernorm_f32_launch(x32_, d, M, d, tp_norm_.g, tp_norm_.b, cfg_.ln_eps, enc16_, d, enc32_, d, stream_);
+        ++launches;
+    }
+}
+
+void DeviceCtx::predictor_forward(int B, int T) {
+    const int d = cfg_.d_model;
+    EncoderPlan& plan = encoder_plan(B, T);
+    gemm(plan.kv_all);                                  // decoder K/V of all layers; independent of the CIF result
+    im2col3_launch(enc16_, B, T, d, qkv16_, stream_);
+    gemm(plan.pred_conv);
+    alpha_head_launch(mem32_, B, T, d, w_alpha_, b_alpha_, cfg_.smooth_factor, cfg_.noise_threshold, cfg_.cif_tail, alphas_, stream_);
+    PF_CUDA(cudaMemsetAsync(meta_, 0, 4 * sizeof(int), stream_));
+    cif_scan_launch(alphas_, B, T + 1, cfg_.cif_threshold, wcur_, wrem_, fire_idx_, peaks_, token_num_, fires_, meta_, stream_);
+    launches += 3;
+}
+
+void DeviceCtx::decoder_forward(int B, int T, int L) {
+    const int Md = B * L, d = cfg_.d_model, f = cfg_.dec_ffn, H = cfg_.heads;
+    DecoderPlan& plan = decoder_plan(B, T, L);
+    const float eps = cfg_.ln_eps;
+    PF_CUDA(cudaMemsetAsync(xd32_, 0, static_cast<size_t>(Md) * d * sizeof(float), stream_));
+    cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
+    ++launches;
+    auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
+        layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_);
+        gemm(g1);
+        layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_);
+        gemm(g2);
+        launches += 2;
+    };
+    const int ldkv = cfg_.dec_layers * 2 * d;
+    for (size_t i = 0; i < dec_.size(); ++i) {
+        const DecLayerW& w = dec_[i];
+        const DecLayerPlan& lp = plan.layers[i];
+        ffn(w.ffn, lp.w1, lp.w2);
+        layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_);
+        fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
+        layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_);
+        gemm(lp.q);
+        attention_launch(q16_, kv16_ + i * 2 * d, kv16_ + i * 2 * d + d, ctxd16_, B, H, L, T, d, ldkv, ldkv, d, d / H, stream_);
+        gemm(lp.out);
+        launches += 4;
+    }
+    ffn(dec3_, plan.d3_w1, plan.d3_w2);
+    layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, nullptr, 0, stream_);
+    gemm(plan.head);
+    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, cfg_.vocab, tokens_, 1, stream_);
+    launches += 2;
+}
+
+void DeviceCtx::run(uint32_t flags, SharedRun* shared, int idx) {
+    arrived_ = false;
+    try {
+        run_impl(flags, shared, idx);
+    } catch (...) {
+        // never leave the sibling device threads parked on the Lmax exchange
+        if (shared && !arrived_) { shared->failed = true; shared->lmax[idx] = 0; arrived_ = true; shared->barrier.arrive_and_wait(); }
+        ev0_armed_ = false;
+        throw;
+    }
+    ev0_armed_ = false;
+}
+
+void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (!ev0_armed_) PF_CUDA(cudaEventRecord(ev_[0], stream_));   // run_staged: time from here, not from staging
+    const bool sv = cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL;
+    const int B = staged_B_;
+    int T = staged_T_;
+    launches = 0;
+    gemm_flops = 0.0;
+    if (B <= 0) throw StatusError{PF_ERR_BAD_ARG, "nothing staged"};
+    const int din = cfg_.input_size;
+    // ---- front-end
+    if (staged_is_pcm_) {
+        float* dst = sv ? feats_raw_ : feats_;
+        if (T > 0) {
+            FrontendLaunch a;
+            a.tables = fe_tables_; a.pcm = pcm_; a.pcm_off = d_off_; a.nsamp = d_meta_; a.nframes = d_meta_ + B; a.nlfr = d_meta_ + 2 * B;
+            a.add_shift = cmvn_shift_; a.rescale = cmvn_scale_;
+            a.feats_out = dst; a.feats_off = d_off_ + B;
+            a.batch = B; a.max_frames = staged_maxframes_; a.tmax_lfr = T; a.lfr_m = cfg_.lfr_m; a.lfr_n = cfg_.lfr_n;
+            a.snip_edges = cfg_.snip_edges != 0;
+            a.pad_quirk = true; a.pad_fill = true;
+            a.pad_value = -23.025850929940457f * 32768.0f;      // Utils/PadHelper.cs:63
+            frontend_launch(a, stream_);
+            launches += 2;
+        }
+        if (sv) {
+            // Q6: language slot = textnorm id (14 with use_itn else 15), textnorm slot = 15; Q7: [lang, 1, 2, textnorm]
+            const int ids[4] = {cfg_.use_itn ? 14 : 15, 1, 2, 15};
+            memcpy(h_meta_ + 8, ids, sizeof(ids));
+            PF_CUDA(cudaMemcpyAsync(prompt_ids_, h_meta_ + 8, sizeof(ids), cudaMemcpyHostToDevice, stream_));
+            prepend_rows_launch(feats_raw_, embed_table_, prompt_ids_, 4, feats_, B, T, din, stream_);
+            ++launches;
+            T += 4;
+        }
+    }
+    B_ = B;
+    T_ = T;
+    PF_CUDA(cudaEventRecord(ev_[1], stream_));
+    if (T <= 0) {   // no frames at all (utterances shorter than one LFR frame): empty result, like a [B,0,V] tensor
+        Lmax_ = 0; Lpad_ = 0;
+        ensure_pinned(reinterpret_cast<void**>(&h_token_num), &h_tn_cap_, static_cast<size_t>(B) * sizeof(int32_t));
+        for (int b = 0; b < B; ++b) h_token_num[b] = 0;
+        if (shared) { shared->lmax[idx] = 0; arrived_ = true; shared->barrier.arrive_and_wait(); }
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        return;
+    }
+    // ---- encoder
+    encoder_forward(B, T);
+    PF_CUDA(cudaEventRecord(ev_[2], stream_));
+    ensure_pinned(reinterpret_cast<void**>(&h_token_num), &h_tn_cap_, static_cast<size_t>(B) * sizeof(int32_t));
+    if (sv) {
+        const int M = B * T;
+        gemm(encoder_plan(B, T).ctc_head);
+        PF_CUDA(cudaEventRecord(ev_[3], stream_));
+        PF_CUDA(cudaEventRecord(ev_[4], stream_));
+        logsoftmax_argmax_launch(logits_, M, cfg_.vocab, cfg_.vocab, tokens_, (flags & PF_RUN_WANT_LOGITS) ? 1 : 0, stream_);
+        ++launches;
+        PF_CUDA(cudaEventRecord(ev_[5], stream_));
+        Lmax_ = T; Lpad_ = T;
+        if (shared) { shared->lmax[idx] = T; arrived_ = true; shared->barrier.arrive_and_wait(); }
+        ensure_host(static_cast<size_t>(M), (flags & PF_RUN_WANT_LOGITS) ? static_cast<size_t>(M) * cfg_.vocab : 0, 0);
+        PF_CUDA(cudaMemcpyAsync(h_tokens, tokens_, static_cast<size_t>(M) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        if (flags & PF_RUN_WANT_LOGITS)
+            PF_CUDA(cudaMemcpyAsync(h_logits, logits_, static_cast<size_t>(M) * cfg_.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaEventRecord(ev_[6], stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        for (int b = 0; b < B; ++b) h_token_num[b] = T;
+    } else {
+        // ---- predictor + CIF scan; the token count decides the decoder's shape -> one small D2H + sync
+        predictor_forward(B, T);
+        PF_CUDA(cudaMemcpyAsync(h_meta_, meta_, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaMemcpyAsync(h_token_num, token_num_, static_cast<size_t>(B) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaEventRecord(ev_[3], stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        int lmax = h_meta_[0];
+        if (shared) {
+            shared->lmax[idx] = lmax;
+            arrived_ = true; shared->barrier.arrive_and_wait();
+            for (int v : shared->lmax) lmax = std::max(lmax, v);
+        }
+        Lmax_ = lmax;
+        Lpad_ = lmax;
+        if (lmax > 0) {
+            decoder_forward(B, T, lmax);
+            PF_CUDA(cudaEventRecord(ev_[4], stream_));
+            PF_CUDA(cudaEventRecord(ev_[5], stream_));
+            const size_t ntok = static_cast<size_t>(B) * lmax;
+            const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0, wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0;
+            ensure_host(ntok, wl ? ntok * cfg_.vocab : 0, wp ? static_cast<size_t>(B) * (T + 1) : 0);
+            PF_CUDA(cudaMemcpyAsync(h_tokens, tokens_, ntok * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            if (wl) PF_CUDA(cudaMemcpyAsync(h_logits, logits_, ntok * cfg_.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            if (wp) PF_CUDA(cudaMemcpyAsync(h_peaks, peaks_, static_cast<size_t>(B) * (T + 1) * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        } else {
+            PF_CUDA(cudaEventRecord(ev_[4], stream_));
+            PF_CUDA(cudaEventRecord(ev_[5], stream_));
+        }
+        PF_CUDA(cudaEventRecord(ev_[6], stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+    }
+    float ms = 0.0f;
+    for (int i = 0; i < 5; ++i) {
+        cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
+        timings_ms[i] = ms;
+    }
+    cudaEventElapsedTime(&ms, ev_[0], ev_[6]);
+    timings_ms[5] = ms;
+}
+
+void DeviceCtx::get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim) {
+    PF_CUDA(cudaSetDevice(dev_));
+    const float* src = nullptr;
+    int dims[4] = {1, 1, 1, 1};
+    int nd = 0;
+    const int d = cfg_.d_model;
+    if (name == "feats") { src = feats_; dims[0] = B_; dims[1] = T_; dims[2] = cfg_.input_size; nd = 3; }
+    else if (name == "enc") { src = enc32_; dims[0] = B_; dims[1] = T_; dims[2] = d; nd = 3; }
+    else if (name == "alphas") { src = alphas_; dims[0] = B_; dims[1] = T_ + 1; nd = 2; }
+    else if (name == "cif_peak") { src = peaks_; dims[0] = B_; dims[1] = T_ + 1; nd = 2; }
+    else if (name == "logits") { src = logits_; dims[0] = B_; dims[1] = Lpad_; dims[2] = cfg_.vocab; nd = 3; }
+    else if (name == "x") { src = x32_; dims[0] = B_; dims[1] = T_; dims[2] = d; nd = 3; }
+    else if (name == "dec_x") { src = xd32_; dims[0] = B_; dims[1] = Lpad_; dims[2] = d; nd = 3; }
+    else throw StatusError{PF_ERR_BAD_ARG, "unknown tensor '" + name + "'"};
+    if (!src) throw StatusError{PF_ERR_BAD_ARG, "tensor '" + name + "' not available for this model / before a run"};
+    size_t n = 1;
+    for (int i = 0; i < nd; ++i) n *= static_cast<size_t>(dims[i]);
+    if (dims4) for (int i = 0; i < 4; ++i) dims4[i] = dims[i];
+    if (ndim) *ndim = nd;
+    const size_t cnt = std::min(n, capacity);
+    if (dst && cnt) {
+        PF_CUDA(cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+    }
+}
+
+}  // namespace pf

@@ -1,0 +1,220 @@
+// Offline engine: weights, workspace, cached launch plans and the forward passes for one device, plus the
+// multi-device handle behind the C-ABI.  See engine.cu / abi.cu.
+#pragma once
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pf_abi.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "frontend.cuh"
+#include "gemm.cuh"
+#include "ops.cuh"
+
+namespace pf {
+
+struct StatusError {
+    pf_status code;
+    std::string what;
+};
+
+// ------------------------------------------------------------------ PFW1 weight blob (host view)
+struct BlobEntry {
+    std::string name;
+    int ndim = 0;
+    int64_t dims[4] = {1, 1, 1, 1};
+    const float* data = nullptr;
+    size_t count = 0;
+};
+
+class Blob {
+public:
+    void parse(const void* data, size_t bytes);
+    const BlobEntry& get(const std::string& name) const;
+    bool has(const std::string& name) const { return entries_.count(name) != 0; }
+
+private:
+    std::map<std::string, BlobEntry> entries_;
+};
+
+// ------------------------------------------------------------------ device weights
+struct LnW {
+    float* g = nullptr;
+    float* b = nullptr;
+};
+struct EncLayerW {
+    int in_size = 0;
+    LnW ln1, ln2;
+    __half* w_qkv = nullptr; float* b_qkv = nullptr;
+    float* fsmn = nullptr;
+    __half* w_out = nullptr; float* b_out = nullptr;
+    __half* w_ffn1 = nullptr; float* b_ffn1 = nullptr;
+    __half* w_ffn2 = nullptr; float* b_ffn2 = nullptr;
+};
+struct DecFfnW {
+    LnW ln_in;                                   // norm1
+    __half* w1 = nullptr; float* b1 = nullptr;
+    LnW ln_mid;                                  // feed_forward.norm (width dec_ffn)
+    __half* w2 = nullptr;                        // no bias
+};
+struct DecLayerW {
+    DecFfnW ffn;
+    LnW ln2, ln3;
+    float* fsmn = nullptr;
+    __half* wq = nullptr; float* bq = nullptr;
+    __half* wo = nullptr; float* bo = nullptr;
+};
+
+struct EncLayerPlan { GemmOp qkv, out, ffn1, ffn2; };
+struct DecLayerPlan { GemmOp w1, w2, q, out; };
+struct EncoderPlan {
+    std::vector<EncLayerPlan> layers;            // encoders0 + encoders + tp_encoders
+    GemmOp pred_conv, kv_all, ctc_head;
+};
+struct DecoderPlan {
+    std::vector<DecLayerPlan> layers;
+    GemmOp d3_w1, d3_w2, head;
+};
+
+class Barrier {                                   // reusable host barrier for the per-device worker threads
+public:
+    explicit Barrier(int n) : n_(n) {}
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        const int gen = gen_;
+        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
+
+struct SharedRun {                                // cross-device exchange for one run (Lmax is a batch-wide max)
+    explicit SharedRun(int n) : barrier(n), lmax(n, 0), failed(false) {}
+    Barrier barrier;
+    std::vector<int> lmax;
+    bool failed;
+};
+
+class DeviceCtx {
+public:
+    DeviceCtx(int dev, const pf_config& cfg);
+    ~DeviceCtx();
+    void load_weights(const Blob& blob);
+    void set_cmvn(const float* shift, const float* scale, int dim);
+
+    // inputs
+    void stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr);
+    void stage_feats(const float* speech, int B, int T);
+    // front-end only (single utterance); returns frames written
+    int extract(const float* samples, int nsamp, float* out, int capacity_frames, bool raw_fbank);
+
+    // full forward on the staged batch.  shared/idx: cross-device Lmax exchange (may be null for 1 device).
+    void run(uint32_t flags, SharedRun* shared, int idx);
+    int staged_batch() const { return staged_B_; }
+
+    // results of the last run (host, pinned)
+    int B_ = 0, T_ = 0, Lmax_ = 0, Lpad_ = 0;
+    int32_t* h_tokens = nullptr;      // [B, Lmax]
+    int32_t* h_token_num = nullptr;   // [B]
+    float* h_logits = nullptr;        // [B, Lmax, V] (on request)
+    float* h_peaks = nullptr;         // [B, T+1] (on request)
+    float timings_ms[6] = {0, 0, 0, 0, 0, 0};
+    int64_t launches = 0;
+    double gemm_flops = 0.0;
+
+    void get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim);
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return dev_; }
+
+private:
+    template <typename T> T* dalloc(size_t n, std::vector<void*>& pool);
+    float* up_f32(const BlobEntry& e);
+    float* up_f32(const float* host, size_t n);
+    __half* up_f16(const float* host, size_t n);
+    LnW up_ln(const Blob& b, const std::string& prefix);
+    void load_enc_layer(const Blob& b, const std::string& prefix, int in_size, EncLayerW& w);
+    void load_dec_ffn(const Blob& b, const std::string& prefix, DecFfnW& w);
+
+    void ensure_workspace(int B, int T);
+    void ensure_host(size_t tokens, size_t logits, size_t peaks);
+    EncoderPlan& encoder_plan(int B, int T);
+    DecoderPlan& decoder_plan(int B, int T, int L);
+    void gemm(const GemmOp& op);
+    void encoder_forward(int B, int T);
+    void predictor_forward(int B, int T);
+    void decoder_forward(int B, int T, int L);
+    void free_pool(std::vector<void*>& pool);
+    void run_impl(uint32_t flags, SharedRun* shared, int idx);
+    bool arrived_ = false, ev0_armed_ = false;
+
+    int dev_;
+    pf_config cfg_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[7] = {};
+    std::vector<void*> wpool_, apool_;
+    std::vector<void*> tmp_;           // upload staging, freed after load
+
+    // weights
+    std::vector<EncLayerW> enc_, tp_;
+    LnW after_norm_, tp_norm_;
+    __half* w_conv_ = nullptr; float* b_conv_ = nullptr;
+    float* w_alpha_ = nullptr; float* b_alpha_ = nullptr;
+    std::vector<DecLayerW> dec_;
+    __half* w_kv_all_ = nullptr; float* b_kv_all_ = nullptr;
+    DecFfnW dec3_;
+    LnW dec_after_;
+    __half* w_head_ = nullptr; float* b_head_ = nullptr;
+    float* embed_table_ = nullptr;     // SenseVoice prompt table [16, input_size]
+    float* inv_ts_ = nullptr;          // PE inverse timescales [input_size/2]
+    float* cmvn_shift_ = nullptr; float* cmvn_scale_ = nullptr;
+    void* fe_tables_ = nullptr;
+
+    // workspace (capacity in rows)
+    int capB_ = 0, capT_ = 0;
+    float* feats_ = nullptr; float* feats_raw_ = nullptr;
+    __half* a16_ = nullptr; __half* qkv16_ = nullptr; __half* ctx16_ = nullptr; __half* h16_ = nullptr;
+    float* mem32_ = nullptr; float* x32_ = nullptr; float* enc32_ = nullptr; __half* enc16_ = nullptr;
+    __half* kv16_ = nullptr;
+    float* alphas_ = nullptr; float* wcur_ = nullptr; float* wrem_ = nullptr; float* peaks_ = nullptr;
+    int* fire_idx_ = nullptr; int* token_num_ = nullptr; int* fires_ = nullptr; int* meta_ = nullptr;
+    float* xd32_ = nullptr; __half* ad16_ = nullptr; float* hd32_ = nullptr; __half* hd16_ = nullptr;
+    float* t32_ = nullptr; float* tn32_ = nullptr; __half* q16_ = nullptr; __half* ctxd16_ = nullptr;
+    float* logits_ = nullptr; int* tokens_ = nullptr;
+    int* prompt_ids_ = nullptr;
+    // staged PCM
+    float* pcm_ = nullptr; size_t pcm_cap_ = 0;
+    long long* d_off_ = nullptr; int* d_meta_ = nullptr; int meta_capB_ = 0;   // per-utterance tables
+    void* h_stage_ = nullptr; size_t h_stage_bytes_ = 0;
+    int staged_B_ = 0, staged_T_ = 0, staged_maxframes_ = 0;
+    bool staged_is_pcm_ = false;
+
+    // host results
+    int* h_meta_ = nullptr;
+    size_t h_tokens_cap_ = 0, h_logits_cap_ = 0, h_peaks_cap_ = 0, h_tn_cap_ = 0;
+
+    std::map<std::pair<int, int>, EncoderPlan> enc_plans_;
+    std::map<std::pair<int, int>, DecoderPlan> dec_plans_;   // key (B*capT-independent: B, L) for current T
+    int dec_plan_T_ = -1;
+};
+
+struct OfflineHandle {
+    pf_config cfg;
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::mutex mu;
+    // last run layout
+    std::vector<int> shard_begin, shard_count;
+    int B = 0, Lmax = 0, T = 0;
+    std::vector<int32_t> tokens, token_num;
+    std::vector<float> logits, peaks;
+    bool staged = false;
+    bool staged_pcm = false;
+};
+
+}  // namespace pf

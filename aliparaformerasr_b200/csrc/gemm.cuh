@@ -1,0 +1,36 @@
+// tcgen05 / TMEM / TMA GEMM used for every dense projection on the path:
+//   C[M,N] = A[M,K] (fp16, K-major) x W[N,K]^T (fp16, K-major = torch Linear layout), fp32 accumulate in TMEM,
+// with a fused epilogue (bias, ReLU, fp32 residual, fp32 addend, fp16 or fp32 output).
+#pragma once
+#include "common.cuh"
+
+namespace pf {
+
+struct GemmEpi {
+    const float* bias = nullptr;     // [N] fp32 or null
+    const float* resid = nullptr;    // fp32 [M, ld_resid] added to the result (may alias out_f32: in-place residual)
+    const float* addend = nullptr;   // fp32 [M, ld_addend] second addend (FSMN memory) or null
+    float* out_f32 = nullptr;        // exactly one of out_f32 / out_f16 is set
+    __half* out_f16 = nullptr;
+    int ld_out = 0;
+    int ld_resid = 0;
+    int ld_addend = 0;
+    int relu = 0;
+};
+
+struct GemmOp {
+    CUtensorMap tmA;
+    CUtensorMap tmB;
+    GemmEpi epi;
+    int M = 0, N = 0, K = 0;
+    int bn = 128;    // N tile: 64, 128 or 256
+};
+
+// Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).
+// bn = 0 picks a tile width from the shape.
+void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                  const GemmEpi& epi, int bn = 0);
+void gemm_launch(const GemmOp& op, cudaStream_t stream);
+double gemm_flops(const GemmOp& op);
+
+}  // namespace pf

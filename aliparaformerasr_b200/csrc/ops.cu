@@ -1,0 +1,424 @@
+// HBM/L2-bound stages of the SAN-M path: positional encoding + LayerNorm, LayerNorm, FSMN depthwise memory,
+// predictor im2col + alpha head, CIF integrate-and-fire, log-softmax + greedy pick.
+//
+// Reference semantics: the FunASR export graph executed by OfflineProjOfParaformer.cs:68, the host CIF
+// recurrence in /root/reference/AliParaformerAsr/OnlineRecognizer.cs:149-200 and the greedy pick in
+// OfflineRecognizer.cs:139-152.
+#include "ops.cuh"
+
+#include <math.h>
+
+namespace pf {
+
+namespace {
+
+// ------------------------------------------------------------------ embed (scale + PE) + LayerNorm(D) -> fp16
+// One warp per row.  Statistics in fp64 so rows made of the huge pad constant (Q4) normalise deterministically.
+template <int kMaxPerLane>
+__global__ void __launch_bounds__(256)
+pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale, const float* __restrict__ inv_ts,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ out16) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int half = D >> 1;
+    const float pos = static_cast<float>((row % T) + 1);
+    const float* x = feats + static_cast<size_t>(row) * D;
+    float v[kMaxPerLane];
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        float val = 0.0f;
+        if (c < D) {
+            const int ti = c < half ? c : c - half;
+            const float ang = __fmul_rn(pos, inv_ts[ti]);
+            const float pe = c < half ? sinf(ang) : cosf(ang);
+            val = __fadd_rn(__fmul_rn(x[c], scale), pe);     // same rounding as torch: (x*s) then (+pe)
+            sum += static_cast<double>(val);
+        }
+        v[i] = val;
+    }
+    sum = warp_sum(sum);
+    const double mean = sum / D;
+    double sq = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) {
+            const double d = static_cast<double>(v[i]) - mean;
+            sq += d * d;
+        }
+    }
+    sq = warp_sum(sq);
+    const double rstd = 1.0 / sqrt(sq / D + static_cast<double>(eps));
+    __half* o = out16 + static_cast<size_t>(row) * D;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) {
+            const float nrm = static_cast<float>((static_cast<double>(v[i]) - mean) * rstd);
+            o[c] = __float2half_rn(nrm * gamma[c] + beta[c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm, D = NV * 128, warp per row
+template <int NV>
+__global__ void __launch_bounds__(256)
+pf_layernorm(const float* __restrict__ in, int ld_in, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
+             float eps, __half* __restrict__ out16, int ld16, float* __restrict__ out32, int ld32) {
+    constexpr int D = NV * 128;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* x4 = reinterpret_cast<const float4*>(in + static_cast<size_t>(row) * ld_in);
+    float4 v[NV];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = x4[lane + 32 * i];
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    sum = warp_sum(sum);
+    const float mean = sum * (1.0f / D);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    sq = warp_sum(sq);
+    const float rstd = 1.0f / sqrtf(sq * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(g4 + lane + 32 * i);
+        const float4 b = __ldg(b4 + lane + 32 * i);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (out32) reinterpret_cast<float4*>(out32 + static_cast<size_t>(row) * ld32)[lane + 32 * i] = y;
+        if (out16) {
+            __half2 h0 = __floats2half2_rn(y.x, y.y);
+            __half2 h1 = __floats2half2_rn(y.z, y.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            reinterpret_cast<uint2*>(out16 + static_cast<size_t>(row) * ld16)[lane + 32 * i] = pk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ FSMN depthwise memory (register sliding window)
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
+
+template <typename TIn, int K>
+__global__ void __launch_bounds__(256)
+pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, float* __restrict__ out, int ld_out,
+        const float* __restrict__ resid, int ld_res, const int* __restrict__ lens, int T, int D) {
+    constexpr int TT = 16;
+    constexpr int LEFT = (K - 1) / 2;
+    const int c = blockIdx.z * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * TT;
+    if (c >= D) return;
+    const int len = lens ? min(lens[b], T) : T;
+    float wk[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) wk[j] = w[c * K + j];
+    float x[TT + K - 1];
+    const size_t rowbase = static_cast<size_t>(b) * T;
+#pragma unroll
+    for (int i = 0; i < TT + K - 1; ++i) {
+        const int t = t0 - LEFT + i;
+        x[i] = (t >= 0 && t < len) ? to_f32(in[(rowbase + t) * ld_in + c]) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+        const int t = t0 + i;
+        if (t < T) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc += wk[j] * x[i + j];
+            float y = (t < len) ? acc + x[i + LEFT] : 0.0f;
+            if (resid) y += resid[(rowbase + t) * ld_res + c];
+            out[(rowbase + t) * ld_out + c] = y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ predictor
+__global__ void pf_im2col3(const __half* __restrict__ in, int B, int T, int D, __half* __restrict__ out) {
+    // one thread per 8 halfs (16 B) of the output row [3*D]
+    const int vec_per_row = 3 * D / 8;
+    const long long total = static_cast<long long>(B) * T * vec_per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vec_per_row);
+        const long long m = i / vec_per_row;
+        const int t = static_cast<int>(m % T);
+        const int j = v / (D / 8);            // 0,1,2 -> t-1, t, t+1
+        const int cv = v % (D / 8);
+        const int ts = t + j - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (ts >= 0 && ts < T) val = reinterpret_cast<const uint4*>(in + (m + (j - 1)) * D)[cv];
+        reinterpret_cast<uint4*>(out + m * 3 * D)[v] = val;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pf_alpha_head(const float* __restrict__ h, int B, int T, int D, const float* __restrict__ w, const float* __restrict__ bias,
+              float smooth, float noise, float tail, float* __restrict__ alphas) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int M = B * T;
+    if (row >= M) return;
+    const float* x = h + static_cast<size_t>(row) * D;
+    float acc = 0.0f;
+    for (int c = lane; c < D; c += 32) acc += x[c] * w[c];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const int b = row / T, t = row % T;
+        const float z = acc + bias[0];
+        const float sg = 1.0f / (1.0f + expf(-z));
+        alphas[static_cast<size_t>(b) * (T + 1) + t] = fmaxf(sg * smooth - noise, 0.0f);
+        if (t == 0) alphas[static_cast<size_t>(b) * (T + 1) + T] = tail;
+    }
+}
+
+// CIF scalar recurrence, one thread per utterance (the recurrence is inherently sequential in t; T1 <= ~1000).
+__global__ void pf_cif_scan(const float* __restrict__ alphas, int B, int T1, float threshold, float* __restrict__ w_cur,
+                            float* __restrict__ w_rem, int* __restrict__ fire_idx, float* __restrict__ peaks,
+                            int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float integrate = 0.0f, total = 0.0f;
+    int nf = 0;
+    const size_t base = static_cast<size_t>(b) * T1;
+    for (int t = 0; t < T1; ++t) {
+        const float a = alphas[base + t];
+        total = __fadd_rn(total, a);
+        const float completion = __fsub_rn(1.0f, integrate);
+        integrate = __fadd_rn(integrate, a);
+        if (peaks) peaks[base + t] = integrate;
+        const bool fire = integrate >= threshold;
+        const float cur = fire ? completion : a;
+        w_cur[base + t] = cur;
+        if (fire) {
+            integrate = __fsub_rn(integrate, 1.0f);
+            w_rem[base + t] = __fsub_rn(a, cur);
+            fire_idx[base + t] = nf++;
+        } else {
+            w_rem[base + t] = 0.0f;
+            fire_idx[base + t] = -1;
+        }
+    }
+    token_num[b] = static_cast<int>(floorf(total));
+    fires[b] = nf;
+    atomicMax(meta, nf);
+}
+
+__global__ void __launch_bounds__(256)
+pf_cif_gather(const float* __restrict__ hidden, int T, int D, const float* __restrict__ w_cur,
+              const float* __restrict__ w_rem, const int* __restrict__ fire_idx, int T1, float* __restrict__ out, int Lpad) {
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const size_t abase = static_cast<size_t>(b) * T1;
+    const float* h = hidden + static_cast<size_t>(b) * T * D + d;
+    float frame = 0.0f;
+    for (int t = 0; t < T1; ++t) {
+        const float hv = t < T ? h[static_cast<size_t>(t) * D] : 0.0f;     // tail step has zero hidden
+        frame = __fadd_rn(frame, __fmul_rn(w_cur[abase + t], hv));
+        const int l = fire_idx[abase + t];
+        if (l >= 0) {
+            if (l < Lpad) out[(static_cast<size_t>(b) * Lpad + l) * D + d] = frame;
+            frame = __fmul_rn(w_rem[abase + t], hv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ log-softmax + greedy pick, one CTA per row
+__global__ void __launch_bounds__(256)
+pf_logsoftmax_argmax(float* __restrict__ logits, int V, int ld, int* __restrict__ tokens, int write_logp) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ int s_nan[8];
+    __shared__ float s_sum[8];
+    __shared__ float s_bcast[2];
+    __shared__ int s_ibcast;
+    float* x = logits + static_cast<size_t>(blockIdx.x) * ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // pass 1: last NaN index (the reference's scan restarts there) and the plain maximum for the softmax
+    int last_nan = -1;
+    float mx = -INFINITY;
+    for (int i = tid; i < V; i += blockDim.x) {
+        const float v = x[i];
+        if (v != v) last_nan = i;
+        else mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        last_nan = max(last_nan, __shfl_xor_sync(0xffffffffu, last_nan, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_nan[warp] = last_nan; s_val[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        int ln = -1; float m = -INFINITY;
+        for (int i = 0; i < 8; ++i) { ln = max(ln, s_nan[i]); m = fmaxf(m, s_val[i]); }
+        s_ibcast = ln; s_bcast[0] = m;
+    }
+    __syncthreads();
+    last_nan = s_ibcast;
+    mx = s_bcast[0];
+
+    // pass 2: sum of exp + greedy pick over indices >= max(last_nan, 0) with "last maximum wins"
+    // (best = x[best] > x[k] ? best : k, OfflineRecognizer.cs:145-149)
+    const int start = last_nan < 0 ? 0 : last_nan;
+    float best = -INFINITY;
+    int best_i = start;
+    float sum = 0.0f;
+    for (int i = tid; i < V; i += blockDim.x) {
+        const float v = x[i];
+        sum += expf(v - mx);
+        if (i > start && v >= best) { best = v; best_i = i; }
+        else if (i == start && last_nan < 0) { if (v >= best) { best = v; best_i = i; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi > best_i)) { best = ov; best_i = oi; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) { s_val[warp] = best; s_idx[warp] = best_i; s_sum[warp] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        float bv = s_val[0]; int bi = s_idx[0]; float sm = s_sum[0];
+        for (int i = 1; i < 8; ++i) {
+            if (s_val[i] > bv || (s_val[i] == bv && s_idx[i] > bi)) { bv = s_val[i]; bi = s_idx[i]; }
+            sm += s_sum[i];
+        }
+        // a NaN in the last position wins outright; a NaN elsewhere restarts the scan right after it
+        if (last_nan >= 0 && bv == -INFINITY) bi = max(bi, last_nan);
+        tokens[blockIdx.x] = bi;
+        s_bcast[1] = logf(sm);
+    }
+    __syncthreads();
+    if (write_logp) {
+        const float lse = mx + s_bcast[1];
+        for (int i = tid; i < V; i += blockDim.x) x[i] = x[i] - lse;
+    }
+}
+
+__global__ void pf_f32_to_f16(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __float2half_rn(in[i]);
+}
+
+__global__ void pf_prepend_rows(const float* __restrict__ src, const float* __restrict__ table, const int* __restrict__ ids,
+                                int nprompt, float* __restrict__ dst, int B, int T, int D) {
+    const long long total = static_cast<long long>(B) * (T + nprompt) * D;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % D);
+        const long long r = i / D;
+        const int t = static_cast<int>(r % (T + nprompt));
+        const long long b = r / (T + nprompt);
+        dst[i] = t < nprompt ? table[static_cast<size_t>(ids[t]) * D + c] : src[(b * T + (t - nprompt)) * D + c];
+    }
+}
+
+}  // namespace
+
+void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
+                        const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s) {
+    if (D > 32 * 20) throw CudaError{"embed_pe_ln: input_size > 640 unsupported"};
+    pf_embed_pe_ln<20><<<ceil_div(M, 8), 256, 0, s>>>(feats, M, T, D, scale, inv_timescales, gamma, beta, eps, out16);
+    PF_CUDA(cudaGetLastError());
+}
+
+void layernorm_f32_launch(const float* in, int ld_in, int M, int D, const float* gamma, const float* beta, float eps,
+                          __half* out16, int ld16, float* out32, int ld32, cudaStream_t s) {
+    const int grid = ceil_div(M, 8);
+    if (D == 512) pf_layernorm<4><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    else if (D == 1024) pf_layernorm<8><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    else if (D == 2048) pf_layernorm<16><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    else throw CudaError{"layernorm: unsupported width " + std::to_string(D)};
+    PF_CUDA(cudaGetLastError());
+}
+
+template <typename TIn>
+static void fsmn_launch_t(const TIn* in, int ld_in, const float* w, int K, float* out, int ld_out, const float* resid,
+                          int ld_res, const int* lens, int B, int T, int D, cudaStream_t s) {
+    dim3 grid(ceil_div(T, 16), B, ceil_div(D, 256));
+    if (K == 11) pf_fsmn<TIn, 11><<<grid, 256, 0, s>>>(in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
+    else if (K == 21) pf_fsmn<TIn, 21><<<grid, 256, 0, s>>>(in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
+    else throw CudaError{"fsmn: unsupported kernel size " + std::to_string(K)};
+    PF_CUDA(cudaGetLastError());
+}
+void fsmn_f16_launch(const __half* in, int ld_in, const float* w, int K, float* out, int ld_out, const float* resid,
+                     int ld_res, const int* lens, int B, int T, int D, cudaStream_t s) {
+    fsmn_launch_t(in, ld_in, w, K, out, ld_out, resid, ld_res, lens, B, T, D, s);
+}
+void fsmn_f32_launch(const float* in, int ld_in, const float* w, int K, float* out, int ld_out, const float* resid,
+                     int ld_res, const int* lens, int B, int T, int D, cudaStream_t s) {
+    fsmn_launch_t(in, ld_in, w, K, out, ld_out, resid, ld_res, lens, B, T, D, s);
+}
+
+void im2col3_launch(const __half* in, int B, int T, int D, __half* out, cudaStream_t s) {
+    const long long total = static_cast<long long>(B) * T * (3 * D / 8);
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    pf_im2col3<<<grid, 256, 0, s>>>(in, B, T, D, out);
+    PF_CUDA(cudaGetLastError());
+}
+
+void alpha_head_launch(const float* h, int B, int T, int D, const float* w, const float* bias, float smooth, float noise,
+                       float tail, float* alphas, cudaStream_t s) {
+    pf_alpha_head<<<ceil_div(B * T, 8), 256, 0, s>>>(h, B, T, D, w, bias, smooth, noise, tail, alphas);
+    PF_CUDA(cudaGetLastError());
+}
+
+void cif_scan_launch(const float* alphas, int B, int T1, float threshold, float* w_cur, float* w_rem, int* fire_idx,
+                     float* peaks, int* token_num, int* fires, int* meta, cudaStream_t s) {
+    pf_cif_scan<<<ceil_div(B, 32), 32, 0, s>>>(alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
+    PF_CUDA(cudaGetLastError());
+}
+
+void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_cur, const float* w_rem,
+                       const int* fire_idx, int T1, float* out, int Lpad, cudaStream_t s) {
+    dim3 grid(ceil_div(D, 256), B);
+    pf_cif_gather<<<grid, 256, 0, s>>>(hidden, T, D, w_cur, w_rem, fire_idx, T1, out, Lpad);
+    PF_CUDA(cudaGetLastError());
+}
+
+void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, int write_logp, cudaStream_t s) {
+    if (M <= 0) return;
+    pf_logsoftmax_argmax<<<M, 256, 0, s>>>(logits, V, ld, tokens, write_logp);
+    PF_CUDA(cudaGetLastError());
+}
+
+void f32_to_f16_launch(const float* in, __half* out, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 32));
+    pf_f32_to_f16<<<grid, 256, 0, s>>>(in, out, n);
+    PF_CUDA(cudaGetLastError());
+}
+
+void prepend_rows_launch(const float* src, const float* table, const int* ids, int nprompt, float* dst, int B, int T,
+                         int D, cudaStream_t s) {
+    const long long total = static_cast<long long>(B) * (T + nprompt) * D;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    pf_prepend_rows<<<grid, 256, 0, s>>>(src, table, ids, nprompt, dst, B, T, D);
+    PF_CUDA(cudaGetLastError());
+}
+
+}  // namespace pf

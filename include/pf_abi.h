@@ -1,0 +1,168 @@
+/*
+ * libpfasr C-ABI: the drop-in boundary for the AliParaformerAsr offline hot path on B200 (sm_100a).
+ *
+ * Every entry point is what the reference's managed code would bind with [DllImport("pfasr")] in place of the two
+ * native crossings it has today:
+ *   - Microsoft.ML.OnnxRuntime  InferenceSession.Run      OfflineProjOfParaformer.cs:68,
+ *                                                          OfflineProjOfSenseVoiceSmall.cs:156
+ *   - ManySpeech.SpeechFeatures OnlineFbank.GetFbank       WavFrontend.cs:21-37
+ * Plain pointers and sizes only; no C++/torch types.  All tensors are row-major contiguous.
+ *
+ * Error model (replaces the reference's exceptions, OfflineProjOfParaformer.cs:82-85): every call returns a
+ * pf_status; the message is available from pf_last_error() on the calling thread.  There is NO CPU fallback: a
+ * missing GPU / non-sm_100 device is PF_ERR_CUDA.
+ *
+ * Ownership: inputs stay owned by the caller and may be pageable.  Outputs referenced from pf_result are owned by
+ * the handle (pinned host memory) and stay valid until the next run on that handle or pf_offline_destroy.
+ * Threading: calls on one handle are serialised internally; distinct handles are independent.
+ */
+#ifndef PF_ABI_H_
+#define PF_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+typedef int32_t pf_status;
+enum {
+    PF_OK = 0,
+    PF_ERR_BAD_ARG = -1,
+    PF_ERR_CUDA = -2,
+    PF_ERR_OOM = -3,
+    PF_ERR_SHAPE = -4,
+    PF_ERR_DISPOSED = -5,
+    PF_ERR_WEIGHTS = -6,
+    PF_ERR_UNSUPPORTED = -7
+};
+
+/* asr.yaml `model:` dispatch of OfflineRecognizer.cs:39-53 */
+enum { PF_MODEL_PARAFORMER = 0, PF_MODEL_SENSEVOICE_SMALL = 1 };
+
+/* Flat POD mirror of the ConfEntity fields the path consumes (Model/ConfEntity.cs:5-43, EncoderConfEntity.cs:13-25,
+ * DecoderConfEntity.cs:7-16, PredictorConfEntity.cs:13-17, FrontendConfEntity.cs:7-15).  The C# side keeps parsing
+ * asr.yaml / asr.json (Utils/PreloadHelper.cs:39-118) and fills this struct. */
+typedef struct pf_config {
+    int32_t struct_bytes;      /* = sizeof(pf_config) */
+    int32_t model_kind;        /* PF_MODEL_* */
+    int32_t input_size;        /* 560 = lfr_m * n_mels */
+    int32_t d_model;           /* encoder_conf.output_size 512 */
+    int32_t heads;             /* attention_heads 4 */
+    int32_t ffn;               /* linear_units 2048 */
+    int32_t enc_layers;        /* num_blocks 50 (encoders0 + encoders) */
+    int32_t tp_layers;         /* SenseVoice tp_blocks 20, else 0 */
+    int32_t enc_kernel;        /* kernel_size 11 */
+    int32_t dec_layers;        /* decoder_conf.num_blocks 16 */
+    int32_t dec_ffn;           /* decoder_conf.linear_units 2048 */
+    int32_t dec_kernel;        /* decoder_conf.kernel_size 11 */
+    int32_t vocab;             /* 8404 paraformer-large zh-en / 25055 SenseVoiceSmall */
+    float ln_eps;              /* 1e-12 (ESPnet LayerNorm) / 1e-5 */
+    float cif_threshold;       /* predictor_conf.threshold 1.0 */
+    float cif_tail;            /* predictor_conf.tail_threshold 0.45 */
+    float smooth_factor;       /* 1.0 */
+    float noise_threshold;     /* 0.0 */
+    int32_t fs;                /* frontend_conf.fs 16000 */
+    int32_t n_mels;            /* 80 (the reference hard-codes 80, WavFrontend.cs:75) */
+    int32_t lfr_m;             /* 7 */
+    int32_t lfr_n;             /* 6 */
+    int32_t snip_edges;        /* frontend_conf.snip_edges */
+    int32_t use_itn;           /* ConfEntity.use_itn (SenseVoice prompt, quirk Q6) */
+    int32_t reserved[4];
+} pf_config;
+
+/* ModelOutputEntity (Model/ModelOutputEntity.cs:10-19) plus the greedy ids that OfflineRecognizer.Forward derives
+ * from it (OfflineRecognizer.cs:139-152). */
+typedef struct pf_result {
+    int32_t batch;             /* B */
+    int32_t max_len;           /* L = model_out.Dimensions[1] */
+    int32_t vocab;             /* V */
+    int32_t feat_frames;       /* T fed to the encoder (incl. SenseVoice prompt rows) */
+    const int32_t* tokens;     /* [B, L] greedy ids, ties -> largest index (Q5) */
+    const int32_t* token_num;  /* [B] model_out_lens */
+    const float* logits;       /* [B, L, V] log-softmax, only with PF_RUN_WANT_LOGITS, else NULL */
+    const float* cif_peak;     /* [B, T+1] integrate-and-fire trace, only with PF_RUN_WANT_CIF_PEAK, else NULL */
+} pf_result;
+
+enum { PF_RUN_WANT_LOGITS = 1, PF_RUN_WANT_CIF_PEAK = 2 };
+
+typedef struct pf_offline pf_offline;
+
+/* -------- lifecycle: replaces OfflineModel.initModel (OfflineModel.cs:35-70) + the IOfflineProj constructors.
+ * weights_path: PFW1 blob (see aliparaformerasr_b200/weights.py).  devices/ndev: CUDA ordinals to shard batches over
+ * (NULL/0 = current device).  The batch is split contiguously across devices, weights are replicated. */
+pf_status pf_offline_create(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev,
+                            pf_offline** out);
+pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes,
+                                        const int32_t* devices, int32_t ndev, pf_offline** out);
+/* replaces IOfflineProj.Dispose / InferenceSession.Dispose (OfflineProjOfParaformer.cs:88-101) */
+pf_status pf_offline_destroy(pf_offline* h);
+
+/* am.mvn vectors parsed by WavFrontend.LoadCmvn (WavFrontend.cs:112-153): <AddShift> and <Rescale>, dim = 560 */
+pf_status pf_offline_set_cmvn(pf_offline* h, const float* add_shift, const float* rescale, int32_t dim);
+
+/* -------- front-end only: replaces WavFrontend.GetFbank + LfrCmvn as called by OfflineStream.AddSamples
+ * (OfflineStream.cs:40-41).  samples: float PCM in [-1, 1].  feats: [capacity_frames, 560] out; *out_frames = T_lfr.
+ * No Q4 substitution here (the reference applies it later, in PadHelper). */
+pf_status pf_frontend_extract(pf_offline* h, const float* samples, int32_t nsamp, float* feats,
+                              int32_t capacity_frames, int32_t* out_frames);
+/* raw Kaldi fbank [T, 80] of one utterance (x32768 scaling included), for parity checks of OnlineFbank.GetFbank */
+pf_status pf_frontend_fbank(pf_offline* h, const float* samples, int32_t nsamp, float* fbank, int32_t capacity_frames,
+                            int32_t* out_frames);
+/* number of LFR frames AddSamples would produce for nsamp samples */
+int32_t pf_frontend_num_frames(const pf_offline* h, int32_t nsamp);
+
+/* -------- the hot path.
+ * pf_offline_run_pcm: one AddSamples per stream then GetResults(streams) (OfflineRecognizer.cs:110-198): fused
+ *   fbank+LFR+CMVN+PadSequence (Q1,Q2,Q4) -> encoder -> CIF -> decoder -> log-softmax -> greedy ids.
+ * pf_offline_run_feats: IOfflineProj.ModelProj's InferenceSession.Run on an already padded `speech [B,T,560]`
+ *   (speech_lengths = T for every item, Q3), keeping the C# front-end / PadHelper for A/B checks. */
+pf_status pf_offline_run_pcm(pf_offline* h, const float* const* pcm, const int32_t* nsamp, int32_t batch,
+                             uint32_t flags, pf_result* out);
+pf_status pf_offline_run_feats(pf_offline* h, const float* speech, int32_t batch, int32_t frames, uint32_t flags,
+                               pf_result* out);
+/* Split form used to time the device path alone: stage uploads PCM to HBM, run_staged consumes it. */
+pf_status pf_offline_stage_pcm(pf_offline* h, const float* const* pcm, const int32_t* nsamp, int32_t batch);
+pf_status pf_offline_run_staged(pf_offline* h, uint32_t flags, pf_result* out);
+
+/* -------- introspection */
+/* intermediate of the last run on device `dev_index` (0-based within the handle): "feats", "enc", "alphas",
+ * "acoustic_embeds", "logits".  Copies min(capacity, size) floats, reports dims. */
+pf_status pf_offline_get_tensor(pf_offline* h, int32_t dev_index, const char* name, float* dst, size_t capacity,
+                                int32_t* dims4, int32_t* ndim);
+/* per-stage device times of the last run (ms, CUDA events, device 0 of the handle):
+ * [0] h2d+frontend [1] encoder [2] predictor+cif [3] decoder [4] head+pick [5] total.  Returns count written. */
+int32_t pf_offline_get_timings(pf_offline* h, float* ms, int32_t capacity);
+/* kernels launched by the last run (all devices), algorithmic GEMM flops of the last run */
+int64_t pf_offline_get_launch_count(pf_offline* h);
+double pf_offline_get_gemm_flops(pf_offline* h);
+/* CUDA stream of device dev_index (as a cudaStream_t), so callers can bracket runs with their own events */
+void* pf_offline_get_stream(pf_offline* h, int32_t dev_index);
+
+const char* pf_last_error(void);
+int32_t pf_abi_version(void);
+
+/* -------- op-level test hooks (device 0 of the process; fp32 host in/out, the library converts to its compute
+ * types).  Not used by the product path; they let tests/ check each kernel against the oracle through the C-ABI. */
+pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
+                      const float* resid, const float* addend, int32_t relu, int32_t out_half, int32_t tile_n,
+                      float* out, float* elapsed_ms, int32_t iters);
+pf_status pf_dbg_layernorm(int32_t M, int32_t D, const float* x, const float* gamma, const float* beta, float eps,
+                           float* out);
+pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats, float scale, const float* gamma,
+                             const float* beta, float eps, float* out);
+pf_status pf_dbg_attention(int32_t B, int32_t H, int32_t Tq, int32_t Tk, const float* q, const float* k, const float* v,
+                           float* out);
+pf_status pf_dbg_fsmn(int32_t B, int32_t T, int32_t D, int32_t K, const float* x, const float* w, const float* resid,
+                      const int32_t* lens, int32_t half_input, float* out);
+pf_status pf_dbg_cif(int32_t B, int32_t T, int32_t D, const float* hidden, const float* alphas_with_tail,
+                     float threshold, int32_t lcap, float* embeds, int32_t* token_num, int32_t* fires, float* peaks);
+pf_status pf_dbg_logsoftmax_argmax(int32_t M, int32_t V, float* logits_inout, int32_t* tokens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_ABI_H_ */

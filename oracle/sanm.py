@@ -1,0 +1,296 @@
+"""CPU restatement (torch, float32) of the network graph the reference executes through
+OnnxRuntime for the offline path (test infrastructure; parity UNPINNED, see oracle/__init__.py).
+
+Call sites in the reference that define the tensor contract:
+  * ``OfflineProjOfParaformer.ModelProj``       OfflineProjOfParaformer.cs:39-87
+      inputs  ``speech [B,T,560] f32``, ``speech_lengths [B] i32`` (= T for every item, Q3)
+      outputs ``logits [B,L,V] f32`` (log-softmax), ``token_num [B] i32``
+  * ``OfflineProjOfSenseVoiceSmall.ModelProj``  OfflineProjOfSenseVoiceSmall.cs:53-175
+      prompt rows from ``data/embed.onnx`` prepended (Q6, Q7), CTC log-softmax over T+4 frames
+  * greedy pick ``OfflineRecognizer.Forward``   OfflineRecognizer.cs:139-152 (Q5: last max wins)
+
+Graph semantics = the FunASR ONNX export of paraformer-large / SenseVoiceSmall
+(SURVEY.md section 2.5): SANMEncoder (encoders0 + encoders + after_norm [+ tp_encoders + tp_norm]),
+CifPredictorV2 (+ tail 0.45, threshold 1.0), ParaformerSANMDecoder (16 + 1 layers).
+
+Weights are a ``dict[str, np.ndarray]`` keyed by FunASR state-dict names, float32.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as Fn
+
+
+@dataclass
+class ModelDims:
+    """Subset of ``asr.yaml`` the graph depends on (Model/EncoderConfEntity.cs:13-25,
+    Model/DecoderConfEntity.cs:7-16, Model/PredictorConfEntity.cs:13-17)."""
+    model: str = "paraformer"          # "paraformer" | "sensevoicesmall"
+    input_size: int = 560
+    d_model: int = 512
+    heads: int = 4
+    ffn: int = 2048
+    enc_layers: int = 50               # encoders0 (1) + encoders (49)
+    tp_layers: int = 0                 # SenseVoice tp_encoders
+    enc_kernel: int = 11
+    dec_layers: int = 16
+    dec_ffn: int = 2048
+    dec_kernel: int = 11
+    vocab: int = 8404
+    ln_eps: float = 1e-12
+    cif_threshold: float = 1.0
+    cif_tail: float = 0.45
+    smooth_factor: float = 1.0
+    noise_threshold: float = 0.0
+
+
+def _t(w: Dict[str, np.ndarray], name: str) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(w[name]))
+
+
+def _ln(x: torch.Tensor, w, name: str, eps: float) -> torch.Tensor:
+    return Fn.layer_norm(x, (x.shape[-1],), _t(w, name + ".weight"), _t(w, name + ".bias"), eps)
+
+
+def sinusoidal_pe(t: int, depth: int, start: int = 1) -> torch.Tensor:
+    """FunASR ``SinusoidalPositionEncoder``: positions start..start+t-1, [sin | cos] halves,
+    ``inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1))``."""
+    pos = torch.arange(start, start + t, dtype=torch.float32)
+    half = depth // 2
+    inc = math.log(10000.0) / (half - 1)
+    inv = torch.exp(torch.arange(half, dtype=torch.float32) * (-inc))
+    ang = pos[:, None] * inv[None, :]
+    return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
+
+
+def _fsmn(v: torch.Tensor, weight: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """Depthwise memory block: ``conv1d(pad(v*mask)) + v*mask`` then ``*mask``; kernel k, pad (k-1)/2
+    both sides (sanm_shfit = 0), no bias.  v: [B,T,D]; weight: [D,1,k]; mask: [B,T,1] or None."""
+    if mask is not None:
+        v = v * mask
+    k = weight.shape[-1]
+    left = (k - 1) // 2
+    x = Fn.pad(v.transpose(1, 2), (left, k - 1 - left))
+    x = Fn.conv1d(x, weight, None, groups=weight.shape[0]).transpose(1, 2)
+    x = x + v
+    if mask is not None:
+        x = x * mask
+    return x
+
+
+def _mha(q, k, v, heads: int) -> torch.Tensor:
+    """softmax(q k^T / sqrt(d_k)) v over [B,Tq,D] x [B,Tk,D]; masks are all-ones (Q3)."""
+    b, tq, d = q.shape
+    tk = k.shape[1]
+    dk = d // heads
+    qh = q.view(b, tq, heads, dk).transpose(1, 2) * (dk ** -0.5)
+    kh = k.view(b, tk, heads, dk).transpose(1, 2)
+    vh = v.view(b, tk, heads, dk).transpose(1, 2)
+    att = torch.softmax(qh @ kh.transpose(-2, -1), dim=-1)
+    return (att @ vh).transpose(1, 2).reshape(b, tq, d)
+
+
+def encoder_layer(x: torch.Tensor, w, p: str, dims: ModelDims) -> torch.Tensor:
+    """EncoderLayerSANM (export form): pre-LN SAN-M attention (+FSMN memory) then FFN."""
+    in_size = x.shape[-1]
+    d = dims.d_model
+    h = _ln(x, w, p + ".norm1", dims.ln_eps)
+    qkv = Fn.linear(h, _t(w, p + ".self_attn.linear_q_k_v.weight"), _t(w, p + ".self_attn.linear_q_k_v.bias"))
+    q, k, v = torch.split(qkv, d, dim=-1)
+    mem = _fsmn(v, _t(w, p + ".self_attn.fsmn_block.weight"), None)
+    ctx = _mha(q, k, v, dims.heads)
+    att = Fn.linear(ctx, _t(w, p + ".self_attn.linear_out.weight"), _t(w, p + ".self_attn.linear_out.bias")) + mem
+    x = att + x if in_size == d else att
+    h = _ln(x, w, p + ".norm2", dims.ln_eps)
+    h = torch.relu(Fn.linear(h, _t(w, p + ".feed_forward.w_1.weight"), _t(w, p + ".feed_forward.w_1.bias")))
+    h = Fn.linear(h, _t(w, p + ".feed_forward.w_2.weight"), _t(w, p + ".feed_forward.w_2.bias"))
+    return x + h
+
+
+def encoder(speech: torch.Tensor, w, dims: ModelDims, collect: Optional[dict] = None) -> torch.Tensor:
+    """SANMEncoder: ``speech [B,T,560]`` -> ``[B,T,512]``."""
+    b, t, din = speech.shape
+    x = speech * (dims.d_model ** 0.5) + sinusoidal_pe(t, din)[None]
+    x = encoder_layer(x, w, "encoder.encoders0.0", dims)
+    if collect is not None:
+        collect["enc_layer0"] = x.clone()
+    for i in range(dims.enc_layers - 1):
+        x = encoder_layer(x, w, f"encoder.encoders.{i}", dims)
+    x = _ln(x, w, "encoder.after_norm", dims.ln_eps)
+    if dims.tp_layers:
+        for i in range(dims.tp_layers):
+            x = encoder_layer(x, w, f"encoder.tp_encoders.{i}", dims)
+        x = _ln(x, w, "encoder.tp_norm", dims.ln_eps)
+    return x
+
+
+def predictor_alphas(enc: torch.Tensor, w, dims: ModelDims) -> torch.Tensor:
+    """CifPredictorV2 alpha head + tail: returns alphas [B, T+1] (last column = tail_threshold)."""
+    ctx = Fn.pad(enc.transpose(1, 2), (1, 1))
+    out = torch.relu(Fn.conv1d(ctx, _t(w, "predictor.cif_conv1d.weight"), _t(w, "predictor.cif_conv1d.bias")))
+    out = Fn.linear(out.transpose(1, 2), _t(w, "predictor.cif_output.weight"), _t(w, "predictor.cif_output.bias"))
+    alphas = torch.sigmoid(out).squeeze(-1)
+    alphas = torch.relu(alphas * dims.smooth_factor - dims.noise_threshold)
+    # mask is all ones (speech_lengths == T for every item, Q3); tail: one extra step of 0.45 at t = T
+    tail = torch.full((enc.shape[0], 1), dims.cif_tail, dtype=alphas.dtype)
+    return torch.cat([alphas, tail], dim=1)
+
+
+def cif(hidden: np.ndarray, alphas: np.ndarray, threshold: float = 1.0):
+    """Continuous integrate-and-fire, the export recurrence (same rule as the reference's host
+    version ``OnlineRecognizer.cs:149-200``, Q15), float32 sequential arithmetic.
+
+    hidden [B,T1,D] (T1 = T+1, last row zeros), alphas [B,T1].
+    Returns (acoustic_embeds [B,Lmax,D], token_num [B] int32 = floor(sum alpha), fires [B] counts,
+             cif_peak [B,T1] = integrate value before reset at each step).
+    """
+    b, t1, d = hidden.shape
+    thr = np.float32(threshold)
+    one = np.float32(1.0)
+    frames: List[List[np.ndarray]] = []
+    peaks = np.zeros((b, t1), dtype=np.float32)
+    token_num = np.zeros(b, dtype=np.int32)
+    for bi in range(b):
+        integrate = np.float32(0.0)
+        frame = np.zeros(d, dtype=np.float32)
+        total = np.float32(0.0)
+        out: List[np.ndarray] = []
+        for t in range(t1):
+            a = np.float32(alphas[bi, t])
+            total = np.float32(total + a)
+            completion = np.float32(one - integrate)
+            integrate = np.float32(integrate + a)
+            peaks[bi, t] = integrate
+            fire = integrate >= thr
+            cur = completion if fire else a
+            frame = frame + cur * hidden[bi, t]
+            if fire:
+                integrate = np.float32(integrate - one)
+                out.append(frame)
+                frame = np.float32(a - cur) * hidden[bi, t]
+        frames.append(out)
+        token_num[bi] = int(math.floor(float(total)))
+    fires = np.array([len(f) for f in frames], dtype=np.int32)
+    lmax = int(fires.max()) if b else 0
+    emb = np.zeros((b, lmax, d), dtype=np.float32)
+    for bi, out in enumerate(frames):
+        if out:
+            emb[bi, : len(out)] = np.stack(out)
+    return emb, token_num, fires, peaks
+
+
+def _dec_ffn(x: torch.Tensor, w, p: str, dims: ModelDims) -> torch.Tensor:
+    """PositionwiseFeedForwardDecoderSANM: w_2(LN(relu(w_1 x))), w_2 has no bias."""
+    h = torch.relu(Fn.linear(x, _t(w, p + ".w_1.weight"), _t(w, p + ".w_1.bias")))
+    h = _ln(h, w, p + ".norm", dims.ln_eps)
+    return Fn.linear(h, _t(w, p + ".w_2.weight"), None)
+
+
+def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w, dims: ModelDims,
+            collect: Optional[dict] = None) -> torch.Tensor:
+    """ParaformerSANMDecoder (export form) -> logits [B,L,V] before log-softmax."""
+    b, l, d = embeds.shape
+    tgt_mask = (torch.arange(l)[None, :] < token_num[:, None]).to(embeds.dtype)[:, :, None]
+    x = embeds
+    for i in range(dims.dec_layers):
+        p = f"decoder.decoders.{i}"
+        t = _dec_ffn(_ln(x, w, p + ".norm1", dims.ln_eps), w, p + ".feed_forward", dims)
+        tn = _ln(t, w, p + ".norm2", dims.ln_eps)
+        x = x + _fsmn(tn, _t(w, p + ".self_attn.fsmn_block.weight"), tgt_mask)
+        h = _ln(x, w, p + ".norm3", dims.ln_eps)
+        q = Fn.linear(h, _t(w, p + ".src_attn.linear_q.weight"), _t(w, p + ".src_attn.linear_q.bias"))
+        kv = Fn.linear(enc, _t(w, p + ".src_attn.linear_k_v.weight"), _t(w, p + ".src_attn.linear_k_v.bias"))
+        k, v = torch.split(kv, d, dim=-1)
+        ctx = _mha(q, k, v, dims.heads)
+        x = x + Fn.linear(ctx, _t(w, p + ".src_attn.linear_out.weight"), _t(w, p + ".src_attn.linear_out.bias"))
+        if collect is not None and i == 0:
+            collect["dec_layer0"] = x.clone()
+    p = "decoder.decoders3.0"
+    x = _dec_ffn(_ln(x, w, p + ".norm1", dims.ln_eps), w, p + ".feed_forward", dims)
+    x = _ln(x, w, "decoder.after_norm", dims.ln_eps)
+    return Fn.linear(x, _t(w, "decoder.output_layer.weight"), _t(w, "decoder.output_layer.bias"))
+
+
+def greedy_pick(logp: np.ndarray) -> np.ndarray:
+    """OfflineRecognizer.Forward argmax (OfflineRecognizer.cs:139-152): ``best = x[best] > x[k] ? best : k``
+    for k = 1..V-1, i.e. ties (and NaN) resolve to the LARGEST index (Q5).  [.., V] -> [..] int32."""
+    v = logp.shape[-1]
+    flat = logp.reshape(-1, v)
+    mx = flat.max(axis=1, keepdims=True)
+    # last index attaining the maximum
+    rev = np.argmax((flat == mx)[:, ::-1], axis=1)
+    best = (v - 1 - rev).astype(np.int32)
+    # NaN rows: comparison is always false -> walks to the last NaN-or-later index; emulate exactly
+    nan_rows = np.isnan(flat).any(axis=1)
+    for r in np.nonzero(nan_rows)[0]:
+        cur = 0
+        row = flat[r]
+        for k in range(1, v):
+            cur = cur if row[cur] > row[k] else k
+        best[r] = cur
+    return best.reshape(logp.shape[:-1])
+
+
+def paraformer_forward(speech: np.ndarray, w, dims: ModelDims, collect: Optional[dict] = None):
+    """The whole ``InferenceSession.Run`` of OfflineProjOfParaformer.cs:68 on ``speech [B,T,560]``.
+
+    Returns dict(logits [B,L,V] log-probs, token_num [B], tokens [B,L] greedy ids, enc, alphas, ...)."""
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(speech, dtype=np.float32))
+        enc = encoder(x, w, dims, collect)
+        alphas = predictor_alphas(enc, w, dims)
+        hidden = torch.cat([enc, torch.zeros(enc.shape[0], 1, enc.shape[2])], dim=1)
+        emb, token_num, fires, peaks = cif(hidden.numpy(), alphas.numpy(), dims.cif_threshold)
+        logits = decoder(enc, torch.from_numpy(emb), torch.from_numpy(token_num.astype(np.int64)), w, dims, collect)
+        logp = torch.log_softmax(logits, dim=-1).numpy()
+    return {
+        "logits": logp,
+        "token_num": token_num,
+        "tokens": greedy_pick(logp),
+        "enc": enc.numpy(),
+        "alphas": alphas.numpy(),
+        "acoustic_embeds": emb,
+        "fires": fires,
+        "cif_peak": peaks,
+    }
+
+
+# --------------------------------------------------------------------------- SenseVoice
+
+SENSEVOICE_LID = {"auto": 0, "zh": 3, "en": 4, "yue": 7, "ja": 11, "ko": 12, "nospeech": 13}
+SENSEVOICE_TEXTNORM = {"withitn": 14, "woitn": 15}
+
+
+def sensevoice_prompt_ids(use_itn: bool) -> Tuple[int, int]:
+    """OfflineProjOfSenseVoiceSmall.cs:57-74 as written (Q6): ``languageId`` is first set from the
+    hard-coded ``"ja"`` (11) and then OVERWRITTEN by the textnorm lookup (``out languageId``), while
+    ``textnormId`` keeps its initial value 15.  -> language = 14 (use_itn) or 15; textnorm = 15."""
+    language_id = SENSEVOICE_LID["ja"]
+    textnorm_id = 15
+    language_id = SENSEVOICE_TEXTNORM["withitn" if use_itn else "woitn"]
+    return language_id, textnorm_id
+
+
+def sensevoice_prepend(feats: np.ndarray, table: np.ndarray, use_itn: bool) -> np.ndarray:
+    """Split-embed layout per utterance (OfflineProjOfSenseVoiceSmall.cs:84-100, Q7):
+    ``[embed(language), embed(1), embed(2), embed(textnorm), speech...]`` -> [T+4, 560]."""
+    lang, tn = sensevoice_prompt_ids(use_itn)
+    rows = table[[lang, 1, 2, tn]].astype(np.float32)
+    return np.concatenate([rows, feats.astype(np.float32)], axis=0)
+
+
+def sensevoice_forward(speech: np.ndarray, w, dims: ModelDims):
+    """SenseVoiceSmall graph on already-prompted ``speech [B,T+4,560]``: encoder (+tp) -> CTC head ->
+    log-softmax; the reference does NO CTC collapse (OfflineRecognizer.cs:153-168 is commented out)."""
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(speech, dtype=np.float32))
+        enc = encoder(x, w, dims)
+        logits = Fn.linear(enc, _t(w, "ctc.ctc_lo.weight"), _t(w, "ctc.ctc_lo.bias"))
+        logp = torch.log_softmax(logits, dim=-1).numpy()
+    return {"logits": logp, "tokens": greedy_pick(logp), "enc": enc.numpy(),
+            "token_num": np.full(speech.shape[0], speech.shape[1], dtype=np.int32)}

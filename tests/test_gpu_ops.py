@@ -1,0 +1,144 @@
+"""Op-level parity of every CUDA kernel against the CPU oracle, through the C-ABI test hooks."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from aliparaformerasr_b200 import _lib
+from oracle import sanm
+from _util import dbg_gemm, f, half_round
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K,tile", [
+    (128, 128, 64, 128), (128, 64, 128, 64), (256, 256, 512, 256), (5312, 1536, 560, 0), (5312, 512, 512, 0),
+    (5312, 2048, 512, 0), (5312, 512, 2048, 0), (1344, 8404, 512, 0), (83, 512, 512, 0), (100, 520, 72, 64),
+    (300, 8404, 512, 128), (640, 1024, 512, 256),
+])
+def test_gemm_plain(lib, M, N, K, tile):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    out, _ = dbg_gemm(lib, A, W, tile_n=tile)
+    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T
+    err = np.abs(out - ref).max()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("out_half,relu", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_epilogue(lib, out_half, relu):
+    rng = np.random.default_rng(5)
+    M, N, K = 333, 520, 512
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = rng.standard_normal((M, N)).astype(np.float32)
+    addend = rng.standard_normal((M, N)).astype(np.float32)
+    out, _ = dbg_gemm(lib, A, W, bias, resid, addend, relu=relu, out_half=out_half)
+    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias + resid + addend
+    if relu:
+        ref = np.maximum(ref, 0)
+    tol = 2e-2 if out_half else 2e-3
+    assert np.abs(out - ref).max() < tol
+
+
+@pytest.mark.parametrize("M,D", [(7, 512), (1000, 512), (333, 2048)])
+def test_layernorm(lib, M, D):
+    rng = np.random.default_rng(D + M)
+    x = (rng.standard_normal((M, D)) * 3 + 1).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(D)).astype(np.float32)
+    out = np.zeros_like(x)
+    _lib.check(lib.pf_dbg_layernorm(M, D, _lib.fptr(x), _lib.fptr(g), _lib.fptr(b), 1e-12, _lib.fptr(out)))
+    ref = torch.nn.functional.layer_norm(torch.from_numpy(x), (D,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
+    assert np.abs(out - ref).max() < 1e-5
+
+
+def test_embed_pe_ln(lib):
+    rng = np.random.default_rng(11)
+    B, T, D = 3, 50, 560
+    x = (rng.standard_normal((B, T, D)) * 0.8 + 2.4).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(D)).astype(np.float32)
+    out = np.zeros_like(x)
+    _lib.check(lib.pf_dbg_embed_pe_ln(B, T, D, _lib.fptr(x), float(np.sqrt(512.0)), _lib.fptr(g), _lib.fptr(b), 1e-12, _lib.fptr(out)))
+    xt = torch.from_numpy(x) * (512 ** 0.5) + sanm.sinusoidal_pe(T, D)[None]
+    ref = torch.nn.functional.layer_norm(xt, (D,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
+    assert np.abs(out - ref).max() < 5e-3      # output is fp16
+
+
+@pytest.mark.parametrize("B,Tq,Tk", [(2, 166, 166), (3, 40, 166), (1, 5, 7), (2, 64, 64), (1, 130, 300)])
+def test_attention(lib, B, Tq, Tk):
+    rng = np.random.default_rng(Tq * 31 + Tk)
+    H, D = 4, 512
+    q = rng.standard_normal((B, Tq, D)).astype(np.float32)
+    k = rng.standard_normal((B, Tk, D)).astype(np.float32)
+    v = rng.standard_normal((B, Tk, D)).astype(np.float32)
+    out = np.zeros_like(q)
+    _lib.check(lib.pf_dbg_attention(B, H, Tq, Tk, _lib.fptr(q), _lib.fptr(k), _lib.fptr(v), _lib.fptr(out)))
+    ref = sanm._mha(torch.from_numpy(half_round(q)), torch.from_numpy(half_round(k)), torch.from_numpy(half_round(v)), H).numpy()
+    assert np.abs(out - ref).max() < 5e-3
+
+
+@pytest.mark.parametrize("K,half_in,masked", [(11, 1, False), (11, 0, True), (21, 0, True)])
+def test_fsmn(lib, K, half_in, masked):
+    rng = np.random.default_rng(K)
+    B, T, D = 3, 45, 512
+    x = rng.standard_normal((B, T, D)).astype(np.float32)
+    w = (0.1 * rng.standard_normal((D, 1, K))).astype(np.float32)
+    resid = rng.standard_normal((B, T, D)).astype(np.float32)
+    lens = np.array([45, 17, 0], dtype=np.int32)
+    out = np.zeros_like(x)
+    _lib.check(lib.pf_dbg_fsmn(B, T, D, K, _lib.fptr(x), _lib.fptr(f(w.reshape(D, K))), _lib.fptr(resid),
+                               _lib.iptr(lens) if masked else None, half_in, _lib.fptr(out)))
+    xin = torch.from_numpy(half_round(x) if half_in else x)
+    mask = None
+    if masked:
+        mask = (torch.arange(T)[None, :] < torch.from_numpy(lens.astype(np.int64))[:, None]).float()[:, :, None]
+    ref = (torch.from_numpy(resid) + sanm._fsmn(xin, torch.from_numpy(w), mask)).numpy()
+    assert np.abs(out - ref).max() < 1e-5
+
+
+def test_cif_matches_oracle_bit_exact(lib):
+    rng = np.random.default_rng(3)
+    B, T, D = 4, 166, 512
+    hidden = rng.standard_normal((B, T, D)).astype(np.float32)
+    alphas = np.concatenate([rng.uniform(0, 0.6, (B, T)).astype(np.float32), np.full((B, 1), 0.45, np.float32)], axis=1)
+    alphas[3, :] = 0.0           # silent utterance: only the tail -> zero tokens
+    alphas[3, T] = 0.45
+    hid1 = np.concatenate([hidden, np.zeros((B, 1, D), np.float32)], axis=1)
+    emb_ref, tn_ref, fires_ref, peaks_ref = sanm.cif(hid1, alphas, 1.0)
+    lcap = T + 1
+    emb = np.zeros((B, lcap, D), np.float32)
+    tn = np.zeros(B, np.int32)
+    fires = np.zeros(B, np.int32)
+    peaks = np.zeros((B, T + 1), np.float32)
+    _lib.check(lib.pf_dbg_cif(B, T, D, _lib.fptr(hidden), _lib.fptr(alphas), 1.0, lcap, _lib.fptr(emb), _lib.iptr(tn),
+                              _lib.iptr(fires), _lib.fptr(peaks)))
+    assert np.array_equal(tn, tn_ref)
+    assert np.array_equal(fires, fires_ref)
+    assert np.array_equal(peaks, peaks_ref)
+    L = emb_ref.shape[1]
+    assert np.array_equal(emb[:, :L], emb_ref)
+    assert not emb[:, L:].any()
+
+
+def test_logsoftmax_argmax_tie_and_nan_rules(lib):
+    rng = np.random.default_rng(9)
+    M, V = 37, 8404
+    x = (rng.standard_normal((M, V)) * 4).astype(np.float32)
+    x[0, 100] = x[0, 7000] = x[0].max() + 1          # tie -> largest index (Q5)
+    x[1, :] = 0.25                                    # all equal -> V-1
+    x[2, 50] = np.nan                                 # NaN restarts the scan after it
+    x[3, V - 1] = np.nan                              # NaN last -> V-1
+    ref_tok = sanm.greedy_pick(x.copy())
+    ref_lp = torch.log_softmax(torch.from_numpy(x), dim=-1).numpy()
+    y = x.copy()
+    tok = np.zeros(M, np.int32)
+    _lib.check(lib.pf_dbg_logsoftmax_argmax(M, V, _lib.fptr(y), _lib.iptr(tok)))
+    assert np.array_equal(tok, ref_tok)
+    assert tok[0] == 7000 and tok[1] == V - 1 and tok[3] == V - 1
+    ok = ~np.isnan(ref_lp)
+    assert np.abs(y[ok] - ref_lp[ok]).max() < 1e-4
