@@ -75,6 +75,9 @@ SIGNATURES = {
     "pf_offline_get_timings": (C.c_int32, [C.c_void_p, _F, C.c_int32]),
     "pf_offline_get_launch_count": (C.c_int64, [C.c_void_p]),
     "pf_offline_get_gemm_flops": (C.c_double, [C.c_void_p]),
+    "pf_offline_set_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pf_offline_get_gemm_ms": (C.c_double, [C.c_void_p]),
+    "pf_offline_get_profile_json": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),
     "pf_offline_get_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),

@@ -50,7 +50,7 @@ static void validate_config(const pf_config& c) {
         if (c.dec_ffn != 2048 && c.dec_ffn != 1024 && c.dec_ffn != 512) throw StatusError{PF_ERR_UNSUPPORTED, "decoder ffn width must be 512/1024/2048"};
         if (c.dec_kernel != 11 && c.dec_kernel != 21) throw StatusError{PF_ERR_UNSUPPORTED, "decoder FSMN kernel must be 11 or 21"};
     }
-    if (c.vocab < 8 || c.vocab % 4) throw StatusError{PF_ERR_SHAPE, "vocab must be a positive multiple of 4 (fp32 row alignment)"};
+    if (c.vocab < 8) throw StatusError{PF_ERR_SHAPE, "vocab too small"};
 }
 
 static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
@@ -256,6 +256,11 @@ pf_status pf_offline_stage_pcm(pf_offline* hh, const float* const* pcm, const in
         OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
         std::lock_guard<std::mutex> g(h->mu);
         stage_pcm_all(h, pcm, nsamp, batch);
+        // standalone staging returns only once the PCM is resident in HBM (the caller may free its buffers)
+        for (auto& d : h->devs) {
+            PF_CUDA(cudaSetDevice(d->device()));
+            PF_CUDA(cudaStreamSynchronize(d->stream()));
+        }
     });
 }
 
@@ -332,6 +337,29 @@ double pf_offline_get_gemm_flops(pf_offline* hh) {
     OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
     double n = 0;
     for (auto& d : h->devs) n += d->gemm_flops;
+    return n;
+}
+
+pf_status pf_offline_set_profile(pf_offline* hh, int32_t on) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        for (auto& d : h->devs) d->set_profile(on != 0);
+    });
+}
+
+double pf_offline_get_gemm_ms(pf_offline* hh) {
+    if (!hh) return 0;
+    return reinterpret_cast<OfflineHandle*>(hh)->devs[0]->gemm_ms;
+}
+
+int32_t pf_offline_get_profile_json(pf_offline* hh, char* buf, int32_t capacity) {
+    if (!hh || !buf || capacity <= 0) return 0;
+    const std::string& js = reinterpret_cast<OfflineHandle*>(hh)->devs[0]->profile_json;
+    const int n = std::min<int>(capacity - 1, static_cast<int>(js.size()));
+    memcpy(buf, js.data(), n);
+    buf[n] = 0;
     return n;
 }
 

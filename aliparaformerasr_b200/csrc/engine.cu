@@ -119,6 +119,8 @@ DeviceCtx::~DeviceCtx() {
     if (h_logits) cudaFreeHost(h_logits);
     if (h_peaks) cudaFreeHost(h_peaks);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    for (auto& e : prof_pool_) cudaEventDestroy(e);
+    for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -306,7 +308,7 @@ void DeviceCtx::ensure_workspace(int B, int T) {
     enc16_ = dalloc<__half>(M * d, apool_);
     prompt_ids_ = dalloc<int>(4, apool_);
     if (sv) {
-        logits_ = dalloc<float>(M * cfg_.vocab, apool_);
+        logits_ = dalloc<float>(M * ldv(), apool_);
         tokens_ = dalloc<int>(M, apool_);
         token_num_ = dalloc<int>(capB_, apool_);
         return;
@@ -329,7 +331,7 @@ void DeviceCtx::ensure_workspace(int B, int T) {
     tn32_ = dalloc<float>(Md * d, apool_);
     q16_ = dalloc<__half>(Md * d, apool_);
     ctxd16_ = dalloc<__half>(Md * d, apool_);
-    logits_ = dalloc<float>(Md * cfg_.vocab, apool_);
+    logits_ = dalloc<float>(Md * ldv(), apool_);
     tokens_ = dalloc<int>(Md, apool_);
 }
 
@@ -376,7 +378,7 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
     for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], enc_[i].in_size == d);
     for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i], true);
     if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
-        GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = cfg_.vocab;
+        GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = ldv();
         gemm_prepare(plan.ctc_head, enc16_, d, w_head_, d, M, cfg_.vocab, d, e);
     } else {
         GemmEpi e; e.bias = b_conv_; e.relu = 1; e.out_f32 = mem32_; e.ld_out = d;
@@ -410,15 +412,56 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
         plan.layers.push_back(lp);
     }
     ffn(dec3_, plan.d3_w1, plan.d3_w2);
-    GemmEpi h; h.bias = b_head_; h.out_f32 = logits_; h.ld_out = cfg_.vocab;
+    GemmEpi h; h.bias = b_head_; h.out_f32 = logits_; h.ld_out = ldv();
     gemm_prepare(plan.head, ad16_, d, w_head_, d, Md, cfg_.vocab, d, h);
     return dec_plans_.emplace(key, std::move(plan)).first->second;
 }
 
 void DeviceCtx::gemm(const GemmOp& op) {
-    gemm_launch(op, stream_);
+    if (profile_) {
+        ProfRec r{op.M, op.N, op.K, op.bn, nullptr, nullptr};
+        for (cudaEvent_t* e : {&r.a, &r.b}) {
+            if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
+            else PF_CUDA(cudaEventCreate(e));
+        }
+        PF_CUDA(cudaEventRecord(r.a, stream_));
+        gemm_launch(op, stream_);
+        PF_CUDA(cudaEventRecord(r.b, stream_));
+        prof_.push_back(r);
+    } else {
+        gemm_launch(op, stream_);
+    }
     ++launches;
     gemm_flops += pf::gemm_flops(op);
+}
+
+void DeviceCtx::finish_profile() {
+    gemm_ms = 0.0;
+    profile_json.clear();
+    if (prof_.empty()) return;
+    struct Agg { int count = 0; double ms = 0.0; };
+    std::map<std::vector<int>, Agg> agg;
+    for (ProfRec& r : prof_) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        gemm_ms += ms;
+        Agg& a = agg[{r.M, r.N, r.K, r.bn}];
+        a.count++;
+        a.ms += ms;
+        prof_pool_.push_back(r.a);
+        prof_pool_.push_back(r.b);
+    }
+    prof_.clear();
+    std::string js = "[";
+    for (auto& kv : agg) {
+        if (js.size() > 1) js += ",";
+        const double fl = 2.0 * kv.first[0] * static_cast<double>(kv.first[1]) * kv.first[2] * kv.second.count;
+        js += "{\"M\":" + std::to_string(kv.first[0]) + ",\"N\":" + std::to_string(kv.first[1]) + ",\"K\":" + std::to_string(kv.first[2]) +
+              ",\"tile_n\":" + std::to_string(kv.first[3]) + ",\"launches\":" + std::to_string(kv.second.count) + ",\"ms\":" +
+              std::to_string(kv.second.ms) + ",\"tflops\":" + std::to_string(kv.second.ms > 0 ? fl / (kv.second.ms * 1e9) : 0.0) + "}";
+    }
+    js += "]";
+    profile_json = js;
 }
 
 // ------------------------------------------------------------------ staging
@@ -596,7 +639,7 @@ void DeviceCtx::decoder_forward(int B, int T, int L) {
     ffn(dec3_, plan.d3_w1, plan.d3_w2);
     layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, nullptr, 0, stream_);
     gemm(plan.head);
-    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, cfg_.vocab, tokens_, 1, stream_);
+    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, 1, stream_);
     launches += 2;
 }
 
@@ -668,7 +711,7 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
         gemm(encoder_plan(B, T).ctc_head);
         PF_CUDA(cudaEventRecord(ev_[3], stream_));
         PF_CUDA(cudaEventRecord(ev_[4], stream_));
-        logsoftmax_argmax_launch(logits_, M, cfg_.vocab, cfg_.vocab, tokens_, (flags & PF_RUN_WANT_LOGITS) ? 1 : 0, stream_);
+        logsoftmax_argmax_launch(logits_, M, cfg_.vocab, ldv(), tokens_, (flags & PF_RUN_WANT_LOGITS) ? 1 : 0, stream_);
         ++launches;
         PF_CUDA(cudaEventRecord(ev_[5], stream_));
         Lmax_ = T; Lpad_ = T;
@@ -676,7 +719,8 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
         ensure_host(static_cast<size_t>(M), (flags & PF_RUN_WANT_LOGITS) ? static_cast<size_t>(M) * cfg_.vocab : 0, 0);
         PF_CUDA(cudaMemcpyAsync(h_tokens, tokens_, static_cast<size_t>(M) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         if (flags & PF_RUN_WANT_LOGITS)
-            PF_CUDA(cudaMemcpyAsync(h_logits, logits_, static_cast<size_t>(M) * cfg_.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            PF_CUDA(cudaMemcpy2DAsync(h_logits, static_cast<size_t>(cfg_.vocab) * sizeof(float), logits_, static_cast<size_t>(ldv()) * sizeof(float),
+                                      static_cast<size_t>(cfg_.vocab) * sizeof(float), M, cudaMemcpyDeviceToHost, stream_));
         PF_CUDA(cudaEventRecord(ev_[6], stream_));
         PF_CUDA(cudaStreamSynchronize(stream_));
         for (int b = 0; b < B; ++b) h_token_num[b] = T;
@@ -703,7 +747,8 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
             const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0, wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0;
             ensure_host(ntok, wl ? ntok * cfg_.vocab : 0, wp ? static_cast<size_t>(B) * (T + 1) : 0);
             PF_CUDA(cudaMemcpyAsync(h_tokens, tokens_, ntok * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-            if (wl) PF_CUDA(cudaMemcpyAsync(h_logits, logits_, ntok * cfg_.vocab * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            if (wl) PF_CUDA(cudaMemcpy2DAsync(h_logits, static_cast<size_t>(cfg_.vocab) * sizeof(float), logits_, static_cast<size_t>(ldv()) * sizeof(float),
+                                              static_cast<size_t>(cfg_.vocab) * sizeof(float), ntok, cudaMemcpyDeviceToHost, stream_));
             if (wp) PF_CUDA(cudaMemcpyAsync(h_peaks, peaks_, static_cast<size_t>(B) * (T + 1) * sizeof(float), cudaMemcpyDeviceToHost, stream_));
         } else {
             PF_CUDA(cudaEventRecord(ev_[4], stream_));
@@ -712,6 +757,7 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
         PF_CUDA(cudaEventRecord(ev_[6], stream_));
         PF_CUDA(cudaStreamSynchronize(stream_));
     }
+    finish_profile();
     float ms = 0.0f;
     for (int i = 0; i < 5; ++i) {
         cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
@@ -731,7 +777,7 @@ void DeviceCtx::get_tensor(const std::string& name, float* dst, size_t capacity,
     else if (name == "enc") { src = enc32_; dims[0] = B_; dims[1] = T_; dims[2] = d; nd = 3; }
     else if (name == "alphas") { src = alphas_; dims[0] = B_; dims[1] = T_ + 1; nd = 2; }
     else if (name == "cif_peak") { src = peaks_; dims[0] = B_; dims[1] = T_ + 1; nd = 2; }
-    else if (name == "logits") { src = logits_; dims[0] = B_; dims[1] = Lpad_; dims[2] = cfg_.vocab; nd = 3; }
+    else if (name == "logits") { src = logits_; dims[0] = B_; dims[1] = Lpad_; dims[2] = ldv(); nd = 3; }   // padded row pitch
     else if (name == "x") { src = x32_; dims[0] = B_; dims[1] = T_; dims[2] = d; nd = 3; }
     else if (name == "dec_x") { src = xd32_; dims[0] = B_; dims[1] = Lpad_; dims[2] = d; nd = 3; }
     else throw StatusError{PF_ERR_BAD_ARG, "unknown tensor '" + name + "'"};

@@ -129,9 +129,15 @@ public:
     int64_t launches = 0;
     double gemm_flops = 0.0;
 
+    // per-launch CUDA-event profiling of the GEMM kernel (bench.py roofline leg); adds two events per launch
+    void set_profile(bool on) { profile_ = on; }
+    double gemm_ms = 0.0;              // sum of GEMM launch durations of the last profiled run
+    std::string profile_json;          // per-shape breakdown of the last profiled run
+
     void get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim);
     cudaStream_t stream() const { return stream_; }
     int device() const { return dev_; }
+    int ldv() const { return (cfg_.vocab + 3) & ~3; }   // fp32 logits row pitch (16-byte aligned rows)
 
 private:
     template <typename T> T* dalloc(size_t n, std::vector<void*>& pool);
@@ -153,6 +159,11 @@ private:
     void free_pool(std::vector<void*>& pool);
     void run_impl(uint32_t flags, SharedRun* shared, int idx);
     bool arrived_ = false, ev0_armed_ = false;
+    void finish_profile();
+    struct ProfRec { int M, N, K, bn; cudaEvent_t a, b; };
+    bool profile_ = false;
+    std::vector<ProfRec> prof_;
+    std::vector<cudaEvent_t> prof_pool_;
 
     int dev_;
     pf_config cfg_;

@@ -167,6 +167,21 @@ class Engine:
         keys = ["h2d_frontend", "encoder", "predictor_cif", "decoder", "head_pick", "total"]
         return {k: float(ms[i]) for i, k in enumerate(keys)}
 
+    def set_profile(self, on: bool) -> None:
+        _lib.check(self._lib.pf_offline_set_profile(self._handle(), int(on)))
+
+    def gemm_ms(self) -> float:
+        return float(self._lib.pf_offline_get_gemm_ms(self._handle()))
+
+    def profile(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.pf_offline_get_profile_json(self._handle(), buf, len(buf))
+        return json.loads(buf.value[:n].decode()) if n else []
+
+    def stream_ptr(self, dev_index: int = 0) -> int:
+        return int(self._lib.pf_offline_get_stream(self._handle(), dev_index) or 0)
+
     def launch_count(self) -> int:
         return int(self._lib.pf_offline_get_launch_count(self._handle()))
 

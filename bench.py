@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds/sec (1/RTF) of the offline hot path, paraformer-large, batch 32 x 10 s per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libpfasr.so via the C-ABI)
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle port), host cores
+
+One "step" = one pass of the hot path over one batch: PCM -> fbank/LFR/CMVN -> SAN-M encoder -> CIF -> decoder ->
+log-softmax -> greedy ids (what OfflineRecognizer.GetResults does for 32 streams, OfflineRecognizer.cs:110-198).
+
+* value  : whole-job audio-s/s with the PCM already resident in HBM (pf_offline_run_staged), device-timed per step
+           with CUDA events on the engine's stream, L2 flushed between steps, max over ranks.
+* e2e    : the same metric through the public call a user makes (pf_offline_run_pcm) with pinned HOST buffers:
+           H2D of the PCM and D2H of the token ids are inside the timed region.
+* roofline: dominant kernel = the tcgen05 GEMM; achieved = algorithmic GEMM FLOPs / summed per-launch CUDA-event
+           durations of one profiled step; peak = MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step).
+* cpu_baseline: the oracle (a port of the reference's CPU path; OnnxRuntime/dotnet are not available) on a bounded
+           sample of the same workload, all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-seconds/sec (RTF^-1) paraformer-large offline @ batch 32"
+UNIT = "audio-s/s"
+BATCH = 32
+SECONDS = 10.0
+WORKLOAD = "paraformer-large-zh-en offline, batch=32x10 s synthetic 16 kHz per GPU (BASELINE configs[1])"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1403.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": reasons}
+
+
+def _oracle_dims(cfg):
+    from oracle import sanm
+    return sanm.ModelDims(**{k: v for k, v in cfg.as_dict().items() if k in sanm.ModelDims.__dataclass_fields__})
+
+
+def cpu_reference_step(pcm, weights, cfg):
+    """One pass of the reference's CPU path (oracle port): PCM in host RAM -> token ids in host RAM."""
+    from oracle import frontend as F, sanm
+    from aliparaformerasr_b200 import synth
+    shift, scale = synth.make_cmvn()
+    speech = F.pad_sequence([F.extract_features(p, shift, scale, snip_edges=cfg.snip_edges) for p in pcm])
+    return sanm.paraformer_forward(speech, weights, _oracle_dims(cfg))["tokens"]
+
+
+def time_cpu(pcm_sample, weights, cfg, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(warmup):
+        cpu_reference_step(pcm_sample, weights, cfg)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(pcm_sample, weights, cfg)
+        ts.append(time.perf_counter() - t0)
+    return ts, cores
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from aliparaformerasr_b200 import synth
+    cfg = synth.paraformer_large()
+
+    # ------------------------------------------------------------------ reference arm: CPU, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        weights = synth.make_weights(cfg)
+        nb = max(1, min(args.cpu_sample, BATCH))
+        pcm = [synth.make_pcm(i, SECONDS) for i in range(nb)]
+        ts, cores = time_cpu(pcm, weights, cfg, max(1, args.steps), args.warmup)
+        sec = statistics.mean(ts)
+        val = nb * SECONDS / sec
+        sample = f"{nb} of the {BATCH} utterances (10 s each) per step; oracle port of the reference CPU path (OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from aliparaformerasr_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    weights = synth.make_weights(cfg)
+    eng = Engine(cfg, weights, devices=[local_rank])
+    eng.set_cmvn(*synth.make_cmvn())
+    nsamp = int(SECONDS * cfg.fs)
+    # pinned host PCM for this rank's shard (global utterance index = rank * BATCH + i)
+    host = torch.empty((BATCH, nsamp), dtype=torch.float32, pin_memory=True)
+    for i in range(BATCH):
+        host[i].copy_(torch.from_numpy(synth.make_pcm(rank * BATCH + i, SECONDS)))
+    pcm = [host[i].numpy() for i in range(BATCH)]
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(0), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # 2x the 126 MB L2
+    tok_dev = torch.zeros((BATCH, 256), dtype=torch.int32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # -------- value: inputs resident in HBM
+    eng.stage_pcm(pcm)
+    out = None
+    for _ in range(args.warmup):
+        out = eng.run_staged()
+    launches_per_step = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    dev_ms = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = eng.run_staged()
+        e1.record(stream)
+        e1.synchronize()
+        dev_ms.append(e0.elapsed_time(e1))
+    barrier()
+    wall_resident = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(dev_ms)
+    stage_ms = eng.timings()
+
+    # -------- e2e: host PCM -> host token ids through the public call
+    for _ in range(2):
+        eng.run_pcm(pcm)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = eng.run_pcm(pcm)
+        if world > 1:   # C1: gather the ids on rank 0 (NCCL over NVLink), padded to a fixed width
+            tok_dev.zero_()
+            tok_dev[:, : o.tokens.shape[1]].copy_(torch.from_numpy(o.tokens), non_blocking=True)
+            gl = [torch.empty_like(tok_dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(tok_dev, gl, dst=0)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = BATCH * nsamp * 4 + BATCH * 28
+    d2h = int(out.tokens.size * 4 + BATCH * 4 + 16)
+
+    # -------- roofline leg: one profiled step (per-launch CUDA events on the GEMM kernel)
+    eng.set_profile(True)
+    eng.run_staged()
+    gemm_ms = eng.gemm_ms()
+    gemm_flops = eng.gemm_flops()
+    prof = eng.profile()
+    eng.set_profile(False)
+    n_gemm = sum(p["launches"] for p in prof) or 1
+
+    # -------- reduce over ranks (max time)
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        audio_per_step = BATCH * SECONDS * world
+        value = audio_per_step * args.steps / (total_ms / 1e3)
+        e2e_val = audio_per_step * args.steps / (e2e_ms / 1e3)
+        peak, peak_src = _peaks()
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "audio_seconds_per_utt": SECONDS,
+                       "T_lfr": int(out.feat_frames), "Lmax": int(out.tokens.shape[1]), "weights": "random-init paraformer-large (seed 20260917), fp16 operands / fp32 accumulate",
+                       "l2": "256 MB buffer written between timed steps (L2 flush); weights alone (0.43 GB) also exceed L2",
+                       "parallelism": f"dp{world} (utterances sharded, weights replicated, no data-path collective)"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "api": "pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids)"},
+            "gpu_launches": int(launches_per_step * args.steps * world),
+            "launches_per_step": int(launches_per_step),
+            "rtf": (total_ms / 1e3) / (audio_per_step * args.steps),
+            "stage_ms": stage_ms,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "pf_gemm_f16_tn_tcgen05", "peak_source": peak_src,
+                         "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
+                         "gemm_share_of_step": gemm_ms / (total_ms / args.steps) if total_ms else None,
+                         "avg_launch_us": gemm_ms * 1e3 / n_gemm, "by_shape": prof},
+            "clocks": clocks,
+            "wall_s_resident_loop": wall_resident,
+        }
+        if not args.no_cpu_baseline:
+            nb = max(1, min(args.cpu_sample, BATCH))
+            ts, cores = time_cpu(pcm[:nb], weights, cfg, 3, 1)
+            sec = statistics.mean(ts)
+            line["cpu_baseline"] = {"value": nb * SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{nb} of the {BATCH} utterances per pass, 1 warm-up + 3 timed passes; oracle port of the reference CPU path "
+                                              f"(OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

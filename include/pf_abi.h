@@ -139,6 +139,12 @@ int32_t pf_offline_get_timings(pf_offline* h, float* ms, int32_t capacity);
 /* kernels launched by the last run (all devices), algorithmic GEMM flops of the last run */
 int64_t pf_offline_get_launch_count(pf_offline* h);
 double pf_offline_get_gemm_flops(pf_offline* h);
+/* per-launch CUDA-event profiling of the GEMM kernel (two extra events per launch; off by default).  After a profiled
+ * run: pf_offline_get_gemm_ms = summed GEMM launch durations on device 0 of the handle, pf_offline_get_profile_json =
+ * per-shape breakdown [{"M","N","K","tile_n","launches","ms","tflops"}, ...] (returns bytes written). */
+pf_status pf_offline_set_profile(pf_offline* h, int32_t on);
+double pf_offline_get_gemm_ms(pf_offline* h);
+int32_t pf_offline_get_profile_json(pf_offline* h, char* buf, int32_t capacity);
 /* CUDA stream of device dev_index (as a cudaStream_t), so callers can bracket runs with their own events */
 void* pf_offline_get_stream(pf_offline* h, int32_t dev_index);
 
