@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's public offline API, driving libpfasr.so through the C-ABI.
+
+The reference's host language is C#; this image has no dotnet, so the host side above the C-ABI is written in
+Python with the same type names, call sequence, argument meaning and error behaviour:
+
+  * ``OfflineRecognizer``  /root/reference/AliParaformerAsr/OfflineRecognizer.cs:23 (ctor), :92 CreateOfflineStream,
+                           :102 GetResult, :110 GetResults, :441 DisposeOfflineStream, :468 Dispose
+  * ``OfflineStream``      OfflineStream.cs:30-36 (Tokens / Timestamps / Hotwords / AddSamples)
+  * result entity          Model/OfflineRecognizerResultEntity.cs:9-29
+
+What moved to the GPU: everything between ``AddSamples`` and the argmax loop of ``Forward``
+(WavFrontend, PadHelper, IOfflineProj.ModelProj, greedy pick).  What stays on the host, as in the reference:
+config / token-table parsing and ``DecodeMulti`` (ids -> text).
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .engine import Engine
+from .synth import ModelConfig
+
+PAD_QUIRK_VALUE = np.float32(np.float32(-23.025850929940457) * np.float32(32768.0))   # Utils/PadHelper.cs:63
+
+
+class ArgumentNullError(ValueError):
+    """``ArgumentNullException``; ``param_name`` mirrors ``ParamName`` (tests expect "source", WavFrontend.cs:34)."""
+
+    def __init__(self, param_name: str):
+        super().__init__(f"Value cannot be null. (Parameter '{param_name}')")
+        self.param_name = param_name
+
+
+class ObjectDisposedError(RuntimeError):
+    """``ObjectDisposedException``; ``object_name`` mirrors ``ObjectName`` (OfflineRecognizer.cs:94-97)."""
+
+    def __init__(self, object_name: str):
+        super().__init__(f"Cannot access a disposed object. Object name: '{object_name}'.")
+        self.object_name = object_name
+
+
+# --------------------------------------------------------------------------- config / asset loading (host, as in C#)
+def read_tokens(path: str) -> Optional[List[str]]:
+    """Utils/PreloadHelper.cs:120-141 ``ReadTokens``: one token per line; empty path -> null."""
+    if not path:
+        return None
+    with open(path, "r", encoding="utf-8") as f:
+        return f.read().splitlines()
+
+
+def load_cmvn(path: str):
+    """``WavFrontend.LoadCmvn`` (WavFrontend.cs:112-153): the bracketed vectors on the ``<LearnRateCoef>`` lines
+    following ``<AddShift>`` and ``<Rescale>`` of a Kaldi-nnet ``am.mvn``."""
+    state = 0
+    shift: List[float] = []
+    scale: List[float] = []
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f.read().splitlines():
+            if not line:
+                continue
+            if line.startswith("<AddShift>"):
+                state = 1
+            elif line.startswith("<Rescale>"):
+                state = 2
+            elif line.startswith("<LearnRateCoef>") and state in (1, 2):
+                body = line[line.index("[") + 1: line.rindex("]")]
+                vals = [float(t) for t in body.split(" ") if t.strip()]
+                if state == 1:
+                    shift = vals
+                else:
+                    scale = vals
+    return np.asarray(shift, dtype=np.float32), np.asarray(scale, dtype=np.float32)
+
+
+def load_conf(path: str) -> ModelConfig:
+    """``OfflineRecognizer.LoadConf`` (OfflineRecognizer.cs:55-71): ``.json`` or ``.yaml`` -> the ConfEntity fields the
+    hot path consumes.  Missing keys keep the paraformer-large defaults baked into the C# entities."""
+    cfg = ModelConfig()
+    if not path:
+        return cfg
+    raw = {}
+    low = path.lower()
+    if low.endswith(".json"):
+        with open(path, "r", encoding="utf-8") as f:
+            raw = json.load(f) or {}
+    elif low.endswith(".yaml"):
+        import yaml
+        with open(path, "r", encoding="utf-8") as f:
+            raw = yaml.safe_load(f) or {}
+    cfg.model = str(raw.get("model", cfg.model) or cfg.model)
+    cfg.use_itn = bool(raw.get("use_itn", cfg.use_itn))
+    enc = raw.get("encoder_conf") or {}
+    cfg.d_model = int(enc.get("output_size", cfg.d_model))
+    cfg.heads = int(enc.get("attention_heads", cfg.heads))
+    cfg.ffn = int(enc.get("linear_units", cfg.ffn))
+    cfg.enc_layers = int(enc.get("num_blocks", cfg.enc_layers))
+    cfg.tp_layers = int(enc.get("tp_blocks", cfg.tp_layers))
+    cfg.enc_kernel = int(enc.get("kernel_size", cfg.enc_kernel))
+    dec = raw.get("decoder_conf") or {}
+    cfg.dec_layers = int(dec.get("num_blocks", cfg.dec_layers))
+    cfg.dec_ffn = int(dec.get("linear_units", cfg.dec_ffn))
+    cfg.dec_kernel = int(dec.get("kernel_size", cfg.dec_kernel))
+    pred = raw.get("predictor_conf") or {}
+    cfg.cif_threshold = float(pred.get("threshold", cfg.cif_threshold))
+    cfg.cif_tail = float(pred.get("tail_threshold", cfg.cif_tail))
+    cfg.smooth_factor = float(pred.get("smooth_factor", cfg.smooth_factor))
+    cfg.noise_threshold = float(pred.get("noise_threshold", cfg.noise_threshold))
+    fe = raw.get("frontend_conf") or {}
+    cfg.fs = int(fe.get("fs", cfg.fs))
+    cfg.n_mels = int(fe.get("n_mels", cfg.n_mels))
+    cfg.lfr_m = int(fe.get("lfr_m", cfg.lfr_m))
+    cfg.lfr_n = int(fe.get("lfr_n", cfg.lfr_n))
+    cfg.snip_edges = bool(fe.get("snip_edges", cfg.snip_edges))
+    cfg.input_size = cfg.lfr_m * cfg.n_mels
+    if "vocab_size" in raw:
+        cfg.vocab = int(raw["vocab_size"])
+    if "ln_eps" in raw:
+        cfg.ln_eps = float(raw["ln_eps"])
+    if cfg.model.lower() == "sensevoicesmall":
+        cfg.dec_layers = 0
+    return cfg
+
+
+# --------------------------------------------------------------------------- entities
+@dataclass
+class OfflineRecognizerResultEntity:
+    """Model/OfflineRecognizerResultEntity.cs:9-29"""
+    text: str = ""
+    text_len: int = 0
+    tokens: List[str] = field(default_factory=list)
+    timestamps: List[List[int]] = field(default_factory=list)
+
+    # C#-style aliases
+    @property
+    def Text(self):
+        return self.text
+
+    @property
+    def Tokens(self):
+        return self.tokens
+
+    @property
+    def Timestamps(self):
+        return self.timestamps
+
+
+class OfflineStream:
+    """OfflineStream.cs: holds one utterance's input until ``GetResults`` consumes it."""
+
+    def __init__(self, recognizer: "OfflineRecognizer"):
+        self._rec = recognizer
+        self._chunks: List[np.ndarray] = []      # one entry per AddSamples call (Q10: features are concatenated)
+        self.hotwords: Optional[List[List[int]]] = []
+        self.tokens: List[int] = [0, 0]          # OfflineStream.cs:26 {blank, blank}
+        self.timestamps: List[List[int]] = []
+        self._disposed = False
+
+    def add_samples(self, samples) -> None:
+        """OfflineStream.AddSamples (OfflineStream.cs:36-57).  ``None`` raises like the LINQ ``Select`` in
+        WavFrontend.GetFbank does (ArgumentNullException, ParamName "source")."""
+        if samples is None:
+            raise ArgumentNullError("source")
+        self._chunks.append(np.ascontiguousarray(samples, dtype=np.float32).reshape(-1))
+
+    AddSamples = add_samples
+
+    def features(self) -> np.ndarray:
+        """What ``OfflineInputEntity.Speech`` holds: per-call fbank->LFR->CMVN, concatenated (Q10)."""
+        eng = self._rec._engine
+        parts = [eng.extract(c) for c in self._chunks]
+        dim = eng.cfg.lfr_m * eng.cfg.n_mels
+        return np.concatenate(parts, axis=0) if parts else np.zeros((0, dim), np.float32)
+
+    def remove_chunk(self) -> None:
+        """OfflineStream.RemoveChunk (OfflineStream.cs:69-79): input is dropped once tokens were produced."""
+        if len(self.tokens) > 2:
+            self._chunks = []
+
+    def dispose(self) -> None:
+        self._disposed = True
+        self._chunks = []
+
+    Dispose = dispose
+
+
+def pad_sequence(feats: Sequence[np.ndarray]) -> np.ndarray:
+    """PadHelper.PadSequence (Utils/PadHelper.cs:23-65) on the host, used only when a stream received several
+    AddSamples calls: right-pad with 0 to the longest item, then every exact 0.0 -> -23.0258509f*32768 (Q4)."""
+    dim = feats[0].shape[-1]
+    tmax = max(int(f.shape[0]) for f in feats)
+    out = np.zeros((len(feats), tmax, dim), dtype=np.float32)
+    for i, f in enumerate(feats):
+        out[i, : f.shape[0]] = f
+    out[out == 0] = PAD_QUIRK_VALUE
+    return out
+
+
+_CHINESE = re.compile(r"^[一-龥]+$")
+
+
+class OfflineRecognizer:
+    """OfflineRecognizer.cs:23 — same constructor arguments; ``model_file_path`` is the PFW1 weight blob that replaces
+    ``model.onnx``.  ``threads_num`` is accepted and ignored (it only set ORT inter-op threads, Q17)."""
+
+    def __init__(self, model_file_path: str, config_file_path: str, mvn_file_path: str, tokens_file_path: str,
+                 modeleb_file_path: str = "", hotword_file_path: str = "", batch_size: int = 1, threads_num: int = 1,
+                 devices: Optional[Sequence[int]] = None, weights=None, config: Optional[ModelConfig] = None):
+        self._disposed = False
+        self._conf = config if config is not None else load_conf(config_file_path)
+        self._tokens = read_tokens(tokens_file_path)
+        if not self._tokens:
+            raise Exception("tokens invalid")                      # OfflineRecognizer.cs:30-33
+        self._mvn_file_path = mvn_file_path
+        if modeleb_file_path or self._conf.model.lower() == "seacoparaformer":
+            raise NotImplementedError("SeACo hot-word bias decoder is not built yet (SURVEY.md section 8, cfg 4)")
+        self._engine = Engine(self._conf, weights if weights is not None else model_file_path, devices=devices)
+        if mvn_file_path:
+            shift, scale = load_cmvn(mvn_file_path)
+            self._engine.set_cmvn(shift, scale)
+
+    # -- API surface of the reference
+    def create_offline_stream(self) -> OfflineStream:
+        if self._disposed:
+            raise ObjectDisposedError("OfflineRecognizer")          # OfflineRecognizer.cs:94-97
+        return OfflineStream(self)
+
+    def get_result(self, stream: OfflineStream) -> OfflineRecognizerResultEntity:
+        return self.get_results([stream])[0]
+
+    def get_results(self, streams: List[OfflineStream]) -> List[OfflineRecognizerResultEntity]:
+        self._forward(streams)
+        return self._decode_multi(streams)
+
+    def dispose_offline_stream(self, stream: Optional[OfflineStream]) -> None:
+        if stream is not None:
+            stream.dispose()
+
+    def dispose(self) -> None:
+        if not self._disposed:
+            self._engine.close()
+            self._tokens = None
+            self._disposed = True
+
+    CreateOfflineStream = create_offline_stream
+    GetResult = get_result
+    GetResults = get_results
+    DisposeOfflineStream = dispose_offline_stream
+    Dispose = dispose
+
+    # -- OfflineRecognizer.Forward (OfflineRecognizer.cs:118-198)
+    def _forward(self, streams: List[OfflineStream]) -> None:
+        if not streams:
+            return
+        if self._disposed:
+            raise ObjectDisposedError("OfflineRecognizer")
+        try:
+            if all(len(s._chunks) == 1 for s in streams):
+                # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
+                out = self._engine.run_pcm([s._chunks[0] for s in streams])
+            else:
+                feats = [s.features() for s in streams]
+                if any(f.shape[0] == 0 for f in feats) and max(f.shape[0] for f in feats) == 0:
+                    raise ValueError("no input samples")
+                out = self._engine.run_feats(pad_sequence(feats))
+        except _lib.PfError as ex:
+            raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
+        for i, s in enumerate(streams):
+            s.tokens = [int(t) for t in out.tokens[i]]
+            s.timestamps.extend([[0, 0] for _ in s.tokens])         # 3-output models: {0,0} per token (:151)
+            s.remove_chunk()
+
+    # -- OfflineRecognizer.DecodeMulti (OfflineRecognizer.cs:304-418)
+    def _decode_multi(self, streams: List[OfflineStream]) -> List[OfflineRecognizerResultEntity]:
+        results = []
+        for s in streams:
+            ent = OfflineRecognizerResultEntity()
+            text = ""
+            last_token = ""
+            last_ts = None
+            for token, ts in zip(s.tokens, s.timestamps):
+                if token == 2:
+                    break
+                cur = self._tokens[token].split("\t")[0] if 0 <= token < len(self._tokens) else "<unk>"
+                if cur in ("</s>", "<s>", "<blank>", "<unk>"):
+                    continue
+                if _CHINESE.match(cur):
+                    text += cur
+                    ent.tokens.append(cur)
+                    ent.timestamps.append(ts)
+                    continue
+                text += "▁" + cur + "▁"
+                joined = last_token + "▁" + cur + "▁"
+                if joined.find("@@▁▁") > 0:
+                    cur_token = joined.replace("@@▁▁", "")
+                    cur_ts = ts if last_ts is None else list(last_ts) + list(ts)
+                    if ent.tokens:
+                        ent.tokens.pop()
+                        ent.timestamps.pop()
+                    ent.tokens.append(cur_token.replace("▁", ""))
+                    ent.timestamps.append(cur_ts)
+                    last_token, last_ts = cur_token, cur_ts
+                elif joined.count("▁") in (3, 5) and joined.find("▁▁▁") < 0:
+                    cur_token = joined.replace("▁▁", "")
+                    cur_ts = ts if last_ts is None else list(last_ts) + list(ts)
+                    if ent.tokens:
+                        ent.tokens.pop()
+                    ent.tokens.append(cur_token.replace("▁", ""))
+                    if ent.timestamps:
+                        ent.timestamps.pop()
+                    ent.timestamps.append(cur_ts)
+                    last_token, last_ts = cur_token, cur_ts
+                else:
+                    ent.tokens.append(cur.replace("▁", ""))
+                    ent.timestamps.append(ts)
+                    last_token, last_ts = "▁" + cur + "▁", ts
+            if text.find("@@▁▁") > 0 or text.find("▁▁▁") < 0:
+                text = text.replace("@@▁▁", "").replace("▁▁", " ").replace("@@", " ").replace("▁", " ")
+            else:
+                text = text.replace("▁▁▁", " ").replace("▁▁", "").replace("▁", "")
+            ent.text = text
+            ent.text_len = len(text)
+            results.append(ent)
+        return results

@@ -1,0 +1,82 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/pf_abi.h declares, validates arguments
+before touching a device, and (on a box without a GPU) refuses to run instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from aliparaformerasr_b200 import _lib, synth, weights
+from aliparaformerasr_b200.engine import Engine, to_pf_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pf_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pf_abi.h but not exported by libpfasr.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert lib.pf_abi_version() == 1
+
+
+def test_config_struct_layout():
+    assert C.sizeof(_lib.PfConfig) == 4 * 28
+    c = to_pf_config(synth.paraformer_large())
+    assert (c.input_size, c.d_model, c.enc_layers, c.dec_layers, c.vocab, c.lfr_m, c.lfr_n) == (560, 512, 50, 16, 8404, 7, 6)
+    assert to_pf_config(synth.sensevoice_small()).model_kind == _lib.PF_MODEL_SENSEVOICE_SMALL
+
+
+def test_bad_arguments_are_rejected_before_any_device_work(lib):
+    h = C.c_void_p()
+    cfg = to_pf_config(synth.tiny())
+    blob = weights.pack({"x": np.zeros(4, np.float32)})
+    bad = to_pf_config(synth.tiny())
+    bad.struct_bytes = 12
+    assert lib.pf_offline_create_from_memory(C.byref(bad), blob.ctypes.data_as(C.c_void_p), blob.nbytes, None, 0, C.byref(h)) == _lib.PF_ERR_BAD_ARG
+    assert b"struct_bytes" in lib.pf_last_error()
+    bad = to_pf_config(synth.tiny())
+    bad.d_model = 256
+    assert lib.pf_offline_create_from_memory(C.byref(bad), blob.ctypes.data_as(C.c_void_p), blob.nbytes, None, 0, C.byref(h)) == _lib.PF_ERR_UNSUPPORTED
+    assert lib.pf_offline_create(C.byref(cfg), b"", None, 0, C.byref(h)) == _lib.PF_ERR_WEIGHTS
+    assert lib.pf_offline_create(C.byref(cfg), b"/nonexistent/model.pfw", None, 0, C.byref(h)) == _lib.PF_ERR_WEIGHTS
+    # disposed / null handle (ObjectDisposedException in the reference)
+    res = _lib.PfResult()
+    assert lib.pf_offline_run_staged(None, 0, C.byref(res)) == _lib.PF_ERR_DISPOSED
+    assert lib.pf_offline_destroy(None) == _lib.PF_ERR_DISPOSED
+    assert lib.pf_frontend_num_frames(None, 100) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = synth.tiny()
+    with pytest.raises(_lib.PfError) as ei:
+        Engine(cfg, synth.make_weights(cfg))
+    assert ei.value.code == _lib.PF_ERR_CUDA and "no CPU fallback" in ei.value.message
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "aliparaformerasr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_blob_roundtrip():
+    w = synth.make_weights(synth.tiny())
+    back = weights.unpack(weights.pack(w))
+    assert set(back) == set(w)
+    for k in w:
+        assert back[k].shape == w[k].shape and np.array_equal(back[k], w[k])

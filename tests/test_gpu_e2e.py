@@ -103,7 +103,7 @@ def test_sensevoice_matches_oracle():
     speech = np.stack([sanm.sensevoice_prepend(x, w["embed.weight"], cfg.use_itn) for x in feats])
     ref = sanm.sensevoice_forward(speech, w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
-    assert out.tokens.shape == ref["tokens"].shape == (2, 49 + 4)
+    assert out.tokens.shape == ref["tokens"].shape == (2, 50 + 4)
     _check_logits(out.logits, ref["logits"])
     safe = margins(ref["logits"]) > TOKEN_MARGIN
     assert np.array_equal(out.tokens[safe], ref["tokens"][safe])
