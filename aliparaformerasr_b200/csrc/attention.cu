@@ -50,6 +50,8 @@ __device__ __forceinline__ void stage_tile(uint32_t smem_base, const __half* g, 
 __global__ void __launch_bounds__(kThreads)
 pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
                   __half* __restrict__ O, int Tq, int Tk, int ldq, int ldk, int ldv, int ldo, float scale_log2e) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sK = sQ + BQ * LDS * 2;
@@ -201,8 +203,7 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
     }
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
     dim3 grid(ceil_div(Tq, BQ), H, B);
-    pf_sanm_attention<<<grid, kThreads, kSmemBytes, s>>>(Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_sanm_attention, grid, dim3(kThreads), kSmemBytes, s, Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e);
 }
 
 }  // namespace pf

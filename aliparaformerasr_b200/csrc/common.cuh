@@ -31,8 +31,35 @@ struct CudaError {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Every kernel of the path is launched with programmatic dependent launch (PDL): the next kernel's CTAs may become
+// resident and run their prologue (barrier init, TMEM allocation, descriptor prefetch, table staging) while the
+// previous kernel drains; each kernel calls pdl_wait() before it touches global memory written by its predecessor.
+// PFASR_NO_PDL=1 falls back to plain stream ordering (A/B switch).
+bool pdl_enabled();   // engine.cu
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    PF_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+#endif
+
 // ---------------------------------------------------------------- device PTX wrappers
 #ifdef __CUDACC__
+
+// PDL: let the dependent grid start launching / wait until the prerequisite grid has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -6,11 +6,20 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 namespace pf {
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PFASR_NO_PDL");
+        return !(e && *e && *e != '0');
+    }();
+    return on;
+}
 
 // ------------------------------------------------------------------ blob
 // Layout (little endian): "PFW1" | u32 version | u32 count | u32 reserved |

@@ -54,6 +54,8 @@ pf_frontend_fbank_lfr_cmvn(const FrontendTables* __restrict__ tab, const float* 
                            float* __restrict__ fbank_out, const long long* __restrict__ fbank_off,
                            float* __restrict__ feats_out, const long long* __restrict__ feats_off,
                            int lfr_m, int lfr_n, int snip_edges, int pad_quirk, float pad_value) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float2 s_tw[256];
     __shared__ float s_win[kFrameLen];
     __shared__ float2 s_z[kWarps][256];
@@ -202,6 +204,8 @@ pf_frontend_fbank_lfr_cmvn(const FrontendTables* __restrict__ tab, const float* 
 // Right padding of short utterances: PadSequence pads with 0 and then maps 0 -> pad_value (Q4).
 __global__ void pf_frontend_pad_fill(float* __restrict__ feats, const long long* __restrict__ feats_off,
                                      const int* __restrict__ nlfr, int tmax, int dim, float pad_value) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const int t0 = nlfr[b];
     const long long total = static_cast<long long>(tmax - t0) * dim;
@@ -270,15 +274,13 @@ void frontend_tables_destroy(void* tables) {
 void frontend_launch(const FrontendLaunch& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_frames <= 0) return;
     dim3 grid(ceil_div(a.max_frames, kWarps), a.batch);
-    pf_frontend_fbank_lfr_cmvn<<<grid, kWarps * 32, 0, stream>>>(
-        static_cast<const FrontendTables*>(a.tables), a.pcm, a.pcm_off, a.nsamp, a.nframes, a.nlfr, a.add_shift, a.rescale,
-        a.fbank_out, a.fbank_off, a.feats_out, a.feats_off, a.lfr_m, a.lfr_n, a.snip_edges ? 1 : 0, a.pad_quirk ? 1 : 0,
-        a.pad_value);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_frontend_fbank_lfr_cmvn, grid, dim3(kWarps * 32), 0, stream,
+             static_cast<const FrontendTables*>(a.tables), a.pcm, a.pcm_off, a.nsamp, a.nframes, a.nlfr, a.add_shift, a.rescale,
+             a.fbank_out, a.fbank_off, a.feats_out, a.feats_off, a.lfr_m, a.lfr_n, a.snip_edges ? 1 : 0, a.pad_quirk ? 1 : 0,
+             a.pad_value);
     if (a.feats_out && a.pad_fill && a.tmax_lfr > 0) {
         dim3 g2(32, a.batch);
-        pf_frontend_pad_fill<<<g2, 256, 0, stream>>>(a.feats_out, a.feats_off, a.nlfr, a.tmax_lfr, a.lfr_m * kMel, a.pad_value);
-        PF_CUDA(cudaGetLastError());
+        launch_k(pf_frontend_pad_fill, g2, dim3(256), 0, stream, a.feats_out, a.feats_off, a.nlfr, a.tmax_lfr, a.lfr_m * kMel, a.pad_value);
     }
 }
 

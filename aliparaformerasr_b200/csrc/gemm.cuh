@@ -24,6 +24,7 @@ struct GemmOp {
     GemmEpi epi;
     int M = 0, N = 0, K = 0;
     int bn = 128;    // N tile: 64, 128 or 256
+    int vec_ok = 0;  // all epilogue tensors 16-byte aligned with pitches % 4 == 0
 };
 
 // Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).

@@ -18,6 +18,8 @@ template <int kMaxPerLane>
 __global__ void __launch_bounds__(256)
 pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale, const float* __restrict__ inv_ts,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ out16) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -68,6 +70,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 pf_layernorm(const float* __restrict__ in, int ld_in, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
              float eps, __half* __restrict__ out16, int ld16, float* __restrict__ out32, int ld32) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int D = NV * 128;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -121,6 +125,8 @@ template <typename TIn, int K>
 __global__ void __launch_bounds__(256)
 pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, float* __restrict__ out, int ld_out,
         const float* __restrict__ resid, int ld_res, const int* __restrict__ lens, int T, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int TT = 16;
     constexpr int LEFT = (K - 1) / 2;
     const int c = blockIdx.z * blockDim.x + threadIdx.x;
@@ -154,6 +160,8 @@ pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, floa
 
 // ------------------------------------------------------------------ predictor
 __global__ void pf_im2col3(const __half* __restrict__ in, int B, int T, int D, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     // one thread per 8 halfs (16 B) of the output row [3*D]
     const int vec_per_row = 3 * D / 8;
     const long long total = static_cast<long long>(B) * T * vec_per_row;
@@ -174,6 +182,8 @@ __global__ void pf_im2col3(const __half* __restrict__ in, int B, int T, int D, _
 __global__ void __launch_bounds__(256)
 pf_alpha_head(const float* __restrict__ h, int B, int T, int D, const float* __restrict__ w, const float* __restrict__ bias,
               float smooth, float noise, float tail, float* __restrict__ alphas) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int M = B * T;
@@ -195,6 +205,8 @@ pf_alpha_head(const float* __restrict__ h, int B, int T, int D, const float* __r
 __global__ void pf_cif_scan(const float* __restrict__ alphas, int B, int T1, float threshold, float* __restrict__ w_cur,
                             float* __restrict__ w_rem, int* __restrict__ fire_idx, float* __restrict__ peaks,
                             int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     float integrate = 0.0f, total = 0.0f;
@@ -226,6 +238,8 @@ __global__ void pf_cif_scan(const float* __restrict__ alphas, int B, int T1, flo
 __global__ void __launch_bounds__(256)
 pf_cif_gather(const float* __restrict__ hidden, int T, int D, const float* __restrict__ w_cur,
               const float* __restrict__ w_rem, const int* __restrict__ fire_idx, int T1, float* __restrict__ out, int Lpad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
@@ -246,6 +260,8 @@ pf_cif_gather(const float* __restrict__ hidden, int T, int D, const float* __res
 // ------------------------------------------------------------------ log-softmax + greedy pick, one CTA per row
 __global__ void __launch_bounds__(256)
 pf_logsoftmax_argmax(float* __restrict__ logits, int V, int ld, int* __restrict__ tokens, int write_logp) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_val[8];
     __shared__ int s_idx[8];
     __shared__ int s_nan[8];
@@ -326,6 +342,8 @@ __global__ void pf_f32_to_f16(const float* __restrict__ in, __half* __restrict__
 
 __global__ void pf_prepend_rows(const float* __restrict__ src, const float* __restrict__ table, const int* __restrict__ ids,
                                 int nprompt, float* __restrict__ dst, int B, int T, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = static_cast<long long>(B) * (T + nprompt) * D;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -342,16 +360,15 @@ __global__ void pf_prepend_rows(const float* __restrict__ src, const float* __re
 void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
                         const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s) {
     if (D > 32 * 20) throw CudaError{"embed_pe_ln: input_size > 640 unsupported"};
-    pf_embed_pe_ln<20><<<ceil_div(M, 8), 256, 0, s>>>(feats, M, T, D, scale, inv_timescales, gamma, beta, eps, out16);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_embed_pe_ln<20>, dim3(ceil_div(M, 8)), dim3(256), 0, s, feats, M, T, D, scale, inv_timescales, gamma, beta, eps, out16);
 }
 
 void layernorm_f32_launch(const float* in, int ld_in, int M, int D, const float* gamma, const float* beta, float eps,
                           __half* out16, int ld16, float* out32, int ld32, cudaStream_t s) {
     const int grid = ceil_div(M, 8);
-    if (D == 512) pf_layernorm<4><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
-    else if (D == 1024) pf_layernorm<8><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
-    else if (D == 2048) pf_layernorm<16><<<grid, 256, 0, s>>>(in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    if (D == 512) launch_k(pf_layernorm<4>, dim3(grid), dim3(256), 0, s, in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    else if (D == 1024) launch_k(pf_layernorm<8>, dim3(grid), dim3(256), 0, s, in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
+    else if (D == 2048) launch_k(pf_layernorm<16>, dim3(grid), dim3(256), 0, s, in, ld_in, M, gamma, beta, eps, out16, ld16, out32, ld32);
     else throw CudaError{"layernorm: unsupported width " + std::to_string(D)};
     PF_CUDA(cudaGetLastError());
 }
@@ -360,8 +377,8 @@ template <typename TIn>
 static void fsmn_launch_t(const TIn* in, int ld_in, const float* w, int K, float* out, int ld_out, const float* resid,
                           int ld_res, const int* lens, int B, int T, int D, cudaStream_t s) {
     dim3 grid(ceil_div(T, 16), B, ceil_div(D, 256));
-    if (K == 11) pf_fsmn<TIn, 11><<<grid, 256, 0, s>>>(in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
-    else if (K == 21) pf_fsmn<TIn, 21><<<grid, 256, 0, s>>>(in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
+    if (K == 11) launch_k(pf_fsmn<TIn, 11>, grid, dim3(256), 0, s, in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
+    else if (K == 21) launch_k(pf_fsmn<TIn, 21>, grid, dim3(256), 0, s, in, ld_in, w, out, ld_out, resid, ld_res, lens, T, D);
     else throw CudaError{"fsmn: unsupported kernel size " + std::to_string(K)};
     PF_CUDA(cudaGetLastError());
 }
@@ -377,33 +394,28 @@ void fsmn_f32_launch(const float* in, int ld_in, const float* w, int K, float* o
 void im2col3_launch(const __half* in, int B, int T, int D, __half* out, cudaStream_t s) {
     const long long total = static_cast<long long>(B) * T * (3 * D / 8);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-    pf_im2col3<<<grid, 256, 0, s>>>(in, B, T, D, out);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_im2col3, dim3(grid), dim3(256), 0, s, in, B, T, D, out);
 }
 
 void alpha_head_launch(const float* h, int B, int T, int D, const float* w, const float* bias, float smooth, float noise,
                        float tail, float* alphas, cudaStream_t s) {
-    pf_alpha_head<<<ceil_div(B * T, 8), 256, 0, s>>>(h, B, T, D, w, bias, smooth, noise, tail, alphas);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_alpha_head, dim3(ceil_div(B * T, 8)), dim3(256), 0, s, h, B, T, D, w, bias, smooth, noise, tail, alphas);
 }
 
 void cif_scan_launch(const float* alphas, int B, int T1, float threshold, float* w_cur, float* w_rem, int* fire_idx,
                      float* peaks, int* token_num, int* fires, int* meta, cudaStream_t s) {
-    pf_cif_scan<<<ceil_div(B, 32), 32, 0, s>>>(alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_cif_scan, dim3(ceil_div(B, 32)), dim3(32), 0, s, alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
 }
 
 void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_cur, const float* w_rem,
                        const int* fire_idx, int T1, float* out, int Lpad, cudaStream_t s) {
     dim3 grid(ceil_div(D, 256), B);
-    pf_cif_gather<<<grid, 256, 0, s>>>(hidden, T, D, w_cur, w_rem, fire_idx, T1, out, Lpad);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_cif_gather, grid, dim3(256), 0, s, hidden, T, D, w_cur, w_rem, fire_idx, T1, out, Lpad);
 }
 
 void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, int write_logp, cudaStream_t s) {
     if (M <= 0) return;
-    pf_logsoftmax_argmax<<<M, 256, 0, s>>>(logits, V, ld, tokens, write_logp);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_logsoftmax_argmax, dim3(M), dim3(256), 0, s, logits, V, ld, tokens, write_logp);
 }
 
 void f32_to_f16_launch(const float* in, __half* out, size_t n, cudaStream_t s) {
@@ -417,8 +429,7 @@ void prepend_rows_launch(const float* src, const float* table, const int* ids, i
                          int D, cudaStream_t s) {
     const long long total = static_cast<long long>(B) * (T + nprompt) * D;
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-    pf_prepend_rows<<<grid, 256, 0, s>>>(src, table, ids, nprompt, dst, B, T, D);
-    PF_CUDA(cudaGetLastError());
+    launch_k(pf_prepend_rows, dim3(grid), dim3(256), 0, s, src, table, ids, nprompt, dst, B, T, D);
 }
 
 }  // namespace pf
