@@ -428,7 +428,7 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
 
 void DeviceCtx::gemm(const GemmOp& op) {
     if (profile_) {
-        ProfRec r{op.M, op.N, op.K, op.bn, nullptr, nullptr};
+        ProfRec r{op.M, op.N, op.K, op.bn + 1000 * (op.cm * 10 + op.cn), nullptr, nullptr};
         for (cudaEvent_t* e : {&r.a, &r.b}) {
             if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
             else PF_CUDA(cudaEventCreate(e));
@@ -466,7 +466,7 @@ void DeviceCtx::finish_profile() {
         if (js.size() > 1) js += ",";
         const double fl = 2.0 * kv.first[0] * static_cast<double>(kv.first[1]) * kv.first[2] * kv.second.count;
         js += "{\"M\":" + std::to_string(kv.first[0]) + ",\"N\":" + std::to_string(kv.first[1]) + ",\"K\":" + std::to_string(kv.first[2]) +
-              ",\"tile_n\":" + std::to_string(kv.first[3]) + ",\"launches\":" + std::to_string(kv.second.count) + ",\"ms\":" +
+              ",\"tile_n\":" + std::to_string(kv.first[3] % 1000) + ",\"cluster\":\"" + std::to_string(kv.first[3] / 10000) + "x" + std::to_string(kv.first[3] / 1000 % 10) + "\"" + ",\"launches\":" + std::to_string(kv.second.count) + ",\"ms\":" +
               std::to_string(kv.second.ms) + ",\"tflops\":" + std::to_string(kv.second.ms > 0 ? fl / (kv.second.ms * 1e9) : 0.0) + "}";
     }
     js += "]";

@@ -59,60 +59,93 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
            | (static_cast<uint32_t>(m >> 4) << 24);   // m_dim
 }
 
-// One 32x32 accumulator chunk of one warp: registers (thread = row) -> swizzled smem -> (thread = 4 columns of a
-// row, 8 lanes per row) -> bias / addend / residual / ReLU -> coalesced store.
-template <bool kOutHalf>
+// One 32x32 accumulator chunk of one warp: registers (thread = row) -> XOR-swizzled smem (conflict-free both ways)
+// -> row-segment layout (fp32 out: 8 lanes x float4 per row, 4 rows per instruction; fp16 out: 4 lanes x 8 halfs per
+// row, 8 rows per instruction) -> bias / addends / ReLU -> 16-byte coalesced stores.  kAdds = number of fp32 tensors
+// added to the product (FSMN memory, residual); the adds of a chunk are all issued before the first use.
+template <bool kOutHalf, int kAdds>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* stage, int lane, int row0, int col0,
                                                int M, int N, const GemmEpi& e, bool vec_ok) {
-    // ---- transpose through shared memory (XOR swizzle on the float4 index: conflict-free both ways)
     float4* st4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
     __syncwarp();
-    const int jj = lane & 7;
-    const int rsub = lane >> 3;
-    const int col = col0 + jj * 4;
-    if (vec_ok && col + 4 <= N) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-        float4 ad[8], rs[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int row = row0 + it * 4 + rsub;
-            ad[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < M) {
-                if (e.addend) ad[it] = *reinterpret_cast<const float4*>(e.addend + static_cast<size_t>(row) * e.ld_addend + col);
-                if (e.resid) rs[it] = *reinterpret_cast<const float4*>(e.resid + static_cast<size_t>(row) * e.ld_resid + col);
+    const float lo = e.relu ? 0.0f : -INFINITY;
+    if (vec_ok && col0 + 32 <= N) {
+        if (kOutHalf) {
+            const int g = lane & 3, rsub = lane >> 2;
+            const int col = col0 + g * 8;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (e.bias) {
+                b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+                b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
             }
-        }
+            __half* optr = e.out_f16 + static_cast<size_t>(row0 + rsub) * e.ld_out + col;
+            const float* a0p = kAdds > 0 ? e.add0 + static_cast<size_t>(row0 + rsub) * e.ld_add0 + col : nullptr;
+            const float* a1p = kAdds > 1 ? e.add1 + static_cast<size_t>(row0 + rsub) * e.ld_add1 + col : nullptr;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + rsub;
-            const int row = row0 + rl;
-            float4 v = st4[rl * 8 + (jj ^ (rl & 7))];
-            v.x += b.x + ad[it].x + rs[it].x;
-            v.y += b.y + ad[it].y + rs[it].y;
-            v.z += b.z + ad[it].z + rs[it].z;
-            v.w += b.w + ad[it].w + rs[it].w;
-            if (e.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (row < M) {
-                if (kOutHalf) {
-                    __half2 h0 = __floats2half2_rn(v.x, v.y);
-                    __half2 h1 = __floats2half2_rn(v.z, v.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(e.out_f16 + static_cast<size_t>(row) * e.ld_out + col) = pk;
-                } else {
-                    *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ld_out + col) = v;
+            for (int it = 0; it < 4; ++it) {
+                const int rl = it * 8 + rsub;
+                const bool ok = row0 + rl < M;
+                float4 v0 = st4[rl * 8 + ((2 * g) ^ (rl & 7))];
+                float4 v1 = st4[rl * 8 + ((2 * g + 1) ^ (rl & 7))];
+                v0.x += b0.x; v0.y += b0.y; v0.z += b0.z; v0.w += b0.w;
+                v1.x += b1.x; v1.y += b1.y; v1.z += b1.z; v1.w += b1.w;
+                if (kAdds > 0 && ok) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(a0p + static_cast<size_t>(it) * 8 * e.ld_add0);
+                    const float4 x1 = *reinterpret_cast<const float4*>(a0p + static_cast<size_t>(it) * 8 * e.ld_add0 + 4);
+                    v0.x += x0.x; v0.y += x0.y; v0.z += x0.z; v0.w += x0.w;
+                    v1.x += x1.x; v1.y += x1.y; v1.z += x1.z; v1.w += x1.w;
                 }
+                if (kAdds > 1 && ok) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(a1p + static_cast<size_t>(it) * 8 * e.ld_add1);
+                    const float4 x1 = *reinterpret_cast<const float4*>(a1p + static_cast<size_t>(it) * 8 * e.ld_add1 + 4);
+                    v0.x += x0.x; v0.y += x0.y; v0.z += x0.z; v0.w += x0.w;
+                    v1.x += x1.x; v1.y += x1.y; v1.z += x1.z; v1.w += x1.w;
+                }
+                __half2 h0 = __floats2half2_rn(fmaxf(v0.x, lo), fmaxf(v0.y, lo));
+                __half2 h1 = __floats2half2_rn(fmaxf(v0.z, lo), fmaxf(v0.w, lo));
+                __half2 h2 = __floats2half2_rn(fmaxf(v1.x, lo), fmaxf(v1.y, lo));
+                __half2 h3 = __floats2half2_rn(fmaxf(v1.z, lo), fmaxf(v1.w, lo));
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                if (ok) *reinterpret_cast<uint4*>(optr + static_cast<size_t>(it) * 8 * e.ld_out) = pk;
+            }
+        } else {
+            const int jj = lane & 7, rsub = lane >> 3;
+            const int col = col0 + jj * 4;
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+            float* optr = e.out_f32 + static_cast<size_t>(row0 + rsub) * e.ld_out + col;
+            float4 x0[8], x1[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const bool ok = row0 + it * 4 + rsub < M;
+                x0[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                x1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kAdds > 0 && ok) x0[it] = *reinterpret_cast<const float4*>(e.add0 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add0 + col);
+                if (kAdds > 1 && ok) x1[it] = *reinterpret_cast<const float4*>(e.add1 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add1 + col);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rl = it * 4 + rsub;
+                float4 v = st4[rl * 8 + (jj ^ (rl & 7))];
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                if (kAdds > 0) { v.x += x0[it].x; v.y += x0[it].y; v.z += x0[it].z; v.w += x0[it].w; }
+                if (kAdds > 1) { v.x += x1[it].x; v.y += x1[it].y; v.z += x1[it].z; v.w += x1[it].w; }
+                v.x = fmaxf(v.x, lo); v.y = fmaxf(v.y, lo); v.z = fmaxf(v.z, lo); v.w = fmaxf(v.w, lo);
+                if (row0 + rl < M) *reinterpret_cast<float4*>(optr + static_cast<size_t>(it) * 4 * e.ld_out) = v;
             }
         }
     } else {
         // ragged N edge (e.g. vocab 25055) or unaligned pitches: scalar, bounds-checked
+        const int jj = lane & 7, rsub = lane >> 3;
+        const int col = col0 + jj * 4;
 #pragma unroll 1
         for (int it = 0; it < 8; ++it) {
             const int rl = it * 4 + rsub;
@@ -126,9 +159,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
                     if (c < N) {
                         float x = v[i];
                         if (e.bias) x += __ldg(e.bias + c);
-                        if (e.addend) x += e.addend[static_cast<size_t>(row) * e.ld_addend + c];
-                        if (e.resid) x += e.resid[static_cast<size_t>(row) * e.ld_resid + c];
-                        if (e.relu) x = fmaxf(x, 0.0f);
+                        if (kAdds > 0) x += e.add0[static_cast<size_t>(row) * e.ld_add0 + c];
+                        if (kAdds > 1) x += e.add1[static_cast<size_t>(row) * e.ld_add1 + c];
+                        x = fmaxf(x, lo);
                         if (kOutHalf) e.out_f16[static_cast<size_t>(row) * e.ld_out + c] = __float2half_rn(x);
                         else e.out_f32[static_cast<size_t>(row) * e.ld_out + c] = x;
                     }
@@ -139,13 +172,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
     __syncwarp();   // the transpose buffer is reused by the next chunk
 }
 
-template <int BN, bool kOutHalf>
+// Thread-block cluster of CM x CN CTAs computes a (CM*128) x (CN*BN) super-tile.  CTA (rm, rn) owns the 128 x BN
+// sub-tile and issues its own 1-CTA MMAs, but operand tiles are fetched from L2 once per cluster: the CTA loads
+// 1/CN of its A tile and 1/CM of its B tile and TMA-multicasts each slice to the CTAs that share it (row peers share
+// A, column peers share B).  L2->SM bytes per k-block drop from 16K + BN*128 to 16K/CN + BN*128/CM, which is what
+// bounds this kernel (see pick_config).  A stage may be refilled only when every CTA that receives my slices has
+// consumed it, so the MMA commit arrives on the empty barrier of all row and column peers (count CM + CN - 1).
+template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
 __global__ void __launch_bounds__(kThreads, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi, const int M, const int N, const int K, const int tiles_n, const int num_tiles,
+                       const GemmEpi epi, const int M, const int N, const int K, const int stiles_n, const int num_stiles,
                        const int vec_ok) {
     using C = Cfg<BN>;
     constexpr int STAGES = C::kStages;
+    constexpr int CSIZE = CM * CN;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
@@ -163,6 +203,17 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = (K + BK - 1) / BK;
+    const int crank = CSIZE > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int rm = crank % CM, rn = crank / CM;
+    const int cluster_id = blockIdx.x / CSIZE;
+    const int num_clusters = gridDim.x / CSIZE;
+    // CTAs exchanging operand slices with me: row peers (same rm) share A, column peers (same rn) share B
+    uint16_t mask_a = 0, mask_b = 0;
+#pragma unroll
+    for (int j = 0; j < CN; ++j) mask_a |= static_cast<uint16_t>(1u << (rm + CM * j));
+#pragma unroll
+    for (int i = 0; i < CM; ++i) mask_b |= static_cast<uint16_t>(1u << (i + CM * rn));
+    const uint16_t mask_peers = mask_a | mask_b;
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -173,7 +224,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CM + CN - 1);
         }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -187,7 +238,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tmem_relinquish();
     }
     tc_fence_before_sync();
-    __syncthreads();
+    if (CSIZE > 1) cluster_sync(); else __syncthreads();        // peers' barriers are initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // prologue above overlaps the previous kernel's tail; operands / residuals are read below
@@ -196,17 +247,19 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;                                     // global k-block counter across tiles
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM;
-                const int n0 = (tile % tiles_n) * BN;
+            for (int st = cluster_id; st < num_stiles; st += num_clusters) {
+                const int m0 = ((st / stiles_n) * CM + rm) * BM;
+                const int n0 = ((st % stiles_n) * CN + rn) * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
                     const uint32_t a_s = base + s * C::kStageBytes;
-                    tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
-                    tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
+                    if (CN == 1) tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
+                    else tma_load_2d_mc(a_s + rn * (kABytes / CN), &tmA, full_bar(s), kb * BK, m0 + rn * (BM / CN), mask_a);
+                    if (CM == 1) tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
+                    else tma_load_2d_mc(a_s + kABytes + rm * (C::kBBytes / CM), &tmB, full_bar(s), kb * BK, n0 + rm * (BN / CM), mask_b);
                 }
             }
         }
@@ -217,7 +270,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             constexpr uint32_t idesc = make_idesc(BM, BN);
             uint32_t it = 0;
             uint32_t local = 0;                                  // tiles processed by this CTA
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            for (int st = cluster_id; st < num_stiles; st += num_clusters, ++local) {
                 const uint32_t acc = local & 1u;
                 const uint32_t acc_ph = (local >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);     // epilogue has drained this accumulator stage
@@ -236,7 +289,9 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
                         umma_f16(d_tmem, adesc0 + 2u * k, bdesc0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(s));                   // frees this smem stage once the MMAs above have read it
+                    // frees this smem stage (here and in every peer that multicasts into it) once the MMAs have read it
+                    if (CSIZE == 1) umma_commit(empty_bar(s));
+                    else umma_commit_mc(empty_bar(s), mask_peers);
                 }
                 umma_commit(tmem_full_bar(acc));                 // accumulator complete
             }
@@ -249,21 +304,23 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int grp = ew >> 2;                                 // warpgroup: chunks grp, grp+2, ...
         float* stage = reinterpret_cast<float*>(smem + kEpiOff + ew * kStageTileBytes);
         uint32_t local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        for (int st = cluster_id; st < num_stiles; st += num_clusters, ++local) {
             const uint32_t acc = local & 1u;
             const uint32_t acc_ph = (local >> 1) & 1u;
-            const int m0 = (tile / tiles_n) * BM;
-            const int n0 = (tile % tiles_n) * BN;
+            const int m0 = ((st / stiles_n) * CM + rm) * BM;
+            const int n0 = ((st % stiles_n) * CN + rn) * BN;
             mbar_wait(tmem_full_bar(acc), acc_ph);
             tc_fence_after_sync();
+            if (m0 < M) {
 #pragma unroll 1
-            for (int c = grp; c < BN / 32; c += 2) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= N) break;                            // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + static_cast<uint32_t>(c * 32), r);
-                tmem_ld_wait();
-                epilogue_chunk<kOutHalf>(r, stage, lane, m0 + q * 32, col0, M, N, epi, vec_ok != 0);
+                for (int c = grp; c < BN / 32; c += 2) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= N) break;                        // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + static_cast<uint32_t>(c * 32), r);
+                    tmem_ld_wait();
+                    epilogue_chunk<kOutHalf, kAdds>(r, stage, lane, m0 + q * 32, col0, M, N, epi, vec_ok != 0);
+                }
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -271,7 +328,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     }
     tc_fence_before_sync();
-    __syncthreads();
+    if (CSIZE > 1) cluster_sync(); else __syncthreads();        // no CTA exits while a peer may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
@@ -319,75 +376,142 @@ int num_sms() {
     return n;
 }
 
-// Tile width from a cycle model of the persistent kernel fitted to scripts/gemm_sweep.py on B200: a tile's k-block
-// costs max(MMA floor = 2*BN cycles for four K=16 steps, operand bytes / L2->SM bandwidth).  The L2 fabric delivers
-// ~6300 B/cycle chip-wide (B300_MICROARCH.md, TMA chip throughput), at most ~80 B/cycle to one SM, and is what
-// bounds the 1-CTA 128xBN tile (85 FLOP/B at BN=256); plus the un-overlapped epilogue of the last tile.
-int pick_bn(int M, int N, int K) {
-    const int mt = ceil_div(M, BM), kb = ceil_div(K, BK), sms = num_sms();
-    int best = 128;
-    double best_cost = 1e30;
-    for (int bn : {256, 128, 64}) {
-        const int tiles = mt * ceil_div(N, bn);
-        const int waves = ceil_div(tiles, sms);
-        const double bw = std::min(80.0, 6300.0 / std::min(tiles, sms));
-        const double t_kb = std::max(2.0 * bn, (16384.0 + 128.0 * bn) / bw);
-        const double cost = waves * kb * t_kb + 150.0 * (bn / 32);
-        if (cost < best_cost) { best_cost = cost; best = bn; }
-    }
-    return best;
-}
+template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
+struct Launcher {
+    static int max_clusters;   // co-resident clusters of this shape (GPC boundaries make it < sms / cluster size)
 
-template <int BN, bool kOutHalf>
-void launch_impl(const GemmOp& op, cudaStream_t stream) {
-    using C = Cfg<BN>;
-    auto kern = pf_gemm_f16_tn_tcgen05<BN, kOutHalf>;
-    static bool attr_set = false;   // per instantiation; attribute is per-device but identical everywhere we run
-    static std::mutex mu;
-    {
-        std::lock_guard<std::mutex> g(mu);
-        if (!attr_set) {
-            int ndev = 0;
+    static void run(const GemmOp& op, cudaStream_t stream) {
+        using C = Cfg<BN>;
+        constexpr int CSIZE = CM * CN;
+        auto kern = pf_gemm_f16_tn_tcgen05<BN, CM, CN, kOutHalf, kAdds>;
+        static std::once_flag once;
+        std::call_once(once, [&] {
+            int ndev = 0, cur = 0;
             PF_CUDA(cudaGetDeviceCount(&ndev));
-            int cur = 0;
             PF_CUDA(cudaGetDevice(&cur));
             for (int d = 0; d < ndev; ++d) {
                 PF_CUDA(cudaSetDevice(d));
                 PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
             }
             PF_CUDA(cudaSetDevice(cur));
-            attr_set = true;
+            max_clusters = num_sms() / CSIZE;
+            if (CSIZE > 1) {
+                cudaLaunchConfig_t q{};
+                q.gridDim = dim3(num_sms() / CSIZE * CSIZE);
+                q.blockDim = dim3(kThreads);
+                q.dynamicSmemBytes = C::kSmemBytes;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = CSIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                q.attrs = at; q.numAttrs = 1;
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) == cudaSuccess && nc > 0) max_clusters = std::min(max_clusters, nc);
+                else cudaGetLastError();
+            }
+        });
+        const int stiles_n = ceil_div(ceil_div(op.N, BN), CN);
+        const int num_stiles = stiles_n * ceil_div(ceil_div(op.M, BM), CM);
+        const int grid = std::min(num_stiles, max_clusters) * CSIZE;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = C::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (pdl_enabled()) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (CSIZE > 1) {
+            at[na].id = cudaLaunchAttributeClusterDimension;
+            at[na].val.clusterDim.x = CSIZE; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = at;
+        cfg.numAttrs = na;
+        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.epi, op.M, op.N, op.K, stiles_n, num_stiles, op.vec_ok));
+    }
+};
+template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
+int Launcher<BN, CM, CN, kOutHalf, kAdds>::max_clusters = 1;
+
+template <int BN, bool kOutHalf, int kAdds>
+void launch_cl(const GemmOp& op, cudaStream_t stream) {
+    if (op.cm == 2 && op.cn == 1) Launcher<BN, 2, 1, kOutHalf, kAdds>::run(op, stream);
+    else if (op.cm == 1 && op.cn == 1) Launcher<BN, 1, 1, kOutHalf, kAdds>::run(op, stream);
+    else throw CudaError{"gemm: cluster shape not instantiated"};
+}
+
+template <int BN>
+void launch_bn(const GemmOp& op, cudaStream_t stream) {
+    const bool h = op.epi.out_f16 != nullptr;
+    switch (op.n_adds) {
+        case 0:  h ? launch_cl<BN, true, 0>(op, stream) : launch_cl<BN, false, 0>(op, stream); break;
+        case 1:  h ? launch_cl<BN, true, 1>(op, stream) : launch_cl<BN, false, 1>(op, stream); break;
+        default: h ? launch_cl<BN, true, 2>(op, stream) : launch_cl<BN, false, 2>(op, stream); break;
+    }
+}
+
+// Tile width and cluster shape from a cycle model of the persistent kernel fitted to scripts/gemm_sweep.py on B200:
+// a tile's k-block costs max(MMA floor = 2*BN cycles for four K=16 steps, operand bytes / L2->SM bandwidth).  The L2
+// fabric delivers ~6300 B/cycle chip-wide (B300_MICROARCH.md, TMA chip throughput), at most ~80 B/cycle to one SM,
+// and is what bounds the 1-CTA 128xBN tile (85 FLOP/B at BN=256); multicast clusters cut the bytes per CTA.
+void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
+    const int mt = ceil_div(M, BM), kb = ceil_div(K, BK), sms = num_sms();
+    double best_cost = 1e30;
+    for (int bn : {256, 128, 64}) {
+        for (int cfg = 0; cfg < 1; ++cfg) {     // 2x1 multicast clusters measured slower on every shape of the path
+            const int cm = cfg >= 1 ? 2 : 1, cn = 1;
+            const int csize = cm * cn;
+            const int stiles = ceil_div(mt, cm) * ceil_div(ceil_div(N, bn), cn);
+            const int slots = csize == 4 ? sms / 4 - 1 : sms / csize;      // GPC boundaries cost a 4-cluster slot
+            const int waves = ceil_div(stiles, slots);
+            const int active = std::min(stiles, slots) * csize;
+            const double bw = std::min(80.0, 6300.0 / active);
+            const double t_kb = std::max(2.0 * bn, (16384.0 / cn + 128.0 * bn / cm) / bw) + (csize > 1 ? 20.0 : 0.0);
+            const double cost = waves * kb * t_kb + 150.0 * (bn / 32);
+            if (cost < best_cost) { best_cost = cost; bn_out = bn; cm_out = cm; cn_out = cn; }
         }
     }
-    const int tiles_n = ceil_div(op.N, BN);
-    const int num_tiles = tiles_n * ceil_div(op.M, BM);
-    const int grid = std::min(num_tiles, num_sms());
-    launch_k(kern, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, op.tmA, op.tmB, op.epi, op.M, op.N, op.K, tiles_n, num_tiles, op.vec_ok);
 }
 
 }  // namespace
 
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
-                  const GemmEpi& epi, int bn) {
+                  const GemmEpi& epi, int tile_code) {
     if ((epi.out_f32 != nullptr) == (epi.out_f16 != nullptr)) throw CudaError{"gemm: exactly one output pointer must be set"};
     if (M <= 0 || N <= 0 || K <= 0) throw CudaError{"gemm: empty problem"};
-    if (bn == 0) bn = pick_bn(M, N, K);
+    int bn = tile_code & 0xFFF, cm = (tile_code >> 12) & 0xF, cn = (tile_code >> 16) & 0xF;
+    if (tile_code == 0) pick_config(M, N, K, bn, cm, cn);
+    cm = std::max(cm, 1);
+    cn = std::max(cn, 1);
     if (bn != 64 && bn != 128 && bn != 256) throw CudaError{"gemm: unsupported N tile"};
-    op.M = M; op.N = N; op.K = K; op.bn = bn; op.epi = epi;
+    if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and 2x1 are instantiated)"};
+    op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
+    // the kernel adds up to two fp32 tensors in a fixed order: FSMN memory first, then the residual
+    op.n_adds = 0;
+    op.epi.add0 = op.epi.add1 = nullptr;
+    if (epi.addend) { op.epi.add0 = epi.addend; op.epi.ld_add0 = epi.ld_addend; op.n_adds = 1; }
+    if (epi.resid) {
+        if (op.n_adds == 0) { op.epi.add0 = epi.resid; op.epi.ld_add0 = epi.ld_resid; }
+        else { op.epi.add1 = epi.resid; op.epi.ld_add1 = epi.ld_resid; }
+        ++op.n_adds;
+    }
     // vector epilogue: 16-byte row segments of every fp32 tensor (8-byte for the fp16 output) must be aligned
     auto al = [](const void* p, int ld, int bytes) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % bytes) == 0 && ld % 4 == 0); };
     op.vec_ok = (al(epi.bias, 0, 16) && al(epi.resid, epi.ld_resid, 16) && al(epi.addend, epi.ld_addend, 16) &&
                  al(epi.out_f32, epi.ld_out, 16) && al(epi.out_f16, epi.ld_out, 8)) ? 1 : 0;
-    make_tmap(&op.tmA, A, M, K, lda, BM);
-    make_tmap(&op.tmB, W, N, K, ldw, bn);
+    make_tmap(&op.tmA, A, M, K, lda, BM / cn);      // each CTA loads (and multicasts) 1/cn of its A tile
+    make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and 1/cm of its B tile
 }
 
 void gemm_launch(const GemmOp& op, cudaStream_t stream) {
-    const bool h = op.epi.out_f16 != nullptr;
     switch (op.bn) {
-        case 64:  h ? launch_impl<64, true>(op, stream)  : launch_impl<64, false>(op, stream);  break;
-        case 128: h ? launch_impl<128, true>(op, stream) : launch_impl<128, false>(op, stream); break;
-        default:  h ? launch_impl<256, true>(op, stream) : launch_impl<256, false>(op, stream); break;
+        case 64:  launch_bn<64>(op, stream);  break;
+        case 128: launch_bn<128>(op, stream); break;
+        default:  launch_bn<256>(op, stream); break;
     }
 }
 

@@ -16,6 +16,10 @@ struct GemmEpi {
     int ld_resid = 0;
     int ld_addend = 0;
     int relu = 0;
+    // filled by gemm_prepare: the (up to two) fp32 addends in the order the kernel applies them
+    const float* add0 = nullptr;
+    const float* add1 = nullptr;
+    int ld_add0 = 0, ld_add1 = 0;
 };
 
 struct GemmOp {
@@ -24,13 +28,15 @@ struct GemmOp {
     GemmEpi epi;
     int M = 0, N = 0, K = 0;
     int bn = 128;    // N tile: 64, 128 or 256
+    int cm = 1, cn = 1;   // thread-block cluster shape (CTAs along M x along N) sharing operand tiles by TMA multicast
+    int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
     int vec_ok = 0;  // all epilogue tensors 16-byte aligned with pitches % 4 == 0
 };
 
 // Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).
-// bn = 0 picks a tile width from the shape.
+// tile_code = 0 picks tile width and cluster shape from the problem shape; otherwise bn | (cm << 12) | (cn << 16).
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
-                  const GemmEpi& epi, int bn = 0);
+                  const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
 double gemm_flops(const GemmOp& op);
 

@@ -31,11 +31,16 @@ def main():
         bias = rng.standard_normal(N).astype(np.float32)
         resid = rng.standard_normal((M, N)).astype(np.float32) if "res" in epi else None
         addend = rng.standard_normal((M, N)).astype(np.float32) if "add" in epi else None
-        for tile in (64, 128, 256, 0):
-            _, ms = dbg_gemm(lib, A, W, bias, resid, addend, relu=int("relu" in epi), out_half=int(epi.startswith("f16")), tile_n=tile, iters=50)
+        ref = None
+        for tile, cm, cn in [(t, cm, cn) for t in (64, 128, 256) for cm, cn in ((1, 1), (2, 1))] + [(0, 0, 0)]:
+            code = tile | (cm << 12) | (cn << 16)
+            out, ms = dbg_gemm(lib, A, W, bias, resid, addend, relu=int("relu" in epi), out_half=int(epi.startswith("f16")), tile_n=code, iters=50)
+            if ref is None:
+                ref = out
+            err = float(np.abs(out - ref).max())      # every configuration must give the same result as 64 / 1x1
             tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
-            rows.append({"M": M, "N": N, "K": K, "epi": epi, "tile_n": tile, "us": ms * 1e3, "tflops": tf})
-            print(f"{M:6d} {N:6d} {K:5d} {epi:12s} tile {tile:3d}: {ms * 1e3:8.2f} us  {tf:7.1f} TFLOP/s", flush=True)
+            rows.append({"M": M, "N": N, "K": K, "epi": epi, "tile_n": tile, "cluster": f"{cm}x{cn}", "us": ms * 1e3, "tflops": tf, "max_diff_vs_first": err})
+            print(f"{M:6d} {N:6d} {K:5d} {epi:12s} tile {tile:3d} cluster {cm}x{cn}: {ms * 1e3:8.2f} us  {tf:7.1f} TFLOP/s  diff {err:.2e}", flush=True)
     if len(sys.argv) > 1:
         json.dump(rows, open(sys.argv[1], "w"), indent=1)
 

@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
     (128, 128, 64, 128), (128, 64, 128, 64), (256, 256, 512, 256), (5312, 1536, 560, 0), (5312, 512, 512, 0),
     (5312, 2048, 512, 0), (5312, 512, 2048, 0), (1344, 8404, 512, 0), (83, 512, 512, 0), (100, 520, 72, 64),
     (300, 8404, 512, 128), (640, 1024, 512, 256),
+    # thread-block clusters with TMA-multicast operand sharing: tile | (cm << 12) | (cn << 16)
+    (5312, 1536, 512, 256 | (2 << 12)), (640, 1024, 512, 256 | (2 << 12)), (300, 8404, 512, 128 | (2 << 12)),
+    (83, 512, 512, 64 | (2 << 12)), (5312, 512, 2048, 128 | (2 << 12)), (1600, 8404, 512, 256 | (2 << 12)),
+    (1000, 520, 72, 64 | (2 << 12)), (200, 25055, 512, 256),
 ])
 def test_gemm_plain(lib, M, N, K, tile):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
@@ -28,16 +32,22 @@ def test_gemm_plain(lib, M, N, K, tile):
 
 
 @pytest.mark.parametrize("out_half,relu", [(0, 0), (0, 1), (1, 0), (1, 1)])
-def test_gemm_epilogue(lib, out_half, relu):
+@pytest.mark.parametrize("adds", [0, 1, 2])
+@pytest.mark.parametrize("N", [520, 517])          # 517: unaligned pitch -> scalar epilogue path
+def test_gemm_epilogue(lib, out_half, relu, adds, N):
     rng = np.random.default_rng(5)
-    M, N, K = 333, 520, 512
+    M, K = 333, 512
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    resid = rng.standard_normal((M, N)).astype(np.float32)
-    addend = rng.standard_normal((M, N)).astype(np.float32)
+    resid = rng.standard_normal((M, N)).astype(np.float32) if adds >= 1 else None
+    addend = rng.standard_normal((M, N)).astype(np.float32) if adds >= 2 else None
     out, _ = dbg_gemm(lib, A, W, bias, resid, addend, relu=relu, out_half=out_half)
-    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias + resid + addend
+    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias
+    if resid is not None:
+        ref = ref + resid
+    if addend is not None:
+        ref = ref + addend
     if relu:
         ref = np.maximum(ref, 0)
     tol = 2e-2 if out_half else 2e-3
