@@ -85,6 +85,7 @@ SIGNATURES = {
     "pf_dbg_layernorm": (C.c_int32, [C.c_int32, C.c_int32, _F, _F, _F, C.c_float, _F]),
     "pf_dbg_embed_pe_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, C.c_float, _F, _F, C.c_float, _F]),
     "pf_dbg_attention": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F]),
+    "pf_dbg_attention_fsmn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F]),
     "pf_dbg_fsmn": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _I, C.c_int32, _F]),
     "pf_dbg_cif": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_float, C.c_int32, _F, _I, _I, _F]),
     "pf_dbg_logsoftmax_argmax": (C.c_int32, [C.c_int32, C.c_int32, _F, _I]),

@@ -345,7 +345,7 @@ pf_status pf_offline_set_profile(pf_offline* hh, int32_t on) {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
         std::lock_guard<std::mutex> g(h->mu);
-        for (auto& d : h->devs) d->set_profile(on != 0);
+        for (auto& d : h->devs) d->set_profile(on);
     });
 }
 

@@ -6,6 +6,8 @@
 // masks are all ones; only the chunk tail (kv >= Tk) is masked here.
 #include "attention.cuh"
 
+#include "ops.cuh"
+
 namespace pf {
 
 namespace {
@@ -189,6 +191,10 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
                       int ldk, int ldv, int ldo, int head_dim, cudaStream_t s) {
     if (head_dim != HD) throw CudaError{"attention: head dim must be 128"};
     if (Tq <= 0 || Tk <= 0 || B <= 0) return;
+    if (attention_tc_eligible(Tq, Tk, head_dim)) {
+        attention_tc_launch(Q, K, V, O, B, H, Tq, Tk, ldq, ldk, ldv, ldo, nullptr, 0, nullptr, 0, s);
+        return;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
@@ -204,6 +210,18 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
     dim3 grid(ceil_div(Tq, BQ), H, B);
     launch_k(pf_sanm_attention, grid, dim3(kThreads), kSmemBytes, s, Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e);
+}
+
+int attention_fsmn_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int T, int ldqkv, int ldo,
+                          const float* fsmn_w, int taps, float* mem, int ld_mem, cudaStream_t s) {
+    if (T <= 0 || B <= 0) return 0;
+    if (attention_tc_eligible(T, T, HD)) {
+        attention_tc_launch(Q, K, V, O, B, H, T, T, ldqkv, ldqkv, ldqkv, ldo, fsmn_w, taps, mem, ld_mem, s);
+        return 1;
+    }
+    fsmn_f16_launch(V, ldqkv, fsmn_w, taps, mem, ld_mem, nullptr, 0, nullptr, B, T, H * HD, s);
+    attention_launch(Q, K, V, O, B, H, T, T, ldqkv, ldqkv, ldqkv, ldo, HD, s);
+    return 2;
 }
 
 }  // namespace pf

@@ -164,6 +164,24 @@ pf_status pf_dbg_attention(int32_t B, int32_t H, int32_t Tq, int32_t Tk, const f
     });
 }
 
+pf_status pf_dbg_attention_fsmn(int32_t B, int32_t H, int32_t T, int32_t taps, const float* qkv, const float* w, float* ctx, float* mem) {
+    return guarded([&] {
+        Scratch s;
+        const int D = H * 128;
+        const size_t n = static_cast<size_t>(B) * T * D;
+        __half* dqkv = s.up_half(qkv, 3 * n);                    // [B*T, 3*D] = q | k | v
+        float* dw = s.up(w, static_cast<size_t>(D) * taps);
+        __half* o16 = s.alloc<__half>(n);
+        float* o32 = s.alloc<float>(n);
+        float* m32 = s.alloc<float>(n);
+        attention_fsmn_launch(dqkv, dqkv + D, dqkv + 2 * D, o16, B, H, T, 3 * D, D, dw, taps, m32, D, 0);
+        pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, n);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(ctx, o32, n * sizeof(float), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(mem, m32, n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
 pf_status pf_dbg_fsmn(int32_t B, int32_t T, int32_t D, int32_t K, const float* x, const float* w, const float* resid,
                       const int32_t* lens, int32_t half_input, float* out) {
     return guarded([&] {

@@ -428,7 +428,7 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
 
 void DeviceCtx::gemm(const GemmOp& op) {
     if (profile_) {
-        ProfRec r{op.M, op.N, op.K, op.bn + 1000 * (op.cm * 10 + op.cn), nullptr, nullptr};
+        ProfRec r{op.M, op.N, op.K, op.bn + 1000 * (op.cm * 10 + op.cn), nullptr, nullptr, nullptr};
         for (cudaEvent_t* e : {&r.a, &r.b}) {
             if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
             else PF_CUDA(cudaEventCreate(e));
@@ -444,19 +444,40 @@ void DeviceCtx::gemm(const GemmOp& op) {
     gemm_flops += pf::gemm_flops(op);
 }
 
+template <typename F>
+void DeviceCtx::timed(const char* label, F&& f) {
+    if (profile_ < 2) { f(); return; }
+    ProfRec r{0, 0, 0, 0, nullptr, nullptr, label};
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
+        else PF_CUDA(cudaEventCreate(e));
+    }
+    PF_CUDA(cudaEventRecord(r.a, stream_));
+    f();
+    PF_CUDA(cudaEventRecord(r.b, stream_));
+    prof_.push_back(r);
+}
+
 void DeviceCtx::finish_profile() {
     gemm_ms = 0.0;
     profile_json.clear();
     if (prof_.empty()) return;
     struct Agg { int count = 0; double ms = 0.0; };
     std::map<std::vector<int>, Agg> agg;
+    std::map<std::string, Agg> other;
     for (ProfRec& r : prof_) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, r.a, r.b);
-        gemm_ms += ms;
-        Agg& a = agg[{r.M, r.N, r.K, r.bn}];
-        a.count++;
-        a.ms += ms;
+        if (r.label) {
+            Agg& a = other[r.label];
+            a.count++;
+            a.ms += ms;
+        } else {
+            gemm_ms += ms;
+            Agg& a = agg[{r.M, r.N, r.K, r.bn}];
+            a.count++;
+            a.ms += ms;
+        }
         prof_pool_.push_back(r.a);
         prof_pool_.push_back(r.b);
     }
@@ -465,9 +486,13 @@ void DeviceCtx::finish_profile() {
     for (auto& kv : agg) {
         if (js.size() > 1) js += ",";
         const double fl = 2.0 * kv.first[0] * static_cast<double>(kv.first[1]) * kv.first[2] * kv.second.count;
-        js += "{\"M\":" + std::to_string(kv.first[0]) + ",\"N\":" + std::to_string(kv.first[1]) + ",\"K\":" + std::to_string(kv.first[2]) +
+        js += "{\"name\":\"gemm\",\"M\":" + std::to_string(kv.first[0]) + ",\"N\":" + std::to_string(kv.first[1]) + ",\"K\":" + std::to_string(kv.first[2]) +
               ",\"tile_n\":" + std::to_string(kv.first[3] % 1000) + ",\"cluster\":\"" + std::to_string(kv.first[3] / 10000) + "x" + std::to_string(kv.first[3] / 1000 % 10) + "\"" + ",\"launches\":" + std::to_string(kv.second.count) + ",\"ms\":" +
               std::to_string(kv.second.ms) + ",\"tflops\":" + std::to_string(kv.second.ms > 0 ? fl / (kv.second.ms * 1e9) : 0.0) + "}";
+    }
+    for (auto& kv : other) {
+        if (js.size() > 1) js += ",";
+        js += "{\"name\":\"" + kv.first + "\",\"launches\":" + std::to_string(kv.second.count) + ",\"ms\":" + std::to_string(kv.second.ms) + "}";
     }
     js += "]";
     profile_json = js;
@@ -577,17 +602,23 @@ int DeviceCtx::extract(const float* samples, int nsamp, float* out, int capacity
 void DeviceCtx::encoder_forward(int B, int T) {
     const int M = B * T, d = cfg_.d_model, H = cfg_.heads;
     EncoderPlan& plan = encoder_plan(B, T);
-    embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), inv_ts_, enc_[0].ln1.g, enc_[0].ln1.b,
-                       cfg_.ln_eps, a16_, stream_);
+    timed("embed_pe_ln", [&] {
+        embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), inv_ts_, enc_[0].ln1.g, enc_[0].ln1.b,
+                           cfg_.ln_eps, a16_, stream_);
+    });
     ++launches;
     auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool first) {
-        if (!first) { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); ++launches; }
+        if (!first) {
+            timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
+            ++launches;
+        }
         gemm(lp.qkv);
-        fsmn_f16_launch(qkv16_ + 2 * d, 3 * d, w.fsmn, cfg_.enc_kernel, mem32_, d, nullptr, 0, nullptr, B, T, d, stream_);
-        attention_launch(qkv16_, qkv16_ + d, qkv16_ + 2 * d, ctx16_, B, H, T, T, 3 * d, 3 * d, 3 * d, d, d / H, stream_);
-        launches += 2;
+        timed("enc_attention_fsmn", [&] {
+            launches += attention_fsmn_launch(qkv16_, qkv16_ + d, qkv16_ + 2 * d, ctx16_, B, H, T, 3 * d, d, w.fsmn, cfg_.enc_kernel,
+                                              mem32_, d, stream_);
+        });
         gemm(lp.out);
-        layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_);
+        timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
         ++launches;
         gemm(lp.ffn1);
         gemm(lp.ffn2);
@@ -626,9 +657,9 @@ void DeviceCtx::decoder_forward(int B, int T, int L) {
     cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
     ++launches;
     auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
-        layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_);
+        timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(g1);
-        layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_);
+        timed("dec_layernorm_ffn", [&] { layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_); });
         gemm(g2);
         launches += 2;
     };
@@ -637,11 +668,13 @@ void DeviceCtx::decoder_forward(int B, int T, int L) {
         const DecLayerW& w = dec_[i];
         const DecLayerPlan& lp = plan.layers[i];
         ffn(w.ffn, lp.w1, lp.w2);
-        layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_);
-        fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
-        layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_);
+        timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
+        timed("dec_fsmn", [&] { fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_); });
+        timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(lp.q);
-        attention_launch(q16_, kv16_ + i * 2 * d, kv16_ + i * 2 * d + d, ctxd16_, B, H, L, T, d, ldkv, ldkv, d, d / H, stream_);
+        timed("dec_cross_attention", [&] {
+            attention_launch(q16_, kv16_ + i * 2 * d, kv16_ + i * 2 * d + d, ctxd16_, B, H, L, T, d, ldkv, ldkv, d, d / H, stream_);
+        });
         gemm(lp.out);
         launches += 4;
     }

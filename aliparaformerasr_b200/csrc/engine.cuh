@@ -130,7 +130,7 @@ public:
     double gemm_flops = 0.0;
 
     // per-launch CUDA-event profiling of the GEMM kernel (bench.py roofline leg); adds two events per launch
-    void set_profile(bool on) { profile_ = on; }
+    void set_profile(int level) { profile_ = level; }   // 0 off, 1 GEMM launches, 2 every kernel (labelled)
     double gemm_ms = 0.0;              // sum of GEMM launch durations of the last profiled run
     std::string profile_json;          // per-shape breakdown of the last profiled run
 
@@ -160,8 +160,9 @@ private:
     void run_impl(uint32_t flags, SharedRun* shared, int idx);
     bool arrived_ = false, ev0_armed_ = false;
     void finish_profile();
-    struct ProfRec { int M, N, K, bn; cudaEvent_t a, b; };
-    bool profile_ = false;
+    struct ProfRec { int M, N, K, bn; cudaEvent_t a, b; const char* label; };
+    int profile_ = 0;
+    template <typename F> void timed(const char* label, F&& f);   // level-2 profiling of a non-GEMM launch
     std::vector<ProfRec> prof_;
     std::vector<cudaEvent_t> prof_pool_;
 

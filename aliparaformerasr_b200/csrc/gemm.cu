@@ -479,6 +479,8 @@ void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
 
 }  // namespace
 
+void* tensormap_encode_fn() { return reinterpret_cast<void*>(get_encode_fn()); }
+
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code) {
     if ((epi.out_f32 != nullptr) == (epi.out_f16 != nullptr)) throw CudaError{"gemm: exactly one output pointer must be set"};

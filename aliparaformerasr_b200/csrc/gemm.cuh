@@ -39,5 +39,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
 double gemm_flops(const GemmOp& op);
+// cuTensorMapEncodeTiled entry point (resolved through the runtime, no libcuda link dependency); throws if missing
+void* tensormap_encode_fn();
 
 }  // namespace pf

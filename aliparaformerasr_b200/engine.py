@@ -167,7 +167,7 @@ class Engine:
         keys = ["h2d_frontend", "encoder", "predictor_cif", "decoder", "head_pick", "total"]
         return {k: float(ms[i]) for i, k in enumerate(keys)}
 
-    def set_profile(self, on: bool) -> None:
+    def set_profile(self, on: int) -> None:
         _lib.check(self._lib.pf_offline_set_profile(self._handle(), int(on)))
 
     def gemm_ms(self) -> float:

@@ -248,9 +248,15 @@ def main():
     eng.run_staged()
     gemm_ms = eng.gemm_ms()
     gemm_flops = eng.gemm_flops()
-    prof = eng.profile()
-    eng.set_profile(False)
+    prof = [p for p in eng.profile() if p.get("name", "gemm") == "gemm"]
     n_gemm = sum(p["launches"] for p in prof) or 1
+    # in-situ (warm, stream-ordered, no PDL overlap) time of every kernel family of the layers
+    eng.set_profile(2)
+    eng.run_staged()
+    kernel_ms = {}
+    for p in eng.profile():
+        kernel_ms[p.get("name", "gemm")] = kernel_ms.get(p.get("name", "gemm"), 0.0) + p["ms"]
+    eng.set_profile(0)
 
     # -------- reduce over ranks (max time)
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -278,6 +284,7 @@ def main():
             "launches_per_step": int(launches_per_step),
             "rtf": (total_ms / 1e3) / (audio_per_step * args.steps),
             "stage_ms": stage_ms,
+            "kernel_ms_profiled_step": kernel_ms,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": None, "kernel": "pf_gemm_f16_tn_tcgen05", "peak_source": peak_src,
                          "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,

@@ -139,7 +139,8 @@ int32_t pf_offline_get_timings(pf_offline* h, float* ms, int32_t capacity);
 /* kernels launched by the last run (all devices), algorithmic GEMM flops of the last run */
 int64_t pf_offline_get_launch_count(pf_offline* h);
 double pf_offline_get_gemm_flops(pf_offline* h);
-/* per-launch CUDA-event profiling of the GEMM kernel (two extra events per launch; off by default).  After a profiled
+/* per-launch CUDA-event profiling (two extra events per launch; off by default): on = 1 times the GEMM launches,
+ * on = 2 also the other kernels of the encoder / decoder layers (rows carry "name").  After a profiled
  * run: pf_offline_get_gemm_ms = summed GEMM launch durations on device 0 of the handle, pf_offline_get_profile_json =
  * per-shape breakdown [{"M","N","K","tile_n","launches","ms","tflops"}, ...] (returns bytes written). */
 pf_status pf_offline_set_profile(pf_offline* h, int32_t on);
@@ -162,6 +163,9 @@ pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats
                              const float* beta, float eps, float* out);
 pf_status pf_dbg_attention(int32_t B, int32_t H, int32_t Tq, int32_t Tk, const float* q, const float* k, const float* v,
                            float* out);
+/* encoder self-attention + FSMN memory of one layer from a packed qkv [B*T, 3*H*128] (fused tcgen05 kernel when T <= 192) */
+pf_status pf_dbg_attention_fsmn(int32_t B, int32_t H, int32_t T, int32_t taps, const float* qkv, const float* w, float* ctx,
+                                float* mem);
 pf_status pf_dbg_fsmn(int32_t B, int32_t T, int32_t D, int32_t K, const float* x, const float* w, const float* resid,
                       const int32_t* lens, int32_t half_input, float* out);
 pf_status pf_dbg_cif(int32_t B, int32_t T, int32_t D, const float* hidden, const float* alphas_with_tail,

@@ -79,7 +79,7 @@ def test_embed_pe_ln(lib):
     assert np.abs(out - ref).max() < 5e-3      # output is fp16
 
 
-@pytest.mark.parametrize("B,Tq,Tk", [(2, 166, 166), (3, 40, 166), (1, 5, 7), (2, 64, 64), (1, 130, 300)])
+@pytest.mark.parametrize("B,Tq,Tk", [(2, 166, 166), (3, 40, 166), (1, 5, 7), (2, 64, 64), (1, 130, 300), (2, 256, 192), (1, 1, 1), (33, 50, 166)])
 def test_attention(lib, B, Tq, Tk):
     rng = np.random.default_rng(Tq * 31 + Tk)
     H, D = 4, 512
@@ -90,6 +90,47 @@ def test_attention(lib, B, Tq, Tk):
     _lib.check(lib.pf_dbg_attention(B, H, Tq, Tk, _lib.fptr(q), _lib.fptr(k), _lib.fptr(v), _lib.fptr(out)))
     ref = sanm._mha(torch.from_numpy(half_round(q)), torch.from_numpy(half_round(k)), torch.from_numpy(half_round(v)), H).numpy()
     assert np.abs(out - ref).max() < 5e-3
+
+
+@pytest.mark.parametrize("B,Tq,Tk", [(2, 166, 166), (3, 40, 166), (2, 200, 192), (1, 1, 1), (2, 129, 16)])
+def test_attention_streaming_kernel_matches(lib, B, Tq, Tk):
+    """The mma.sync streaming kernel (long sequences) stays covered: force it with PFASR_NO_ATT_TC in a subprocess."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent(f"""
+        import sys, numpy as np, torch
+        sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))}); sys.path.insert(0, {repr(os.path.dirname(os.path.abspath(__file__)))})
+        from aliparaformerasr_b200 import _lib
+        from oracle import sanm
+        from _util import half_round
+        lib = _lib.load(); rng = np.random.default_rng(7)
+        B, Tq, Tk, H, D = {B}, {Tq}, {Tk}, 4, 512
+        q = rng.standard_normal((B, Tq, D)).astype(np.float32); k = rng.standard_normal((B, Tk, D)).astype(np.float32); v = rng.standard_normal((B, Tk, D)).astype(np.float32)
+        out = np.zeros_like(q)
+        _lib.check(lib.pf_dbg_attention(B, H, Tq, Tk, _lib.fptr(q), _lib.fptr(k), _lib.fptr(v), _lib.fptr(out)))
+        ref = sanm._mha(torch.from_numpy(half_round(q)), torch.from_numpy(half_round(k)), torch.from_numpy(half_round(v)), H).numpy()
+        assert np.abs(out - ref).max() < 5e-3, np.abs(out - ref).max()
+    """)
+    env = dict(os.environ, PFASR_NO_ATT_TC="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,T,K", [(2, 166, 11), (3, 83, 11), (1, 137, 11), (2, 192, 21), (2, 16, 11), (1, 5, 11), (2, 200, 11)])
+def test_attention_fsmn_fused(lib, B, T, K):
+    """Encoder self-attention + FSMN memory in one launch (tcgen05 path for T <= 192; T = 200 takes the two-kernel path)."""
+    rng = np.random.default_rng(T * 13 + K)
+    H, D = 4, 512
+    qkv = rng.standard_normal((B, T, 3 * D)).astype(np.float32)
+    w = (0.1 * rng.standard_normal((D, 1, K))).astype(np.float32)
+    ctx = np.zeros((B, T, D), np.float32)
+    mem = np.zeros((B, T, D), np.float32)
+    _lib.check(lib.pf_dbg_attention_fsmn(B, H, T, K, _lib.fptr(qkv), _lib.fptr(f(w.reshape(D, K))), _lib.fptr(ctx), _lib.fptr(mem)))
+    hq = torch.from_numpy(half_round(qkv))
+    q, k, v = hq[..., :D], hq[..., D:2 * D], hq[..., 2 * D:]
+    ref_ctx = sanm._mha(q.contiguous(), k.contiguous(), v.contiguous(), H).numpy()
+    ref_mem = sanm._fsmn(v.contiguous(), torch.from_numpy(w), None).numpy()
+    assert np.abs(ctx - ref_ctx).max() < 5e-3
+    assert np.abs(mem - ref_mem).max() < 1e-5
 
 
 @pytest.mark.parametrize("K,half_in,masked", [(11, 1, False), (11, 0, True), (21, 0, True)])
