@@ -192,7 +192,7 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
     if (head_dim != HD) throw CudaError{"attention: head dim must be 128"};
     if (Tq <= 0 || Tk <= 0 || B <= 0) return;
     if (attention_tc_eligible(Tq, Tk, head_dim)) {
-        attention_tc_launch(Q, K, V, O, B, H, Tq, Tk, ldq, ldk, ldv, ldo, nullptr, 0, nullptr, 0, s);
+        attention_tc_launch(Q, K, V, O, B, H, Tq, Tk, ldq, ldk, ldv, ldo, nullptr, 0, nullptr, 0, false, s);
         return;
     }
     static bool attr_set = false;
@@ -213,13 +213,13 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
 }
 
 int attention_fsmn_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int T, int ldqkv, int ldo,
-                          const float* fsmn_w, int taps, float* mem, int ld_mem, cudaStream_t s) {
+                          const float* fsmn_w, int taps, float* mem, int ld_mem, bool mem_accum, cudaStream_t s) {
     if (T <= 0 || B <= 0) return 0;
     if (attention_tc_eligible(T, T, HD)) {
-        attention_tc_launch(Q, K, V, O, B, H, T, T, ldqkv, ldqkv, ldqkv, ldo, fsmn_w, taps, mem, ld_mem, s);
+        attention_tc_launch(Q, K, V, O, B, H, T, T, ldqkv, ldqkv, ldqkv, ldo, fsmn_w, taps, mem, ld_mem, mem_accum, s);
         return 1;
     }
-    fsmn_f16_launch(V, ldqkv, fsmn_w, taps, mem, ld_mem, nullptr, 0, nullptr, B, T, H * HD, s);
+    fsmn_f16_launch(V, ldqkv, fsmn_w, taps, mem, ld_mem, mem_accum ? mem : nullptr, ld_mem, nullptr, B, T, H * HD, s);
     attention_launch(Q, K, V, O, B, H, T, T, ldqkv, ldqkv, ldqkv, ldo, HD, s);
     return 2;
 }

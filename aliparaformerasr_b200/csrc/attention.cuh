@@ -10,14 +10,15 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
 
 // SAN-M self-attention of one encoder layer: context O plus the FSMN memory of V (mem = dwconv_taps(v) + v, fp32).
 // One fused tcgen05 kernel when the sequence fits (see below), else the FSMN kernel + the streaming attention kernel.
-// Returns the number of kernels launched.
+// mem_accum: add the memory into `mem` (the fp32 residual stream, so the out-projection has one addend) instead of
+// overwriting it.  Returns the number of kernels launched.
 int attention_fsmn_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int T, int ldqkv, int ldo,
-                          const float* fsmn_w, int taps, float* mem, int ld_mem, cudaStream_t s);
+                          const float* fsmn_w, int taps, float* mem, int ld_mem, bool mem_accum, cudaStream_t s);
 
 // One-pass tcgen05 path (attention_tc.cu) for Tk <= 192, Tq <= 256, head_dim 128; optionally also writes the SAN-M
 // FSMN memory  mem[b,t,:] = dwconv_taps(v)[b,t,:] + v[b,t,:]  (fp32, row pitch ld_mem) of the same V (self-attention).
 bool attention_tc_eligible(int Tq, int Tk, int head_dim);
 void attention_tc_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int Tq, int Tk, int ldq,
-                         int ldk, int ldv, int ldo, const float* fsmn_w, int taps, float* mem, int ld_mem, cudaStream_t s);
+                         int ldk, int ldv, int ldo, const float* fsmn_w, int taps, float* mem, int ld_mem, bool mem_accum, cudaStream_t s);
 
 }  // namespace pf

@@ -5,8 +5,9 @@
 // zero-fill), both 128-row query tiles run concurrently on two softmax warpgroups:
 //   control warp : TMA loads, S = Q K^T (tcgen05.mma, K-major operands), O = P V (V is the MN-major B operand)
 //   softmax group: tcgen05.ld row of S (thread = query row, so max / sum are thread-local), exp2, P -> smem as the
-//                  fp16 A operand (128B-swizzled), FSMN from the V tile already in smem while P V runs, then
-//                  O / sum -> smem -> TMA store.
+//                  fp16 A operand (128B-swizzled), then O / sum -> smem -> TMA store.
+//   FSMN warps   : depthwise memory of this head from the V tile in shared memory, concurrently with the softmax
+//                  (thread = channel x half of the time axis, 16 outputs per register block).
 // Reference semantics: FunASR MultiHeadedAttentionSANM inside the graph run by OfflineProjOfParaformer.cs:68
 // (SURVEY.md 2.5); key masks are all ones because the reference feeds speech_lengths = T (Q3).
 #include "attention.cuh"
@@ -27,8 +28,15 @@ constexpr int HD = 128;
 constexpr int BQ = 128;
 constexpr int kMaxTk = 192;
 constexpr int kGroups = 2;
-constexpr int kThreads = (kGroups * 4 + 1) * 32;     // 2 softmax warpgroups + control warp
+constexpr int kFsmnWarps = 8;                        // dedicated FSMN warps: run while the softmax groups work
+constexpr int kThreads = (kGroups * 4 + 1 + kFsmnWarps) * 32;   // 2 softmax warpgroups + control warp + FSMN warps
 constexpr int kQBytes = BQ * HD * 2;                 // 32 KiB: two 64-column boxes of 128 rows
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct AttParams {
     int Tq, Tk, Tkp;          // Tkp = Tk rounded up to 16 (MMA N of S, K extent of P V)
@@ -38,6 +46,7 @@ struct AttParams {
     const float* fsmn_w;      // [H*128, taps] or null
     float* mem;               // [B*Tk, ld_mem] fp32
     int ld_mem, taps;
+    int mem_accum;            // 1: mem += FSMN memory (the residual stream already holds x), 0: mem = FSMN memory
     uint32_t v_lbo, v_sbo;    // MN-major descriptor strides of the V tile (bytes)
 };
 
@@ -97,6 +106,43 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 // 128B-swizzled K-major tile of 128-byte rows: byte offset of the 16-byte chunk `chunk` (0..7) of row r
 __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+// mem[b, t, h*128 + c] = sum_j w[c, j] v[t + j - (TAPS-1)/2, c] + v[t, c], v read from the 128B-swizzled V tile (two
+// 64-channel boxes of Tkp rows).  Thread ft: channel ft % 128, time range half ft / 128; 16 outputs per register block.
+template <int TAPS>
+__device__ __forceinline__ void fsmn_from_smem(const AttParams& p, const uint8_t* sV, int ft, int h, int b) {
+    constexpr int TB = TAPS > 11 ? 8 : 16;                        // outputs per register block
+    constexpr int LEFT = (TAPS - 1) / 2;
+    const int c = ft & 127;
+    const int parts = kFsmnWarps * 32 / 128;
+    const int per = (p.Tk + parts - 1) / parts;
+    const int t_begin = (ft >> 7) * per;
+    const int t_end = min(p.Tk, t_begin + per);
+    float w[TAPS];
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) w[j] = __ldg(p.fsmn_w + (h * HD + c) * TAPS + j);
+    const uint8_t* vb = sV + (c >> 6) * (p.Tkp * 128) + (c & 7) * 2;
+    const int cchunk = (c & 63) >> 3;
+    float* out = p.mem + (static_cast<size_t>(b) * p.Tk) * p.ld_mem + h * HD + c;
+    for (int t0 = t_begin; t0 < t_end; t0 += TB) {
+        float x[TB + TAPS - 1];
+#pragma unroll
+        for (int i = 0; i < TB + TAPS - 1; ++i) {
+            const int t = t0 - LEFT + i;
+            x[i] = (t >= 0 && t < p.Tk) ? __half2float(*reinterpret_cast<const __half*>(vb + sw128_off(t, cchunk))) : 0.0f;
+        }
+        float old[TB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i) old[i] = (p.mem_accum && t0 + i < t_end) ? out[static_cast<size_t>(t0 + i) * p.ld_mem] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < TB; ++i) {
+            float acc = x[i + LEFT];
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) acc = fmaf(w[j], x[i + j], acc);
+            if (t0 + i < t_end) out[static_cast<size_t>(t0 + i) * p.ld_mem] = old[i] + acc;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -197,8 +243,16 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
         __syncwarp();
+    } else if (warp > 8) {
+        // ------------------------------------------------ FSMN memory of this head from the V tile in shared memory
+        if (p.fsmn_w != nullptr) {
+            mbar_wait(bar_v, 0);
+            const int ft = threadIdx.x - 9 * 32;                  // 0 .. kFsmnWarps*32-1
+            if (p.taps == 11) fsmn_from_smem<11>(p, smem + p.kv_bytes, ft, h, b);
+            else fsmn_from_smem<21>(p, smem + p.kv_bytes, ft, h, b);
+        }
     } else {
-        // ------------------------------------------------ softmax / FSMN / epilogue warpgroups
+        // ------------------------------------------------ softmax / epilogue warpgroups
         const int g = warp >> 2;                                  // query tile of this warpgroup
         const int q = warp & 3;                                   // TMEM lane quadrant
         const int r = q * 32 + lane;                              // query row inside the tile = TMEM lane
@@ -210,16 +264,28 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (active) {
             mbar_wait(bar_s(g), 0);
             tc_fence_after_sync();
-            // pass 1: row maximum over the valid keys
+            // pass 1: row maximum over the valid keys (only the last chunk can hold padded keys)
             float mx = -INFINITY;
             for (int c0 = 0; c0 < p.Tkp; c0 += 32) {
                 uint32_t v[32];
                 const int n = min(32, p.Tkp - c0);                // 32 or 16 (Tkp % 16 == 0)
                 if (n == 32) tmem_ld_32x32(trow + c0, v); else tmem_ld_32x32b_x16(trow + c0, v);
                 tmem_ld_wait();
+                if (c0 + 32 <= p.Tk) {
+                    float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < n && c0 + i < p.Tk) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; i += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(v[i]));
+                        m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+                    }
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < n && c0 + i < p.Tk) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             const float mxs = mx * p.scale_log2e;
             // pass 2: p = exp2(s * scale - max * scale); fp32 row sum; fp16 P into the A-operand layout
@@ -230,11 +296,24 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 if (n == 32) tmem_ld_32x32(trow + c0, v); else tmem_ld_32x32b_x16(trow + c0, v);
                 tmem_ld_wait();
                 float e[32];
+                if (c0 + 32 <= p.Tk) {
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const bool ok = i < n && c0 + i < p.Tk;
-                    e[i] = ok ? exp2f(__uint_as_float(v[i]) * p.scale_log2e - mxs) : 0.0f;
-                    sum += e[i];
+                    for (int i = 0; i < 32; i += 4) {
+                        e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs));
+                        e[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -mxs));
+                        e[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, -mxs));
+                        e[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, -mxs));
+                        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+                    }
+                    sum += (s0 + s1) + (s2 + s3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const bool ok = i < n && c0 + i < p.Tk;
+                        e[i] = ok ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs)) : 0.0f;
+                        sum += e[i];
+                    }
                 }
                 uint8_t* kblk = tile + (c0 >> 6) * 16384;         // 64 keys per 16 KiB k-block
                 const int chunk0 = (c0 & 63) >> 3;
@@ -258,49 +337,6 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             fence_proxy_async();                                  // generic-proxy smem writes -> visible to tcgen05.mma
             tc_fence_before_sync();
             mbar_arrive(bar_p(g));
-        }
-        // FSMN memory of this head from the V tile in shared memory (overlaps the P V MMAs)
-        if (p.fsmn_w != nullptr) {
-            mbar_wait(bar_v, 0);
-            const int c = tid & 127;                              // channel inside the head
-            const int half_t = (p.Tk + 1) >> 1;
-            const int t_begin = (tid >> 7) * half_t;
-            const int t_end = min(p.Tk, t_begin + half_t);
-            const int taps = p.taps, left = (taps - 1) >> 1;
-            float w[21];
-#pragma unroll
-            for (int j = 0; j < 21; ++j) w[j] = j < taps ? p.fsmn_w[(h * HD + c) * taps + j] : 0.0f;
-            const uint8_t* vb = smem + p.kv_bytes + (c >> 6) * (p.Tkp * 128) + (c & 7) * 2;
-            const int cchunk = (c & 63) >> 3;
-            auto vload = [&](int t) -> float {
-                if (t < 0 || t >= p.Tk) return 0.0f;
-                return __half2float(*reinterpret_cast<const __half*>(vb + sw128_off(t, cchunk)));
-            };
-            float win[21];
-#pragma unroll
-            for (int j = 0; j < 21; ++j) win[j] = (j < taps - 1) ? vload(t_begin - left + j) : 0.0f;
-            float* out = p.mem + (static_cast<size_t>(b) * p.Tk) * p.ld_mem + h * HD + c;
-            for (int t = t_begin; t < t_end; ++t) {
-                // window holds v[t-left .. t-left+taps-2]; bring in v[t-left+taps-1]
-                const float incoming = vload(t - left + taps - 1);
-                float acc = 0.0f;
-                if (taps == 11) {
-                    win[10] = incoming;
-#pragma unroll
-                    for (int j = 0; j < 11; ++j) acc += w[j] * win[j];
-                    acc += win[5];
-#pragma unroll
-                    for (int j = 0; j < 10; ++j) win[j] = win[j + 1];
-                } else {
-                    win[20] = incoming;
-#pragma unroll
-                    for (int j = 0; j < 21; ++j) acc += w[j] * win[j];
-                    acc += win[10];
-#pragma unroll
-                    for (int j = 0; j < 20; ++j) win[j] = win[j + 1];
-                }
-                out[static_cast<size_t>(t) * p.ld_mem] = acc;
-            }
         }
         if (active) {
             mbar_wait(bar_o(g), 0);
@@ -369,7 +405,7 @@ bool attention_tc_eligible(int Tq, int Tk, int head_dim) {
 }
 
 void attention_tc_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int Tq, int Tk, int ldq,
-                         int ldk, int ldv, int ldo, const float* fsmn_w, int taps, float* mem, int ld_mem, cudaStream_t s) {
+                         int ldk, int ldv, int ldo, const float* fsmn_w, int taps, float* mem, int ld_mem, bool mem_accum, cudaStream_t s) {
     if (fsmn_w && (taps != 11 && taps != 21)) throw CudaError{"attention: FSMN kernel must be 11 or 21"};
     if (fsmn_w && Tq != Tk) throw CudaError{"attention: fused FSMN needs self-attention (Tq == Tk)"};
     AttParams p{};
@@ -377,7 +413,7 @@ void attention_tc_launch(const __half* Q, const __half* K, const __half* V, __ha
     p.kv_bytes = 2 * p.Tkp * 128;
     p.tile_bytes = std::max(kQBytes, ((p.Tkp + 63) / 64) * 16384);
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-    p.fsmn_w = fsmn_w; p.mem = mem; p.ld_mem = ld_mem; p.taps = taps;
+    p.fsmn_w = fsmn_w; p.mem = mem; p.ld_mem = ld_mem; p.taps = taps; p.mem_accum = mem_accum ? 1 : 0;
     p.v_lbo = static_cast<uint32_t>(p.Tkp * 128);
     p.v_sbo = 1024;
     if (const char* e = getenv("PFASR_ATT_VDESC")) {             // experiment hook: "lbo,sbo" in bytes

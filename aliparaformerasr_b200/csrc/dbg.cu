@@ -174,7 +174,7 @@ pf_status pf_dbg_attention_fsmn(int32_t B, int32_t H, int32_t T, int32_t taps, c
         __half* o16 = s.alloc<__half>(n);
         float* o32 = s.alloc<float>(n);
         float* m32 = s.alloc<float>(n);
-        attention_fsmn_launch(dqkv, dqkv + D, dqkv + 2 * D, o16, B, H, T, 3 * D, D, dw, taps, m32, D, 0);
+        attention_fsmn_launch(dqkv, dqkv + D, dqkv + 2 * D, o16, B, H, T, 3 * D, D, dw, taps, m32, D, false, 0);
         pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, n);
         PF_CUDA(cudaGetLastError());
         PF_CUDA(cudaMemcpy(ctx, o32, n * sizeof(float), cudaMemcpyDeviceToHost));

@@ -370,13 +370,13 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
     if (it != enc_plans_.end()) return it->second;
     EncoderPlan plan;
     const int M = B * T, d = cfg_.d_model, f = cfg_.ffn;
-    auto build_layer = [&](const EncLayerW& w, bool residual) {
+    auto build_layer = [&](const EncLayerW& w) {
         EncLayerPlan lp;
         GemmEpi e;
         e = GemmEpi{}; e.bias = w.b_qkv; e.out_f16 = qkv16_; e.ld_out = 3 * d;
         gemm_prepare(lp.qkv, a16_, w.in_size, w.w_qkv, w.in_size, M, 3 * d, w.in_size, e);
-        e = GemmEpi{}; e.bias = w.b_out; e.addend = mem32_; e.ld_addend = d; e.out_f32 = x32_; e.ld_out = d;
-        if (residual) { e.resid = x32_; e.ld_resid = d; }
+        // x32_ already holds residual + FSMN memory (the attention kernel accumulates the memory into it)
+        e = GemmEpi{}; e.bias = w.b_out; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
         gemm_prepare(lp.out, ctx16_, d, w.w_out, d, M, d, d, e);
         e = GemmEpi{}; e.bias = w.b_ffn1; e.relu = 1; e.out_f16 = h16_; e.ld_out = f;
         gemm_prepare(lp.ffn1, a16_, d, w.w_ffn1, d, M, f, d, e);
@@ -384,8 +384,8 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
         gemm_prepare(lp.ffn2, h16_, f, w.w_ffn2, f, M, d, f, e);
         plan.layers.push_back(lp);
     };
-    for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], enc_[i].in_size == d);
-    for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i], true);
+    for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i]);
+    for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i]);
     if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
         GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = ldv();
         gemm_prepare(plan.ctc_head, enc16_, d, w_head_, d, M, cfg_.vocab, d, e);
@@ -614,8 +614,10 @@ void DeviceCtx::encoder_forward(int B, int T) {
         }
         gemm(lp.qkv);
         timed("enc_attention_fsmn", [&] {
+            // x += mem (layer with a residual) or x = mem (encoders0: in_size != d_model, no residual); the
+            // out-projection then adds ctx W_o + b on top of x32_
             launches += attention_fsmn_launch(qkv16_, qkv16_ + d, qkv16_ + 2 * d, ctx16_, B, H, T, 3 * d, d, w.fsmn, cfg_.enc_kernel,
-                                              mem32_, d, stream_);
+                                              x32_, d, w.in_size == d, stream_);
         });
         gemm(lp.out);
         timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });

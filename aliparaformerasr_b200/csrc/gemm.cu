@@ -10,6 +10,8 @@
 // 32-column chunk).  The epilogue of tile i overlaps the main loop of tile i+1 (two TMEM accumulator stages).
 #include "gemm.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -26,15 +28,23 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kStageTileBytes = 32 * 32 * 4;   // per-warp transpose buffer: 32 rows x 32 fp32
 
-template <int BN>
+constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+
+template <int BN, bool kPair, bool kOutHalf>
 struct Cfg {
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBRows = kPair ? BN / 2 : BN;              // rows of the W tile this CTA stages per k-block
+    static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kEpiBytes = kEpiWarps * kStageTileBytes;   // 32 KiB
-    static constexpr int kBarBytes = 256;
+    // per-warp staging: fp16 output = two 32 x 32 boxes (2 KiB each); fp32 output = two 32 x 32 boxes (4 KiB each)
+    static constexpr int kWarpStageBytes = kOutHalf ? 4096 : 8192;
+    static constexpr int kEpiBytes = kEpiWarps * kWarpStageBytes;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kBiasBytes = 2 * BN * 4;                    // two tiles' bias columns
+    static constexpr int kFit = (kSmemMax - 1024 - kBarBytes - kBiasBytes - kEpiBytes) / kStageBytes;
+    static constexpr int kStages = kFit > 8 ? 8 : kFit;
     static constexpr int kTmemCols = 2 * BN;                         // two accumulator stages (128 / 256 / 512)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // +1024: alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + 1024;  // +1024: alignment slack
+    static_assert(kStages >= 3, "operand ring too shallow");
 };
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -63,9 +73,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // -> row-segment layout (fp32 out: 8 lanes x float4 per row, 4 rows per instruction; fp16 out: 4 lanes x 8 halfs per
 // row, 8 rows per instruction) -> bias / addends / ReLU -> 16-byte coalesced stores.  kAdds = number of fp32 tensors
 // added to the product (FSMN memory, residual); the adds of a chunk are all issued before the first use.
-template <bool kOutHalf, int kAdds>
+// fp32 addend rows of one 32x32 chunk in the layout the fp32-output path consumes (lane: column group lane & 7, rows
+// (lane >> 3) + 4 * it): loaded one chunk ahead so their L2 latency overlaps the previous chunk's work.
+__device__ __forceinline__ void load_addend_chunk(float4 (&x)[8], const float* add, int ld, int lane, int row0, int col0, int M) {
+    const int jj = lane & 7, rsub = lane >> 3;
+    const float* p = add + static_cast<size_t>(row0 + rsub) * ld + col0 + jj * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + it * 4 + rsub < M) x[it] = *reinterpret_cast<const float4*>(p + static_cast<size_t>(it) * 4 * ld);
+    }
+}
+
+template <bool kOutHalf, int kAdds, bool kPre = false>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* stage, int lane, int row0, int col0,
-                                               int M, int N, const GemmEpi& e, bool vec_ok) {
+                                               int M, int N, const GemmEpi& e, bool vec_ok, const float* bias_t, int n0,
+                                               const float4* pre = nullptr) {
     float4* st4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -77,11 +100,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
         if (kOutHalf) {
             const int g = lane & 3, rsub = lane >> 2;
             const int col = col0 + g * 8;
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (e.bias) {
-                b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-                b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-            }
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_t + (col - n0));
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_t + (col - n0) + 4);
             __half* optr = e.out_f16 + static_cast<size_t>(row0 + rsub) * e.ld_out + col;
             const float* a0p = kAdds > 0 ? e.add0 + static_cast<size_t>(row0 + rsub) * e.ld_add0 + col : nullptr;
             const float* a1p = kAdds > 1 ? e.add1 + static_cast<size_t>(row0 + rsub) * e.ld_add1 + col : nullptr;
@@ -119,8 +139,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
         } else {
             const int jj = lane & 7, rsub = lane >> 3;
             const int col = col0 + jj * 4;
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+            const float4 b = *reinterpret_cast<const float4*>(bias_t + (col - n0));
             float* optr = e.out_f32 + static_cast<size_t>(row0 + rsub) * e.ld_out + col;
             float4 x0[8], x1[8];
 #pragma unroll
@@ -128,7 +147,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
                 const bool ok = row0 + it * 4 + rsub < M;
                 x0[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 x1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kAdds > 0 && ok) x0[it] = *reinterpret_cast<const float4*>(e.add0 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add0 + col);
+                if (kPre) x0[it] = pre[it];
+                else if (kAdds > 0 && ok) x0[it] = *reinterpret_cast<const float4*>(e.add0 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add0 + col);
                 if (kAdds > 1 && ok) x1[it] = *reinterpret_cast<const float4*>(e.add1 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add1 + col);
             }
 #pragma unroll
@@ -158,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
                     const int c = col + i;
                     if (c < N) {
                         float x = v[i];
-                        if (e.bias) x += __ldg(e.bias + c);
+                        x += bias_t[c - n0];
                         if (kAdds > 0) x += e.add0[static_cast<size_t>(row) * e.ld_add0 + c];
                         if (kAdds > 1) x += e.add1[static_cast<size_t>(row) * e.ld_add1 + c];
                         x = fmaxf(x, lo);
@@ -172,20 +192,165 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
     __syncwarp();   // the transpose buffer is reused by the next chunk
 }
 
-// Thread-block cluster of CM x CN CTAs computes a (CM*128) x (CN*BN) super-tile.  CTA (rm, rn) owns the 128 x BN
-// sub-tile and issues its own 1-CTA MMAs, but operand tiles are fetched from L2 once per cluster: the CTA loads
-// 1/CN of its A tile and 1/CM of its B tile and TMA-multicasts each slice to the CTAs that share it (row peers share
-// A, column peers share B).  L2->SM bytes per k-block drop from 16K + BN*128 to 16K/CN + BN*128/CM, which is what
-// bounds this kernel (see pick_config).  A stage may be refilled only when every CTA that receives my slices has
-// consumed it, so the MMA commit arrives on the empty barrier of all row and column peers (count CM + CN - 1).
-template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
+// ---- asynchronous (TMA) epilogue --------------------------------------------------------------------------------
+// The register -> smem transpose + per-thread global stores above cost ~6000 cycles per 128 x 256 tile (measured
+// with scripts/gemm_probe.py: the epilogue alone ran longer than the MMAs of a K = 512 tile) and kept the accumulator
+// stage busy.  Here every warp writes its TMEM rows (thread = row) straight into a 128B-swizzled staging box and one
+// lane hands the box to the TMA store engine; the fp32 residual is TMA-loaded into the same box ahead of time and
+// updated in place.  No ld.shared of other threads' data, no per-thread global traffic, edges clipped by the maps.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
+// fp16 output: this warp's rows [row0, row0+32) x columns [colw, colw + 32*nchunks) of the tile.  One 32 x 32 box
+// (64-byte rows, SWIZZLE_64B) per chunk, two alternating 2 KiB staging boxes, so a box is rewritten two chunks after
+// its store was issued.
+template <int kMaxChunks>
+__device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, uint8_t* stg, const CUtensorMap* tmC,
+                                                 const float* bias_w, float lo, int row0, int colw, int lane) {
+    const uint32_t stg_u32 = smem_u32(stg);
+    uint32_t ra[32], rb[32];
+    tmem_ld_issue(t_acc, ra);
+    if (lane == 0) tma_store_wait_read();                          // the previous tile's stores have read both boxes
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+        if (k < nchunks) {
+            uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+            const int buf = k & 1;
+            tmem_ld_wait();
+            if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
+            if (k >= 2) {                                         // box reuse: at most the previous chunk's store may be pending
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            uint8_t* box = stg + buf * 2048 + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_w + k * 32 + 8 * j);       // smem broadcast
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_w + k * 32 + 8 * j + 4);
+                __half2 h0 = __floats2half2_rn(fmaxf(__uint_as_float(cur[8 * j]) + b0.x, lo), fmaxf(__uint_as_float(cur[8 * j + 1]) + b0.y, lo));
+                __half2 h1 = __floats2half2_rn(fmaxf(__uint_as_float(cur[8 * j + 2]) + b0.z, lo), fmaxf(__uint_as_float(cur[8 * j + 3]) + b0.w, lo));
+                __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(cur[8 * j + 4]) + b1.x, lo), fmaxf(__uint_as_float(cur[8 * j + 5]) + b1.y, lo));
+                __half2 h3 = __floats2half2_rn(fmaxf(__uint_as_float(cur[8 * j + 6]) + b1.z, lo), fmaxf(__uint_as_float(cur[8 * j + 7]) + b1.w, lo));
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(box + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;      // SWIZZLE_64B: chunk ^= (row / 2) % 4
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tmC, stg_u32 + buf * 2048, colw + k * 32, row0);
+                tma_store_commit();
+            }
+        }
+    }
+}
+
+// fp32 output (+ optional fp32 residual, TMA-prefetched into the staging boxes): 32 columns per box, two boxes.
+// rbar: the two "residual landed" mbarriers of this warp; rcount: loads issued so far per buffer (phase tracking).
+struct ResidPipe {
+    uint32_t bar[2];
+    uint32_t count[2];
+};
+template <bool kResid>
+__device__ __forceinline__ void resid_issue(ResidPipe& rp, int buf, uint32_t stg_u32, const CUtensorMap* tmR, int col, int row0, int lane) {
+    if (kResid && lane == 0) {
+        mbar_arrive_expect_tx(rp.bar[buf], 4096);
+        tma_load_2d(stg_u32 + buf * 4096, tmR, rp.bar[buf], col, row0);
+    }
+}
+template <int kMaxChunks, bool kResid>
+__device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, uint8_t* stg, ResidPipe& rp, const CUtensorMap* tmC,
+                                                 const CUtensorMap* tmR, const float* bias_w, float lo, int row0,
+                                                 int colw, int lane, int prefetched) {
+    const uint32_t stg_u32 = smem_u32(stg);
+    uint32_t ra[32], rb[32];
+    tmem_ld_issue(t_acc, ra);
+    if (!kResid) {                                                 // (with a residual the caller waited before prefetching)
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+    }
+    for (int k = prefetched; k < 2 && k < nchunks; ++k) resid_issue<kResid>(rp, k, stg_u32, tmR, colw + k * 32, row0, lane);
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+        if (k < nchunks) {
+            uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+            const int buf = k & 1;
+            tmem_ld_wait();
+            if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
+            if (kResid) {
+                mbar_wait(rp.bar[buf], rp.count[buf] & 1u);
+                rp.count[buf]++;
+            } else if (k >= 2) {                                   // buffer reuse without a residual load in between
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
+            uint8_t* box = stg + buf * 4096 + lane * 128;
+            const int col = colw + k * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4* slot = reinterpret_cast<float4*>(box + ((j ^ (lane & 7)) << 4));
+                float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]),
+                                       __uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3]));
+                const float4 b = *reinterpret_cast<const float4*>(bias_w + k * 32 + 4 * j);            // smem broadcast
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                if (kResid) {
+                    const float4 x = *slot;
+                    v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                }
+                v.x = fmaxf(v.x, lo); v.y = fmaxf(v.y, lo); v.z = fmaxf(v.z, lo); v.w = fmaxf(v.w, lo);
+                *slot = v;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(tmC, stg_u32 + buf * 4096, col, row0);
+                tma_store_commit();
+                if (kResid && k + 2 < nchunks) tma_store_wait_read();     // box k is read before chunk k+2 lands in it
+            }
+            if (kResid && k + 2 < nchunks) {
+                __syncwarp();
+                resid_issue<kResid>(rp, buf, stg_u32, tmR, colw + (k + 2) * 32, row0, lane);
+            }
+        }
+    }
+}
+
+// kPair = false: one CTA computes a 128 x BN tile with cta_group::1 MMAs.
+// kPair = true : a CTA pair (thread-block cluster of 2) computes a 256 x BN tile with cta_group::2 MMAs issued by the
+// leader (cluster rank 0).  CTA r stages its own 128 rows of A and only rows [r*BN/2, (r+1)*BN/2) of the W tile, and
+// owns the accumulator rows m0 + r*128 .. +127 (all BN columns) in its own TMEM.  L2->SM bytes per k-block drop from
+// 16K + BN*128 to 16K + BN*64 per SM, which is what bounds the 1-CTA kernel on this path (TMA chip throughput
+// ~6300 B/cycle => ~42 B/cycle/SM with 148 CTAs pulling operands; B300_MICROARCH.md "TMA chip-throughput").  TMA
+// multicast does not help at cluster size 2 (the L2 dedup window only pays from ~8 CTAs), the 2-SM MMA does.
+// Protocol (same shape as CUTLASS's 2-SM pipelines): both CTAs' TMA loads complete_tx on the LEADER's full barrier
+// (the leader alone arms it with the pair's total bytes); the leader's tcgen05.commit multicasts the "stage free"
+// and "accumulator complete" arrivals to both CTAs; epilogue warps of both CTAs arrive on the leader's
+// tmem_empty barrier (the peer through a mapa-translated shared::cluster address).
+template <int BN, bool kPair, bool kOutHalf, int kAdds>
 __global__ void __launch_bounds__(kThreads, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const GemmEpi epi, const int M, const int N, const int K, const int stiles_n, const int num_stiles,
-                       const int vec_ok) {
-    using C = Cfg<BN>;
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                       const GemmEpi epi, const int M, const int N, const int K, const int tiles_n, const int num_tiles,
+                       const int vec_ok_flags) {
+    const int vec_ok = vec_ok_flags & 1;
+    const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
+    using C = Cfg<BN, kPair, kOutHalf>;
     constexpr int STAGES = C::kStages;
-    constexpr int CSIZE = CM * CN;
+    constexpr int CS = kPair ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
@@ -199,78 +364,91 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 8 * (2 * STAGES + 4));
+    auto resid_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * ew + b); };
+    float* bias_s = reinterpret_cast<float*>(smem + kBarOff + C::kBarBytes);       // [2][BN] bias of the current tiles
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_kb = (K + BK - 1) / BK;
-    const int crank = CSIZE > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-    const int rm = crank % CM, rn = crank / CM;
-    const int cluster_id = blockIdx.x / CSIZE;
-    const int num_clusters = gridDim.x / CSIZE;
-    // CTAs exchanging operand slices with me: row peers (same rm) share A, column peers (same rn) share B
-    uint16_t mask_a = 0, mask_b = 0;
-#pragma unroll
-    for (int j = 0; j < CN; ++j) mask_a |= static_cast<uint16_t>(1u << (rm + CM * j));
-#pragma unroll
-    for (int i = 0; i < CM; ++i) mask_b |= static_cast<uint16_t>(1u << (i + CM * rn));
-    const uint16_t mask_peers = mask_a | mask_b;
+    const int rank = kPair ? static_cast<int>(cluster_ctarank()) : 0;
+    const bool leader = rank == 0;
+    const bool dbg_no_epi = (vec_ok_flags & 0x100) != 0;               // PFASR_GEMM_DBG bottleneck probes (results are garbage)
+    const bool dbg_no_tma = (vec_ok_flags & 0x200) != 0;
+    const bool dbg_no_mma = (vec_ok_flags & 0x400) != 0;
+    const int unit = blockIdx.x / CS;                            // CTA (or CTA pair) index = tile scheduler slot
+    const int num_units = gridDim.x / CS;
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (tma_epi) {
+            tma_prefetch_desc(&tmC);
+            if (kAdds == 1) tma_prefetch_desc(&tmR);
+        }
     }
     if (warp == 1 && lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), CM + CN - 1);
+            mbar_init(empty_bar(s), 1);
         }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), kEpiWarps);
+            mbar_init(tmem_empty_bar(a), kEpiWarps * CS);        // pair: the leader's barrier collects both CTAs' warps
+        }
+        for (int w = 0; w < kEpiWarps; ++w) {
+            mbar_init(resid_bar(w, 0), 1);
+            mbar_init(resid_bar(w, 1), 1);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
-        tmem_relinquish();
+        tmem_alloc<CS>(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::kTmemCols);
+        tmem_relinquish<CS>();
     }
     tc_fence_before_sync();
-    if (CSIZE > 1) cluster_sync(); else __syncthreads();        // peers' barriers are initialised before any remote arrive
+    if (kPair) cluster_sync(); else __syncthreads();             // peer barriers are initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // prologue above overlaps the previous kernel's tail; operands / residuals are read below
 
     if (warp == 0) {
-        // ------------------------------------------------ TMA producer
+        // ------------------------------------------------ TMA producer (one thread in every CTA)
         if (lane == 0) {
             uint32_t it = 0;                                     // global k-block counter across tiles
-            for (int st = cluster_id; st < num_stiles; st += num_clusters) {
-                const int m0 = ((st / stiles_n) * CM + rm) * BM;
-                const int n0 = ((st % stiles_n) * CN + rn) * BN;
+            for (int t = unit; t < num_tiles; t += num_units) {
+                const int m0 = (t / tiles_n) * (BM * CS) + rank * BM;
+                const int n0 = (t % tiles_n) * BN + rank * C::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
                     const uint32_t a_s = base + s * C::kStageBytes;
-                    if (CN == 1) tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
-                    else tma_load_2d_mc(a_s + rn * (kABytes / CN), &tmA, full_bar(s), kb * BK, m0 + rn * (BM / CN), mask_a);
-                    if (CM == 1) tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
-                    else tma_load_2d_mc(a_s + kABytes + rm * (C::kBBytes / CM), &tmB, full_bar(s), kb * BK, n0 + rm * (BN / CM), mask_b);
+                    if (dbg_no_tma) {
+                        if (leader) mbar_arrive(full_bar(s));
+                    } else if (!kPair) {
+                        mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+                        tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
+                        tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::kStageBytes);
+                        const uint32_t lead_full = mapa_shared(full_bar(s), 0);
+                        tma_load_2d_pair(a_s, &tmA, lead_full, kb * BK, m0);
+                        tma_load_2d_pair(a_s + kABytes, &tmB, lead_full, kb * BK, n0);
+                    }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+        // ------------------------------------------------ MMA issuer (one thread; of the leader CTA in pair mode)
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc(BM * CS, BN);
             uint32_t it = 0;
-            uint32_t local = 0;                                  // tiles processed by this CTA
-            for (int st = cluster_id; st < num_stiles; st += num_clusters, ++local) {
+            uint32_t local = 0;                                  // tiles processed by this CTA (pair)
+            for (int t = unit; t < num_tiles; t += num_units, ++local) {
                 const uint32_t acc = local & 1u;
                 const uint32_t acc_ph = (local >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);     // epilogue has drained this accumulator stage
@@ -284,16 +462,19 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const uint32_t a_s = base + s * C::kStageBytes;
                     const uint64_t adesc0 = make_sw128_kmajor_desc(a_s);
                     const uint64_t bdesc0 = make_sw128_kmajor_desc(a_s + kABytes);
+                    if (!dbg_no_mma) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
-                        umma_f16(d_tmem, adesc0 + 2u * k, bdesc0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advancing K inside the swizzle atom = +32 bytes on the start address (>>4 => +2)
+                            umma_f16<CS>(d_tmem, adesc0 + 2u * k, bdesc0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    // frees this smem stage (here and in every peer that multicasts into it) once the MMAs have read it
-                    if (CSIZE == 1) umma_commit(empty_bar(s));
-                    else umma_commit_mc(empty_bar(s), mask_peers);
+                    // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+                    if (!kPair) umma_commit(empty_bar(s));
+                    else umma_commit_pair(empty_bar(s));
                 }
-                umma_commit(tmem_full_bar(acc));                 // accumulator complete
+                if (!kPair) umma_commit(tmem_full_bar(acc));     // accumulator complete
+                else umma_commit_pair(tmem_full_bar(acc));
             }
         }
         __syncwarp();
@@ -301,35 +482,85 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // ------------------------------------------------ epilogue: TMEM -> registers -> smem transpose -> global
         const int ew = warp - kEpiWarp0;
         const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
-        const int grp = ew >> 2;                                 // warpgroup: chunks grp, grp+2, ...
-        float* stage = reinterpret_cast<float*>(smem + kEpiOff + ew * kStageTileBytes);
+        const int grp = ew >> 2;                                 // warpgroup: left / right half of the tile's columns
+        uint8_t* wstage = smem + kEpiOff + ew * C::kWarpStageBytes;
+        float* stage = reinterpret_cast<float*>(wstage);         // legacy path: 32 x 32 fp32 transpose buffer
+        constexpr bool kTmaOk = kOutHalf ? (kAdds == 0) : (kAdds <= 1);     // shapes the asynchronous epilogue covers
+        constexpr int kCpw = BN >= 128 ? BN / 64 : 1;                       // 32-column chunks per warp (TMA epilogue)
+        const int cbase = grp * kCpw;
+        ResidPipe rp;
+        rp.bar[0] = resid_bar(ew, 0); rp.bar[1] = resid_bar(ew, 1);
+        rp.count[0] = rp.count[1] = 0;
+        const float lo = epi.relu ? 0.0f : -INFINITY;
         uint32_t local = 0;
-        for (int st = cluster_id; st < num_stiles; st += num_clusters, ++local) {
+        for (int t = unit; t < num_tiles; t += num_units, ++local) {
             const uint32_t acc = local & 1u;
             const uint32_t acc_ph = (local >> 1) & 1u;
-            const int m0 = ((st / stiles_n) * CM + rm) * BM;
-            const int n0 = ((st % stiles_n) * CN + rn) * BN;
-            mbar_wait(tmem_full_bar(acc), acc_ph);
-            tc_fence_after_sync();
-            if (m0 < M) {
+            const int m0 = (t / tiles_n) * (BM * CS) + rank * BM;
+            const int n0 = (t % tiles_n) * BN;
+            const int row0 = m0 + q * 32;
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            // bias of this tile's columns -> shared memory (zeros past N / without bias), one L2 round trip per tile
+            // taken while the MMAs still run; two buffers so a fast warp may already fill the next tile's
+            float* bias_t = bias_s + (local & 1u) * BN;
+            for (int i = ew * 32 + lane; i < BN; i += kEpiWarps * 32)
+                bias_t[i] = (epi.bias != nullptr && n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.0f;
+            if (kTmaOk && tma_epi) {
+                int nchunks = 0;
+                for (int c = cbase; c < cbase + kCpw && c < BN / 32; ++c)
+                    if (n0 + c * 32 < N) ++nchunks;
+                const bool work = row0 < M && nchunks > 0 && !dbg_no_epi;
+                const int colw = n0 + cbase * 32;
+                int prefetched = 0;
+                if constexpr (!kOutHalf && kAdds == 1) {
+                    // residual boxes of the first two chunks travel while the MMAs of this tile still run
+                    if (work) {
+                        const uint32_t stg_u32 = smem_u32(wstage);
+                        if (lane == 0) tma_store_wait_read();    // the previous tile's stores have read the boxes
+                        __syncwarp();
+                        for (; prefetched < 2 && prefetched < nchunks; ++prefetched)
+                            resid_issue<true>(rp, prefetched, stg_u32, &tmR, colw + prefetched * 32, row0, lane);
+                    }
+                }
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after_sync();
+                epi_bar_sync();                                   // bias tile visible to all epilogue warps
+                if (work) {
+                    if constexpr (kOutHalf && kAdds == 0)
+                        epilogue_tma_f16<kCpw>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane);
+                    else if constexpr (!kOutHalf && kAdds == 0)
+                        epilogue_tma_f32<kCpw, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
+                    else if constexpr (!kOutHalf && kAdds == 1)
+                        epilogue_tma_f32<kCpw, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
+                }
+            } else {
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after_sync();
+                epi_bar_sync();
+                if (m0 < M && !dbg_no_epi) {
 #pragma unroll 1
-                for (int c = grp; c < BN / 32; c += 2) {
-                    const int col0 = n0 + c * 32;
-                    if (col0 >= N) break;                        // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + static_cast<uint32_t>(c * 32), r);
-                    tmem_ld_wait();
-                    epilogue_chunk<kOutHalf, kAdds>(r, stage, lane, m0 + q * 32, col0, M, N, epi, vec_ok != 0);
+                    for (int c = grp; c < BN / 32; c += 2) {
+                        const int col0 = n0 + c * 32;
+                        if (col0 >= N) break;                    // warp-uniform
+                        uint32_t r[32];
+                        tmem_ld_32x32(t_acc + static_cast<uint32_t>(c * 32), r);
+                        tmem_ld_wait();
+                        epilogue_chunk<kOutHalf, kAdds>(r, stage, lane, row0, col0, M, N, epi, vec_ok != 0, bias_t, n0);
+                    }
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (lane == 0) {
+                if (!kPair || leader) mbar_arrive(tmem_empty_bar(acc));
+                else mbar_arrive_remote(mapa_shared(tmem_empty_bar(acc), 0));
+            }
         }
+        if (lane == 0) tma_store_wait_read();                    // staging boxes stay valid until the stores have read them
     }
     tc_fence_before_sync();
-    if (CSIZE > 1) cluster_sync(); else __syncthreads();        // no CTA exits while a peer may still signal its barriers
-    if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+    if (kPair) cluster_sync(); else __syncthreads();            // no CTA exits while its peer may still signal its barriers
+    if (warp == 2) tmem_dealloc<CS>(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------ host side
@@ -350,18 +581,24 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp16 row-major [rows, cols] with row pitch ld elements; box = [box_rows, 64 cols], 128B swizzle, OOB -> 0.
-void make_tmap(CUtensorMap* tm, const __half* ptr, int rows, int cols, int ld, int box_rows) {
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0)
-        throw CudaError{"gemm operand must be 16-byte aligned with a row pitch that is a multiple of 8 elements"};
+// 2-D row-major [rows, cols] (fp16 or fp32) with row pitch ld elements; box = [box_rows, 128 bytes of columns],
+// 128B swizzle; loads read out-of-bounds elements as 0, stores clip them.
+void make_tmap_any(CUtensorMap* tm, const void* ptr, bool f32, int rows, int cols, int ld, int box_rows, int box_bytes = 128) {
+    const int esz = f32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (static_cast<size_t>(ld) * esz) % 16 != 0)
+        throw CudaError{"gemm tensor must be 16-byte aligned with a row pitch that is a multiple of 16 bytes"};
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * sizeof(__half)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / esz), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = get_encode_fn()(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr),
+                                 dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+void make_tmap(CUtensorMap* tm, const __half* ptr, int rows, int cols, int ld, int box_rows) {
+    make_tmap_any(tm, ptr, false, rows, cols, ld, box_rows);
 }
 
 int num_sms() {
@@ -376,14 +613,14 @@ int num_sms() {
     return n;
 }
 
-template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
+template <int BN, bool kPair, bool kOutHalf, int kAdds>
 struct Launcher {
-    static int max_clusters;   // co-resident clusters of this shape (GPC boundaries make it < sms / cluster size)
+    static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
-        using C = Cfg<BN>;
-        constexpr int CSIZE = CM * CN;
-        auto kern = pf_gemm_f16_tn_tcgen05<BN, CM, CN, kOutHalf, kAdds>;
+        using C = Cfg<BN, kPair, kOutHalf>;
+        constexpr int CS = kPair ? 2 : 1;
+        auto kern = pf_gemm_f16_tn_tcgen05<BN, kPair, kOutHalf, kAdds>;
         static std::once_flag once;
         std::call_once(once, [&] {
             int ndev = 0, cur = 0;
@@ -394,24 +631,24 @@ struct Launcher {
                 PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
             }
             PF_CUDA(cudaSetDevice(cur));
-            max_clusters = num_sms() / CSIZE;
-            if (CSIZE > 1) {
+            max_units = num_sms() / CS;
+            if (kPair) {
                 cudaLaunchConfig_t q{};
-                q.gridDim = dim3(num_sms() / CSIZE * CSIZE);
+                q.gridDim = dim3(num_sms() / CS * CS);
                 q.blockDim = dim3(kThreads);
                 q.dynamicSmemBytes = C::kSmemBytes;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = CSIZE; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 q.attrs = at; q.numAttrs = 1;
                 int nc = 0;
-                if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) == cudaSuccess && nc > 0) max_clusters = std::min(max_clusters, nc);
+                if (cudaOccupancyMaxActiveClusters(&nc, kern, &q) == cudaSuccess && nc > 0) max_units = std::min(max_units, nc);
                 else cudaGetLastError();
             }
         });
-        const int stiles_n = ceil_div(ceil_div(op.N, BN), CN);
-        const int num_stiles = stiles_n * ceil_div(ceil_div(op.M, BM), CM);
-        const int grid = std::min(num_stiles, max_clusters) * CSIZE;
+        const int tiles_n = ceil_div(op.N, BN);
+        const int num_tiles = tiles_n * ceil_div(op.M, BM * CS);
+        const int grid = std::min(num_tiles, max_units) * CS;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kThreads);
@@ -424,24 +661,29 @@ struct Launcher {
             at[na].val.programmaticStreamSerializationAllowed = 1;
             ++na;
         }
-        if (CSIZE > 1) {
+        if (kPair) {
             at[na].id = cudaLaunchAttributeClusterDimension;
-            at[na].val.clusterDim.x = CSIZE; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            at[na].val.clusterDim.x = CS; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
             ++na;
         }
         cfg.attrs = at;
         cfg.numAttrs = na;
-        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.epi, op.M, op.N, op.K, stiles_n, num_stiles, op.vec_ok));
+        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.epi, op.M, op.N, op.K, tiles_n, num_tiles, op.vec_ok));
     }
 };
-template <int BN, int CM, int CN, bool kOutHalf, int kAdds>
-int Launcher<BN, CM, CN, kOutHalf, kAdds>::max_clusters = 1;
+template <int BN, bool kPair, bool kOutHalf, int kAdds>
+int Launcher<BN, kPair, kOutHalf, kAdds>::max_units = 1;
 
 template <int BN, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
-    if (op.cm == 2 && op.cn == 1) Launcher<BN, 2, 1, kOutHalf, kAdds>::run(op, stream);
-    else if (op.cm == 1 && op.cn == 1) Launcher<BN, 1, 1, kOutHalf, kAdds>::run(op, stream);
-    else throw CudaError{"gemm: cluster shape not instantiated"};
+    if (op.cm == 2 && op.cn == 1) {
+        if constexpr (BN >= 128) Launcher<BN, true, kOutHalf, kAdds>::run(op, stream);
+        else throw CudaError{"gemm: CTA-pair MMA is instantiated for N tiles 128 and 256"};
+    } else if (op.cm == 1 && op.cn == 1) {
+        Launcher<BN, false, kOutHalf, kAdds>::run(op, stream);
+    } else {
+        throw CudaError{"gemm: cluster shape not instantiated"};
+    }
 }
 
 template <int BN>
@@ -457,20 +699,25 @@ void launch_bn(const GemmOp& op, cudaStream_t stream) {
 // Tile width and cluster shape from a cycle model of the persistent kernel fitted to scripts/gemm_sweep.py on B200:
 // a tile's k-block costs max(MMA floor = 2*BN cycles for four K=16 steps, operand bytes / L2->SM bandwidth).  The L2
 // fabric delivers ~6300 B/cycle chip-wide (B300_MICROARCH.md, TMA chip throughput), at most ~80 B/cycle to one SM,
-// and is what bounds the 1-CTA 128xBN tile (85 FLOP/B at BN=256); multicast clusters cut the bytes per CTA.
+// and is what bounds the 1-CTA 128xBN tile (85 FLOP/B at BN=256); the CTA-pair MMA halves the W bytes per CTA.
+bool pair_enabled() {
+    static const bool on = [] { const char* e = getenv("PFASR_GEMM_PAIR"); return e && *e && *e != '0'; }();
+    return on;
+}
+
 void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
     const int mt = ceil_div(M, BM), kb = ceil_div(K, BK), sms = num_sms();
     double best_cost = 1e30;
     for (int bn : {256, 128, 64}) {
-        for (int cfg = 0; cfg < 1; ++cfg) {     // 2x1 multicast clusters measured slower on every shape of the path
-            const int cm = cfg >= 1 ? 2 : 1, cn = 1;
+        for (int cfg = 0; cfg < (pair_enabled() && bn >= 128 ? 2 : 1); ++cfg) {
+            const int cm = cfg >= 1 ? 2 : 1, cn = 1;                       // cm = 2: CTA-pair (cta_group::2) MMA
             const int csize = cm * cn;
-            const int stiles = ceil_div(mt, cm) * ceil_div(ceil_div(N, bn), cn);
-            const int slots = csize == 4 ? sms / 4 - 1 : sms / csize;      // GPC boundaries cost a 4-cluster slot
+            const int stiles = ceil_div(mt, cm) * ceil_div(N, bn);
+            const int slots = sms / csize;
             const int waves = ceil_div(stiles, slots);
             const int active = std::min(stiles, slots) * csize;
             const double bw = std::min(80.0, 6300.0 / active);
-            const double t_kb = std::max(2.0 * bn, (16384.0 / cn + 128.0 * bn / cm) / bw) + (csize > 1 ? 20.0 : 0.0);
+            const double t_kb = std::max(2.0 * bn, (16384.0 + 128.0 * bn / cm) / bw) + (csize > 1 ? 20.0 : 0.0);
             const double cost = waves * kb * t_kb + 150.0 * (bn / 32);
             if (cost < best_cost) { best_cost = cost; bn_out = bn; cm_out = cm; cn_out = cn; }
         }
@@ -490,7 +737,8 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     cm = std::max(cm, 1);
     cn = std::max(cn, 1);
     if (bn != 64 && bn != 128 && bn != 256) throw CudaError{"gemm: unsupported N tile"};
-    if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and 2x1 are instantiated)"};
+    if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and the 2x1 CTA pair are instantiated)"};
+    if (cm == 2 && bn < 128) throw CudaError{"gemm: the CTA-pair MMA needs an N tile of 128 or 256"};
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
     // the kernel adds up to two fp32 tensors in a fixed order: FSMN memory first, then the residual
     op.n_adds = 0;
@@ -505,8 +753,25 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     auto al = [](const void* p, int ld, int bytes) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % bytes) == 0 && ld % 4 == 0); };
     op.vec_ok = (al(epi.bias, 0, 16) && al(epi.resid, epi.ld_resid, 16) && al(epi.addend, epi.ld_addend, 16) &&
                  al(epi.out_f32, epi.ld_out, 16) && al(epi.out_f16, epi.ld_out, 8)) ? 1 : 0;
-    make_tmap(&op.tmA, A, M, K, lda, BM / cn);      // each CTA loads (and multicasts) 1/cn of its A tile
-    make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and 1/cm of its B tile
+    // asynchronous epilogue (TMA store, TMA-prefetched residual): fp16 output without addends, fp32 output with at
+    // most one; everything 16-byte aligned.  PFASR_GEMM_LEGACY_EPI=1 keeps the smem-transposed epilogue (A/B switch).
+    static const bool legacy_epi = [] { const char* e = getenv("PFASR_GEMM_LEGACY_EPI"); return e && *e && *e != '0'; }();
+    auto row_ok = [](const void* p, int ld, int esz) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (static_cast<size_t>(ld) * esz) % 16 == 0; };
+    const bool tma_epi = !legacy_epi && op.vec_ok &&
+                         (epi.out_f16 ? (op.n_adds == 0 && row_ok(epi.out_f16, epi.ld_out, 2))
+                                      : (op.n_adds <= 1 && row_ok(epi.out_f32, epi.ld_out, 4) &&
+                                         (op.n_adds == 0 || row_ok(op.epi.add0, op.epi.ld_add0, 4))));
+    op.tmC = CUtensorMap{};
+    op.tmR = CUtensorMap{};
+    if (tma_epi) {
+        op.vec_ok |= 2;
+        if (epi.out_f16) make_tmap_any(&op.tmC, epi.out_f16, false, M, N, epi.ld_out, 32, 64);   // 32 x 32 fp16 boxes
+        else make_tmap_any(&op.tmC, epi.out_f32, true, M, N, epi.ld_out, 32);
+        if (op.n_adds == 1) make_tmap_any(&op.tmR, op.epi.add0, true, M, N, op.epi.ld_add0, 32);
+    }
+    if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 7) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA
+    make_tmap(&op.tmA, A, M, K, lda, BM);           // every CTA stages its own 128 rows of A
+    make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and (in a CTA pair) half of the W tile
 }
 
 void gemm_launch(const GemmOp& op, cudaStream_t stream) {

@@ -25,16 +25,18 @@ struct GemmEpi {
 struct GemmOp {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmC;      // output (TMA store epilogue), valid when vec_ok & 2
+    CUtensorMap tmR;      // fp32 residual (TMA-prefetched into the epilogue staging), valid when vec_ok & 2 and n_adds == 1
     GemmEpi epi;
     int M = 0, N = 0, K = 0;
     int bn = 128;    // N tile: 64, 128 or 256
-    int cm = 1, cn = 1;   // thread-block cluster shape (CTAs along M x along N) sharing operand tiles by TMA multicast
+    int cm = 1, cn = 1;   // cm = 2: CTA pair (cluster of 2 along M) driving cta_group::2 MMAs on a 256 x bn tile; cn is always 1
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
-    int vec_ok = 0;  // all epilogue tensors 16-byte aligned with pitches % 4 == 0
+    int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
 
 // Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).
-// tile_code = 0 picks tile width and cluster shape from the problem shape; otherwise bn | (cm << 12) | (cn << 16).
+// tile_code = 0 picks tile width and pairing from the problem shape; otherwise bn | (cm << 12).
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);

@@ -32,7 +32,7 @@ def main():
         resid = rng.standard_normal((M, N)).astype(np.float32) if "res" in epi else None
         addend = rng.standard_normal((M, N)).astype(np.float32) if "add" in epi else None
         ref = None
-        for tile, cm, cn in [(t, cm, cn) for t in (64, 128, 256) for cm, cn in ((1, 1), (2, 1))] + [(0, 0, 0)]:
+        for tile, cm, cn in [(64, 1, 1)] + [(t, cm, cn) for t in (128, 256) for cm, cn in ((1, 1), (2, 1))] + [(0, 0, 0)]:
             code = tile | (cm << 12) | (cn << 16)
             out, ms = dbg_gemm(lib, A, W, bias, resid, addend, relu=int("relu" in epi), out_half=int(epi.startswith("f16")), tile_n=code, iters=50)
             if ref is None:

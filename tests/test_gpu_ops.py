@@ -16,10 +16,10 @@ pytestmark = pytest.mark.gpu
     (128, 128, 64, 128), (128, 64, 128, 64), (256, 256, 512, 256), (5312, 1536, 560, 0), (5312, 512, 512, 0),
     (5312, 2048, 512, 0), (5312, 512, 2048, 0), (1344, 8404, 512, 0), (83, 512, 512, 0), (100, 520, 72, 64),
     (300, 8404, 512, 128), (640, 1024, 512, 256),
-    # thread-block clusters with TMA-multicast operand sharing: tile | (cm << 12) | (cn << 16)
+    # CTA-pair (cta_group::2) MMA, 256 x tile per pair: tile | (2 << 12)
     (5312, 1536, 512, 256 | (2 << 12)), (640, 1024, 512, 256 | (2 << 12)), (300, 8404, 512, 128 | (2 << 12)),
-    (83, 512, 512, 64 | (2 << 12)), (5312, 512, 2048, 128 | (2 << 12)), (1600, 8404, 512, 256 | (2 << 12)),
-    (1000, 520, 72, 64 | (2 << 12)), (200, 25055, 512, 256),
+    (83, 512, 512, 128 | (2 << 12)), (5312, 512, 2048, 128 | (2 << 12)), (1600, 8404, 512, 256 | (2 << 12)),
+    (1000, 520, 72, 128 | (2 << 12)), (129, 256, 64, 256 | (2 << 12)), (1600, 2048, 512, 256 | (2 << 12)), (200, 25055, 512, 256),
 ])
 def test_gemm_plain(lib, M, N, K, tile):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
