@@ -48,6 +48,14 @@ class PfResult(C.Structure):
     ]
 
 
+class PfOnlineResult(C.Structure):
+    _fields_ = [
+        ("n_streams", C.c_int32), ("max_new", C.c_int32), ("vocab", C.c_int32), ("n_working", C.c_int32),
+        ("appended", C.POINTER(C.c_int32)), ("new_tokens", C.POINTER(C.c_int32)), ("embeds_len", C.POINTER(C.c_int32)),
+        ("logits", C.POINTER(C.c_float)),
+    ]
+
+
 class PfError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libpfasr error {code}: {message}")
@@ -79,6 +87,19 @@ SIGNATURES = {
     "pf_offline_get_gemm_ms": (C.c_double, [C.c_void_p]),
     "pf_offline_get_profile_json": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),
     "pf_offline_get_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "pf_online_create": (C.c_int32, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_online_create_from_memory": (C.c_int32, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_online_destroy": (C.c_int32, [C.c_void_p]),
+    "pf_online_set_cmvn": (C.c_int32, [C.c_void_p, _F, _F, C.c_int32]),
+    "pf_online_stream_open": (C.c_int32, [C.c_void_p, _I]),
+    "pf_online_stream_close": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pf_online_stream_push": (C.c_int32, [C.c_void_p, C.c_int32, _F, C.c_int32]),
+    "pf_online_stream_ready": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pf_online_step": (C.c_int32, [C.c_void_p, _I, C.c_int32, C.c_uint32, C.POINTER(PfOnlineResult)]),
+    "pf_online_get_state": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p, _F, C.c_size_t]),
+    "pf_online_get_timings": (C.c_int32, [C.c_void_p, _F, C.c_int32]),
+    "pf_online_get_launch_count": (C.c_int64, [C.c_void_p]),
+    "pf_online_get_gemm_flops": (C.c_double, [C.c_void_p]),
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),
     "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),

@@ -53,7 +53,8 @@ static void validate_config(const pf_config& c) {
     if (c.vocab < 8) throw StatusError{PF_ERR_SHAPE, "vocab too small"};
 }
 
-static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
+template <typename Handle>
+static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
     if (!cfg || !blob) throw StatusError{PF_ERR_BAD_ARG, "null config or weights"};
     validate_config(*cfg);
     int count = 0;
@@ -72,7 +73,7 @@ static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size
     for (int d : devs) if (d < 0 || d >= count) throw StatusError{PF_ERR_BAD_ARG, "device ordinal out of range"};
     Blob b;
     b.parse(blob, bytes);
-    std::unique_ptr<OfflineHandle> h(new OfflineHandle());
+    std::unique_ptr<Handle> h(new Handle());
     h->cfg = *cfg;
     for (int d : devs) {
         std::unique_ptr<DeviceCtx> ctx(new DeviceCtx(d, *cfg));
@@ -80,6 +81,93 @@ static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size
         h->devs.push_back(std::move(ctx));
     }
     return h.release();
+}
+
+static OfflineHandle* create_handle(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
+    return create_handle_t<OfflineHandle>(cfg, blob, bytes, devices, ndev);
+}
+
+static std::vector<char> read_file(const char* path) {
+    if (!path || !*path) throw StatusError{PF_ERR_WEIGHTS, "weights path is empty"};
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw StatusError{PF_ERR_WEIGHTS, std::string("cannot open weights file ") + path};
+    const std::streamsize sz = f.tellg();
+    f.seekg(0);
+    std::vector<char> buf(static_cast<size_t>(sz));
+    if (!f.read(buf.data(), sz)) throw StatusError{PF_ERR_WEIGHTS, "short read on weights file"};
+    return buf;
+}
+
+// ------------------------------------------------------------------ streaming (online) handle
+static constexpr int kChunkSamples = 160 * 60;        // OnlineStream.cs:61,101 (160 * ChunkLength)
+
+static OnlineStreamHost& stream_of(OnlineHandle* h, int32_t id) {
+    if (id < 0 || id >= static_cast<int>(h->streams.size()) || !h->streams[id].open)
+        throw StatusError{PF_ERR_BAD_ARG, "unknown or closed stream id " + std::to_string(id)};
+    return h->streams[id];
+}
+
+static void online_step_all(OnlineHandle* h, const int32_t* ids, int32_t n, uint32_t flags, pf_online_result* out) {
+    const int nd = static_cast<int>(h->devs.size());
+    std::vector<std::vector<int>> slots(nd), pos(nd);            // per device: slots in caller order, and their index in ids
+    for (int i = 0; i < n; ++i) {
+        OnlineStreamHost& st = stream_of(h, ids[i]);
+        for (int j = 0; j < i; ++j) if (ids[j] == ids[i]) throw StatusError{PF_ERR_BAD_ARG, "duplicate stream id in one step"};
+        slots[st.dev].push_back(st.slot);
+        pos[st.dev].push_back(i);
+    }
+    std::vector<int> active;
+    for (int d = 0; d < nd; ++d) if (!slots[d].empty()) active.push_back(d);
+    const int na = static_cast<int>(active.size());
+    if (na == 1) {
+        h->devs[active[0]]->online_step(slots[active[0]], flags, nullptr, 0);
+    } else if (na > 1) {
+        SharedRun shared(na);
+        std::vector<std::thread> threads;
+        std::vector<std::pair<pf_status, std::string>> errs(na, {PF_OK, ""});
+        for (int k = 0; k < na; ++k) {
+            threads.emplace_back([&, k] {
+                try {
+                    h->devs[active[k]]->online_step(slots[active[k]], flags, &shared, k);
+                } catch (const StatusError& e) {
+                    errs[k] = {e.code, e.what};
+                } catch (const CudaError& e) {
+                    errs[k] = {PF_ERR_CUDA, e.what};
+                } catch (const std::exception& e) {
+                    errs[k] = {PF_ERR_BAD_ARG, e.what()};
+                }
+            });
+        }
+        for (auto& t : threads) t.join();
+        for (auto& er : errs) if (er.first != PF_OK) throw StatusError{er.first, er.second};
+        if (shared.failed) throw StatusError{PF_ERR_CUDA, "a device shard failed"};
+    }
+    int lmax = 0, nwork = 0;
+    for (int d : active) { lmax = std::max(lmax, h->devs[d]->Lmax_); nwork += static_cast<int>(h->devs[d]->online_working.size()); }
+    const int V = h->cfg.vocab;
+    const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0 && lmax > 0;
+    h->appended.assign(n, 0);
+    h->embeds_len.assign(n, 0);
+    h->new_tokens.assign(static_cast<size_t>(n) * lmax, 0);
+    if (wl) h->logits.assign(static_cast<size_t>(n) * lmax * V, 0.0f);
+    for (int d : active) {
+        DeviceCtx* ctx = h->devs[d].get();
+        for (size_t b = 0; b < ctx->online_working.size(); ++b) {
+            const int i = pos[d][ctx->online_working[b]];
+            h->embeds_len[i] = ctx->h_online_counts[b];
+            h->appended[i] = lmax;
+            if (lmax > 0) memcpy(h->new_tokens.data() + static_cast<size_t>(i) * lmax, ctx->h_tokens + b * lmax, static_cast<size_t>(lmax) * sizeof(int32_t));
+            if (wl) memcpy(h->logits.data() + static_cast<size_t>(i) * lmax * V, ctx->h_logits + b * static_cast<size_t>(lmax) * V, static_cast<size_t>(lmax) * V * sizeof(float));
+        }
+    }
+    out->n_streams = n;
+    out->max_new = lmax;
+    out->vocab = V;
+    out->n_working = nwork;
+    out->appended = h->appended.data();
+    out->new_tokens = h->new_tokens.data();
+    out->embeds_len = h->embeds_len.data();
+    out->logits = wl ? h->logits.data() : nullptr;
 }
 
 // contiguous split of B items over n shards
@@ -199,13 +287,7 @@ pf_status pf_offline_create(const pf_config* cfg, const char* weights_path, cons
     return guarded([&] {
         if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
         *out = nullptr;
-        if (!weights_path || !*weights_path) throw StatusError{PF_ERR_WEIGHTS, "weights path is empty"};
-        std::ifstream f(weights_path, std::ios::binary | std::ios::ate);
-        if (!f) throw StatusError{PF_ERR_WEIGHTS, std::string("cannot open weights file ") + weights_path};
-        const std::streamsize sz = f.tellg();
-        f.seekg(0);
-        std::vector<char> buf(static_cast<size_t>(sz));
-        if (!f.read(buf.data(), sz)) throw StatusError{PF_ERR_WEIGHTS, "short read on weights file"};
+        const std::vector<char> buf = read_file(weights_path);
         *out = reinterpret_cast<pf_offline*>(create_handle(cfg, buf.data(), buf.size(), devices, ndev));
     });
 }
@@ -368,6 +450,150 @@ void* pf_offline_get_stream(pf_offline* hh, int32_t dev_index) {
     OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
     if (dev_index < 0 || dev_index >= static_cast<int>(h->devs.size())) return nullptr;
     return h->devs[dev_index]->stream();
+}
+
+// ------------------------------------------------------------------ streaming (online) exports
+static OnlineHandle* create_online(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
+    if (cfg && cfg->model_kind != PF_MODEL_PARAFORMER) throw StatusError{PF_ERR_UNSUPPORTED, "streaming is a paraformer path"};
+    return create_handle_t<OnlineHandle>(cfg, blob, bytes, devices, ndev);
+}
+
+pf_status pf_online_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes, const int32_t* devices,
+                                       int32_t ndev, pf_online** out) {
+    return guarded([&] {
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        *out = nullptr;
+        *out = reinterpret_cast<pf_online*>(create_online(cfg, blob, blob_bytes, devices, ndev));
+    });
+}
+
+pf_status pf_online_create(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev, pf_online** out) {
+    return guarded([&] {
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        *out = nullptr;
+        const std::vector<char> buf = read_file(weights_path);
+        *out = reinterpret_cast<pf_online*>(create_online(cfg, buf.data(), buf.size(), devices, ndev));
+    });
+}
+
+pf_status pf_online_destroy(pf_online* hh) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        delete reinterpret_cast<OnlineHandle*>(hh);
+    });
+}
+
+pf_status pf_online_set_cmvn(pf_online* hh, const float* add_shift, const float* rescale, int32_t dim) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!add_shift || !rescale) throw StatusError{PF_ERR_BAD_ARG, "null cmvn vectors"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        for (auto& d : h->devs) d->set_cmvn(add_shift, rescale, dim);
+    });
+}
+
+pf_status pf_online_stream_open(pf_online* hh, int32_t* stream_id) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!stream_id) throw StatusError{PF_ERR_BAD_ARG, "stream_id is null"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        int id = -1;
+        for (size_t i = 0; i < h->streams.size(); ++i) if (!h->streams[i].open) { id = static_cast<int>(i); break; }
+        if (id < 0) { id = static_cast<int>(h->streams.size()); h->streams.emplace_back(); }
+        OnlineStreamHost& st = h->streams[id];
+        st.dev = id % static_cast<int>(h->devs.size());               // sticky placement, state never migrates
+        st.slot = h->devs[st.dev]->online_open();
+        st.cache_samples.assign(kChunkSamples, 0.0f);                  // _cacheSamples = new float[160 * ChunkLength] (Q13)
+        st.open = true;
+        *stream_id = id;
+    });
+}
+
+pf_status pf_online_stream_close(pf_online* hh, int32_t stream_id) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        OnlineStreamHost& st = stream_of(h, stream_id);
+        h->devs[st.dev]->online_close(st.slot);
+        st.open = false;
+        st.cache_samples.clear();
+        st.cache_samples.shrink_to_fit();
+    });
+}
+
+pf_status pf_online_stream_push(pf_online* hh, int32_t stream_id, const float* samples, int32_t nsamp) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!samples && nsamp != 0) throw StatusError{PF_ERR_BAD_ARG, "samples is null (NullReferenceException in OnlineStream.AddSamples)"};
+        if (nsamp < 0) throw StatusError{PF_ERR_BAD_ARG, "negative sample count"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        OnlineStreamHost& st = stream_of(h, stream_id);
+        st.cache_samples.insert(st.cache_samples.end(), samples, samples + nsamp);
+        if (static_cast<int>(st.cache_samples.size()) > kChunkSamples) {          // strictly more than one chunk (OnlineStream.cs:102)
+            h->devs[st.dev]->online_push_chunk(st.slot, st.cache_samples.data(), kChunkSamples);
+            st.cache_samples.erase(st.cache_samples.begin(), st.cache_samples.begin() + kChunkSamples);
+        }
+    });
+}
+
+int32_t pf_online_stream_ready(pf_online* hh, int32_t stream_id) {
+    if (!hh) return -1;
+    OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+    std::lock_guard<std::mutex> g(h->mu);
+    if (stream_id < 0 || stream_id >= static_cast<int>(h->streams.size()) || !h->streams[stream_id].open) return -1;
+    const OnlineStreamHost& st = h->streams[stream_id];
+    return h->devs[st.dev]->online_ready(st.slot) ? 1 : 0;
+}
+
+pf_status pf_online_step(pf_online* hh, const int32_t* stream_ids, int32_t n, uint32_t flags, pf_online_result* out) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        memset(out, 0, sizeof(*out));
+        if (n == 0) return;                                            // streams.Count == 0 (OnlineRecognizer.cs:343-346)
+        if (!stream_ids || n < 0) throw StatusError{PF_ERR_BAD_ARG, "stream_ids is null"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        online_step_all(h, stream_ids, n, flags, out);
+    });
+}
+
+pf_status pf_online_get_state(pf_online* hh, int32_t stream_id, const char* name, float* dst, size_t capacity) {
+    return guarded([&] {
+        if (!hh || !name) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
+        OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        OnlineStreamHost& st = stream_of(h, stream_id);
+        h->devs[st.dev]->online_get_state(st.slot, name, dst, capacity);
+    });
+}
+
+int32_t pf_online_get_timings(pf_online* hh, float* ms, int32_t capacity) {
+    if (!hh || !ms) return 0;
+    OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+    const int n = std::min(capacity, 6);
+    for (int i = 0; i < n; ++i) ms[i] = h->devs[0]->timings_ms[i];
+    return n;
+}
+
+int64_t pf_online_get_launch_count(pf_online* hh) {
+    if (!hh) return 0;
+    OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+    int64_t n = 0;
+    for (auto& d : h->devs) n += d->launches;
+    return n;
+}
+
+double pf_online_get_gemm_flops(pf_online* hh) {
+    if (!hh) return 0;
+    OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
+    double n = 0;
+    for (auto& d : h->devs) n += d->gemm_flops;
+    return n;
 }
 
 }  // extern "C"

@@ -127,6 +127,12 @@ DeviceCtx::~DeviceCtx() {
     if (h_token_num) cudaFreeHost(h_token_num);
     if (h_logits) cudaFreeHost(h_logits);
     if (h_peaks) cudaFreeHost(h_peaks);
+    if (h_online_counts) cudaFreeHost(h_online_counts);
+    if (h_ostage_) cudaFreeHost(h_ostage_);
+    for (float* p : {ofifo_, opcm_, osplice_, ocache_, ocif_a_, ocif_h_, ofsmn_}) if (p) cudaFree(p);
+    if (ofe_off_) cudaFree(ofe_off_);
+    if (ofe_meta_) cudaFree(ofe_meta_);
+    free_pool(opool_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
     for (auto& e : prof_pool_) cudaEventDestroy(e);
     for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -599,12 +605,13 @@ int DeviceCtx::extract(const float* samples, int nsamp, float* out, int capacity
 }
 
 // ------------------------------------------------------------------ forward passes
-void DeviceCtx::encoder_forward(int B, int T) {
+void DeviceCtx::encoder_forward(int B, int T, bool online) {
     const int M = B * T, d = cfg_.d_model, H = cfg_.heads;
     EncoderPlan& plan = encoder_plan(B, T);
     timed("embed_pe_ln", [&] {
-        embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), inv_ts_, enc_[0].ln1.g, enc_[0].ln1.b,
-                           cfg_.ln_eps, a16_, stream_);
+        // streaming windows arrive scaled and position-encoded (OnlineStream.cs:203-206): LayerNorm only
+        embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), online ? nullptr : inv_ts_, enc_[0].ln1.g,
+                           enc_[0].ln1.b, cfg_.ln_eps, a16_, stream_);
     });
     ++launches;
     auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool first) {
@@ -639,25 +646,33 @@ void DeviceCtx::encoder_forward(int B, int T) {
     }
 }
 
-void DeviceCtx::predictor_forward(int B, int T) {
+void DeviceCtx::predictor_forward(int B, int T, bool online) {
     const int d = cfg_.d_model;
     EncoderPlan& plan = encoder_plan(B, T);
     gemm(plan.kv_all);                                  // decoder K/V of all layers; independent of the CIF result
     im2col3_launch(enc16_, B, T, d, qkv16_, stream_);
     gemm(plan.pred_conv);
-    alpha_head_launch(mem32_, B, T, d, w_alpha_, b_alpha_, cfg_.smooth_factor, cfg_.noise_threshold, cfg_.cif_tail, alphas_, stream_);
+    alpha_head_launch(mem32_, B, T, d, w_alpha_, b_alpha_, cfg_.smooth_factor, cfg_.noise_threshold, online ? 0.0f : cfg_.cif_tail,
+                      alphas_, stream_);
     PF_CUDA(cudaMemsetAsync(meta_, 0, 4 * sizeof(int), stream_));
+    launches += 2;
+    if (online) return;                                 // the streaming CIF (with carry, no tail) is online_cif_launch
     cif_scan_launch(alphas_, B, T + 1, cfg_.cif_threshold, wcur_, wrem_, fire_idx_, peaks_, token_num_, fires_, meta_, stream_);
-    launches += 3;
+    ++launches;
 }
 
-void DeviceCtx::decoder_forward(int B, int T, int L) {
+void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
     const int Md = B * L, d = cfg_.d_model, f = cfg_.dec_ffn, H = cfg_.heads;
     DecoderPlan& plan = decoder_plan(B, T, L);
     const float eps = cfg_.ln_eps;
-    PF_CUDA(cudaMemsetAsync(xd32_, 0, static_cast<size_t>(Md) * d * sizeof(float), stream_));
-    cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
-    ++launches;
+    if (!online) {                                      // streaming: xd32_ already holds the compacted CIF frames
+        PF_CUDA(cudaMemsetAsync(xd32_, 0, static_cast<size_t>(Md) * d * sizeof(float), stream_));
+        cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
+        ++launches;
+    }
+    // Q11 (OnlineModel.cs:222): stack_states hands every layer the stream's LAYER-0 cache; reserved[0] bit 0 opts out
+    const bool per_layer_cache = (cfg_.reserved[0] & 1) != 0;
+    const size_t cache_layer = static_cast<size_t>(cfg_.dec_kernel - 1) * d;
     auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
         timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(g1);
@@ -671,7 +686,11 @@ void DeviceCtx::decoder_forward(int B, int T, int L) {
         const DecLayerPlan& lp = plan.layers[i];
         ffn(w.ffn, lp.w1, lp.w2);
         timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
-        timed("dec_fsmn", [&] { fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_); });
+        timed("dec_fsmn", [&] {
+            if (!online) fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
+            else online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, cfg_.dec_kernel, ofsmn_, fsmn_state_stride(),
+                                    per_layer_cache ? i * cache_layer : 0, xd32_, ocache_new_, fsmn_state_stride(), i * cache_layer, stream_);
+        });
         timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(lp.q);
         timed("dec_cross_attention", [&] {
@@ -683,7 +702,8 @@ void DeviceCtx::decoder_forward(int B, int T, int L) {
     ffn(dec3_, plan.d3_w1, plan.d3_w2);
     layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, nullptr, 0, stream_);
     gemm(plan.head);
-    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, 1, stream_);
+    // offline model_out is log-softmax; the streaming decoder graph returns raw logits (the pick is the same)
+    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, online ? 0 : 1, stream_);
     launches += 2;
 }
 
@@ -809,6 +829,264 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
     }
     cudaEventElapsedTime(&ms, ev_[0], ev_[6]);
     timings_ms[5] = ms;
+}
+
+// ------------------------------------------------------------------ streaming (online) path
+void DeviceCtx::online_grow(int min_slots) {
+    if (min_slots <= ocap_) return;
+    PF_CUDA(cudaSetDevice(dev_));
+    if (ocap_ == 0) {
+        // geometry: OnlineModel.cs:15-16,30 (chunk 5, lfr 10 -> 60 frames / 9600 samples per chunk); streaming LFR rule
+        od_.mel = cfg_.n_mels; od_.lfr_m = cfg_.lfr_m; od_.lfr_n = cfg_.lfr_n; od_.d_model = cfg_.d_model;
+        od_.chunk_len = 60;
+        od_.nf = frontend_num_frames(160 * od_.chunk_len, cfg_.snip_edges != 0);
+        const int t = od_.chunk_len + 1;
+        od_.t_new = (t % od_.lfr_n < od_.lfr_m - od_.lfr_n) ? t / od_.lfr_n - 1 : t / od_.lfr_n;
+        od_.cache_rows = 10;
+        if (od_.t_new != od_.cache_rows || od_.nf < 1)
+            throw StatusError{PF_ERR_UNSUPPORTED, "streaming needs lfr_m/lfr_n that turn 61 frames into 10 LFR rows (7/6)"};
+        if (cfg_.model_kind != PF_MODEL_PARAFORMER) throw StatusError{PF_ERR_UNSUPPORTED, "streaming is a paraformer path"};
+        // Q12 (OnlineWavFrontend.cs:163-170): inv_timescale_i = exp(-(i+1) * ln(1e4) / (dim/2 - 1)), float arithmetic
+        const int half = cfg_.input_size / 2;
+        std::vector<float> inv(half);
+        const float inc = static_cast<float>(log(10000.0)) / static_cast<float>(half - 1);
+        for (int i = 0; i < half; ++i) inv[i] = static_cast<float>(exp(static_cast<double>(static_cast<float>(i + 1) * -inc)));
+        inv_ts_online_ = up_f32(inv.data(), inv.size());
+    }
+    int cap = std::max(16, ocap_);
+    while (cap < min_slots) cap *= 2;
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    const size_t dim = static_cast<size_t>(cfg_.lfr_m) * cfg_.n_mels;
+    const size_t per[7] = {static_cast<size_t>(od_.nslot) * (od_.nf + 1) * od_.mel, static_cast<size_t>(od_.nslot) * 160 * od_.chunk_len,
+                           static_cast<size_t>(od_.mel), od_.cache_rows * dim, 1, static_cast<size_t>(cfg_.d_model), fsmn_state_stride()};
+    float** ptrs[7] = {&ofifo_, &opcm_, &osplice_, &ocache_, &ocif_a_, &ocif_h_, &ofsmn_};
+    for (int i = 0; i < 7; ++i) {
+        float* fresh = nullptr;
+        cudaError_t e = cudaMalloc(&fresh, per[i] * cap * sizeof(float));
+        if (e != cudaSuccess) { cudaGetLastError(); throw StatusError{PF_ERR_OOM, "cudaMalloc of streaming state failed"}; }
+        PF_CUDA(cudaMemsetAsync(fresh, 0, per[i] * cap * sizeof(float), stream_));
+        if (*ptrs[i]) {
+            PF_CUDA(cudaMemcpyAsync(fresh, *ptrs[i], per[i] * ocap_ * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+            PF_CUDA(cudaStreamSynchronize(stream_));
+            cudaFree(*ptrs[i]);
+        }
+        *ptrs[i] = fresh;
+    }
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    oslots_.resize(cap);
+    ocap_ = cap;
+}
+
+int DeviceCtx::online_open() {
+    PF_CUDA(cudaSetDevice(dev_));
+    int slot = -1;
+    for (int i = 0; i < ocap_; ++i) if (!oslots_[i].open) { slot = i; break; }
+    if (slot < 0) { slot = ocap_; online_grow(ocap_ + 1); }
+    // fresh OnlineStream state (OnlineStream.cs:53-61): zero feature cache, CIF carry, FSMN caches, no splice
+    const size_t dim = static_cast<size_t>(cfg_.lfr_m) * cfg_.n_mels;
+    PF_CUDA(cudaMemsetAsync(osplice_ + static_cast<size_t>(slot) * od_.mel, 0, od_.mel * sizeof(float), stream_));
+    PF_CUDA(cudaMemsetAsync(ocache_ + static_cast<size_t>(slot) * od_.cache_rows * dim, 0, od_.cache_rows * dim * sizeof(float), stream_));
+    PF_CUDA(cudaMemsetAsync(ocif_a_ + slot, 0, sizeof(float), stream_));
+    PF_CUDA(cudaMemsetAsync(ocif_h_ + static_cast<size_t>(slot) * cfg_.d_model, 0, cfg_.d_model * sizeof(float), stream_));
+    PF_CUDA(cudaMemsetAsync(ofsmn_ + static_cast<size_t>(slot) * fsmn_state_stride(), 0, fsmn_state_stride() * sizeof(float), stream_));
+    oslots_[slot] = OnlineSlot{};
+    oslots_[slot].open = true;
+    return slot;
+}
+
+void DeviceCtx::online_close(int slot) {
+    if (slot < 0 || slot >= ocap_ || !oslots_[slot].open) throw StatusError{PF_ERR_BAD_ARG, "stream slot is not open"};
+    oslots_[slot].open = false;
+}
+
+void DeviceCtx::online_push_chunk(int slot, const float* samples, int nsamp) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (slot < 0 || slot >= ocap_ || !oslots_[slot].open) throw StatusError{PF_ERR_BAD_ARG, "stream slot is not open"};
+    const int chunk = 160 * od_.chunk_len;
+    if (nsamp != chunk) throw StatusError{PF_ERR_SHAPE, "a streaming chunk is 160 * 60 samples"};
+    OnlineSlot& s = oslots_[slot];
+    // the oldest chunk a future window still reads must not be overwritten
+    const long long base = static_cast<long long>(od_.chunk_len) * s.dec;
+    const long long c_min = base < od_.nf + 1 ? 0 : 1 + (base - od_.nf - 1) / od_.nf;
+    if (s.pushed - c_min >= od_.nslot)
+        throw StatusError{PF_ERR_SHAPE, "stream backlog exceeds " + std::to_string(od_.nslot) + " chunks: call the recognizer's GetResults"};
+    float* dst = opcm_ + (static_cast<size_t>(slot) * od_.nslot + static_cast<size_t>(s.pushed % od_.nslot)) * chunk;
+    PF_CUDA(cudaMemcpyAsync(dst, samples, static_cast<size_t>(chunk) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    ++s.pushed;
+}
+
+bool DeviceCtx::online_ready(int slot) const {
+    if (slot < 0 || slot >= ocap_ || !oslots_[slot].open) return false;
+    const OnlineSlot& s = oslots_[slot];
+    const long long avail = s.pushed > 0 ? s.pushed * od_.nf + 1 : 0;      // first chunk repeats its first frame
+    return static_cast<long long>(od_.chunk_len) * (s.dec + 1) <= avail;
+}
+
+void DeviceCtx::online_step(const std::vector<int>& slots, uint32_t flags, SharedRun* shared, int idx) {
+    arrived_ = false;
+    try {
+        online_step_impl(slots, flags, shared, idx);
+    } catch (...) {
+        if (shared && !arrived_) { shared->failed = true; shared->lmax[idx] = 0; arrived_ = true; shared->barrier.arrive_and_wait(); }
+        throw;
+    }
+}
+
+void DeviceCtx::online_step_impl(const std::vector<int>& slots, uint32_t flags, SharedRun* shared, int idx) {
+    PF_CUDA(cudaSetDevice(dev_));
+    launches = 0;
+    gemm_flops = 0.0;
+    online_working.clear();
+    Lmax_ = 0; Lpad_ = 0; B_ = 0; T_ = 0;
+    PF_CUDA(cudaEventRecord(ev_[0], stream_));
+    const int chunk = 160 * od_.chunk_len;
+    // ---- per-chunk fbank (InputSpeech, OnlineStream.cs:114-167) for everything pushed since the last step, one launch
+    int npend = 0;
+    for (int slot : slots) {
+        if (slot < 0 || slot >= ocap_ || !oslots_[slot].open) throw StatusError{PF_ERR_BAD_ARG, "stream slot is not open"};
+        npend += static_cast<int>(oslots_[slot].pushed - oslots_[slot].fbanked);
+    }
+    const int nlist = static_cast<int>(slots.size());
+    const size_t stage_bytes = static_cast<size_t>(std::max(npend, 1)) * (2 * sizeof(long long) + 3 * sizeof(int)) + static_cast<size_t>(std::max(nlist, 1)) * 4 * sizeof(int);
+    ensure_pinned(&h_ostage_, &h_ostage_bytes_, stage_bytes);
+    long long* h_off = static_cast<long long*>(h_ostage_);
+    int* h_m = reinterpret_cast<int*>(h_off + 2 * std::max(npend, 1));
+    int* h_tab = h_m + 3 * std::max(npend, 1);
+    if (npend > 0) {
+        if (npend > ofe_cap_) {
+            if (ofe_off_) cudaFree(ofe_off_);
+            if (ofe_meta_) cudaFree(ofe_meta_);
+            ofe_cap_ = std::max(npend, 2 * ofe_cap_);
+            PF_CUDA(cudaMalloc(&ofe_off_, static_cast<size_t>(ofe_cap_) * 2 * sizeof(long long)));
+            PF_CUDA(cudaMalloc(&ofe_meta_, static_cast<size_t>(ofe_cap_) * 3 * sizeof(int)));
+        }
+        int k = 0;
+        for (int slot : slots) {
+            OnlineSlot& s = oslots_[slot];
+            for (long long c = s.fbanked; c < s.pushed; ++c, ++k) {
+                const size_t cs = static_cast<size_t>(slot) * od_.nslot + static_cast<size_t>(c % od_.nslot);
+                h_off[k] = static_cast<long long>(cs * chunk);
+                // chunk 0 keeps row 0 free: it aliases row 1 (first-frame repeat, OnlineStream.cs:141-153)
+                h_off[npend + k] = static_cast<long long>((cs * (od_.nf + 1) + (c == 0 ? 1 : 0)) * od_.mel);
+                h_m[k] = chunk;
+                h_m[npend + k] = od_.nf;
+                h_m[2 * npend + k] = 0;
+            }
+            s.fbanked = s.pushed;
+        }
+        PF_CUDA(cudaMemcpyAsync(ofe_off_, h_off, static_cast<size_t>(npend) * 2 * sizeof(long long), cudaMemcpyHostToDevice, stream_));
+        PF_CUDA(cudaMemcpyAsync(ofe_meta_, h_m, static_cast<size_t>(npend) * 3 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        FrontendLaunch a;
+        a.tables = fe_tables_; a.pcm = opcm_; a.pcm_off = ofe_off_; a.nsamp = ofe_meta_; a.nframes = ofe_meta_ + npend; a.nlfr = ofe_meta_ + 2 * npend;
+        a.add_shift = cmvn_shift_; a.rescale = cmvn_scale_;
+        a.fbank_out = ofifo_; a.fbank_off = ofe_off_ + npend;
+        a.batch = npend; a.max_frames = od_.nf; a.tmax_lfr = 0; a.lfr_m = cfg_.lfr_m; a.lfr_n = cfg_.lfr_n;
+        a.snip_edges = cfg_.snip_edges != 0;
+        frontend_launch(a, stream_);
+        ++launches;
+    }
+    // ---- working set (GetDecodeChunk returns null without a full chunk: the stream is skipped, OnlineRecognizer.cs:357-361)
+    for (int i = 0; i < nlist; ++i) if (online_ready(slots[i])) online_working.push_back(i);
+    const int B = static_cast<int>(online_working.size());
+    PF_CUDA(cudaEventRecord(ev_[1], stream_));
+    auto finish = [&] {
+        PF_CUDA(cudaEventRecord(ev_[6], stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        finish_profile();
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[6]);
+        timings_ms[5] = ms;
+    };
+    if (B == 0) {
+        if (shared) { shared->lmax[idx] = 0; arrived_ = true; shared->barrier.arrive_and_wait(); }
+        finish();
+        return;
+    }
+    const int T = od_.cache_rows + od_.t_new, d = cfg_.d_model;
+    ensure_workspace(B, T);
+    if (B > owork_cap_) {
+        for (void* p : opool_) cudaFree(p);
+        opool_.clear();
+        owork_cap_ = std::max(B, 2 * owork_cap_);
+        ofresh_ = dalloc<float>(static_cast<size_t>(owork_cap_) * od_.t_new * cfg_.input_size, opool_);
+        ocache_new_ = dalloc<float>(static_cast<size_t>(owork_cap_) * fsmn_state_stride(), opool_);
+        otab_ = dalloc<int>(static_cast<size_t>(owork_cap_) * 4, opool_);
+    }
+    for (int b = 0; b < B; ++b) {
+        const int slot = slots[online_working[b]];
+        const OnlineSlot& s = oslots_[slot];
+        h_tab[4 * b + 0] = slot;
+        h_tab[4 * b + 1] = static_cast<int>(static_cast<long long>(od_.chunk_len) * s.dec);
+        h_tab[4 * b + 2] = s.dec > 0 ? 1 : 0;                            // _cachelfrSplice is empty before the first window
+        h_tab[4 * b + 3] = static_cast<int>(od_.t_new * s.dec);          // _startIdx
+    }
+    PF_CUDA(cudaMemcpyAsync(otab_, h_tab, static_cast<size_t>(B) * 4 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    online_assemble_launch(od_, otab_, B, ofifo_, osplice_, ocache_, cmvn_shift_, cmvn_scale_, inv_ts_online_, feats_, ofresh_, stream_);
+    online_commit_launch(od_, otab_, B, ofifo_, ofresh_, osplice_, ocache_, stream_);
+    launches += 2;
+    for (int b = 0; b < B; ++b) ++oslots_[slots[online_working[b]]].dec;
+    B_ = B; T_ = T;
+    // ---- encoder.onnx: SAN-M encoder + alpha head (OnlineRecognizer.EncoderProj)
+    encoder_forward(B, T, true);
+    PF_CUDA(cudaEventRecord(ev_[2], stream_));
+    predictor_forward(B, T, true);
+    // ---- DynamicMask + host CIF with carry (OnlineRecognizer.PredictorProj); frames land in tn32_ as [B, T+1, d]
+    const int lcap = T + 1;
+    online_cif_launch(otab_, B, enc32_, alphas_, T + 1, T, d, 5, 15, cfg_.cif_threshold, ocif_a_, ocif_h_, tn32_, lcap, fires_, meta_, stream_);
+    ++launches;
+    ensure_pinned(reinterpret_cast<void**>(&h_online_counts), &h_ocounts_cap_, static_cast<size_t>(B) * sizeof(int32_t));
+    PF_CUDA(cudaMemcpyAsync(h_meta_, meta_, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    PF_CUDA(cudaMemcpyAsync(h_online_counts, fires_, static_cast<size_t>(B) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    PF_CUDA(cudaEventRecord(ev_[3], stream_));
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    int lmax = h_meta_[0];
+    if (shared) {
+        shared->lmax[idx] = lmax;
+        arrived_ = true; shared->barrier.arrive_and_wait();
+        for (int v : shared->lmax) lmax = std::max(lmax, v);
+    }
+    if (lmax > lcap) throw StatusError{PF_ERR_SHAPE, "more CIF fires than frames in one chunk"};
+    Lmax_ = lmax; Lpad_ = lmax;
+    if (lmax > 0) {                                                       // Acoustic_embeds.Length > 0 (OnlineRecognizer.cs:381)
+        online_compact_launch(tn32_, lcap, fires_, B, lmax, d, xd32_, stream_);
+        ++launches;
+        decoder_forward(B, T, lmax, true);
+        online_scatter_launch(otab_, B, ocache_new_, ofsmn_, fsmn_state_stride(), stream_);
+        ++launches;
+        const size_t ntok = static_cast<size_t>(B) * lmax;
+        const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0;
+        ensure_host(ntok, wl ? ntok * cfg_.vocab : 0, 0);
+        PF_CUDA(cudaMemcpyAsync(h_tokens, tokens_, ntok * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        if (wl) PF_CUDA(cudaMemcpy2DAsync(h_logits, static_cast<size_t>(cfg_.vocab) * sizeof(float), logits_, static_cast<size_t>(ldv()) * sizeof(float),
+                                          static_cast<size_t>(cfg_.vocab) * sizeof(float), ntok, cudaMemcpyDeviceToHost, stream_));
+    }
+    PF_CUDA(cudaEventRecord(ev_[4], stream_));
+    PF_CUDA(cudaEventRecord(ev_[5], stream_));
+    finish();
+    float ms = 0.0f;
+    for (int i = 0; i < 5; ++i) {
+        cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
+        timings_ms[i] = ms;
+    }
+}
+
+void DeviceCtx::online_get_state(int slot, const std::string& name, float* dst, size_t capacity) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (slot < 0 || slot >= ocap_ || !oslots_[slot].open) throw StatusError{PF_ERR_BAD_ARG, "stream slot is not open"};
+    const float* src = nullptr;
+    size_t n = 0;
+    const size_t dim = static_cast<size_t>(cfg_.lfr_m) * cfg_.n_mels;
+    if (name == "cache_feats") { src = ocache_ + static_cast<size_t>(slot) * od_.cache_rows * dim; n = od_.cache_rows * dim; }
+    else if (name == "cif_alpha") { src = ocif_a_ + slot; n = 1; }
+    else if (name == "cif_hidden") { src = ocif_h_ + static_cast<size_t>(slot) * cfg_.d_model; n = cfg_.d_model; }
+    else if (name == "fsmn") { src = ofsmn_ + static_cast<size_t>(slot) * fsmn_state_stride(); n = fsmn_state_stride(); }   // [layers, k-1, d]
+    else if (name == "splice") { src = osplice_ + static_cast<size_t>(slot) * od_.mel; n = od_.mel; }
+    else throw StatusError{PF_ERR_BAD_ARG, "unknown stream state '" + name + "'"};
+    const size_t cnt = std::min(n, capacity);
+    if (dst && cnt) {
+        PF_CUDA(cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        PF_CUDA(cudaStreamSynchronize(stream_));
+    }
 }
 
 void DeviceCtx::get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim) {

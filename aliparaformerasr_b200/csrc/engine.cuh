@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "frontend.cuh"
 #include "gemm.cuh"
+#include "online.cuh"
 #include "ops.cuh"
 
 namespace pf {
@@ -134,6 +135,20 @@ public:
     double gemm_ms = 0.0;              // sum of GEMM launch durations of the last profiled run
     std::string profile_json;          // per-shape breakdown of the last profiled run
 
+    // ---- streaming (online) path: per-stream state lives in HBM, indexed by slot (OnlineStream.cs:24-37 state,
+    // OnlineRecognizer.Forward OnlineRecognizer.cs:341-401).  The sample FIFO / chunk trigger (Q13) is host logic in abi.cu.
+    int online_open();
+    void online_close(int slot);
+    void online_push_chunk(int slot, const float* samples, int nsamp);    // one 160 * chunk_len sample chunk (InputSpeech)
+    bool online_ready(int slot) const;                                    // GetDecodeChunk would return a window
+    // one Forward over `slots` (caller order); streams without a full chunk are skipped like the reference does.
+    // Results: online_working (indices into slots), h_tokens [n_working, Lmax_], h_online_counts [n_working].
+    void online_step(const std::vector<int>& slots, uint32_t flags, SharedRun* shared, int idx);
+    std::vector<int> online_working;
+    int32_t* h_online_counts = nullptr;
+    const OnlineDims& online_dims() const { return od_; }
+    void online_get_state(int slot, const std::string& name, float* dst, size_t capacity);   // test hook
+
     void get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim);
     cudaStream_t stream() const { return stream_; }
     int device() const { return dev_; }
@@ -153,9 +168,11 @@ private:
     EncoderPlan& encoder_plan(int B, int T);
     DecoderPlan& decoder_plan(int B, int T, int L);
     void gemm(const GemmOp& op);
-    void encoder_forward(int B, int T);
-    void predictor_forward(int B, int T);
-    void decoder_forward(int B, int T, int L);
+    void encoder_forward(int B, int T, bool online = false);
+    void predictor_forward(int B, int T, bool online = false);
+    void decoder_forward(int B, int T, int L, bool online = false);
+    void online_step_impl(const std::vector<int>& slots, uint32_t flags, SharedRun* shared, int idx);
+    void online_grow(int min_slots);
     void free_pool(std::vector<void*>& pool);
     void run_impl(uint32_t flags, SharedRun* shared, int idx);
     bool arrived_ = false, ev0_armed_ = false;
@@ -211,6 +228,21 @@ private:
     int* h_meta_ = nullptr;
     size_t h_tokens_cap_ = 0, h_logits_cap_ = 0, h_peaks_cap_ = 0, h_tn_cap_ = 0;
 
+    // streaming state (capacity ocap_ slots)
+    struct OnlineSlot { bool open = false; long long pushed = 0, fbanked = 0, dec = 0; };
+    OnlineDims od_;
+    std::vector<OnlineSlot> oslots_;
+    int ocap_ = 0;
+    float* ofifo_ = nullptr; float* opcm_ = nullptr; float* osplice_ = nullptr; float* ocache_ = nullptr;
+    float* ocif_a_ = nullptr; float* ocif_h_ = nullptr; float* ofsmn_ = nullptr;
+    float* inv_ts_online_ = nullptr;
+    float* ofresh_ = nullptr; float* ocache_new_ = nullptr; int* otab_ = nullptr; int owork_cap_ = 0;
+    long long* ofe_off_ = nullptr; int* ofe_meta_ = nullptr; int ofe_cap_ = 0;
+    void* h_ostage_ = nullptr; size_t h_ostage_bytes_ = 0;
+    size_t h_ocounts_cap_ = 0;
+    std::vector<void*> opool_;
+    size_t fsmn_state_stride() const { return static_cast<size_t>(cfg_.dec_layers) * (cfg_.dec_kernel - 1) * cfg_.d_model; }
+
     std::map<std::pair<int, int>, EncoderPlan> enc_plans_;
     std::map<std::pair<int, int>, DecoderPlan> dec_plans_;   // key (B*capT-independent: B, L) for current T
     int dec_plan_T_ = -1;
@@ -227,6 +259,22 @@ struct OfflineHandle {
     std::vector<float> logits, peaks;
     bool staged = false;
     bool staged_pcm = false;
+};
+
+struct OnlineStreamHost {             // host half of OnlineStream: the sample cache of AddSamples (OnlineStream.cs:84-112)
+    bool open = false;
+    int dev = 0, slot = -1;
+    std::vector<float> cache_samples;
+};
+
+struct OnlineHandle {
+    pf_config cfg;
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    std::mutex mu;
+    std::vector<OnlineStreamHost> streams;
+    // last step
+    std::vector<int32_t> appended, new_tokens, embeds_len;
+    std::vector<float> logits;
 };
 
 }  // namespace pf

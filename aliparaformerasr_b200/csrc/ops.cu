@@ -33,10 +33,14 @@ pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale
         const int c = lane + 32 * i;
         float val = 0.0f;
         if (c < D) {
-            const int ti = c < half ? c : c - half;
-            const float ang = __fmul_rn(pos, inv_ts[ti]);
-            const float pe = c < half ? sinf(ang) : cosf(ang);
-            val = __fadd_rn(__fmul_rn(x[c], scale), pe);     // same rounding as torch: (x*s) then (+pe)
+            if (inv_ts != nullptr) {
+                const int ti = c < half ? c : c - half;
+                const float ang = __fmul_rn(pos, inv_ts[ti]);
+                const float pe = c < half ? sinf(ang) : cosf(ang);
+                val = __fadd_rn(__fmul_rn(x[c], scale), pe);     // same rounding as torch: (x*s) then (+pe)
+            } else {
+                val = x[c];                                        // streaming: the host side already scaled and encoded
+            }
             sum += static_cast<double>(val);
         }
         v[i] = val;

@@ -4,7 +4,8 @@
 
 namespace pf {
 
-// x = feats * scale + PE(pos)  ->  LayerNorm(D = input_size)  -> fp16     (encoder input + encoders0.norm1)
+// x = feats * scale + PE(pos)  ->  LayerNorm(D = input_size)  -> fp16     (encoder input + encoders0.norm1);
+// inv_timescales == nullptr: x = feats (streaming windows arrive scaled and position-encoded)
 void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
                         const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s);
 

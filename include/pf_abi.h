@@ -71,7 +71,8 @@ typedef struct pf_config {
     int32_t lfr_n;             /* 6 */
     int32_t snip_edges;        /* frontend_conf.snip_edges */
     int32_t use_itn;           /* ConfEntity.use_itn (SenseVoice prompt, quirk Q6) */
-    int32_t reserved[4];
+    int32_t reserved[4];       /* reserved[0] bit 0 (streaming): 1 = per-layer FSMN caches instead of the reference's
+                                * stack_states behaviour that feeds every layer the layer-0 cache (OnlineModel.cs:222) */
 } pf_config;
 
 /* ModelOutputEntity (Model/ModelOutputEntity.cs:10-19) plus the greedy ids that OfflineRecognizer.Forward derives
@@ -148,6 +149,48 @@ double pf_offline_get_gemm_ms(pf_offline* h);
 int32_t pf_offline_get_profile_json(pf_offline* h, char* buf, int32_t capacity);
 /* CUDA stream of device dev_index (as a cudaStream_t), so callers can bracket runs with their own events */
 void* pf_offline_get_stream(pf_offline* h, int32_t dev_index);
+
+/* ================= streaming (online) path: OnlineRecognizer / OnlineStream / OnlineModel =================
+ * Replaces the two InferenceSessions of OnlineModel (OnlineModel.cs:24-32: encoder.onnx, decoder.onnx), the managed
+ * per-stream state of OnlineStream (OnlineStream.cs:24-37: sample cache, fbank FIFO, splice frame, feature cache, CIF
+ * carry, 16 FSMN caches) and OnlineRecognizer.Forward (OnlineRecognizer.cs:341-401).  All per-stream state stays in
+ * HBM between steps; only PCM goes in and token ids come out.  Weights: the same PFW1 blob layout as paraformer. */
+typedef struct pf_online pf_online;
+
+typedef struct pf_online_result {
+    int32_t n_streams;          /* streams passed to the step */
+    int32_t max_new;            /* L = logits.Dimensions[1] of this step; 0 when no decoder pass ran */
+    int32_t vocab;
+    int32_t n_working;          /* streams that had a full decode chunk (GetDecodeChunk != null) */
+    const int32_t* appended;    /* [n] ids appended to stream i's Tokens: max_new for working streams (the reference
+                                 * appends the padded rows too, OnlineRecognizer.cs:390), 0 otherwise */
+    const int32_t* new_tokens;  /* [n, max_new] greedy ids (Q5 tie rule); rows of non-working streams are 0 */
+    const int32_t* embeds_len;  /* [n] acoustic_embeds_len = CIF fires of this step */
+    const float* logits;        /* [n, max_new, V] raw decoder output, only with PF_RUN_WANT_LOGITS */
+} pf_online_result;
+
+pf_status pf_online_create(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev,
+                           pf_online** out);
+pf_status pf_online_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes, const int32_t* devices,
+                                       int32_t ndev, pf_online** out);
+pf_status pf_online_destroy(pf_online* h);
+pf_status pf_online_set_cmvn(pf_online* h, const float* add_shift, const float* rescale, int32_t dim);
+/* OnlineRecognizer.CreateOnlineStream (OnlineRecognizer.cs:27-31); streams are pinned to device stream_id % ndev */
+pf_status pf_online_stream_open(pf_online* h, int32_t* stream_id);
+pf_status pf_online_stream_close(pf_online* h, int32_t stream_id);
+/* OnlineStream.AddSamples (OnlineStream.cs:84-112): appends to the sample cache (which starts as 9600 zeros) and
+ * consumes AT MOST ONE 9600-sample chunk per call, only when the cache holds more than one chunk (Q13) */
+pf_status pf_online_stream_push(pf_online* h, int32_t stream_id, const float* samples, int32_t nsamp);
+/* 1 when GetDecodeChunk would return a window for this stream, 0 when not, < 0 on error */
+int32_t pf_online_stream_ready(pf_online* h, int32_t stream_id);
+/* OnlineRecognizer.GetResults -> Forward over the listed streams (OnlineRecognizer.cs:41-48, 341-401) */
+pf_status pf_online_step(pf_online* h, const int32_t* stream_ids, int32_t n, uint32_t flags, pf_online_result* out);
+/* test hook: per-stream device state "cache_feats" [10,560], "cif_alpha" [1], "cif_hidden" [512], "splice" [80],
+ * "fsmn" [layers, kernel-1, 512] (the reference keeps [512, kernel-1] per layer) */
+pf_status pf_online_get_state(pf_online* h, int32_t stream_id, const char* name, float* dst, size_t capacity);
+int32_t pf_online_get_timings(pf_online* h, float* ms, int32_t capacity);
+int64_t pf_online_get_launch_count(pf_online* h);
+double pf_online_get_gemm_flops(pf_online* h);
 
 const char* pf_last_error(void);
 int32_t pf_abi_version(void);
