@@ -24,6 +24,7 @@ PF_ERR_UNSUPPORTED = -7
 
 PF_MODEL_PARAFORMER = 0
 PF_MODEL_SENSEVOICE_SMALL = 1
+PF_MODEL_SEACO_PARAFORMER = 2
 PF_RUN_WANT_LOGITS = 1
 PF_RUN_WANT_CIF_PEAK = 2
 
@@ -36,7 +37,8 @@ class PfConfig(C.Structure):
         ("vocab", C.c_int32), ("ln_eps", C.c_float), ("cif_threshold", C.c_float), ("cif_tail", C.c_float),
         ("smooth_factor", C.c_float), ("noise_threshold", C.c_float), ("fs", C.c_int32), ("n_mels", C.c_int32),
         ("lfr_m", C.c_int32), ("lfr_n", C.c_int32), ("snip_edges", C.c_int32), ("use_itn", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("online_flags", C.c_int32), ("seaco_layers", C.c_int32), ("seaco_ffn", C.c_int32),
+        ("seaco_kernel", C.c_int32), ("seaco_nobias_id", C.c_int32),
     ]
 
 
@@ -72,6 +74,7 @@ SIGNATURES = {
     "pf_offline_create_from_memory": (C.c_int32, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.POINTER(C.c_void_p)]),
     "pf_offline_destroy": (C.c_int32, [C.c_void_p]),
     "pf_offline_set_cmvn": (C.c_int32, [C.c_void_p, _F, _F, C.c_int32]),
+    "pf_offline_set_hotwords": (C.c_int32, [C.c_void_p, _I, C.c_int32]),
     "pf_frontend_extract": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
     "pf_frontend_fbank": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
     "pf_frontend_num_frames": (C.c_int32, [C.c_void_p, C.c_int32]),

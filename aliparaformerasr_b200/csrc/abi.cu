@@ -36,7 +36,8 @@ static pf_status guarded(F&& f) {
 
 static void validate_config(const pf_config& c) {
     if (c.struct_bytes != static_cast<int32_t>(sizeof(pf_config))) throw StatusError{PF_ERR_BAD_ARG, "pf_config.struct_bytes mismatch (ABI version skew)"};
-    if (c.model_kind != PF_MODEL_PARAFORMER && c.model_kind != PF_MODEL_SENSEVOICE_SMALL) throw StatusError{PF_ERR_UNSUPPORTED, "unsupported model_kind"};
+    if (c.model_kind != PF_MODEL_PARAFORMER && c.model_kind != PF_MODEL_SENSEVOICE_SMALL && c.model_kind != PF_MODEL_SEACO_PARAFORMER)
+        throw StatusError{PF_ERR_UNSUPPORTED, "unsupported model_kind"};
     if (c.n_mels != 80 || c.fs != 16000) throw StatusError{PF_ERR_UNSUPPORTED, "front-end supports fs=16000, n_mels=80 (the reference hard-codes 80, WavFrontend.cs:75)"};
     if (c.lfr_m < 1 || c.lfr_n < 1 || 2 * c.lfr_n < c.lfr_m + 1) throw StatusError{PF_ERR_UNSUPPORTED, "LFR setting would reach the reference's tail-replicate branch; unsupported"};
     if (c.input_size != c.lfr_m * c.n_mels) throw StatusError{PF_ERR_SHAPE, "input_size must equal lfr_m * n_mels"};
@@ -45,7 +46,12 @@ static void validate_config(const pf_config& c) {
     if (c.ffn != 2048 && c.ffn != 1024 && c.ffn != 512) throw StatusError{PF_ERR_UNSUPPORTED, "ffn width must be 512/1024/2048"};
     if (c.enc_layers < 1 || c.tp_layers < 0) throw StatusError{PF_ERR_BAD_ARG, "bad layer counts"};
     if (c.enc_kernel != 11 && c.enc_kernel != 21) throw StatusError{PF_ERR_UNSUPPORTED, "FSMN kernel must be 11 or 21"};
-    if (c.model_kind == PF_MODEL_PARAFORMER) {
+    if (c.model_kind == PF_MODEL_SEACO_PARAFORMER) {
+        if (c.seaco_layers < 1 || (c.seaco_ffn != 512 && c.seaco_ffn != 1024 && c.seaco_ffn != 2048) || (c.seaco_kernel != 11 && c.seaco_kernel != 21))
+            throw StatusError{PF_ERR_UNSUPPORTED, "SeACo bias decoder: need >= 1 layer, ffn 512/1024/2048, kernel 11/21"};
+        if (c.seaco_nobias_id < 0 || c.seaco_nobias_id >= c.vocab) throw StatusError{PF_ERR_BAD_ARG, "seaco_nobias_id outside the vocabulary"};
+    }
+    if (c.model_kind == PF_MODEL_PARAFORMER || c.model_kind == PF_MODEL_SEACO_PARAFORMER) {
         if (c.dec_layers < 1) throw StatusError{PF_ERR_BAD_ARG, "paraformer needs decoder layers"};
         if (c.dec_ffn != 2048 && c.dec_ffn != 1024 && c.dec_ffn != 512) throw StatusError{PF_ERR_UNSUPPORTED, "decoder ffn width must be 512/1024/2048"};
         if (c.dec_kernel != 11 && c.dec_kernel != 21) throw StatusError{PF_ERR_UNSUPPORTED, "decoder FSMN kernel must be 11 or 21"};
@@ -219,7 +225,7 @@ static void run_all(OfflineHandle* h, uint32_t flags, pf_result* out) {
     h->Lmax = lmax;
     h->T = T;
     const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0 && lmax > 0;
-    const bool wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0 && lmax > 0 && h->cfg.model_kind == PF_MODEL_PARAFORMER;
+    const bool wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0 && lmax > 0 && h->cfg.model_kind != PF_MODEL_SENSEVOICE_SMALL;
     out->batch = B;
     out->max_len = lmax;
     out->vocab = V;
@@ -306,6 +312,16 @@ pf_status pf_offline_set_cmvn(pf_offline* hh, const float* add_shift, const floa
         OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
         std::lock_guard<std::mutex> g(h->mu);
         for (auto& d : h->devs) d->set_cmvn(add_shift, rescale, dim);
+    });
+}
+
+pf_status pf_offline_set_hotwords(pf_offline* hh, const int32_t* ids, int32_t n) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (n < 0 || (n > 0 && !ids)) throw StatusError{PF_ERR_BAD_ARG, "ids is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        for (auto& d : h->devs) d->set_hotwords(ids, n);
     });
 }
 

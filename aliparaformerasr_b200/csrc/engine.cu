@@ -116,6 +116,7 @@ DeviceCtx::~DeviceCtx() {
     if (stream_) cudaStreamSynchronize(stream_);
     free_pool(wpool_);
     free_pool(apool_);
+    free_pool(hpool_);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
     if (pcm_) cudaFree(pcm_);
@@ -204,8 +205,8 @@ void DeviceCtx::load_enc_layer(const Blob& b, const std::string& p, int in_size,
     w.b_ffn2 = up_f32(b.get(p + ".feed_forward.w_2.bias"));
 }
 
-void DeviceCtx::load_dec_ffn(const Blob& b, const std::string& p, DecFfnW& w) {
-    const int d = cfg_.d_model, f = cfg_.dec_ffn;
+void DeviceCtx::load_dec_ffn(const Blob& b, const std::string& p, DecFfnW& w, int f) {
+    const int d = cfg_.d_model;
     w.ln_in = up_ln(b, p + ".norm1");
     const BlobEntry& w1 = b.get(p + ".feed_forward.w_1.weight");
     expect_shape(w1, {f, d});
@@ -253,14 +254,51 @@ void DeviceCtx::load_weights(const Blob& b) {
         w_alpha_ = up_f32(b.get("predictor.cif_output.weight"));
         b_alpha_ = up_f32(b.get("predictor.cif_output.bias"));
     }
-    dec_.resize(cfg_.dec_layers);
-    std::vector<float> kvw(static_cast<size_t>(cfg_.dec_layers) * 2 * d * d), kvb(static_cast<size_t>(cfg_.dec_layers) * 2 * d);
-    for (int i = 0; i < cfg_.dec_layers; ++i) {
-        const std::string p = "decoder.decoders." + std::to_string(i);
-        DecLayerW& w = dec_[i];
-        load_dec_ffn(b, p, w.ffn);
+    load_dec_stack(b, "decoder", cfg_.dec_layers, cfg_.dec_ffn, cfg_.dec_kernel, dec_, dec3_, dec_after_, w_kv_all_, b_kv_all_);
+    const BlobEntry& wo = b.get("decoder.output_layer.weight");
+    expect_shape(wo, {cfg_.vocab, d});
+    w_head_ = up_f16(wo.data, wo.count);
+    expect_shape(b.get("decoder.output_layer.bias"), {cfg_.vocab});
+    b_head_ = up_f32(b.get("decoder.output_layer.bias"));
+    if (cfg_.model_kind != PF_MODEL_SEACO_PARAFORMER) return;
+    // SeACo: bias decoder, hot-word head, hot-word encoder (model_eb.onnx: Embedding + 2-layer LSTM)
+    load_dec_stack(b, "seaco_decoder", cfg_.seaco_layers, cfg_.seaco_ffn, cfg_.seaco_kernel, sdec_, sdec3_, sdec_after_, w_skv_all_, b_skv_all_);
+    const BlobEntry& hw = b.get("hotword_output_layer.weight");
+    expect_shape(hw, {cfg_.vocab, d});
+    w_hw_head_ = up_f16(hw.data, hw.count);
+    expect_shape(b.get("hotword_output_layer.bias"), {cfg_.vocab});
+    b_hw_head_ = up_f32(b.get("hotword_output_layer.bias"));
+    expect_shape(b.get("bias_embed.weight"), {cfg_.vocab, d});
+    bias_table_ = up_f32(b.get("bias_embed.weight"));
+    for (int layer = 0; layer < 2; ++layer) {
+        const std::string p = "bias_encoder.", sfx = "_l" + std::to_string(layer);
+        const BlobEntry& wih = b.get(p + "weight_ih" + sfx);
+        const BlobEntry& whh = b.get(p + "weight_hh" + sfx);
+        expect_shape(wih, {4 * d, d});
+        expect_shape(whh, {4 * d, d});
+        lstm_[layer].w_ih = up_f16(wih.data, wih.count);
+        lstm_[layer].w_hh = up_f16(whh.data, whh.count);
+        const BlobEntry& bih = b.get(p + "bias_ih" + sfx);
+        const BlobEntry& bhh = b.get(p + "bias_hh" + sfx);
+        expect_shape(bih, {4 * d});
+        expect_shape(bhh, {4 * d});
+        std::vector<float> bsum(4 * d);
+        for (int i = 0; i < 4 * d; ++i) bsum[i] = bih.data[i] + bhh.data[i];
+        lstm_[layer].b = up_f32(bsum.data(), bsum.size());
+    }
+}
+
+void DeviceCtx::load_dec_stack(const Blob& b, const std::string& prefix, int nlayers, int ffn_width, int kernel,
+                               std::vector<DecLayerW>& layers, DecFfnW& d3, LnW& after, __half*& w_kv_all, float*& b_kv_all) {
+    const int d = cfg_.d_model;
+    layers.resize(nlayers);
+    std::vector<float> kvw(static_cast<size_t>(nlayers) * 2 * d * d), kvb(static_cast<size_t>(nlayers) * 2 * d);
+    for (int i = 0; i < nlayers; ++i) {
+        const std::string p = prefix + ".decoders." + std::to_string(i);
+        DecLayerW& w = layers[i];
+        load_dec_ffn(b, p, w.ffn, ffn_width);
         w.ln2 = up_ln(b, p + ".norm2");
-        expect_shape(b.get(p + ".self_attn.fsmn_block.weight"), {d, 1, cfg_.dec_kernel});
+        expect_shape(b.get(p + ".self_attn.fsmn_block.weight"), {d, 1, kernel});
         w.fsmn = up_f32(b.get(p + ".self_attn.fsmn_block.weight"));
         w.ln3 = up_ln(b, p + ".norm3");
         const BlobEntry& wq = b.get(p + ".src_attn.linear_q.weight");
@@ -278,16 +316,11 @@ void DeviceCtx::load_weights(const Blob& b) {
         w.wo = up_f16(wo.data, wo.count);
         w.bo = up_f32(b.get(p + ".src_attn.linear_out.bias"));
     }
-    // the K/V projections of all decoder layers read the same encoder output: one [layers*2d, d] GEMM
-    w_kv_all_ = up_f16(kvw.data(), kvw.size());
-    b_kv_all_ = up_f32(kvb.data(), kvb.size());
-    load_dec_ffn(b, "decoder.decoders3.0", dec3_);
-    dec_after_ = up_ln(b, "decoder.after_norm");
-    const BlobEntry& wo = b.get("decoder.output_layer.weight");
-    expect_shape(wo, {cfg_.vocab, d});
-    w_head_ = up_f16(wo.data, wo.count);
-    expect_shape(b.get("decoder.output_layer.bias"), {cfg_.vocab});
-    b_head_ = up_f32(b.get("decoder.output_layer.bias"));
+    // the K/V projections of all layers of a stack read the same memory: one [layers*2d, d] GEMM
+    w_kv_all = up_f16(kvw.data(), kvw.size());
+    b_kv_all = up_f32(kvb.data(), kvb.size());
+    load_dec_ffn(b, prefix + ".decoders3.0", d3, ffn_width);
+    after = up_ln(b, prefix + ".after_norm");
 }
 
 void DeviceCtx::set_cmvn(const float* shift, const float* scale, int dim) {
@@ -348,6 +381,13 @@ void DeviceCtx::ensure_workspace(int B, int T) {
     ctxd16_ = dalloc<__half>(Md * d, apool_);
     logits_ = dalloc<float>(Md * ldv(), apool_);
     tokens_ = dalloc<int>(Md, apool_);
+    if (cfg_.model_kind == PF_MODEL_SEACO_PARAFORMER) {
+        emb32_ = dalloc<float>(Md * d, apool_);
+        hid32_ = dalloc<float>(Md * d, apool_);
+        satt32_ = dalloc<float>(Md * d, apool_);
+        logits2_ = dalloc<float>(Md * ldv(), apool_);
+        tokens2_ = dalloc<int>(Md, apool_);
+    }
 }
 
 static void ensure_pinned(void** p, size_t* cap, size_t bytes) {
@@ -429,6 +469,27 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
     ffn(dec3_, plan.d3_w1, plan.d3_w2);
     GemmEpi h; h.bias = b_head_; h.out_f32 = logits_; h.ld_out = ldv();
     gemm_prepare(plan.head, ad16_, d, w_head_, d, Md, cfg_.vocab, d, h);
+    if (cfg_.model_kind == PF_MODEL_SEACO_PARAFORMER) {
+        const int sf = cfg_.seaco_ffn;
+        auto sffn = [&](const DecFfnW& w, GemmOp& g1, GemmOp& g2) {
+            GemmEpi e; e.bias = w.b1; e.relu = 1; e.out_f32 = hd32_; e.ld_out = sf;
+            gemm_prepare(g1, ad16_, d, w.w1, d, Md, sf, d, e);
+            GemmEpi e2; e2.out_f32 = t32_; e2.ld_out = d;
+            gemm_prepare(g2, hd16_, sf, w.w2, sf, Md, d, sf, e2);
+        };
+        for (const DecLayerW& w : sdec_) {
+            DecLayerPlan lp;
+            sffn(w.ffn, lp.w1, lp.w2);
+            GemmEpi e; e.bias = w.bq; e.out_f16 = q16_; e.ld_out = d;
+            gemm_prepare(lp.q, ad16_, d, w.wq, d, Md, d, d, e);
+            GemmEpi o; o.bias = w.bo; o.resid = xd32_; o.ld_resid = d; o.out_f32 = xd32_; o.ld_out = d;
+            gemm_prepare(lp.out, ctxd16_, d, w.wo, d, Md, d, d, o);
+            plan.slayers.push_back(lp);
+        }
+        sffn(sdec3_, plan.s_d3_w1, plan.s_d3_w2);
+        GemmEpi hh; hh.bias = b_hw_head_; hh.out_f32 = logits2_; hh.ld_out = ldv();
+        gemm_prepare(plan.hw_head, ad16_, d, w_hw_head_, d, Md, cfg_.vocab, d, hh);
+    }
     return dec_plans_.emplace(key, std::move(plan)).first->second;
 }
 
@@ -661,17 +722,17 @@ void DeviceCtx::predictor_forward(int B, int T, bool online) {
     ++launches;
 }
 
-void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
-    const int Md = B * L, d = cfg_.d_model, f = cfg_.dec_ffn, H = cfg_.heads;
-    DecoderPlan& plan = decoder_plan(B, T, L);
+// One SANM decoder stack in place on xd32_ [B*L, d]: per layer  t = FFN(LN(x)); x += FSMN(LN(t)); x += CrossAtt(LN(x), memory)
+// followed by the FFN-only decoders3 layer; the result (before after_norm) is left in t32_.  kv16: K|V projections of
+// the memory for every layer of the stack ([rows, ldkv]); kv_shared: the memory is the same for every batch item (SeACo
+// hot-word rows), so all B*L queries attend one [Tk] memory.
+void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d3, const std::vector<DecLayerPlan>& lps,
+                          const GemmOp& d3_w1, const GemmOp& d3_w2, int ffn_width, int kernel, const __half* kv16, int ldkv,
+                          bool kv_shared, int Tk, int B, int L, bool online) {
+    const int Md = B * L, d = cfg_.d_model, f = ffn_width, H = cfg_.heads;
     const float eps = cfg_.ln_eps;
-    if (!online) {                                      // streaming: xd32_ already holds the compacted CIF frames
-        PF_CUDA(cudaMemsetAsync(xd32_, 0, static_cast<size_t>(Md) * d * sizeof(float), stream_));
-        cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
-        ++launches;
-    }
-    // Q11 (OnlineModel.cs:222): stack_states hands every layer the stream's LAYER-0 cache; reserved[0] bit 0 opts out
-    const bool per_layer_cache = (cfg_.reserved[0] & 1) != 0;
+    // Q11 (OnlineModel.cs:222): stack_states hands every layer the stream's LAYER-0 cache; online_flags bit 0 opts out
+    const bool per_layer_cache = (cfg_.online_flags & 1) != 0;
     const size_t cache_layer = static_cast<size_t>(cfg_.dec_kernel - 1) * d;
     auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
         timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
@@ -680,31 +741,130 @@ void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
         gemm(g2);
         launches += 2;
     };
-    const int ldkv = cfg_.dec_layers * 2 * d;
-    for (size_t i = 0; i < dec_.size(); ++i) {
-        const DecLayerW& w = dec_[i];
-        const DecLayerPlan& lp = plan.layers[i];
+    for (size_t i = 0; i < layers.size(); ++i) {
+        const DecLayerW& w = layers[i];
+        const DecLayerPlan& lp = lps[i];
         ffn(w.ffn, lp.w1, lp.w2);
         timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
         timed("dec_fsmn", [&] {
-            if (!online) fsmn_f32_launch(tn32_, d, w.fsmn, cfg_.dec_kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
-            else online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, cfg_.dec_kernel, ofsmn_, fsmn_state_stride(),
+            if (!online) fsmn_f32_launch(tn32_, d, w.fsmn, kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
+            else online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, kernel, ofsmn_, fsmn_state_stride(),
                                     per_layer_cache ? i * cache_layer : 0, xd32_, ocache_new_, fsmn_state_stride(), i * cache_layer, stream_);
         });
         timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(lp.q);
         timed("dec_cross_attention", [&] {
-            attention_launch(q16_, kv16_ + i * 2 * d, kv16_ + i * 2 * d + d, ctxd16_, B, H, L, T, d, ldkv, ldkv, d, d / H, stream_);
+            if (kv_shared) attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, 1, H, Md, Tk, d, ldkv, ldkv, d, d / H, stream_);
+            else attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, B, H, L, Tk, d, ldkv, ldkv, d, d / H, stream_);
         });
         gemm(lp.out);
         launches += 4;
     }
-    ffn(dec3_, plan.d3_w1, plan.d3_w2);
-    layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, nullptr, 0, stream_);
+    ffn(d3, d3_w1, d3_w2);
+}
+
+void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
+    const int Md = B * L, d = cfg_.d_model;
+    DecoderPlan& plan = decoder_plan(B, T, L);
+    const float eps = cfg_.ln_eps;
+    const bool seaco = cfg_.model_kind == PF_MODEL_SEACO_PARAFORMER && nbias_ > 0;
+    if (!online) {                                      // streaming: xd32_ already holds the compacted CIF frames
+        PF_CUDA(cudaMemsetAsync(xd32_, 0, static_cast<size_t>(Md) * d * sizeof(float), stream_));
+        cif_gather_launch(enc32_, B, T, d, wcur_, wrem_, fire_idx_, T + 1, xd32_, L, stream_);
+        ++launches;
+    }
+    if (seaco) PF_CUDA(cudaMemcpyAsync(emb32_, xd32_, static_cast<size_t>(Md) * d * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+    dec_stack(dec_, dec3_, plan.layers, plan.d3_w1, plan.d3_w2, cfg_.dec_ffn, cfg_.dec_kernel, kv16_, cfg_.dec_layers * 2 * d, false, T, B, L, online);
+    // after_norm -> fp16 operand of the output layer (+ fp32 copy: the decoder hidden the SeACo branch queries with)
+    layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, seaco ? hid32_ : nullptr, d, stream_);
     gemm(plan.head);
     // offline model_out is log-softmax; the streaming decoder graph returns raw logits (the pick is the same)
     logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, online ? 0 : 1, stream_);
     launches += 2;
+    if (seaco) seaco_forward(B, L, plan);
+}
+
+// SeACo bias branch (FunASR SeacoParaformer export [EXT]): the bias decoder attends the hot-word rows
+// twice (queries: CIF embeds, decoder hidden); sum -> hotword_output_layer -> log-softmax dha; rows whose dha pick is
+// NO_BIAS keep the ASR posterior, the others take dha.
+void DeviceCtx::seaco_forward(int B, int L, DecoderPlan& plan) {
+    const int Md = B * L, d = cfg_.d_model;
+    const size_t bytes = static_cast<size_t>(Md) * d * sizeof(float);
+    const int ldkv = cfg_.seaco_layers * 2 * d;
+    const float eps = cfg_.ln_eps;
+    for (int pass = 0; pass < 2; ++pass) {
+        PF_CUDA(cudaMemcpyAsync(xd32_, pass == 0 ? emb32_ : hid32_, bytes, cudaMemcpyDeviceToDevice, stream_));
+        dec_stack(sdec_, sdec3_, plan.slayers, plan.s_d3_w1, plan.s_d3_w2, cfg_.seaco_ffn, cfg_.seaco_kernel, skv16_, ldkv, true, nbias_, B, L, false);
+        layernorm_f32_launch(t32_, d, Md, d, sdec_after_.g, sdec_after_.b, eps, nullptr, 0, pass == 0 ? satt32_ : tn32_, d, stream_);
+        ++launches;
+    }
+    add_to_f16_launch(satt32_, tn32_, ad16_, static_cast<size_t>(Md) * d, stream_);
+    gemm(plan.hw_head);
+    logsoftmax_argmax_launch(logits2_, Md, cfg_.vocab, ldv(), tokens2_, 1, stream_);
+    seaco_merge_launch(tokens2_, logits2_, cfg_.seaco_nobias_id, Md, cfg_.vocab, ldv(), tokens_, logits_, stream_);
+    launches += 3;
+}
+
+// EmbedSeacoModel.Forward (EmbedSeacoModel.cs:70-108): Embedding -> 2-layer LSTM over 10 steps (time-major), then the
+// Q8 bias_embed layout (all steps of every hot word, hot-word major) and the K|V projections of the bias decoder.
+void DeviceCtx::set_hotwords(const int32_t* ids, int n) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (cfg_.model_kind != PF_MODEL_SEACO_PARAFORMER) throw StatusError{PF_ERR_UNSUPPORTED, "hot words need a seacoparaformer model"};
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    free_pool(hpool_);
+    nbias_ = 0;
+    bias16_ = nullptr; skv16_ = nullptr;
+    if (n <= 0) return;
+    const int d = cfg_.d_model, steps = 10, rows = steps * n;
+    for (int i = 0; i < n * steps; ++i)
+        if (ids[i] < 0 || ids[i] >= cfg_.vocab) throw StatusError{PF_ERR_BAD_ARG, "hot-word token id out of range"};
+    std::vector<void*> tmp;
+    try {
+        int* d_ids = dalloc<int>(static_cast<size_t>(rows), tmp);
+        PF_CUDA(cudaMemcpyAsync(d_ids, ids, static_cast<size_t>(rows) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+        __half* x16 = dalloc<__half>(static_cast<size_t>(rows) * d, tmp);          // layer input, time-major [t*n + i]
+        __half* y16 = dalloc<__half>(static_cast<size_t>(rows) * d, tmp);          // layer output, time-major
+        float* gin = dalloc<float>(static_cast<size_t>(rows) * 4 * d, tmp);        // W_ih x + b for every step
+        float* gates = dalloc<float>(static_cast<size_t>(n) * 4 * d, tmp);
+        float* cstate = dalloc<float>(static_cast<size_t>(n) * d, tmp);
+        bias16_ = dalloc<__half>(static_cast<size_t>(rows) * d, hpool_);           // [n*10, d] hot-word major (Q8)
+        skv16_ = dalloc<__half>(static_cast<size_t>(rows) * cfg_.seaco_layers * 2 * d, hpool_);
+        embed_rows_tmajor_launch(bias_table_, d_ids, n, steps, d, x16, stream_);
+        for (int layer = 0; layer < 2; ++layer) {
+            const LstmW& w = lstm_[layer];
+            GemmOp gi;
+            GemmEpi e; e.bias = w.b; e.out_f32 = gin; e.ld_out = 4 * d;
+            gemm_prepare(gi, x16, d, w.w_ih, d, rows, 4 * d, d, e);
+            gemm_launch(gi, stream_);
+            PF_CUDA(cudaMemsetAsync(cstate, 0, static_cast<size_t>(n) * d * sizeof(float), stream_));
+            for (int t = 0; t < steps; ++t) {
+                const float* g_t = gin + static_cast<size_t>(t) * n * 4 * d;
+                if (t > 0) {
+                    GemmOp gh;
+                    GemmEpi eh; eh.resid = g_t; eh.ld_resid = 4 * d; eh.out_f32 = gates; eh.ld_out = 4 * d;
+                    gemm_prepare(gh, y16 + static_cast<size_t>(t - 1) * n * d, d, w.w_hh, d, n, 4 * d, d, eh);
+                    gemm_launch(gh, stream_);
+                    g_t = gates;
+                }
+                // last layer also writes the Q8 layout: row (i * 10 + t) of bias_embed
+                lstm_cell_launch(g_t, cstate, n, d, y16 + static_cast<size_t>(t) * n * d, layer == 1 ? bias16_ : nullptr, t, steps, stream_);
+            }
+            std::swap(x16, y16);
+        }
+        GemmOp gk;
+        GemmEpi ek; ek.bias = b_skv_all_; ek.out_f16 = skv16_; ek.ld_out = cfg_.seaco_layers * 2 * d;
+        gemm_prepare(gk, bias16_, d, w_skv_all_, d, rows, cfg_.seaco_layers * 2 * d, d, ek);
+        gemm_launch(gk, stream_);
+        PF_CUDA(cudaStreamSynchronize(stream_));
+    } catch (...) {
+        cudaStreamSynchronize(stream_);
+        free_pool(tmp);
+        free_pool(hpool_);
+        throw;
+    }
+    free_pool(tmp);
+    nbias_ = rows;
+    dec_plans_.clear();
 }
 
 void DeviceCtx::run(uint32_t flags, SharedRun* shared, int idx) {

@@ -79,6 +79,12 @@ struct EncoderPlan {
 struct DecoderPlan {
     std::vector<DecLayerPlan> layers;
     GemmOp d3_w1, d3_w2, head;
+    std::vector<DecLayerPlan> slayers;           // SeACo bias decoder
+    GemmOp s_d3_w1, s_d3_w2, hw_head;
+};
+struct LstmW {
+    __half* w_ih = nullptr; __half* w_hh = nullptr;
+    float* b = nullptr;                          // b_ih + b_hh
 };
 
 class Barrier {                                   // reusable host barrier for the per-device worker threads
@@ -109,6 +115,7 @@ public:
     ~DeviceCtx();
     void load_weights(const Blob& blob);
     void set_cmvn(const float* shift, const float* scale, int dim);
+    void set_hotwords(const int32_t* ids, int n);      // SeACo: [n, 10] padded ids -> bias rows + their K|V (n = 0 clears)
 
     // inputs
     void stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr);
@@ -161,7 +168,13 @@ private:
     __half* up_f16(const float* host, size_t n);
     LnW up_ln(const Blob& b, const std::string& prefix);
     void load_enc_layer(const Blob& b, const std::string& prefix, int in_size, EncLayerW& w);
-    void load_dec_ffn(const Blob& b, const std::string& prefix, DecFfnW& w);
+    void load_dec_ffn(const Blob& b, const std::string& prefix, DecFfnW& w, int ffn_width);
+    void load_dec_stack(const Blob& b, const std::string& prefix, int nlayers, int ffn_width, int kernel, std::vector<DecLayerW>& layers,
+                        DecFfnW& d3, LnW& after, __half*& w_kv_all, float*& b_kv_all);
+    void dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d3, const std::vector<DecLayerPlan>& lps, const GemmOp& d3_w1,
+                   const GemmOp& d3_w2, int ffn_width, int kernel, const __half* kv16, int ldkv, bool kv_shared, int Tk, int B, int L,
+                   bool online);
+    void seaco_forward(int B, int L, DecoderPlan& plan);
 
     void ensure_workspace(int B, int T);
     void ensure_host(size_t tokens, size_t logits, size_t peaks);
@@ -200,6 +213,18 @@ private:
     DecFfnW dec3_;
     LnW dec_after_;
     __half* w_head_ = nullptr; float* b_head_ = nullptr;
+    // SeACo: bias decoder, hot-word head, hot-word encoder
+    std::vector<DecLayerW> sdec_;
+    DecFfnW sdec3_;
+    LnW sdec_after_;
+    __half* w_skv_all_ = nullptr; float* b_skv_all_ = nullptr;
+    __half* w_hw_head_ = nullptr; float* b_hw_head_ = nullptr;
+    float* bias_table_ = nullptr;      // bias_embed.weight [V, d]
+    LstmW lstm_[2];
+    int nbias_ = 0;                    // rows of bias_embed (10 per hot word, Q8); 0 = no hot words set
+    __half* bias16_ = nullptr; __half* skv16_ = nullptr;
+    std::vector<void*> hpool_;
+    float* emb32_ = nullptr; float* hid32_ = nullptr; float* satt32_ = nullptr; float* logits2_ = nullptr; int* tokens2_ = nullptr;
     float* embed_table_ = nullptr;     // SenseVoice prompt table [16, input_size]
     float* inv_ts_ = nullptr;          // PE inverse timescales [input_size/2]
     float* cmvn_shift_ = nullptr; float* cmvn_scale_ = nullptr;

@@ -359,7 +359,88 @@ __global__ void pf_prepend_rows(const float* __restrict__ src, const float* __re
     }
 }
 
+// ------------------------------------------------------------------ SeACo helpers
+// x16[(t * n + i), :] = table[ids[i * steps + t], :]   (Embedding, then time-major as the exported LSTM runs)
+__global__ void pf_embed_rows_tmajor(const float* __restrict__ table, const int* __restrict__ ids, int n, int steps, int D,
+                                     __half* __restrict__ out) {
+    const long long total = static_cast<long long>(n) * steps * D;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(e % D);
+        const long long r = e / D;
+        const int i = static_cast<int>(r % n), t = static_cast<int>(r / n);
+        out[e] = __float2half_rn(table[static_cast<size_t>(ids[i * steps + t]) * D + c]);
+    }
+}
+
+// PyTorch LSTM cell, gate order i | f | g | o in gates [n, 4D]: c = s(f) c + s(i) tanh(g); h = s(o) tanh(c)
+__global__ void pf_lstm_cell(const float* __restrict__ gates, float* __restrict__ cstate, int n, int D, __half* __restrict__ h16,
+                             __half* __restrict__ rows_hw_major, int t, int steps) {
+    const int total = n * D;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int i = e / D, c = e % D;
+        const float* g = gates + static_cast<size_t>(i) * 4 * D;
+        const float gi = 1.0f / (1.0f + expf(-g[c]));
+        const float gf = 1.0f / (1.0f + expf(-g[D + c]));
+        const float gg = tanhf(g[2 * D + c]);
+        const float go = 1.0f / (1.0f + expf(-g[3 * D + c]));
+        const float cn = gf * cstate[e] + gi * gg;
+        cstate[e] = cn;
+        const __half h = __float2half_rn(go * tanhf(cn));
+        h16[e] = h;
+        if (rows_hw_major) rows_hw_major[(static_cast<size_t>(i) * steps + t) * D + c] = h;
+    }
+}
+
+__global__ void pf_add_to_f16(const float* __restrict__ a, const float* __restrict__ b, __half* __restrict__ out, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __float2half_rn(a[i] + b[i]);
+}
+
+// rows whose hot-word pick is not NO_BIAS take the hot-word posterior and pick; the others keep the ASR ones
+__global__ void __launch_bounds__(256)
+pf_seaco_merge(const int* __restrict__ dha_tok, const float* __restrict__ dha, int nobias, int V, int ld, int* __restrict__ tokens,
+               float* __restrict__ logits) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const int t = dha_tok[row];
+    if (t == nobias) return;
+    if (threadIdx.x == 0) tokens[row] = t;
+    const float* src = dha + static_cast<size_t>(row) * ld;
+    float* dst = logits + static_cast<size_t>(row) * ld;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace
+
+void embed_rows_tmajor_launch(const float* table, const int* ids, int n, int steps, int D, __half* out, cudaStream_t s) {
+    const long long total = static_cast<long long>(n) * steps * D;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+    pf_embed_rows_tmajor<<<grid, 256, 0, s>>>(table, ids, n, steps, D, out);
+    PF_CUDA(cudaGetLastError());
+}
+
+void lstm_cell_launch(const float* gates, float* cstate, int n, int D, __half* h16, __half* rows_hw_major, int t, int steps,
+                      cudaStream_t s) {
+    const int grid = std::min((n * D + 255) / 256, 148 * 8);
+    pf_lstm_cell<<<grid, 256, 0, s>>>(gates, cstate, n, D, h16, rows_hw_major, t, steps);
+    PF_CUDA(cudaGetLastError());
+}
+
+void add_to_f16_launch(const float* a, const float* b, __half* out, size_t n, cudaStream_t s) {
+    if (n == 0) return;
+    const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+    launch_k(pf_add_to_f16, dim3(grid), dim3(256), 0, s, a, b, out, n);
+}
+
+void seaco_merge_launch(const int* dha_tok, const float* dha, int nobias, int M, int V, int ld, int* tokens, float* logits,
+                        cudaStream_t s) {
+    if (M <= 0) return;
+    launch_k(pf_seaco_merge, dim3(M), dim3(256), 0, s, dha_tok, dha, nobias, V, ld, tokens, logits);
+}
 
 void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
                         const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s) {

@@ -43,6 +43,14 @@ void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, 
 // Gather rows: dst[b, l, :] = src[b, l, :] for l < L (compacts [B, Lsrc, W] -> [B, L, W]); int32 / fp32 payloads.
 void compact_rows_launch(const void* src, void* dst, int B, int Lsrc, int L, int width_bytes, cudaStream_t s);
 
+// SeACo hot-word encoder / merge helpers (EmbedSeacoModel.cs:70-108, OfflineProjOfSeacoParaformer.cs:85-108)
+void embed_rows_tmajor_launch(const float* table, const int* ids, int n, int steps, int D, __half* out, cudaStream_t s);
+void lstm_cell_launch(const float* gates, float* cstate, int n, int D, __half* h16, __half* rows_hw_major, int t, int steps,
+                      cudaStream_t s);
+void add_to_f16_launch(const float* a, const float* b, __half* out, size_t n, cudaStream_t s);
+void seaco_merge_launch(const int* dha_tok, const float* dha, int nobias, int M, int V, int ld, int* tokens, float* logits,
+                        cudaStream_t s);
+
 void f32_to_f16_launch(const float* in, __half* out, size_t n, cudaStream_t s);
 // SenseVoice prompt prepend (Q6/Q7): dst[b] = [table[ids[0..3]] ; src[b]]  ([B,T,D] -> [B,T+4,D])
 void prepend_rows_launch(const float* src, const float* table, const int* ids, int nprompt, float* dst, int B, int T,

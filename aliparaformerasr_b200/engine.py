@@ -15,7 +15,8 @@ from .weights import pack
 
 
 def to_pf_config(cfg: ModelConfig) -> _lib.PfConfig:
-    kinds = {"paraformer": _lib.PF_MODEL_PARAFORMER, "sensevoicesmall": _lib.PF_MODEL_SENSEVOICE_SMALL}
+    kinds = {"paraformer": _lib.PF_MODEL_PARAFORMER, "sensevoicesmall": _lib.PF_MODEL_SENSEVOICE_SMALL,
+             "seacoparaformer": _lib.PF_MODEL_SEACO_PARAFORMER}
     # OfflineRecognizer.cs:39-53: unknown model names fall back to the paraformer projection
     kind = kinds.get(cfg.model.lower(), _lib.PF_MODEL_PARAFORMER)
     c = _lib.PfConfig()
@@ -26,6 +27,8 @@ def to_pf_config(cfg: ModelConfig) -> _lib.PfConfig:
         setattr(c, f, int(getattr(cfg, f)))
     for f in ("ln_eps", "cif_threshold", "cif_tail", "smooth_factor", "noise_threshold"):
         setattr(c, f, float(getattr(cfg, f)))
+    c.seaco_layers, c.seaco_ffn, c.seaco_kernel = int(cfg.seaco_layers), int(cfg.seaco_ffn), int(cfg.seaco_kernel)
+    c.seaco_nobias_id = int(cfg.nobias_id)
     c.snip_edges = int(bool(cfg.snip_edges))
     c.use_itn = int(bool(cfg.use_itn))
     return c
@@ -84,6 +87,15 @@ class Engine:
         a = np.ascontiguousarray(add_shift, dtype=np.float32)
         b = np.ascontiguousarray(rescale, dtype=np.float32)
         _lib.check(self._lib.pf_offline_set_cmvn(self._handle(), _lib.fptr(a), _lib.fptr(b), a.shape[0]))
+
+    def set_hotwords(self, hotwords: Sequence[Sequence[int]]) -> None:
+        """``EmbedSeacoModel.Forward`` + the Q8 bias_embed assembly; ``hotwords`` = id lists (PadList applied here:
+        truncate to 10, pad with 0, EmbedSeacoModel.cs:110-123).  Empty list clears them."""
+        ids = np.zeros((len(hotwords), 10), dtype=np.int32)
+        for i, h in enumerate(hotwords):
+            h = list(h)[:10]
+            ids[i, : len(h)] = h
+        _lib.check(self._lib.pf_offline_set_hotwords(self._handle(), _lib.iptr(ids) if len(hotwords) else None, len(hotwords)))
 
     # -- front-end only (OfflineStream.AddSamples)
     def num_frames(self, nsamp: int) -> int:

@@ -118,6 +118,10 @@ def load_conf(path: str) -> ModelConfig:
     cfg.lfr_n = int(fe.get("lfr_n", cfg.lfr_n))
     cfg.snip_edges = bool(fe.get("snip_edges", cfg.snip_edges))
     cfg.input_size = cfg.lfr_m * cfg.n_mels
+    sd = raw.get("seaco_decoder_conf") or {}
+    cfg.seaco_layers = int(sd.get("num_blocks", cfg.seaco_layers))
+    cfg.seaco_ffn = int(sd.get("linear_units", cfg.seaco_ffn))
+    cfg.seaco_kernel = int(sd.get("kernel_size", cfg.seaco_kernel))
     if "vocab_size" in raw:
         cfg.vocab = int(raw["vocab_size"])
     if "ln_eps" in raw:
@@ -125,6 +129,25 @@ def load_conf(path: str) -> ModelConfig:
     if cfg.model.lower() == "sensevoicesmall":
         cfg.dec_layers = 0
     return cfg
+
+
+def get_hotwords(tokens: Sequence[str], hotword_file_path: str, sos_eos_id: int = 1) -> List[List[int]]:
+    """``OfflineRecognizer.GetHotwords`` (OfflineRecognizer.cs:72-90, Q9): one hot word per line, tokenised per UTF-16
+    char with ``Array.IndexOf(tokens, ch)`` (first match; unknown chars dropped), plus a trailing ``[sos]`` entry.
+    A missing file yields an empty list."""
+    if not hotword_file_path or not os.path.exists(hotword_file_path):
+        return []
+    index = {}
+    for i, t in enumerate(tokens):
+        index.setdefault(t, i)
+    out: List[List[int]] = []
+    with open(hotword_file_path, "r", encoding="utf-8-sig") as f:
+        for line in f.read().splitlines():
+            units = line.encode("utf-16-le")
+            chars = [units[i:i + 2].decode("utf-16-le", errors="surrogatepass") for i in range(0, len(units), 2)]
+            out.append([index[c] for c in chars if c in index])
+    out.append([sos_eos_id])
+    return out
 
 
 # --------------------------------------------------------------------------- entities
@@ -217,12 +240,16 @@ class OfflineRecognizer:
         if not self._tokens:
             raise Exception("tokens invalid")                      # OfflineRecognizer.cs:30-33
         self._mvn_file_path = mvn_file_path
-        if modeleb_file_path or self._conf.model.lower() == "seacoparaformer":
-            raise NotImplementedError("SeACo hot-word bias decoder is not built yet (SURVEY.md section 8, cfg 4)")
         self._engine = Engine(self._conf, weights if weights is not None else model_file_path, devices=devices)
         if mvn_file_path:
             shift, scale = load_cmvn(mvn_file_path)
             self._engine.set_cmvn(shift, scale)
+        # SeACo: the hot-word encoder (model_eb.onnx in the reference; here part of the same PFW1 blob, so
+        # modeleb_file_path is accepted and unused) runs once on the file hot words (OfflineProjOfSeacoParaformer.cs:29-34)
+        self._seaco = self._conf.model.lower() == "seacoparaformer"
+        self._hotwords = get_hotwords(self._tokens, hotword_file_path) if self._seaco else []
+        if self._seaco and self._hotwords:
+            self._engine.set_hotwords(self._hotwords)
 
     # -- API surface of the reference
     def create_offline_stream(self) -> OfflineStream:
@@ -259,7 +286,11 @@ class OfflineRecognizer:
             return
         if self._disposed:
             raise ObjectDisposedError("OfflineRecognizer")
+        # per-stream hot words replace the file hot words for this call (OfflineProjOfSeacoParaformer.cs:51-60)
+        call_hotwords = [list(h) for s in streams for h in (s.hotwords or [])] if self._seaco else []
         try:
+            if call_hotwords:
+                self._engine.set_hotwords(call_hotwords)
             if all(len(s._chunks) == 1 for s in streams):
                 # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
                 out = self._engine.run_pcm([s._chunks[0] for s in streams])
@@ -270,6 +301,9 @@ class OfflineRecognizer:
                 out = self._engine.run_feats(pad_sequence(feats))
         except _lib.PfError as ex:
             raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
+        finally:
+            if call_hotwords:
+                self._engine.set_hotwords(self._hotwords)
         for i, s in enumerate(streams):
             s.tokens = [int(t) for t in out.tokens[i]]
             s.timestamps.extend([[0, 0] for _ in s.tokens])         # 3-output models: {0,0} per token (:151)

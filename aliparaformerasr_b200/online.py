@@ -56,7 +56,7 @@ class OnlineEngine:
         self.cfg = cfg
         self._h = C.c_void_p()
         pcfg = to_pf_config(cfg)
-        pcfg.reserved[0] = 1 if per_layer_cache else 0        # 0 = bug-compatible stack_states (Q11)
+        pcfg.online_flags = 1 if per_layer_cache else 0        # 0 = bug-compatible stack_states (Q11)
         dev_arr, ndev = None, 0
         if devices is not None:
             dev_np = np.asarray(list(devices), dtype=np.int32)

@@ -51,6 +51,11 @@ class ModelConfig:
     lfr_n: int = 6
     snip_edges: bool = False
     use_itn: bool = True
+    # SeACo bias decoder (seaco_decoder_conf [EXT]) and NO_BIAS class id; unused by the other models
+    seaco_layers: int = 4
+    seaco_ffn: int = 1024
+    seaco_kernel: int = 21
+    nobias_id: int = 8377
 
     def as_dict(self):
         return asdict(self)
@@ -65,8 +70,14 @@ def sensevoice_small() -> ModelConfig:
                        ln_eps=1e-5)
 
 
+def seaco_paraformer() -> ModelConfig:
+    return ModelConfig(model="seacoparaformer")
+
+
 def tiny(model: str = "paraformer") -> ModelConfig:
     """Few-layer variant with the real per-layer shapes: the oracle finishes in seconds."""
+    if model == "seacoparaformer":
+        return ModelConfig(model=model, enc_layers=3, dec_layers=2, seaco_layers=2)
     if model == "sensevoicesmall":
         return ModelConfig(model=model, enc_layers=3, tp_layers=2, dec_layers=0, vocab=25055, ln_eps=1e-5)
     return ModelConfig(model=model, enc_layers=3, dec_layers=2)
@@ -118,9 +129,31 @@ def make_weights(cfg: ModelConfig, seed: int = WEIGHT_SEED) -> Dict[str, np.ndar
     w["predictor.cif_output.weight"] = _normal(g, (1, d), 1.0 / math.sqrt(d))
     w["predictor.cif_output.bias"] = np.asarray([-1.1], dtype=np.float32)
     # ParaformerSANMDecoder
-    f, k = cfg.dec_ffn, cfg.dec_kernel
-    for i in range(cfg.dec_layers):
-        p = f"decoder.decoders.{i}"
+    _sanm_decoder(w, g, "decoder", cfg.dec_layers, cfg.dec_ffn, cfg.dec_kernel, d)
+    w["decoder.output_layer.weight"] = _normal(g, (cfg.vocab, d), 4.0 / math.sqrt(d))
+    w["decoder.output_layer.bias"] = _normal(g, (cfg.vocab,), 0.02)
+    if cfg.model == "seacoparaformer":
+        # bias decoder (no output layer), hot-word head, hot-word encoder (Embedding + 2-layer LSTM)
+        _sanm_decoder(w, g, "seaco_decoder", cfg.seaco_layers, cfg.seaco_ffn, cfg.seaco_kernel, d)
+        w["hotword_output_layer.weight"] = _normal(g, (cfg.vocab, d), 4.0 / math.sqrt(d))
+        hb = _normal(g, (cfg.vocab,), 0.02)
+        hb[cfg.nobias_id] = SEACO_NOBIAS_BIAS        # so that a good share of the rows keeps the ASR posterior
+        w["hotword_output_layer.bias"] = hb
+        w["bias_embed.weight"] = _normal(g, (cfg.vocab, d), 1.0)
+        for layer in range(2):
+            w[f"bias_encoder.weight_ih_l{layer}"] = _normal(g, (4 * d, d), 1.0 / math.sqrt(d))
+            w[f"bias_encoder.weight_hh_l{layer}"] = _normal(g, (4 * d, d), 1.0 / math.sqrt(d))
+            w[f"bias_encoder.bias_ih_l{layer}"] = _normal(g, (4 * d,), 0.05)
+            w[f"bias_encoder.bias_hh_l{layer}"] = _normal(g, (4 * d,), 0.05)
+    return w
+
+
+SEACO_NOBIAS_BIAS = 21.0
+
+
+def _sanm_decoder(w: Dict[str, np.ndarray], g, prefix: str, layers: int, f: int, k: int, d: int):
+    for i in range(layers):
+        p = f"{prefix}.decoders.{i}"
         w[p + ".norm1.weight"], w[p + ".norm1.bias"] = _ln_params(g, d)
         w[p + ".feed_forward.w_1.weight"] = _normal(g, (f, d), 1.0 / math.sqrt(d))
         w[p + ".feed_forward.w_1.bias"] = _normal(g, (f,), 0.02)
@@ -135,16 +168,25 @@ def make_weights(cfg: ModelConfig, seed: int = WEIGHT_SEED) -> Dict[str, np.ndar
         w[p + ".src_attn.linear_k_v.bias"] = _normal(g, (2 * d,), 0.02)
         w[p + ".src_attn.linear_out.weight"] = _normal(g, (d, d), 1.0 / math.sqrt(d))
         w[p + ".src_attn.linear_out.bias"] = _normal(g, (d,), 0.02)
-    p = "decoder.decoders3.0"
+    p = f"{prefix}.decoders3.0"
     w[p + ".norm1.weight"], w[p + ".norm1.bias"] = _ln_params(g, d)
     w[p + ".feed_forward.w_1.weight"] = _normal(g, (f, d), 1.0 / math.sqrt(d))
     w[p + ".feed_forward.w_1.bias"] = _normal(g, (f,), 0.02)
     w[p + ".feed_forward.norm.weight"], w[p + ".feed_forward.norm.bias"] = _ln_params(g, f)
     w[p + ".feed_forward.w_2.weight"] = _normal(g, (d, f), 1.0 / math.sqrt(f))
-    w["decoder.after_norm.weight"], w["decoder.after_norm.bias"] = _ln_params(g, d)
-    w["decoder.output_layer.weight"] = _normal(g, (cfg.vocab, d), 4.0 / math.sqrt(d))
-    w["decoder.output_layer.bias"] = _normal(g, (cfg.vocab,), 0.02)
-    return w
+    w[f"{prefix}.after_norm.weight"], w[f"{prefix}.after_norm.bias"] = _ln_params(g, d)
+
+
+def make_hotwords(n: int = 200, vocab: int = 8404, seed: int = 7):
+    """``n`` id lists of length U{2..6}, ids U{3..vocab-1}, plus the trailing ``[sos]`` entry the
+    reference appends (OfflineRecognizer.cs:87)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        ln = int(torch.randint(2, 7, (1,), generator=g).item())
+        out.append([int(t) for t in torch.randint(3, vocab, (ln,), generator=g)])
+    out.append([1])
+    return out
 
 
 def make_cmvn(dim: int = 560) -> Tuple[np.ndarray, np.ndarray]:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 
 typedef int32_t pf_status;
 enum {
@@ -41,7 +41,7 @@ enum {
 };
 
 /* asr.yaml `model:` dispatch of OfflineRecognizer.cs:39-53 */
-enum { PF_MODEL_PARAFORMER = 0, PF_MODEL_SENSEVOICE_SMALL = 1 };
+enum { PF_MODEL_PARAFORMER = 0, PF_MODEL_SENSEVOICE_SMALL = 1, PF_MODEL_SEACO_PARAFORMER = 2 };
 
 /* Flat POD mirror of the ConfEntity fields the path consumes (Model/ConfEntity.cs:5-43, EncoderConfEntity.cs:13-25,
  * DecoderConfEntity.cs:7-16, PredictorConfEntity.cs:13-17, FrontendConfEntity.cs:7-15).  The C# side keeps parsing
@@ -71,8 +71,12 @@ typedef struct pf_config {
     int32_t lfr_n;             /* 6 */
     int32_t snip_edges;        /* frontend_conf.snip_edges */
     int32_t use_itn;           /* ConfEntity.use_itn (SenseVoice prompt, quirk Q6) */
-    int32_t reserved[4];       /* reserved[0] bit 0 (streaming): 1 = per-layer FSMN caches instead of the reference's
-                                * stack_states behaviour that feeds every layer the layer-0 cache (OnlineModel.cs:222) */
+    int32_t online_flags;      /* streaming, bit 0: 1 = per-layer FSMN caches instead of the reference's stack_states
+                                * behaviour that feeds every layer the stream's layer-0 cache (OnlineModel.cs:222) */
+    int32_t seaco_layers;      /* seaco_decoder_conf.num_blocks 4 (SeACo only) */
+    int32_t seaco_ffn;         /* seaco_decoder_conf.linear_units 1024 */
+    int32_t seaco_kernel;      /* seaco_decoder_conf.kernel_size 21 */
+    int32_t seaco_nobias_id;   /* class id of "no bias" in the hot-word head (8377 for the 8404-token vocabulary) */
 } pf_config;
 
 /* ModelOutputEntity (Model/ModelOutputEntity.cs:10-19) plus the greedy ids that OfflineRecognizer.Forward derives
@@ -101,6 +105,12 @@ pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, 
                                         const int32_t* devices, int32_t ndev, pf_offline** out);
 /* replaces IOfflineProj.Dispose / InferenceSession.Dispose (OfflineProjOfParaformer.cs:88-101) */
 pf_status pf_offline_destroy(pf_offline* h);
+
+/* SeACo hot words: replaces EmbedSeacoModel.Forward (EmbedSeacoModel.cs:70-108, model_eb.onnx = Embedding + 2-layer
+ * LSTM) and the bias_embed assembly of OfflineProjOfSeacoParaformer.cs:85-108 (all 10 LSTM steps of every hot word,
+ * Q8).  ids: [n, 10] int32, already truncated / zero padded as EmbedSeacoModel.PadList does (:110-123).  n = 0 clears
+ * the hot words (the bias branch is skipped).  Valid for PF_MODEL_SEACO_PARAFORMER handles only. */
+pf_status pf_offline_set_hotwords(pf_offline* h, const int32_t* ids, int32_t n);
 
 /* am.mvn vectors parsed by WavFrontend.LoadCmvn (WavFrontend.cs:112-153): <AddShift> and <Rescale>, dim = 560 */
 pf_status pf_offline_set_cmvn(pf_offline* h, const float* add_shift, const float* rescale, int32_t dim);

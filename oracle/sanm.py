@@ -47,6 +47,11 @@ class ModelDims:
     cif_tail: float = 0.45
     smooth_factor: float = 1.0
     noise_threshold: float = 0.0
+    # SeACo bias decoder (seaco_decoder_conf of the seaco-paraformer asr.yaml [EXT]) and its NO_BIAS class id
+    seaco_layers: int = 4
+    seaco_ffn: int = 1024
+    seaco_kernel: int = 21
+    nobias_id: int = 8377
 
 
 def _t(w: Dict[str, np.ndarray], name: str) -> torch.Tensor:
@@ -192,13 +197,16 @@ def _dec_ffn(x: torch.Tensor, w, p: str, dims: ModelDims) -> torch.Tensor:
 
 
 def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w, dims: ModelDims,
-            collect: Optional[dict] = None) -> torch.Tensor:
-    """ParaformerSANMDecoder (export form) -> logits [B,L,V] before log-softmax."""
+            collect: Optional[dict] = None, prefix: str = "decoder", layers: Optional[int] = None,
+            return_hidden: bool = False):
+    """ParaformerSANMDecoder (export form) -> logits [B,L,V] before log-softmax (or, with ``return_hidden``, the
+    after_norm output [B,L,512] that the SeACo branch consumes; ``prefix="seaco_decoder"`` runs the bias decoder, which
+    has no output layer)."""
     b, l, d = embeds.shape
     tgt_mask = (torch.arange(l)[None, :] < token_num[:, None]).to(embeds.dtype)[:, :, None]
     x = embeds
-    for i in range(dims.dec_layers):
-        p = f"decoder.decoders.{i}"
+    for i in range(dims.dec_layers if layers is None else layers):
+        p = f"{prefix}.decoders.{i}"
         t = _dec_ffn(_ln(x, w, p + ".norm1", dims.ln_eps), w, p + ".feed_forward", dims)
         tn = _ln(t, w, p + ".norm2", dims.ln_eps)
         x = x + _fsmn(tn, _t(w, p + ".self_attn.fsmn_block.weight"), tgt_mask)
@@ -210,10 +218,13 @@ def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w,
         x = x + Fn.linear(ctx, _t(w, p + ".src_attn.linear_out.weight"), _t(w, p + ".src_attn.linear_out.bias"))
         if collect is not None and i == 0:
             collect["dec_layer0"] = x.clone()
-    p = "decoder.decoders3.0"
+    p = f"{prefix}.decoders3.0"
     x = _dec_ffn(_ln(x, w, p + ".norm1", dims.ln_eps), w, p + ".feed_forward", dims)
-    x = _ln(x, w, "decoder.after_norm", dims.ln_eps)
-    return Fn.linear(x, _t(w, "decoder.output_layer.weight"), _t(w, "decoder.output_layer.bias"))
+    x = _ln(x, w, f"{prefix}.after_norm", dims.ln_eps)
+    if prefix != "decoder":
+        return x
+    logits = Fn.linear(x, _t(w, "decoder.output_layer.weight"), _t(w, "decoder.output_layer.bias"))
+    return (logits, x) if return_hidden else logits
 
 
 def greedy_pick(logp: np.ndarray) -> np.ndarray:
@@ -294,3 +305,89 @@ def sensevoice_forward(speech: np.ndarray, w, dims: ModelDims):
         logp = torch.log_softmax(logits, dim=-1).numpy()
     return {"logits": logp, "tokens": greedy_pick(logp), "enc": enc.numpy(),
             "token_num": np.full(speech.shape[0], speech.shape[1], dtype=np.int32)}
+
+
+# --------------------------------------------------------------------------- SeACo-paraformer (hot-word bias)
+
+def pad_hotwords(hotwords, max_length: int = 10) -> np.ndarray:
+    """EmbedSeacoModel.PadList (EmbedSeacoModel.cs:110-123): truncate to 10 ids, right-pad with 0 -> [N,10] int32."""
+    out = np.zeros((len(hotwords), max_length), dtype=np.int32)
+    for i, h in enumerate(hotwords):
+        h = list(h)[:max_length]
+        out[i, : len(h)] = h
+    return out
+
+
+def hotword_ids_from_text(tokens, lines, sos_eos_id: int = 1):
+    """OfflineRecognizer.GetHotwords (OfflineRecognizer.cs:72-90, Q9): one hot word per line, tokenised per UTF-16 char
+    with ``Array.IndexOf(tokens, ch)``; unknown chars are dropped; a trailing ``[sos]`` entry is appended."""
+    index = {}
+    for i, t in enumerate(tokens):
+        index.setdefault(t, i)                      # IndexOf = first match
+    out = []
+    for line in lines:
+        units = line.encode("utf-16-le")
+        chars = [units[i:i + 2].decode("utf-16-le", errors="surrogatepass") for i in range(0, len(units), 2)]
+        out.append([index[c] for c in chars if c in index])
+    out.append([sos_eos_id])
+    return out
+
+
+def hotword_embed(hotword: np.ndarray, w) -> np.ndarray:
+    """``model_eb.onnx`` (EmbedSeacoModel.Forward, EmbedSeacoModel.cs:70-108): ``hotword [N,10] i32`` ->
+    Embedding(V,512) -> 2-layer LSTM(512) run time-major -> ``hw_embed [10,N,512]`` (all time steps)."""
+    with torch.no_grad():
+        ids = torch.from_numpy(np.asarray(hotword, dtype=np.int64))
+        x = Fn.embedding(ids, _t(w, "bias_embed.weight")).transpose(0, 1)          # [10, N, 512]
+        for layer in range(2):
+            wih, whh = _t(w, f"bias_encoder.weight_ih_l{layer}"), _t(w, f"bias_encoder.weight_hh_l{layer}")
+            bih, bhh = _t(w, f"bias_encoder.bias_ih_l{layer}"), _t(w, f"bias_encoder.bias_hh_l{layer}")
+            n, hdim = x.shape[1], whh.shape[1]
+            h = torch.zeros(n, hdim)
+            c = torch.zeros(n, hdim)
+            outs = []
+            for t in range(x.shape[0]):
+                gates = Fn.linear(x[t], wih, bih) + Fn.linear(h, whh, bhh)
+                i, f, g, o = gates.chunk(4, dim=1)                                    # PyTorch gate order
+                c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                outs.append(h)
+            x = torch.stack(outs, dim=0)
+    return x.numpy()
+
+
+def bias_embed_rows(hw_embed: np.ndarray) -> np.ndarray:
+    """OfflineProjOfSeacoParaformer.cs:85-108 (Q8): ALL 10 LSTM steps of every hot word, hot-word major:
+    ``[10,N,512]`` -> ``[N*10, 512]`` (the C# then tiles this over the batch)."""
+    return np.ascontiguousarray(np.transpose(hw_embed, (1, 0, 2)).reshape(-1, hw_embed.shape[2]))
+
+
+def seaco_forward(speech: np.ndarray, w, dims: ModelDims, bias_rows: np.ndarray):
+    """The ``InferenceSession.Run`` of OfflineProjOfSeacoParaformer.cs:116 on ``speech [B,T,560]`` and
+    ``bias_embed [B, Nb, 512]`` (identical rows for every batch item).  FunASR SeacoParaformer export [EXT]:
+    ASR decoder (returning its hidden), bias decoder over the hot-word rows queried by the CIF embeds and by the
+    decoder hidden, ``hotword_output_layer`` -> log-softmax ``dha``; rows whose dha argmax is NO_BIAS keep the ASR
+    posterior, the others take ``dha``."""
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(speech, dtype=np.float32))
+        enc = encoder(x, w, dims)
+        alphas = predictor_alphas(enc, w, dims)
+        hidden = torch.cat([enc, torch.zeros(enc.shape[0], 1, enc.shape[2])], dim=1)
+        emb, token_num, fires, peaks = cif(hidden.numpy(), alphas.numpy(), dims.cif_threshold)
+        embeds = torch.from_numpy(emb)
+        tn = torch.from_numpy(token_num.astype(np.int64))
+        logits, dec_hidden = decoder(enc, embeds, tn, w, dims, return_hidden=True)
+        asr = torch.log_softmax(logits, dim=-1)
+        b = enc.shape[0]
+        mem = torch.from_numpy(np.ascontiguousarray(bias_rows, dtype=np.float32))[None].expand(b, -1, -1)
+        sdims = ModelDims(**{**dims.__dict__, "dec_ffn": dims.seaco_ffn, "dec_kernel": dims.seaco_kernel})
+        cif_att = decoder(mem, embeds, tn, w, sdims, prefix="seaco_decoder", layers=dims.seaco_layers)
+        dec_att = decoder(mem, dec_hidden, tn, w, sdims, prefix="seaco_decoder", layers=dims.seaco_layers)
+        merged = cif_att + dec_att
+        dha = torch.log_softmax(Fn.linear(merged, _t(w, "hotword_output_layer.weight"), _t(w, "hotword_output_layer.bias")), dim=-1)
+        dha_ids = dha.argmax(dim=-1)
+        keep_asr = (dha_ids == dims.nobias_id)[..., None]
+        out = torch.where(keep_asr, asr, dha).numpy()
+    return {"logits": out, "token_num": token_num, "tokens": greedy_pick(out), "asr_logits": asr.numpy(), "dha": dha.numpy(),
+            "dha_ids": dha_ids.numpy(), "enc": enc.numpy(), "acoustic_embeds": emb, "dec_hidden": dec_hidden.numpy(),
+            "cif_peak": peaks}
