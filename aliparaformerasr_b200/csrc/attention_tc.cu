@@ -125,18 +125,11 @@ __device__ __forceinline__ void fsmn_from_smem(const AttParams& p, const uint8_t
     const uint8_t* vb = sV + (c >> 6) * (p.Tkp * 128) + (c & 7) * 2;
     const int cchunk = (c & 63) >> 3;
     float* out = p.mem + (static_cast<size_t>(b) * p.Tk) * p.ld_mem + h * HD + c;
-    // the residual-stream values this thread accumulates into are fetched one block ahead (L2 latency off the chain)
-    float old_next[TB];
-#pragma unroll
-    for (int i = 0; i < TB; ++i) old_next[i] = (p.mem_accum && t_begin + i < t_end) ? out[static_cast<size_t>(t_begin + i) * p.ld_mem] : 0.0f;
     for (int t0 = t_begin; t0 < t_end; t0 += TB) {
+        // residual-stream values this thread accumulates into: issued first, consumed after the FMAs below
         float old[TB];
 #pragma unroll
-        for (int i = 0; i < TB; ++i) {
-            old[i] = old_next[i];
-            const int tn = t0 + TB + i;
-            old_next[i] = (p.mem_accum && tn < t_end) ? out[static_cast<size_t>(tn) * p.ld_mem] : 0.0f;
-        }
+        for (int i = 0; i < TB; ++i) old[i] = (p.mem_accum && t0 + i < t_end) ? out[static_cast<size_t>(t0 + i) * p.ld_mem] : 0.0f;
         float x[TB + TAPS - 1];
 #pragma unroll
         for (int i = 0; i < TB + TAPS - 1; ++i) {
