@@ -214,7 +214,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // its store was issued.
 template <int kMaxChunks>
 __device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, uint8_t* stg, const CUtensorMap* tmC,
-                                                 const float* bias_w, float lo, int row0, int colw, int lane) {
+                                                 const float* bias_w, float lo, int row0, int colw, int lane, int dbg = 0) {
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t ra[32], rb[32];
     tmem_ld_issue(t_acc, ra);
@@ -246,11 +246,12 @@ __device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, ui
                 pk.y = *reinterpret_cast<uint32_t*>(&h1);
                 pk.z = *reinterpret_cast<uint32_t*>(&h2);
                 pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(box + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;      // SWIZZLE_64B: chunk ^= (row / 2) % 4
+                if (!(dbg & 2) || pk.x == 0x7fc07fc1u)                                     // probe: no smem traffic
+                    *reinterpret_cast<uint4*>(box + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;      // SWIZZLE_64B: chunk ^= (row / 2) % 4
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(dbg & 3)) {
                 tma_store_2d(tmC, stg_u32 + buf * 2048, colw + k * 32, row0);
                 tma_store_commit();
             }
@@ -527,7 +528,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 epi_bar_sync();                                   // bias tile visible to all epilogue warps
                 if (work) {
                     if constexpr (kOutHalf && kAdds == 0)
-                        epilogue_tma_f16<kCpw>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane);
+                        epilogue_tma_f16<kCpw>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
                     else if constexpr (!kOutHalf && kAdds == 0)
                         epilogue_tma_f32<kCpw, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
                     else if constexpr (!kOutHalf && kAdds == 1)
@@ -769,7 +770,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
         else make_tmap_any(&op.tmC, epi.out_f32, true, M, N, epi.ld_out, 32);
         if (op.n_adds == 1) make_tmap_any(&op.tmR, op.epi.add0, true, M, N, op.epi.ld_add0, 32);
     }
-    if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 7) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA
+    if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 31) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA, 8 no TMA store, 16 no staging either
     make_tmap(&op.tmA, A, M, K, lda, BM);           // every CTA stages its own 128 rows of A
     make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and (in a CTA pair) half of the W tile
 }
