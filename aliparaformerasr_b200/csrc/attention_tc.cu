@@ -108,15 +108,27 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
 }
 
-// mem[b, t, h*128 + c] = sum_j w[c, j] v[t + j - (TAPS-1)/2, c] + v[t, c], v read from the 128B-swizzled V tile (two
-// 64-channel boxes of Tkp rows).  Thread ft: channel ft % 128, time range half ft / 128; 16 outputs per register block.
+__device__ __forceinline__ void tma_store_3d_f32(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1, int c2, bool reduce_add) {
+    if (reduce_add)
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// mem[b, t, h*128 + c] (+)= sum_j w[c, j] v[t + j - (TAPS-1)/2, c] + v[t, c], v read from the 128B-swizzled V tile (two
+// 64-channel boxes of Tkp rows).  Thread ft: channel ft % 128, time part ft / 128; a warp owns 32 channels and stages
+// 16 time steps x 32 channels (2 KiB, two alternating boxes) that one lane hands to the TMA engine: a plain store, or
+// an fp32 reduce-add into the residual stream (mem_accum) - no global loads, so no L2 latency on the FSMN warps' chain.
 template <int TAPS>
-__device__ __forceinline__ void fsmn_from_smem(const AttParams& p, const uint8_t* sV, int ft, int h, int b) {
-    constexpr int TB = TAPS > 11 ? 8 : 16;                        // outputs per register block
+__device__ __forceinline__ void fsmn_from_smem(const AttParams& p, const CUtensorMap* tmX, const uint8_t* sV, float* stage, int ft,
+                                               int h, int b) {
+    constexpr int TB = 16;                                         // outputs per register block = rows of a staging box
     constexpr int LEFT = (TAPS - 1) / 2;
-    const int c = ft & 127;
+    const int c = ft & 127, lane = ft & 31;
     const int parts = kFsmnWarps * 32 / 128;
-    const int per = (p.Tk + parts - 1) / parts;
+    const int per = (((p.Tk + parts - 1) / parts) + TB - 1) / TB * TB;   // whole boxes per part: parts never share a box
     const int t_begin = (ft >> 7) * per;
     const int t_end = min(p.Tk, t_begin + per);
     float w[TAPS];
@@ -124,31 +136,42 @@ __device__ __forceinline__ void fsmn_from_smem(const AttParams& p, const uint8_t
     for (int j = 0; j < TAPS; ++j) w[j] = __ldg(p.fsmn_w + (h * HD + c) * TAPS + j);
     const uint8_t* vb = sV + (c >> 6) * (p.Tkp * 128) + (c & 7) * 2;
     const int cchunk = (c & 63) >> 3;
-    float* out = p.mem + (static_cast<size_t>(b) * p.Tk) * p.ld_mem + h * HD + c;
-    for (int t0 = t_begin; t0 < t_end; t0 += TB) {
-        // residual-stream values this thread accumulates into: issued first, consumed after the FMAs below
-        float old[TB];
-#pragma unroll
-        for (int i = 0; i < TB; ++i) old[i] = (p.mem_accum && t0 + i < t_end) ? out[static_cast<size_t>(t0 + i) * p.ld_mem] : 0.0f;
+    const uint32_t stage_u32 = smem_u32(stage);
+    int blk = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += TB, ++blk) {
         float x[TB + TAPS - 1];
 #pragma unroll
         for (int i = 0; i < TB + TAPS - 1; ++i) {
             const int t = t0 - LEFT + i;
             x[i] = (t >= 0 && t < p.Tk) ? __half2float(*reinterpret_cast<const __half*>(vb + sw128_off(t, cchunk))) : 0.0f;
         }
+        const int buf = blk & 1;
+        if (blk >= 2) {                                            // the box is reused: its store from two blocks ago has read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        float* box = stage + buf * (TB * 32);
 #pragma unroll
         for (int i = 0; i < TB; ++i) {
             float acc = x[i + LEFT];
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) acc = fmaf(w[j], x[i + j], acc);
-            if (t0 + i < t_end) out[static_cast<size_t>(t0 + i) * p.ld_mem] = old[i] + acc;
+            box[i * 32 + lane] = acc;                              // rows past the utterance end are clipped by the map
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d_f32(tmX, stage_u32 + buf * (TB * 32 * 4), h * HD + (c & ~31), t0, b, p.mem_accum != 0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttParams p) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                     const __grid_constant__ CUtensorMap tmX, const AttParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -173,6 +196,7 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+            if (p.fsmn_w != nullptr) tma_prefetch_desc(&tmX);
             mbar_init(bar_k, 1);
             mbar_init(bar_v, 1);
             for (int g = 0; g < kGroups; ++g) {
@@ -249,8 +273,9 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (p.fsmn_w != nullptr) {
             mbar_wait(bar_v, 0);
             const int ft = threadIdx.x - 9 * 32;                  // 0 .. kFsmnWarps*32-1
-            if (p.taps == 11) fsmn_from_smem<11>(p, smem + p.kv_bytes, ft, h, b);
-            else fsmn_from_smem<21>(p, smem + p.kv_bytes, ft, h, b);
+            float* stage = reinterpret_cast<float*>(smem + bar_off + 128) + (ft >> 5) * (2 * 16 * 32);   // 4 KiB per FSMN warp
+            if (p.taps == 11) fsmn_from_smem<11>(p, &tmX, smem + p.kv_bytes, stage, ft, h, b);
+            else fsmn_from_smem<21>(p, &tmX, smem + p.kv_bytes, stage, ft, h, b);
         }
     } else {
         // ------------------------------------------------ softmax / epilogue warpgroups
@@ -398,6 +423,20 @@ void make_tmap3(CUtensorMap* tm, const __half* ptr, int cols, int T, int B, int 
     if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (attention) failed with CUresult " + std::to_string(static_cast<int>(r))};
 }
 
+// fp32 [B, T, ld] viewed as (cols, t, b); box = 32 columns x 16 rows x 1, no swizzle: the FSMN staging boxes
+void make_tmap3_f32(CUtensorMap* tm, const float* ptr, int cols, int T, int B, int ld) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 4) != 0)
+        throw CudaError{"attention: FSMN memory must be 16-byte aligned with a row pitch that is a multiple of 4 floats"};
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(T) * ld * 4};
+    cuuint32_t box[3] = {32, 16, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(tensormap_encode_fn())(
+        tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError{"cuTensorMapEncodeTiled (FSMN memory) failed with CUresult " + std::to_string(static_cast<int>(r))};
+}
+
 }  // namespace
 
 bool attention_tc_eligible(int Tq, int Tk, int head_dim) {
@@ -421,12 +460,13 @@ void attention_tc_launch(const __half* Q, const __half* K, const __half* V, __ha
         unsigned a = 0, b2 = 0;
         if (sscanf(e, "%u,%u", &a, &b2) == 2) { p.v_lbo = a; p.v_sbo = b2; }
     }
-    CUtensorMap tq, tk, tv, to;
+    CUtensorMap tq, tk, tv, to, tx{};
+    if (fsmn_w) make_tmap3_f32(&tx, mem, H * HD, Tk, B, ld_mem);
     make_tmap3(&tq, Q, H * HD, Tq, B, ldq, BQ);
     make_tmap3(&tk, K, H * HD, Tk, B, ldk, p.Tkp);
     make_tmap3(&tv, V, H * HD, Tk, B, ldv, p.Tkp);
     make_tmap3(&to, O, H * HD, Tq, B, ldo, BQ);
-    const int smem_bytes = 2 * p.kv_bytes + kGroups * p.tile_bytes + 128 + 1024;
+    const int smem_bytes = 2 * p.kv_bytes + kGroups * p.tile_bytes + 128 + kFsmnWarps * 4096 + 1024;   // + FSMN staging boxes
     static std::once_flag once;
     std::call_once(once, [] {
         int ndev = 0, cur = 0;
@@ -438,7 +478,7 @@ void attention_tc_launch(const __half* Q, const __half* K, const __half* V, __ha
         }
         PF_CUDA(cudaSetDevice(cur));
     });
-    launch_k(pf_sanm_attention_tc, dim3(H, B), dim3(kThreads), static_cast<size_t>(smem_bytes), s, tq, tk, tv, to, p);
+    launch_k(pf_sanm_attention_tc, dim3(H, B), dim3(kThreads), static_cast<size_t>(smem_bytes), s, tq, tk, tv, to, tx, p);
 }
 
 }  // namespace pf
