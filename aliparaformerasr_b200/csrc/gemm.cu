@@ -30,19 +30,21 @@ constexpr int kStageTileBytes = 32 * 32 * 4;   // per-warp transpose buffer: 32 
 
 constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 
-template <int BN, bool kPair, bool kOutHalf>
+// BNMAX = widest N tile the instantiation can hold (128 or 256); the actual width bn <= BNMAX (a multiple of 32) is a
+// launch parameter, so one instantiation serves every width that shares its shared-memory / TMEM layout.
+template <int BNMAX, bool kPair, bool kOutHalf>
 struct Cfg {
-    static constexpr int kBRows = kPair ? BN / 2 : BN;              // rows of the W tile this CTA stages per k-block
+    static constexpr int kBRows = kPair ? BNMAX / 2 : BNMAX;        // W-tile rows a stage slot can hold
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     // per-warp staging: fp16 output = two 32 x 32 boxes (2 KiB each); fp32 output = two 32 x 32 boxes (4 KiB each)
     static constexpr int kWarpStageBytes = kOutHalf ? 4096 : 8192;
     static constexpr int kEpiBytes = kEpiWarps * kWarpStageBytes;
     static constexpr int kBarBytes = 512;
-    static constexpr int kBiasBytes = 2 * BN * 4;                    // two tiles' bias columns
+    static constexpr int kBiasBytes = 2 * BNMAX * 4;                 // two tiles' bias columns
     static constexpr int kFit = (kSmemMax - 1024 - kBarBytes - kBiasBytes - kEpiBytes) / kStageBytes;
     static constexpr int kStages = kFit > 8 ? 8 : kFit;
-    static constexpr int kTmemCols = BN <= 64 ? 128 : (BN <= 128 ? 256 : 512);   // two accumulator stages, power of two
+    static constexpr int kTmemCols = 2 * BNMAX;                      // two accumulator stages (256 / 512 columns)
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + 1024;  // +1024: alignment slack
     static_assert(kStages >= 3, "operand ring too shallow");
 };
@@ -330,28 +332,30 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
     }
 }
 
-// kPair = false: one CTA computes a 128 x BN tile with cta_group::1 MMAs.
-// kPair = true : a CTA pair (thread-block cluster of 2) computes a 256 x BN tile with cta_group::2 MMAs issued by the
-// leader (cluster rank 0).  CTA r stages its own 128 rows of A and only rows [r*BN/2, (r+1)*BN/2) of the W tile, and
-// owns the accumulator rows m0 + r*128 .. +127 (all BN columns) in its own TMEM.  L2->SM bytes per k-block drop from
-// 16K + BN*128 to 16K + BN*64 per SM, which is what bounds the 1-CTA kernel on this path (TMA chip throughput
+// kPair = false: one CTA computes a 128 x bn tile with cta_group::1 MMAs.
+// kPair = true : a CTA pair (thread-block cluster of 2) computes a 256 x bn tile with cta_group::2 MMAs issued by the
+// leader (cluster rank 0).  CTA r stages its own 128 rows of A and only rows [r*bn/2, (r+1)*bn/2) of the W tile, and
+// owns the accumulator rows m0 + r*128 .. +127 (all bn columns) in its own TMEM.  L2->SM bytes per k-block drop from
+// 16K + bn*128 to 16K + bn*64 per SM, which is what bounds the 1-CTA kernel on this path (TMA chip throughput
 // ~6300 B/cycle => ~42 B/cycle/SM with 148 CTAs pulling operands; B300_MICROARCH.md "TMA chip-throughput").  TMA
 // multicast does not help at cluster size 2 (the L2 dedup window only pays from ~8 CTAs), the 2-SM MMA does.
 // Protocol (same shape as CUTLASS's 2-SM pipelines): both CTAs' TMA loads complete_tx on the LEADER's full barrier
 // (the leader alone arms it with the pair's total bytes); the leader's tcgen05.commit multicasts the "stage free"
 // and "accumulator complete" arrivals to both CTAs; epilogue warps of both CTAs arrive on the leader's
 // tmem_empty barrier (the peer through a mapa-translated shared::cluster address).
-template <int BN, bool kPair, bool kOutHalf, int kAdds>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
 __global__ void __launch_bounds__(kThreads, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                       const GemmEpi epi, const int M, const int N, const int K, const int tiles_n, const int num_tiles,
-                       const int vec_ok_flags) {
+                       const GemmEpi epi, const int M, const int N, const int K, const int bn, const int tiles_n,
+                       const int num_tiles, const int vec_ok_flags) {
     const int vec_ok = vec_ok_flags & 1;
     const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
-    using C = Cfg<BN, kPair, kOutHalf>;
+    using C = Cfg<BNMAX, kPair, kOutHalf>;
     constexpr int STAGES = C::kStages;
     constexpr int CS = kPair ? 2 : 1;
+    const int brows = bn / CS;                                   // W rows this CTA stages per k-block
+    const uint32_t stage_tx = kABytes + static_cast<uint32_t>(brows) * BK * 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
@@ -366,7 +370,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 8 * (2 * STAGES + 4));
     auto resid_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * ew + b); };
-    float* bias_s = reinterpret_cast<float*>(smem + kBarOff + C::kBarBytes);       // [2][BN] bias of the current tiles
+    float* bias_s = reinterpret_cast<float*>(smem + kBarOff + C::kBarBytes);       // [2][BNMAX] bias of the current tiles
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -421,7 +425,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint32_t it = 0;                                     // global k-block counter across tiles
             for (int t = unit; t < num_tiles; t += num_units) {
                 const int m0 = (t / tiles_n) * (BM * CS) + rank * BM;
-                const int n0 = (t % tiles_n) * BN + rank * C::kBRows;
+                const int n0 = (t % tiles_n) * bn + rank * brows;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -430,11 +434,11 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (dbg_no_tma) {
                         if (leader) mbar_arrive(full_bar(s));
                     } else if (!kPair) {
-                        mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+                        mbar_arrive_expect_tx(full_bar(s), stage_tx);
                         tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
                         tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
                     } else {
-                        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * C::kStageBytes);
+                        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * stage_tx);
                         const uint32_t lead_full = mapa_shared(full_bar(s), 0);
                         tma_load_2d_pair(a_s, &tmA, lead_full, kb * BK, m0);
                         tma_load_2d_pair(a_s + kABytes, &tmB, lead_full, kb * BK, n0);
@@ -446,7 +450,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one thread; of the leader CTA in pair mode)
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc(BM * CS, BN);
+            const uint32_t idesc = make_idesc(BM * CS, bn);
             uint32_t it = 0;
             uint32_t local = 0;                                  // tiles processed by this CTA (pair)
             for (int t = unit; t < num_tiles; t += num_units, ++local) {
@@ -454,7 +458,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const uint32_t acc_ph = (local >> 1) & 1u;
                 mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);     // epilogue has drained this accumulator stage
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * BNMAX;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -487,8 +491,10 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* wstage = smem + kEpiOff + ew * C::kWarpStageBytes;
         float* stage = reinterpret_cast<float*>(wstage);         // legacy path: 32 x 32 fp32 transpose buffer
         constexpr bool kTmaOk = kOutHalf ? (kAdds == 0) : (kAdds <= 1);     // shapes the asynchronous epilogue covers
-        constexpr int kCpw = BN >= 128 ? BN / 64 : 1;                       // 32-column chunks per warp (TMA epilogue)
-        const int cbase = grp * kCpw;
+        constexpr int kCpwMax = BNMAX / 64;                                  // 32-column chunks per warp (TMA epilogue), at most
+        const int nch = bn / 32;                                             // chunks of this tile width
+        const int cpw = (nch + 1) / 2;                                       // left / right warpgroup share
+        const int cbase = grp * cpw;
         ResidPipe rp;
         rp.bar[0] = resid_bar(ew, 0); rp.bar[1] = resid_bar(ew, 1);
         rp.count[0] = rp.count[1] = 0;
@@ -498,17 +504,17 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t acc = local & 1u;
             const uint32_t acc_ph = (local >> 1) & 1u;
             const int m0 = (t / tiles_n) * (BM * CS) + rank * BM;
-            const int n0 = (t % tiles_n) * BN;
+            const int n0 = (t % tiles_n) * bn;
             const int row0 = m0 + q * 32;
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BNMAX;
             // bias of this tile's columns -> shared memory (zeros past N / without bias), one L2 round trip per tile
             // taken while the MMAs still run; two buffers so a fast warp may already fill the next tile's
-            float* bias_t = bias_s + (local & 1u) * BN;
-            for (int i = ew * 32 + lane; i < BN; i += kEpiWarps * 32)
+            float* bias_t = bias_s + (local & 1u) * BNMAX;
+            for (int i = ew * 32 + lane; i < bn; i += kEpiWarps * 32)
                 bias_t[i] = (epi.bias != nullptr && n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.0f;
             if (kTmaOk && tma_epi) {
                 int nchunks = 0;
-                for (int c = cbase; c < cbase + kCpw && c < BN / 32; ++c)
+                for (int c = cbase; c < cbase + cpw && c < nch; ++c)
                     if (n0 + c * 32 < N) ++nchunks;
                 const bool work = row0 < M && nchunks > 0 && !dbg_no_epi;
                 const int colw = n0 + cbase * 32;
@@ -528,11 +534,11 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 epi_bar_sync();                                   // bias tile visible to all epilogue warps
                 if (work) {
                     if constexpr (kOutHalf && kAdds == 0)
-                        epilogue_tma_f16<kCpw>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
+                        epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
                     else if constexpr (!kOutHalf && kAdds == 0)
-                        epilogue_tma_f32<kCpw, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
+                        epilogue_tma_f32<kCpwMax, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
                     else if constexpr (!kOutHalf && kAdds == 1)
-                        epilogue_tma_f32<kCpw, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
+                        epilogue_tma_f32<kCpwMax, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
                 }
             } else {
                 mbar_wait(tmem_full_bar(acc), acc_ph);
@@ -540,7 +546,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 epi_bar_sync();
                 if (m0 < M && !dbg_no_epi) {
 #pragma unroll 1
-                    for (int c = grp; c < BN / 32; c += 2) {
+                    for (int c = grp; c < nch; c += 2) {
                         const int col0 = n0 + c * 32;
                         if (col0 >= N) break;                    // warp-uniform
                         uint32_t r[32];
@@ -614,14 +620,14 @@ int num_sms() {
     return n;
 }
 
-template <int BN, bool kPair, bool kOutHalf, int kAdds>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
 struct Launcher {
     static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
-        using C = Cfg<BN, kPair, kOutHalf>;
+        using C = Cfg<BNMAX, kPair, kOutHalf>;
         constexpr int CS = kPair ? 2 : 1;
-        auto kern = pf_gemm_f16_tn_tcgen05<BN, kPair, kOutHalf, kAdds>;
+        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds>;
         static std::once_flag once;
         std::call_once(once, [&] {
             int ndev = 0, cur = 0;
@@ -647,7 +653,7 @@ struct Launcher {
                 else cudaGetLastError();
             }
         });
-        const int tiles_n = ceil_div(op.N, BN);
+        const int tiles_n = ceil_div(op.N, op.bn);
         const int num_tiles = tiles_n * ceil_div(op.M, BM * CS);
         const int grid = std::min(num_tiles, max_units) * CS;
         cudaLaunchConfig_t cfg{};
@@ -669,64 +675,51 @@ struct Launcher {
         }
         cfg.attrs = at;
         cfg.numAttrs = na;
-        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.epi, op.M, op.N, op.K, tiles_n, num_tiles, op.vec_ok));
+        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.epi, op.M, op.N, op.K, op.bn, tiles_n, num_tiles, op.vec_ok));
     }
 };
-template <int BN, bool kPair, bool kOutHalf, int kAdds>
-int Launcher<BN, kPair, kOutHalf, kAdds>::max_units = 1;
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
+int Launcher<BNMAX, kPair, kOutHalf, kAdds>::max_units = 1;
 
-template <int BN, bool kOutHalf, int kAdds>
+template <int BNMAX, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
-    if (op.cm == 2 && op.cn == 1) {
-        if constexpr (BN == 128 || BN == 256) Launcher<BN, true, kOutHalf, kAdds>::run(op, stream);
-        else throw CudaError{"gemm: CTA-pair MMA is instantiated for N tiles 128 and 256"};
-    } else if (op.cm == 1 && op.cn == 1) {
-        Launcher<BN, false, kOutHalf, kAdds>::run(op, stream);
-    } else {
-        throw CudaError{"gemm: cluster shape not instantiated"};
-    }
+    if (op.cm == 2 && op.cn == 1) Launcher<BNMAX, true, kOutHalf, kAdds>::run(op, stream);
+    else if (op.cm == 1 && op.cn == 1) Launcher<BNMAX, false, kOutHalf, kAdds>::run(op, stream);
+    else throw CudaError{"gemm: cluster shape not instantiated"};
 }
 
-template <int BN>
+template <int BNMAX>
 void launch_bn(const GemmOp& op, cudaStream_t stream) {
     const bool h = op.epi.out_f16 != nullptr;
     switch (op.n_adds) {
-        case 0:  h ? launch_cl<BN, true, 0>(op, stream) : launch_cl<BN, false, 0>(op, stream); break;
-        case 1:  h ? launch_cl<BN, true, 1>(op, stream) : launch_cl<BN, false, 1>(op, stream); break;
-        default: h ? launch_cl<BN, true, 2>(op, stream) : launch_cl<BN, false, 2>(op, stream); break;
+        case 0:  h ? launch_cl<BNMAX, true, 0>(op, stream) : launch_cl<BNMAX, false, 0>(op, stream); break;
+        case 1:  h ? launch_cl<BNMAX, true, 1>(op, stream) : launch_cl<BNMAX, false, 1>(op, stream); break;
+        default: h ? launch_cl<BNMAX, true, 2>(op, stream) : launch_cl<BNMAX, false, 2>(op, stream); break;
     }
 }
 
-// Tile width and cluster shape from a cycle model of the persistent kernel fitted to scripts/gemm_sweep.py on B200:
-// a tile's k-block costs max(MMA floor = 2*BN cycles for four K=16 steps, operand bytes / L2->SM bandwidth).  The L2
-// fabric delivers ~6300 B/cycle chip-wide (B300_MICROARCH.md, TMA chip throughput), at most ~80 B/cycle to one SM,
-// and is what bounds the 1-CTA 128xBN tile (85 FLOP/B at BN=256); the CTA-pair MMA halves the W bytes per CTA.
 bool pair_enabled() {
     static const bool on = [] { const char* e = getenv("PFASR_GEMM_PAIR"); return e && *e && *e != '0'; }();
     return on;
 }
 
+// Tile width (any multiple of 32 up to 256) and pairing from a wave model fitted to scripts/gemm_probe.py on B200
+// (K = 512, fp16 epilogue, one wave of 128 x bn tiles: 2.96 us @128, 3.63 us @192, 4.56 us @256):
+//   t_wave(bn, kb) = 0.3 + 0.004 bn  +  kb (0.13 + 0.0011 bn)  us     (tile switch + epilogue, then the k-blocks)
+// and the kernel costs waves(bn) * t_wave.  What it captures: M = 5312 is 41.5 row tiles, so the number of waves jumps
+// with the column-tile count - 224-wide tiles cover N = 1536 / 2048 in 294 / 420 tiles (2 / 3 waves of 0.875-size tiles)
+// where 256-wide ones need 252 / 336 tiles (2 / 3 waves of full-size tiles), and N = 512 fits one wave at 192.
 void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
     const int mt = ceil_div(M, BM), kb = ceil_div(K, BK), sms = num_sms();
-    cm_out = 1; cn_out = 1;
-    // (1) if some tile width covers the problem in ONE wave, take the narrowest such width: every CTA then runs a
-    // single tile, so the kernel's duration is that tile's main loop + epilogue and both shrink with the width
-    // (measured: 5312x512x2048 19.4 us @256 -> 16.8 us @192; 128 needs 168 CTAs, i.e. two waves, 25 us)
-    for (int bn : {64, 128, 192, 256}) {
-        if (mt * ceil_div(N, bn) <= sms) { bn_out = bn; return; }
-    }
-    // (2) several waves: waves x k-blocks x per-k-block cost + epilogue of the last tile
+    cn_out = 1;
     double best_cost = 1e30;
-    for (int bn : {256, 192, 128, 64}) {
-        for (int cfg = 0; cfg < (pair_enabled() && (bn == 128 || bn == 256) ? 2 : 1); ++cfg) {
-            const int cm = cfg >= 1 ? 2 : 1;                               // cm = 2: CTA-pair (cta_group::2) MMA
-            const int stiles = ceil_div(mt, cm) * ceil_div(N, bn);
-            const int slots = sms / cm;
-            const int waves = ceil_div(stiles, slots);
-            const int active = std::min(stiles, slots) * cm;
-            const double bw = std::min(80.0, 6300.0 / active);
-            const double t_kb = std::max(2.0 * bn, (16384.0 + 128.0 * bn / cm) / bw) + (cm > 1 ? 20.0 : 0.0);
-            const double cost = waves * kb * t_kb + 150.0 * (bn / 32);
+    for (int bn = 256; bn >= 32; bn -= 32) {
+        if (bn > 32 && ceil_div(N, bn) == ceil_div(N, bn - 32)) continue;      // a narrower tile covers N with as many columns
+        for (int cm = 1; cm <= ((pair_enabled() && bn % 64 == 0) ? 2 : 1); ++cm) {
+            const int tiles = ceil_div(mt, cm) * ceil_div(N, bn);
+            const int waves = ceil_div(tiles, sms / cm);
+            const double t_wave = 0.3 + 0.004 * bn + kb * (0.13 + 0.0011 * bn) + (cm > 1 ? 0.1 * kb : 0.0);
+            const double cost = waves * t_wave;
             if (cost < best_cost) { best_cost = cost; bn_out = bn; cm_out = cm; }
         }
     }
@@ -744,10 +737,9 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if (tile_code == 0) pick_config(M, N, K, bn, cm, cn);
     cm = std::max(cm, 1);
     cn = std::max(cn, 1);
-    if (bn != 64 && bn != 128 && bn != 192 && bn != 256) throw CudaError{"gemm: unsupported N tile"};
-    if (cm == 2 && bn == 192) throw CudaError{"gemm: the 192-wide tile is instantiated for single CTAs only"};
+    if (bn < 32 || bn > 256 || bn % 32 != 0) throw CudaError{"gemm: the N tile must be a multiple of 32 in [32, 256]"};
     if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and the 2x1 CTA pair are instantiated)"};
-    if (cm == 2 && bn < 128) throw CudaError{"gemm: the CTA-pair MMA needs an N tile of 128 or 256"};
+    if (cm == 2 && bn % 64 != 0) throw CudaError{"gemm: the CTA-pair MMA needs an N tile that is a multiple of 64"};
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
     // the kernel adds up to two fp32 tensors in a fixed order: FSMN memory first, then the residual
     op.n_adds = 0;
@@ -784,12 +776,8 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
 }
 
 void gemm_launch(const GemmOp& op, cudaStream_t stream) {
-    switch (op.bn) {
-        case 64:  launch_bn<64>(op, stream);  break;
-        case 128: launch_bn<128>(op, stream); break;
-        case 192: launch_bn<192>(op, stream); break;
-        default:  launch_bn<256>(op, stream); break;
-    }
+    if (op.bn <= 128) launch_bn<128>(op, stream);      // 32 KiB stage slots, 6 stages
+    else launch_bn<256>(op, stream);                   // 48 KiB stage slots
 }
 
 double gemm_flops(const GemmOp& op) { return 2.0 * op.M * static_cast<double>(op.N) * op.K; }

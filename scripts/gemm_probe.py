@@ -23,7 +23,7 @@ for M, N, K, epi in SHAPES:
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
     resid = rng.standard_normal((M, N)).astype(np.float32) if "res" in epi else None
-    for tile, cm in ((256, 1), (192, 1), (128, 1), (256, 2)):
+    for tile, cm in ((256, 1), (224, 1), (192, 1), (160, 1), (128, 1), (0, 0)):
         _, ms = dbg_gemm(lib, A, W, bias, resid, None, relu=int("relu" in epi), out_half=int(epi.startswith("f16")),
                          tile_n=tile | (cm << 12), iters=30)
         print(f"dbg={mask} {M:6d} {N:6d} {K:5d} {epi:10s} tile {tile} pair {cm}: {ms * 1e3:8.2f} us {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("M,N,K,tile", [
     (128, 128, 64, 128), (128, 64, 128, 64), (256, 256, 512, 256), (5312, 1536, 560, 0), (5312, 512, 512, 0),
     (5312, 2048, 512, 0), (5312, 512, 2048, 0), (1344, 8404, 512, 0), (83, 512, 512, 0), (100, 520, 72, 64),
-    (300, 8404, 512, 128), (640, 1024, 512, 256), (5312, 512, 2048, 192), (333, 520, 512, 192), (1000, 1536, 512, 192),
+    (300, 8404, 512, 128), (640, 1024, 512, 256), (5312, 512, 2048, 192), (333, 520, 512, 192), (1000, 1536, 512, 192), (5312, 1536, 512, 224), (700, 2048, 512, 160), (300, 8404, 512, 96), (129, 96, 64, 32), (1600, 2048, 512, 192 | (2 << 12)),
     # CTA-pair (cta_group::2) MMA, 256 x tile per pair: tile | (2 << 12)
     (5312, 1536, 512, 256 | (2 << 12)), (640, 1024, 512, 256 | (2 << 12)), (300, 8404, 512, 128 | (2 << 12)),
     (83, 512, 512, 128 | (2 << 12)), (5312, 512, 2048, 128 | (2 << 12)), (1600, 8404, 512, 256 | (2 << 12)),
