@@ -13,6 +13,13 @@
 
 namespace pf {
 
+// PFASR_DBG_SKIP (tuning aid, results are garbage): bit 0 encoder LayerNorms, 1 encoder attention, 2 decoder LayerNorms,
+// 3 decoder FSMN, 4 decoder cross attention - skipped launches show what each family really costs inside the pipelined step
+static int dbg_skip() {
+    static const int v = [] { const char* e = getenv("PFASR_DBG_SKIP"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("PFASR_NO_PDL");
@@ -677,18 +684,18 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
     ++launches;
     auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool first) {
         if (!first) {
-            timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
+            if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
             ++launches;
         }
         gemm(lp.qkv);
-        timed("enc_attention_fsmn", [&] {
+        if (!(dbg_skip() & 2)) timed("enc_attention_fsmn", [&] {
             // x += mem (layer with a residual) or x = mem (encoders0: in_size != d_model, no residual); the
             // out-projection then adds ctx W_o + b on top of x32_
             launches += attention_fsmn_launch(qkv16_, qkv16_ + d, qkv16_ + 2 * d, ctx16_, B, H, T, 3 * d, d, w.fsmn, cfg_.enc_kernel,
                                               x32_, d, w.in_size == d, stream_);
         });
         gemm(lp.out);
-        timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
+        if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
         ++launches;
         gemm(lp.ffn1);
         gemm(lp.ffn2);
@@ -735,9 +742,9 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
     const bool per_layer_cache = (cfg_.online_flags & 1) != 0;
     const size_t cache_layer = static_cast<size_t>(cfg_.dec_kernel - 1) * d;
     auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
-        timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
+        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(g1);
-        timed("dec_layernorm_ffn", [&] { layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_); });
+        if (!(dbg_skip() & 4)) timed("dec_layernorm_ffn", [&] { layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_); });
         gemm(g2);
         launches += 2;
     };
@@ -745,15 +752,15 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
         const DecLayerW& w = layers[i];
         const DecLayerPlan& lp = lps[i];
         ffn(w.ffn, lp.w1, lp.w2);
-        timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
-        timed("dec_fsmn", [&] {
+        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
+        if (!(dbg_skip() & 8)) timed("dec_fsmn", [&] {
             if (!online) fsmn_f32_launch(tn32_, d, w.fsmn, kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
             else online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, kernel, ofsmn_, fsmn_state_stride(),
                                     per_layer_cache ? i * cache_layer : 0, xd32_, ocache_new_, fsmn_state_stride(), i * cache_layer, stream_);
         });
-        timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
+        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
         gemm(lp.q);
-        timed("dec_cross_attention", [&] {
+        if (!(dbg_skip() & 16)) timed("dec_cross_attention", [&] {
             if (kv_shared) attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, 1, H, Md, Tk, d, ldkv, ldkv, d, d / H, stream_);
             else attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, B, H, L, Tk, d, ldkv, ldkv, d, d / H, stream_);
         });

@@ -417,7 +417,22 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (kPair) cluster_sync(); else __syncthreads();             // peer barriers are initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();      // prologue above overlaps the previous kernel's tail; operands / residuals are read below
+    // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight tiles do not
+    // depend on that kernel either, so the producer requests the W halves of its first STAGES k-blocks BEFORE waiting
+    // for it; activations (A), residuals and outputs are only touched after the wait.
+    uint32_t npre = 0;
+    if (!kPair && warp == 0 && lane == 0 && !dbg_no_tma) {
+        uint32_t it = 0;
+        for (int t = unit; t < num_tiles && it < STAGES; t += num_units) {
+            const int n0 = (t % tiles_n) * bn;
+            for (int kb = 0; kb < num_kb && it < STAGES; ++kb, ++it) {
+                mbar_arrive_expect_tx(full_bar(it), stage_tx);
+                tma_load_2d(base + it * C::kStageBytes + kABytes, &tmB, full_bar(it), kb * BK, n0);
+            }
+        }
+        npre = it;
+    }
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer (one thread in every CTA)
@@ -429,8 +444,12 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t a_s = base + s * C::kStageBytes;
+                    if (it < npre) {                             // stage armed and its W half already in flight
+                        tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
+                        continue;
+                    }
+                    mbar_wait(empty_bar(s), ph ^ 1u);
                     if (dbg_no_tma) {
                         if (leader) mbar_arrive(full_bar(s));
                     } else if (!kPair) {
