@@ -1,0 +1,94 @@
+"""ONNX initialiser reader (row f3): round trips through a minimal protobuf writer, de-quantisation, MatMul order, and
+- when the reference tree is mounted (build container) - the real ``data/embed.onnx`` against the committed golden."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from aliparaformerasr_b200 import onnx_weights as ow
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "sensevoice_embed.npy")
+REAL = "/root/reference/AliParaformerAsr/data/embed.onnx"
+
+
+def _vi(x):
+    out = b""
+    while True:
+        b = x & 0x7F
+        x >>= 7
+        out += bytes([b | (0x80 if x else 0)])
+        if not x:
+            return out
+
+
+def _ld(num, payload):
+    return _vi((num << 3) | 2) + _vi(len(payload)) + payload
+
+
+def _tensor(name, arr, raw=True):
+    dt = {np.dtype(np.float32): 1, np.dtype(np.uint8): 2, np.dtype(np.int8): 3, np.dtype(np.int64): 7}[arr.dtype]
+    body = b"".join(_vi((1 << 3) | 0) + _vi(int(d)) for d in arr.shape) + _vi((2 << 3) | 0) + _vi(dt) + _ld(8, name.encode())
+    if raw:
+        body += _ld(9, arr.tobytes())
+    else:
+        body += _ld(4, struct.pack(f"<{arr.size}f", *arr.reshape(-1)))
+    return body
+
+
+def _node(op, ins, outs):
+    return b"".join(_ld(1, i.encode()) for i in ins) + b"".join(_ld(2, o.encode()) for o in outs) + _ld(4, op.encode())
+
+
+def _model(tensors, nodes):
+    graph = b"".join(_ld(1, _node(*n)) for n in nodes) + _ld(2, b"g") + b"".join(_ld(5, t) for t in tensors)
+    return _vi((1 << 3) | 0) + _vi(8) + _ld(7, graph)
+
+
+def test_roundtrip_and_matmul_order():
+    rng = np.random.default_rng(0)
+    w1 = rng.standard_normal((4, 6)).astype(np.float32)
+    w2 = rng.standard_normal((6, 3)).astype(np.float32)
+    b = rng.standard_normal(3).astype(np.float32)
+    data = _model([_tensor("onnx::MatMul_7", w1), _tensor("onnx::MatMul_9", w2, raw=False), _tensor("enc.bias", b),
+                   _tensor("shape", np.asarray([1, -1, 3], np.int64))],
+                  [("MatMul", ["x", "onnx::MatMul_7"], ["h"]), ("Relu", ["h"], ["r"]), ("MatMul", ["r", "onnx::MatMul_9"], ["y"]),
+                   ("Add", ["y", "enc.bias"], ["z"])])
+    g = ow.read_onnx(data)
+    assert np.array_equal(g.initializers["onnx::MatMul_7"], w1)
+    assert np.array_equal(g.initializers["onnx::MatMul_9"], w2)
+    assert np.array_equal(g.initializers["shape"], [1, -1, 3])
+    assert ow.matmul_weights_in_order(g) == ["onnx::MatMul_7", "onnx::MatMul_9"]
+    assert [n[0] for n in g.nodes] == ["MatMul", "Relu", "MatMul", "Add"]
+
+
+def test_dequantize_dynamic_quantisation_triplets():
+    rng = np.random.default_rng(1)
+    q = rng.integers(-128, 128, size=(5, 4), dtype=np.int8)
+    scale = np.asarray([0.02, 0.03, 0.01, 0.05], np.float32)
+    zp = np.zeros(4, np.int8)
+    qu = rng.integers(0, 256, size=(3, 2), dtype=np.uint8)
+    data = _model([_tensor("w_quantized", q), _tensor("w_scale", scale), _tensor("w_zero_point", zp),
+                   _tensor("u_quantized", qu), _tensor("u_scale", np.asarray(0.1, np.float32).reshape(())),
+                   _tensor("u_zero_point", np.asarray(128, np.uint8).reshape(())), _tensor("ln.weight", np.ones(4, np.float32))],
+                  [("MatMulInteger", ["a", "w_quantized"], ["y"])])
+    g = ow.read_onnx(data)
+    d = ow.dequantize(g.initializers)
+    assert set(d) == {"w", "u", "ln.weight"}
+    assert np.allclose(d["w"], q.astype(np.float32) * scale[None, :])
+    assert np.allclose(d["u"], (qu.astype(np.float32) - 128.0) * 0.1)
+    assert ow.matmul_weights_in_order(g) == ["w"]
+
+
+def test_embed_table_from_generated_file_matches_golden():
+    gold = np.load(GOLD)
+    data = _model([_tensor("weight", gold)], [("Gather", ["weight", "x"], ["y"])])
+    assert np.array_equal(ow.sensevoice_embed_table(data), gold)
+
+
+@pytest.mark.skipif(not os.path.exists(REAL), reason="reference tree not mounted (GPU box)")
+def test_real_embed_onnx_matches_golden():
+    # the one numeric artefact the reference ships (EmbedSVModel.cs:20-43 loads it as an embedded resource)
+    assert np.array_equal(ow.sensevoice_embed_table(REAL), np.load(GOLD))
+    g = ow.read_onnx(REAL)
+    assert g.nodes == [("Gather", ["weight", "x"], ["y"])]
