@@ -752,13 +752,20 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
         const DecLayerW& w = layers[i];
         const DecLayerPlan& lp = lps[i];
         ffn(w.ffn, lp.w1, lp.w2);
-        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
-        if (!(dbg_skip() & 8)) timed("dec_fsmn", [&] {
-            if (!online) fsmn_f32_launch(tn32_, d, w.fsmn, kernel, xd32_, d, xd32_, d, token_num_, B, L, d, stream_);
-            else online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, kernel, ofsmn_, fsmn_state_stride(),
-                                    per_layer_cache ? i * cache_layer : 0, xd32_, ocache_new_, fsmn_state_stride(), i * cache_layer, stream_);
-        });
-        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
+        if (!online) {
+            // norm2 -> FSMN memory -> residual -> norm3 in one kernel (three launches otherwise)
+            if (!(dbg_skip() & 12)) timed("dec_ln_fsmn_ln", [&] {
+                dec_ln_fsmn_ln_launch(t32_, xd32_, w.ln2.g, w.ln2.b, w.fsmn, kernel, w.ln3.g, w.ln3.b, token_num_, B, L, d, eps, ad16_, stream_);
+            });
+            launches -= 2;
+        } else {
+            timed("dec_layernorm", [&] { layernorm_f32_launch(t32_, d, Md, d, w.ln2.g, w.ln2.b, eps, nullptr, 0, tn32_, d, stream_); });
+            timed("dec_fsmn", [&] {
+                online_fsmn_launch(otab_, B, tn32_, fires_, L, d, w.fsmn, kernel, ofsmn_, fsmn_state_stride(),
+                                   per_layer_cache ? i * cache_layer : 0, xd32_, ocache_new_, fsmn_state_stride(), i * cache_layer, stream_);
+            });
+            timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln3.g, w.ln3.b, eps, ad16_, d, nullptr, 0, stream_); });
+        }
         gemm(lp.q);
         if (!(dbg_skip() & 16)) timed("dec_cross_attention", [&] {
             if (kv_shared) attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, 1, H, Md, Tk, d, ldkv, ldkv, d, d / H, stream_);

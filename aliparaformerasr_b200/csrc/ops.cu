@@ -162,6 +162,115 @@ pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, floa
     }
 }
 
+// ------------------------------------------------------------------ decoder: norm2 -> FSMN memory -> residual -> norm3
+// One CTA per (16-row time block, utterance).  tn = LN2(t) for the block rows plus the FSMN halo goes to shared memory
+// (masked rows are zero), every thread then runs the depthwise memory for two channels, adds it to the residual stream
+// (rows past the utterance's token count keep x), and the block's new x rows are normalised again (norm3) into the fp16
+// operand of the cross-attention query projection.  Replaces three launches per decoder layer (LayerNorm, pf_fsmn,
+// LayerNorm) - the decoder is launch-latency bound at M = B * L ~ 1600 rows.
+template <int K>
+__global__ void __launch_bounds__(256)
+pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const float* __restrict__ g2, const float* __restrict__ b2,
+                  const float* __restrict__ w, const float* __restrict__ g3, const float* __restrict__ b3,
+                  const int* __restrict__ lens, int L, float eps, __half* __restrict__ out16) {
+    pdl_launch_dependents();
+    constexpr int D = 512, TT = 16, LEFT = (K - 1) / 2, ROWS = TT + K - 1;
+    extern __shared__ float s_dec[];
+    float* s_v = s_dec;                    // [ROWS][D]  LN2 output, zero outside [0, len)
+    float* s_x = s_dec + ROWS * D;         // [TT][D]    new residual rows
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* g2v = reinterpret_cast<const float4*>(g2);
+    const float4* b2v = reinterpret_cast<const float4*>(b2);
+    pdl_wait();
+    const int len = min(lens[b], L);
+    const size_t rowbase = static_cast<size_t>(b) * L;
+    for (int r = warp; r < ROWS; r += 8) {
+        const int t = t0 - LEFT + r;
+        float4* dst = reinterpret_cast<float4*>(s_v + r * D);
+        if (t < 0 || t >= len) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const float4* src = reinterpret_cast<const float4*>(t32 + (rowbase + t) * D);
+        float4 v[4];
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = src[lane + 32 * i]; sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        sum = warp_sum(sum);
+        const float mean = sum * (1.0f / D);
+        float sq = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + bb * bb) + (c * c + d * d);
+        }
+        sq = warp_sum(sq);
+        const float rstd = 1.0f / sqrtf(sq * (1.0f / D) + eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 g = __ldg(g2v + lane + 32 * i), bt = __ldg(b2v + lane + 32 * i);
+            dst[lane + 32 * i] = make_float4((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y,
+                                             (v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int c = threadIdx.x + half * 256;
+        float wk[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) wk[j] = __ldg(w + c * K + j);
+#pragma unroll 4
+        for (int i = 0; i < TT; ++i) {
+            const int t = t0 + i;
+            if (t >= L) break;
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc += wk[j] * s_v[(i + j) * D + c];
+            const size_t o = (rowbase + t) * D + c;
+            float xv = x[o];
+            if (t < len) xv += acc + s_v[(i + LEFT) * D + c];
+            x[o] = xv;
+            s_x[i * D + c] = xv;
+        }
+    }
+    __syncthreads();
+    const float4* g3v = reinterpret_cast<const float4*>(g3);
+    const float4* b3v = reinterpret_cast<const float4*>(b3);
+    for (int i = warp; i < TT; i += 8) {
+        const int t = t0 + i;
+        if (t >= L) break;
+        const float4* src = reinterpret_cast<const float4*>(s_x + i * D);
+        float4 v[4];
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = src[lane + 32 * k]; sum += (v[k].x + v[k].y) + (v[k].z + v[k].w); }
+        sum = warp_sum(sum);
+        const float mean = sum * (1.0f / D);
+        float sq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float a = v[k].x - mean, bb = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            sq += (a * a + bb * bb) + (c * c + d * d);
+        }
+        sq = warp_sum(sq);
+        const float rstd = 1.0f / sqrtf(sq * (1.0f / D) + eps);
+        uint2* dst = reinterpret_cast<uint2*>(out16 + (rowbase + t) * D);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 g = __ldg(g3v + lane + 32 * k), bt = __ldg(b3v + lane + 32 * k);
+            __half2 h0 = __floats2half2_rn((v[k].x - mean) * rstd * g.x + bt.x, (v[k].y - mean) * rstd * g.y + bt.y);
+            __half2 h1 = __floats2half2_rn((v[k].z - mean) * rstd * g.z + bt.z, (v[k].w - mean) * rstd * g.w + bt.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            dst[lane + 32 * k] = pk;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ predictor
 __global__ void pf_im2col3(const __half* __restrict__ in, int B, int T, int D, __half* __restrict__ out) {
     pdl_launch_dependents();
@@ -239,25 +348,36 @@ __global__ void pf_cif_scan(const float* __restrict__ alphas, int B, int T1, flo
     atomicMax(meta, nf);
 }
 
+// One CTA per (token l, utterance b): the frames between the previous fire and this one, accumulated in the same order
+// (and with the same fp32 roundings) as the sequential recurrence: start from the remainder weight of the previous
+// firing frame, add w_cur[t] * h[t] for t up to this token's firing frame.
 __global__ void __launch_bounds__(256)
 pf_cif_gather(const float* __restrict__ hidden, int T, int D, const float* __restrict__ w_cur,
               const float* __restrict__ w_rem, const int* __restrict__ fire_idx, int T1, float* __restrict__ out, int Lpad) {
     pdl_launch_dependents();
     pdl_wait();
-    const int b = blockIdx.y;
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
+    __shared__ int s_t[2];
+    const int l = blockIdx.x, b = blockIdx.y;
     const size_t abase = static_cast<size_t>(b) * T1;
-    const float* h = hidden + static_cast<size_t>(b) * T * D + d;
-    float frame = 0.0f;
-    for (int t = 0; t < T1; ++t) {
-        const float hv = t < T ? h[static_cast<size_t>(t) * D] : 0.0f;     // tail step has zero hidden
-        frame = __fadd_rn(frame, __fmul_rn(w_cur[abase + t], hv));
-        const int l = fire_idx[abase + t];
-        if (l >= 0) {
-            if (l < Lpad) out[(static_cast<size_t>(b) * Lpad + l) * D + d] = frame;
-            frame = __fmul_rn(w_rem[abase + t], hv);
+    if (threadIdx.x < 2) s_t[threadIdx.x] = -1;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T1; t += blockDim.x) {
+        const int f = fire_idx[abase + t];
+        if (f == l) s_t[1] = t;
+        else if (f == l - 1 && l > 0) s_t[0] = t;
+    }
+    __syncthreads();
+    const int t_end = s_t[1], t_prev = s_t[0];
+    if (t_end < 0) return;                                   // this utterance fired fewer than l + 1 tokens: row stays zero
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float* h = hidden + static_cast<size_t>(b) * T * D + d;
+        float frame = 0.0f;
+        if (t_prev >= 0) frame = __fmul_rn(w_rem[abase + t_prev], t_prev < T ? h[static_cast<size_t>(t_prev) * D] : 0.0f);
+        for (int t = t_prev + 1; t <= t_end; ++t) {
+            const float hv = t < T ? h[static_cast<size_t>(t) * D] : 0.0f;      // tail step has zero hidden
+            frame = __fadd_rn(frame, __fmul_rn(w_cur[abase + t], hv));
         }
+        out[(static_cast<size_t>(b) * Lpad + l) * D + d] = frame;
     }
 }
 
@@ -476,6 +596,34 @@ void fsmn_f32_launch(const float* in, int ld_in, const float* w, int K, float* o
     fsmn_launch_t(in, ld_in, w, K, out, ld_out, resid, ld_res, lens, B, T, D, s);
 }
 
+template <int K>
+static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2, const float* b2, const float* w, const float* g3,
+                                    const float* b3, const int* lens, int B, int L, float eps, __half* out16, cudaStream_t s) {
+    constexpr int kSmem = (16 + K - 1 + 16) * 512 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int ndev = 0, cur = 0;
+        PF_CUDA(cudaGetDeviceCount(&ndev));
+        PF_CUDA(cudaGetDevice(&cur));
+        for (int d = 0; d < ndev; ++d) {
+            PF_CUDA(cudaSetDevice(d));
+            PF_CUDA(cudaFuncSetAttribute(pf_dec_ln_fsmn_ln<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        }
+        PF_CUDA(cudaSetDevice(cur));
+        attr_set = true;
+    }
+    launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, 16), B), dim3(256), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
+}
+
+void dec_ln_fsmn_ln_launch(const float* t32, float* x, const float* g2, const float* b2, const float* w, int K, const float* g3,
+                           const float* b3, const int* lens, int B, int L, int D, float eps, __half* out16, cudaStream_t s) {
+    if (D != 512) throw CudaError{"dec_ln_fsmn_ln: d_model must be 512"};
+    if (B <= 0 || L <= 0) return;
+    if (K == 11) dec_ln_fsmn_ln_launch_t<11>(t32, x, g2, b2, w, g3, b3, lens, B, L, eps, out16, s);
+    else if (K == 21) dec_ln_fsmn_ln_launch_t<21>(t32, x, g2, b2, w, g3, b3, lens, B, L, eps, out16, s);
+    else throw CudaError{"dec_ln_fsmn_ln: unsupported kernel size " + std::to_string(K)};
+}
+
 void im2col3_launch(const __half* in, int B, int T, int D, __half* out, cudaStream_t s) {
     const long long total = static_cast<long long>(B) * T * (3 * D / 8);
     const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
@@ -494,8 +642,8 @@ void cif_scan_launch(const float* alphas, int B, int T1, float threshold, float*
 
 void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_cur, const float* w_rem,
                        const int* fire_idx, int T1, float* out, int Lpad, cudaStream_t s) {
-    dim3 grid(ceil_div(D, 256), B);
-    launch_k(pf_cif_gather, grid, dim3(256), 0, s, hidden, T, D, w_cur, w_rem, fire_idx, T1, out, Lpad);
+    if (Lpad <= 0) return;
+    launch_k(pf_cif_gather, dim3(Lpad, B), dim3(256), 0, s, hidden, T, D, w_cur, w_rem, fire_idx, T1, out, Lpad);
 }
 
 void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, int write_logp, cudaStream_t s) {

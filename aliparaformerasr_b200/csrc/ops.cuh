@@ -20,6 +20,11 @@ void fsmn_f16_launch(const __half* in, int ld_in, const float* w, int K, float* 
 void fsmn_f32_launch(const float* in, int ld_in, const float* w, int K, float* out, int ld_out, const float* resid,
                      int ld_res, const int* lens, int B, int T, int D, cudaStream_t s);
 
+// Decoder layer middle, fused: x += mask * (FSMN(LN2(t) * mask) + LN2(t) * mask); out16 = fp16(LN3(x)).  t32 / x: [B*L, 512]
+// fp32 (x updated in place), lens: [B] valid token rows, w: [512, K] (K = 11 or 21).
+void dec_ln_fsmn_ln_launch(const float* t32, float* x, const float* g2, const float* b2, const float* w, int K, const float* g3,
+                           const float* b3, const int* lens, int B, int L, int D, float eps, __half* out16, cudaStream_t s);
+
 // Predictor conv1d(k=3, pad 1|1) as a GEMM: rows [h(t-1) | h(t) | h(t+1)] fp16, zero outside the utterance.
 void im2col3_launch(const __half* in, int B, int T, int D, __half* out, cudaStream_t s);
 
