@@ -106,6 +106,7 @@ SIGNATURES = {
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),
     "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),
+    "pf_dbg_gemm_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, _F, C.c_float, _F, _F]),
     "pf_dbg_layernorm": (C.c_int32, [C.c_int32, C.c_int32, _F, _F, _F, C.c_float, _F]),
     "pf_dbg_embed_pe_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, C.c_float, _F, _F, C.c_float, _F]),
     "pf_dbg_attention": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F]),

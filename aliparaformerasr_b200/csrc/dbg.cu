@@ -113,6 +113,32 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
     });
 }
 
+pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, const float* resid,
+                         const float* gamma, const float* beta, float eps, float* out, float* out_ln) {
+    return guarded([&] {
+        if (!gemm_ln_fusable(M, N)) throw CudaError{"shape cannot carry the fused LayerNorm epilogue"};
+        Scratch s;
+        __half* dA = s.up_half(A, static_cast<size_t>(M) * K);
+        __half* dW = s.up_half(W, static_cast<size_t>(N) * K);
+        GemmEpi e;
+        if (bias) e.bias = s.up(bias, N);
+        float* x = s.up(resid, static_cast<size_t>(M) * N);           // in-place residual, like the encoder's x32
+        e.resid = x; e.ld_resid = N; e.out_f32 = x; e.ld_out = N;
+        e.ln_gamma = s.up(gamma, N); e.ln_beta = s.up(beta, N); e.ln_eps = eps;
+        __half* ln16 = s.alloc<__half>(static_cast<size_t>(M) * N);
+        float* ln32 = s.alloc<float>(static_cast<size_t>(M) * N);
+        e.ln_out16 = ln16; e.ld_ln16 = N;
+        GemmOp op;
+        gemm_prepare(op, dA, K, dW, K, M, N, K, e, 0);
+        gemm_launch(op, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        pf_dbg_f16_to_f32<<<256, 256>>>(ln16, ln32, static_cast<size_t>(M) * N);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(out, x, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
+        PF_CUDA(cudaMemcpy(out_ln, ln32, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
 pf_status pf_dbg_layernorm(int32_t M, int32_t D, const float* x, const float* gamma, const float* beta, float eps, float* out) {
     return guarded([&] {
         Scratch s;

@@ -32,7 +32,9 @@ constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA o
 
 // BNMAX = widest N tile the instantiation can hold (128 or 256); the actual width bn <= BNMAX (a multiple of 32) is a
 // launch parameter, so one instantiation serves every width that shares its shared-memory / TMEM layout.
-template <int BNMAX, bool kPair, bool kOutHalf>
+constexpr int kLnMaxCluster = 4;       // column tiles (CTAs of one cluster) a fused-LayerNorm row may span
+
+template <int BNMAX, bool kPair, bool kOutHalf, bool kLn = false>
 struct Cfg {
     static constexpr int kBRows = kPair ? BNMAX / 2 : BNMAX;        // W-tile rows a stage slot can hold
     static constexpr int kBBytes = kBRows * BK * 2;
@@ -42,10 +44,12 @@ struct Cfg {
     static constexpr int kEpiBytes = kEpiWarps * kWarpStageBytes;
     static constexpr int kBarBytes = 512;
     static constexpr int kBiasBytes = 2 * BNMAX * 4;                 // two tiles' bias columns
-    static constexpr int kFit = (kSmemMax - 1024 - kBarBytes - kBiasBytes - kEpiBytes) / kStageBytes;
+    // fused LayerNorm: gamma | beta tiles and the per-row partial sums of every CTA of the cluster
+    static constexpr int kLnBytes = kLn ? 2 * BNMAX * 4 + kLnMaxCluster * 2 * BM * 2 * 4 : 0;
+    static constexpr int kFit = (kSmemMax - 1024 - kBarBytes - kBiasBytes - kLnBytes - kEpiBytes) / kStageBytes;
     static constexpr int kStages = kFit > 8 ? 8 : kFit;
     static constexpr int kTmemCols = 2 * BNMAX;                      // two accumulator stages (256 / 512 columns)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + 1024;  // +1024: alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + kLnBytes + 1024;  // +1024: alignment slack
     static_assert(kStages >= 3, "operand ring too shallow");
 };
 
@@ -274,10 +278,11 @@ __device__ __forceinline__ void resid_issue(ResidPipe& rp, int buf, uint32_t stg
         tma_load_2d(stg_u32 + buf * 4096, tmR, rp.bar[buf], col, row0);
     }
 }
-template <int kMaxChunks, bool kResid>
+template <int kMaxChunks, bool kResid, bool kLn = false>
 __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, uint8_t* stg, ResidPipe& rp, const CUtensorMap* tmC,
                                                  const CUtensorMap* tmR, const float* bias_w, float lo, int row0,
-                                                 int colw, int lane, int prefetched) {
+                                                 int colw, int lane, int prefetched, float* ln_s1 = nullptr, float* ln_s2 = nullptr) {
+    float s1 = 0.0f, s2 = 0.0f;                                    // kLn: this row's sum / sum of squares over the warp's columns
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t ra[32], rb[32];
     tmem_ld_issue(t_acc, ra);
@@ -316,7 +321,14 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
                 }
                 v.x = fmaxf(v.x, lo); v.y = fmaxf(v.y, lo); v.z = fmaxf(v.z, lo); v.w = fmaxf(v.w, lo);
                 *slot = v;
+                if (kLn) {                                         // keep the final values for the normalisation pass
+                    s1 += (v.x + v.y) + (v.z + v.w);
+                    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    cur[4 * j] = __float_as_uint(v.x); cur[4 * j + 1] = __float_as_uint(v.y);
+                    cur[4 * j + 2] = __float_as_uint(v.z); cur[4 * j + 3] = __float_as_uint(v.w);
+                }
             }
+            if (kLn) tmem_st_32x32(t_acc + static_cast<uint32_t>(k * 32), cur);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -327,6 +339,80 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
             if (kResid && k + 2 < nchunks) {
                 __syncwarp();
                 resid_issue<kResid>(rp, buf, stg_u32, tmR, colw + (k + 2) * 32, row0, lane);
+            }
+        }
+    }
+    if (kLn) { *ln_s1 = s1; *ln_s2 = s2; }
+}
+
+// Fused LayerNorm of the rows this GEMM just produced (x = acc + bias + residual): a row spans the CTAs of one
+// cluster (one column tile each).  Every epilogue thread owns a row (TMEM lane): it publishes the row's partial sums
+// to all CTAs of the cluster through distributed shared memory, waits for everybody's, and normalises the values it
+// parked in TMEM into the fp16 operand of the next GEMM (TMA store).  Replaces a LayerNorm launch and its 16 MB round trip.
+struct LnFuse {
+    const CUtensorMap* tmL;      // fp16 [M, N] output, 32 x 32 boxes, SWIZZLE_64B
+    const float* gamma_t;        // smem: gamma | beta of this tile's columns ([2][BNMAX])
+    int bnmax;
+    float* part;                 // smem [kLnMaxCluster][2][BM][2] partial sums landed here by every CTA of the cluster
+    uint32_t part_u32, bar_u32;
+    int cs, rank;
+    float eps, inv_n;
+};
+__device__ __forceinline__ void ln_publish(const LnFuse& f, int grp, int rowq, float s1, float s2) {
+    const uint32_t off = static_cast<uint32_t>((((f.rank * 2 + grp) * BM) + rowq) * 8);
+    for (int j = 0; j < f.cs; ++j) {
+        st_cluster_f32x2(mapa_shared(f.part_u32 + off, j), s1, s2);
+        mbar_arrive_remote(mapa_shared(f.bar_u32, j));                 // release.cluster: orders the store above
+    }
+}
+template <int kMaxChunks>
+__device__ __forceinline__ void epilogue_ln_pass2(const LnFuse& f, uint32_t t_acc, int nchunks, uint8_t* stg, int cbase, int rowq,
+                                                  int row0, int colw, int lane) {
+    mbar_wait_cluster(f.bar_u32, 0);
+    float S1 = 0.0f, S2 = 0.0f;
+    for (int j = 0; j < f.cs; ++j)
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const float2 p = *reinterpret_cast<const float2*>(f.part + (((j * 2 + g) * BM) + rowq) * 2);
+            S1 += p.x; S2 += p.y;
+        }
+    const float mean = S1 * f.inv_n;
+    const float rstd = 1.0f / sqrtf(fmaxf(S2 * f.inv_n - mean * mean, 0.0f) + f.eps);
+    if (nchunks <= 0) return;
+    const uint32_t stg_u32 = smem_u32(stg);
+    tmem_st_wait();
+    if (lane == 0) tma_store_wait_read();                          // the fp32 boxes have been read: reuse them for fp16
+    __syncwarp();
+    uint32_t r[32];
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+        if (k < nchunks) {
+            tmem_ld_32x32(t_acc + static_cast<uint32_t>(k * 32), r);
+            tmem_ld_wait();
+            if (k >= 2) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            uint8_t* box = stg + (k & 1) * 2048 + lane * 64;
+            const float* g_t = f.gamma_t + (cbase + k) * 32;
+            const float* b_t = g_t + f.bnmax;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = (__uint_as_float(r[8 * j + i]) - mean) * rstd * g_t[8 * j + i] + b_t[8 * j + i];
+                __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+                __half2 h2 = __floats2half2_rn(y[4], y[5]), h3 = __floats2half2_rn(y[6], y[7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(box + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(f.tmL, stg_u32 + (k & 1) * 2048, colw + k * 32, row0);
+                tma_store_commit();
             }
         }
     }
@@ -343,15 +429,16 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
 // (the leader alone arms it with the pair's total bytes); the leader's tcgen05.commit multicasts the "stage free"
 // and "accumulator complete" arrivals to both CTAs; epilogue warps of both CTAs arrive on the leader's
 // tmem_empty barrier (the peer through a mapa-translated shared::cluster address).
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false>
 __global__ void __launch_bounds__(kThreads, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                       const GemmEpi epi, const int M, const int N, const int K, const int bn, const int tiles_n,
-                       const int num_tiles, const int vec_ok_flags) {
+                       const __grid_constant__ CUtensorMap tmL, const GemmEpi epi, const int M, const int N, const int K,
+                       const int bn, const int tiles_n, const int num_tiles, const int vec_ok_flags) {
+    static_assert(!kLn || (!kPair && !kOutHalf && kAdds == 1), "fused LayerNorm rides on the fp32 + residual epilogue");
     const int vec_ok = vec_ok_flags & 1;
     const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
-    using C = Cfg<BNMAX, kPair, kOutHalf>;
+    using C = Cfg<BNMAX, kPair, kOutHalf, kLn>;
     constexpr int STAGES = C::kStages;
     constexpr int CS = kPair ? 2 : 1;
     const int brows = bn / CS;                                   // W rows this CTA stages per k-block
@@ -371,6 +458,11 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 8 * (2 * STAGES + 4));
     auto resid_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 5 + 2 * ew + b); };
     float* bias_s = reinterpret_cast<float*>(smem + kBarOff + C::kBarBytes);       // [2][BNMAX] bias of the current tiles
+    float* ln_gb = bias_s + 2 * BNMAX;                                             // kLn: [2][BNMAX] gamma | beta of this tile
+    float* ln_part = ln_gb + 2 * BNMAX;                                            // kLn: [cluster][2][BM][2] partial sums
+    const uint32_t ln_bar = bar_base + 8u * (2 * STAGES + 5 + 2 * kEpiWarps);
+    const int ln_cs = kLn ? static_cast<int>(cluster_nctarank()) : 1;
+    const int ln_rank = kLn ? static_cast<int>(cluster_ctarank()) : 0;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -407,6 +499,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(resid_bar(w, 0), 1);
             mbar_init(resid_bar(w, 1), 1);
         }
+        if (kLn) mbar_init(ln_bar, ln_cs * kEpiWarps * 32);      // every epilogue thread of every CTA of the cluster arrives
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -414,7 +507,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tmem_relinquish<CS>();
     }
     tc_fence_before_sync();
-    if (kPair) cluster_sync(); else __syncthreads();             // peer barriers are initialised before any remote arrive
+    if (kPair || kLn) cluster_sync(); else __syncthreads();      // peer barriers are initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight tiles do not
@@ -531,6 +624,13 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             float* bias_t = bias_s + (local & 1u) * BNMAX;
             for (int i = ew * 32 + lane; i < bn; i += kEpiWarps * 32)
                 bias_t[i] = (epi.bias != nullptr && n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.0f;
+            if (kLn) {                                            // gamma | beta of this tile's columns (fused LayerNorm)
+                for (int i = ew * 32 + lane; i < bn; i += kEpiWarps * 32) {
+                    const bool ok = n0 + i < N;
+                    ln_gb[i] = ok ? __ldg(epi.ln_gamma + n0 + i) : 0.0f;
+                    ln_gb[BNMAX + i] = ok ? __ldg(epi.ln_beta + n0 + i) : 0.0f;
+                }
+            }
             if (kTmaOk && tma_epi) {
                 int nchunks = 0;
                 for (int c = cbase; c < cbase + cpw && c < nch; ++c)
@@ -556,8 +656,19 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
                     else if constexpr (!kOutHalf && kAdds == 0)
                         epilogue_tma_f32<kCpwMax, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
-                    else if constexpr (!kOutHalf && kAdds == 1)
+                    else if constexpr (!kOutHalf && kAdds == 1 && !kLn)
                         epilogue_tma_f32<kCpwMax, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
+                }
+                if constexpr (kLn) {
+                    float s1 = 0.0f, s2 = 0.0f;
+                    if (work)
+                        epilogue_tma_f32<kCpwMax, true, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw,
+                                                              lane, prefetched, &s1, &s2);
+                    LnFuse f;
+                    f.tmL = &tmL; f.gamma_t = ln_gb; f.bnmax = BNMAX; f.part = ln_part; f.part_u32 = smem_u32(ln_part); f.bar_u32 = ln_bar;
+                    f.cs = ln_cs; f.rank = ln_rank; f.eps = epi.ln_eps; f.inv_n = 1.0f / static_cast<float>(N);
+                    ln_publish(f, grp, q * 32 + lane, s1, s2);   // every epilogue thread reports, also the ones without columns
+                    if (work) epilogue_ln_pass2<kCpwMax>(f, t_acc + cbase * 32, nchunks, wstage, cbase, q * 32 + lane, row0, colw, lane);
                 }
             } else {
                 mbar_wait(tmem_full_bar(acc), acc_ph);
@@ -585,7 +696,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (lane == 0) tma_store_wait_read();                    // staging boxes stay valid until the stores have read them
     }
     tc_fence_before_sync();
-    if (kPair) cluster_sync(); else __syncthreads();            // no CTA exits while its peer may still signal its barriers
+    if (kPair || kLn) cluster_sync(); else __syncthreads();     // no CTA exits while a peer may still signal / write to it
     if (warp == 2) tmem_dealloc<CS>(tmem_base, C::kTmemCols);
 }
 
@@ -639,14 +750,14 @@ int num_sms() {
     return n;
 }
 
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false>
 struct Launcher {
     static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
-        using C = Cfg<BNMAX, kPair, kOutHalf>;
+        using C = Cfg<BNMAX, kPair, kOutHalf, kLn>;
         constexpr int CS = kPair ? 2 : 1;
-        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds>;
+        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn>;
         static std::once_flag once;
         std::call_once(once, [&] {
             int ndev = 0, cur = 0;
@@ -674,7 +785,8 @@ struct Launcher {
         });
         const int tiles_n = ceil_div(op.N, op.bn);
         const int num_tiles = tiles_n * ceil_div(op.M, BM * CS);
-        const int grid = std::min(num_tiles, max_units) * CS;
+        // fused LayerNorm: one tile per CTA, the column tiles of a row tile form a cluster
+        const int grid = kLn ? num_tiles : std::min(num_tiles, max_units) * CS;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kThreads);
@@ -687,18 +799,18 @@ struct Launcher {
             at[na].val.programmaticStreamSerializationAllowed = 1;
             ++na;
         }
-        if (kPair) {
+        if (kPair || kLn) {
             at[na].id = cudaLaunchAttributeClusterDimension;
-            at[na].val.clusterDim.x = CS; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+            at[na].val.clusterDim.x = kLn ? tiles_n : CS; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
             ++na;
         }
         cfg.attrs = at;
         cfg.numAttrs = na;
-        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.epi, op.M, op.N, op.K, op.bn, tiles_n, num_tiles, op.vec_ok));
+        PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.tmL, op.epi, op.M, op.N, op.K, op.bn, tiles_n, num_tiles, op.vec_ok));
     }
 };
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds>
-int Launcher<BNMAX, kPair, kOutHalf, kAdds>::max_units = 1;
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn>
+int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn>::max_units = 1;
 
 template <int BNMAX, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
@@ -709,6 +821,7 @@ void launch_cl(const GemmOp& op, cudaStream_t stream) {
 
 template <int BNMAX>
 void launch_bn(const GemmOp& op, cudaStream_t stream) {
+    if (op.ln_cluster > 0) { Launcher<BNMAX, false, false, 1, true>::run(op, stream); return; }
     const bool h = op.epi.out_f16 != nullptr;
     switch (op.n_adds) {
         case 0:  h ? launch_cl<BNMAX, true, 0>(op, stream) : launch_cl<BNMAX, false, 0>(op, stream); break;
@@ -754,6 +867,16 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if (M <= 0 || N <= 0 || K <= 0) throw CudaError{"gemm: empty problem"};
     int bn = tile_code & 0xFFF, cm = (tile_code >> 12) & 0xF, cn = (tile_code >> 16) & 0xF;
     if (tile_code == 0) pick_config(M, N, K, bn, cm, cn);
+    op.ln_cluster = 0;
+    if (epi.ln_out16 != nullptr) {
+        // fused LayerNorm: narrowest tile whose column tiles (<= 4) cover a row inside one cluster and the grid in one wave
+        if (!epi.out_f32 || !epi.resid || epi.addend || !epi.ln_gamma || !epi.ln_beta || !gemm_ln_fusable(M, N))
+            throw CudaError{"gemm: fused LayerNorm needs fp32 output + residual and a row that fits one cluster in one wave"};
+        for (int w = 128; w <= 256; w += 32)
+            if (ceil_div(N, w) <= kLnMaxCluster && ceil_div(M, BM) * ceil_div(N, w) <= num_sms()) { bn = w; break; }
+        cm = 1; cn = 1;
+        op.ln_cluster = ceil_div(N, bn);
+    }
     cm = std::max(cm, 1);
     cn = std::max(cn, 1);
     if (bn < 32 || bn > 256 || bn % 32 != 0) throw CudaError{"gemm: the N tile must be a multiple of 32 in [32, 256]"};
@@ -789,6 +912,12 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
         else make_tmap_any(&op.tmC, epi.out_f32, true, M, N, epi.ld_out, 32);
         if (op.n_adds == 1) make_tmap_any(&op.tmR, op.epi.add0, true, M, N, op.epi.ld_add0, 32);
     }
+    op.tmL = CUtensorMap{};
+    if (op.ln_cluster > 0) {
+        if (!tma_epi || !row_ok(epi.ln_out16, epi.ld_ln16, 2) || (reinterpret_cast<uintptr_t>(epi.ln_gamma) & 3) != 0)
+            throw CudaError{"gemm: fused LayerNorm needs 16-byte aligned tensors"};
+        make_tmap_any(&op.tmL, epi.ln_out16, false, M, N, epi.ld_ln16, 32, 64);
+    }
     if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 31) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA, 8 no TMA store, 16 no staging either
     make_tmap(&op.tmA, A, M, K, lda, BM);           // every CTA stages its own 128 rows of A
     make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and (in a CTA pair) half of the W tile
@@ -800,5 +929,13 @@ void gemm_launch(const GemmOp& op, cudaStream_t stream) {
 }
 
 double gemm_flops(const GemmOp& op) { return 2.0 * op.M * static_cast<double>(op.N) * op.K; }
+
+bool gemm_ln_fusable(int M, int N) {
+    static const bool off = [] { const char* e = getenv("PFASR_NO_LN_FUSE"); return e && *e && *e != '0'; }();
+    if (off || N % 32 != 0 || N > kLnMaxCluster * 256) return false;
+    for (int w = 128; w <= 256; w += 32)
+        if (ceil_div(N, w) <= kLnMaxCluster && ceil_div(M, BM) * ceil_div(N, w) <= num_sms()) return true;
+    return false;
+}
 
 }  // namespace pf

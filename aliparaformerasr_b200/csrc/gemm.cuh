@@ -16,6 +16,14 @@ struct GemmEpi {
     int ld_resid = 0;
     int ld_addend = 0;
     int relu = 0;
+    // fused LayerNorm of the produced rows (fp32 output + residual only): ln_out16 = fp16(LN(out) * gamma + beta), the A
+    // operand of the next GEMM.  The row must fit one cluster of at most 4 column tiles in a single wave (gemm_prepare
+    // picks the tile width; see gemm_ln_fusable).
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    float ln_eps = 0.0f;
+    __half* ln_out16 = nullptr;
+    int ld_ln16 = 0;
     // filled by gemm_prepare: the (up to two) fp32 addends in the order the kernel applies them
     const float* add0 = nullptr;
     const float* add1 = nullptr;
@@ -27,6 +35,8 @@ struct GemmOp {
     CUtensorMap tmB;
     CUtensorMap tmC;      // output (TMA store epilogue), valid when vec_ok & 2
     CUtensorMap tmR;      // fp32 residual (TMA-prefetched into the epilogue staging), valid when vec_ok & 2 and n_adds == 1
+    CUtensorMap tmL;      // fp16 fused-LayerNorm output, valid when ln_cluster > 0
+    int ln_cluster = 0;   // > 0: fused LayerNorm epilogue, cluster of this many column-tile CTAs per row tile
     GemmEpi epi;
     int M = 0, N = 0, K = 0;
     int bn = 128;    // N tile: 64, 128 or 256
@@ -41,6 +51,8 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
 double gemm_flops(const GemmOp& op);
+// can a [M, N] fp32 + residual GEMM carry the fused LayerNorm epilogue (row inside one cluster, one wave)?
+bool gemm_ln_fusable(int M, int N);
 // cuTensorMapEncodeTiled entry point (resolved through the runtime, no libcuda link dependency); throws if missing
 void* tensormap_encode_fn();
 

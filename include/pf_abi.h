@@ -210,6 +210,9 @@ int32_t pf_abi_version(void);
 pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                       const float* resid, const float* addend, int32_t relu, int32_t out_half, int32_t tile_n,
                       float* out, float* elapsed_ms, int32_t iters);
+/* x = A W^T + bias + resid (fp32) and LN(x) * gamma + beta (fp16) from the fused-LayerNorm GEMM epilogue */
+pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
+                         const float* resid, const float* gamma, const float* beta, float eps, float* out, float* out_ln);
 pf_status pf_dbg_layernorm(int32_t M, int32_t D, const float* x, const float* gamma, const float* beta, float eps,
                            float* out);
 pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats, float scale, const float* gamma,

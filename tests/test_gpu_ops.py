@@ -54,6 +54,26 @@ def test_gemm_epilogue(lib, out_half, relu, adds, N):
     assert np.abs(out - ref).max() < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(5312, 512, 512), (5312, 512, 2048), (1600, 512, 512), (333, 512, 512), (83, 512, 64), (700, 1024, 256)])
+def test_gemm_fused_layernorm(lib, M, N, K):
+    """out-projection / FFN2 epilogue: residual add + LayerNorm of the new rows across the CTAs of a cluster."""
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = (rng.standard_normal((M, N)) * 2 + 0.5).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(N)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    out = np.zeros((M, N), np.float32)
+    out_ln = np.zeros((M, N), np.float32)
+    _lib.check(lib.pf_dbg_gemm_ln(M, N, K, _lib.fptr(f(A)), _lib.fptr(f(W)), _lib.fptr(bias), _lib.fptr(resid), _lib.fptr(g), _lib.fptr(b),
+                                  1e-12, _lib.fptr(out), _lib.fptr(out_ln)))
+    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias + resid
+    assert np.abs(out - ref).max() < 2e-3
+    ref_ln = torch.nn.functional.layer_norm(torch.from_numpy(out), (N,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
+    assert np.abs(out_ln - ref_ln).max() < 6e-3      # fp16 output of O(1..4) values
+
+
 @pytest.mark.parametrize("M,D", [(7, 512), (1000, 512), (333, 2048)])
 def test_layernorm(lib, M, D):
     rng = np.random.default_rng(D + M)
