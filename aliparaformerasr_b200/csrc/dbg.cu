@@ -136,6 +136,32 @@ pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const 
         PF_CUDA(cudaGetLastError());
         PF_CUDA(cudaMemcpy(out, x, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
         PF_CUDA(cudaMemcpy(out_ln, ln32, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
+        if (const char* it = getenv("PFASR_DBG_TIME_ITERS")) {        // tuning aid: back-to-back launches, fused vs GEMM + LayerNorm
+            const int iters = atoi(it);
+            GemmEpi e2 = e;
+            e2.ln_out16 = nullptr; e2.ln_gamma = nullptr; e2.ln_beta = nullptr;
+            GemmOp plain;
+            gemm_prepare(plain, dA, K, dW, K, M, N, K, e2, 0);
+            cudaEvent_t a, b;
+            PF_CUDA(cudaEventCreate(&a));
+            PF_CUDA(cudaEventCreate(&b));
+            float ms[2] = {0, 0};
+            for (int variant = 0; variant < 2; ++variant) {
+                for (int i = 0; i < iters + 3; ++i) {
+                    if (i == 3) PF_CUDA(cudaEventRecord(a, 0));
+                    if (variant == 0) gemm_launch(op, 0);
+                    else { gemm_launch(plain, 0); layernorm_f32_launch(x, N, M, N, e.ln_gamma, e.ln_beta, eps, ln16, N, nullptr, 0, 0); }
+                }
+                PF_CUDA(cudaEventRecord(b, 0));
+                PF_CUDA(cudaEventSynchronize(b));
+                PF_CUDA(cudaEventElapsedTime(&ms[variant], a, b));
+            }
+            printf("gemm_ln %d x %d x %d: fused %.2f us (tile %d, cluster %d) vs gemm (tile %d) + layernorm %.2f us\n", M, N, K,
+                   ms[0] * 1e3f / iters, op.bn, op.ln_cluster, plain.bn, ms[1] * 1e3f / iters);
+            fflush(stdout);
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
     });
 }
 

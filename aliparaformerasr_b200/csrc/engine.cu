@@ -20,6 +20,15 @@ static int dbg_skip() {
     return v;
 }
 
+// The fused-LayerNorm GEMM epilogue (gemm.cu: cluster statistics exchange + second pass over TMEM) is parity-green but
+// measured SLOWER than GEMM + LayerNorm kernel on this path (out-projection 12.7 us fused vs 8.6 + 3.2 us; cfg2 step 5.32
+// vs 5.17 ms): the second pass runs on 8 warps per SM where the stand-alone LayerNorm spreads 5312 rows over every warp
+// slot of the chip.  It therefore stays opt-in (PFASR_LN_FUSE=1).
+static bool ln_fuse_enabled() {
+    static const bool on = [] { const char* e = getenv("PFASR_LN_FUSE"); return e && *e && *e != '0'; }();
+    return on;
+}
+
 bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("PFASR_NO_PDL");
@@ -423,22 +432,30 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
     if (it != enc_plans_.end()) return it->second;
     EncoderPlan plan;
     const int M = B * T, d = cfg_.d_model, f = cfg_.ffn;
-    auto build_layer = [&](const EncLayerW& w) {
+    // LayerNorms whose input comes straight out of a residual GEMM are fused into that GEMM's epilogue: norm2 into the
+    // out-projection, the NEXT layer's norm1 into FFN2 (next == nullptr: the stack ends, after_norm stays a kernel)
+    const bool fuse = ln_fuse_enabled() && gemm_ln_fusable(M, d);
+    auto build_layer = [&](const EncLayerW& w, const EncLayerW* next) {
         EncLayerPlan lp;
         GemmEpi e;
         e = GemmEpi{}; e.bias = w.b_qkv; e.out_f16 = qkv16_; e.ld_out = 3 * d;
         gemm_prepare(lp.qkv, a16_, w.in_size, w.w_qkv, w.in_size, M, 3 * d, w.in_size, e);
         // x32_ already holds residual + FSMN memory (the attention kernel accumulates the memory into it)
         e = GemmEpi{}; e.bias = w.b_out; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
+        if (fuse) { e.ln_gamma = w.ln2.g; e.ln_beta = w.ln2.b; e.ln_eps = cfg_.ln_eps; e.ln_out16 = a16_; e.ld_ln16 = d; lp.ln2_fused = true; }
         gemm_prepare(lp.out, ctx16_, d, w.w_out, d, M, d, d, e);
         e = GemmEpi{}; e.bias = w.b_ffn1; e.relu = 1; e.out_f16 = h16_; e.ld_out = f;
         gemm_prepare(lp.ffn1, a16_, d, w.w_ffn1, d, M, f, d, e);
         e = GemmEpi{}; e.bias = w.b_ffn2; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
+        if (fuse && next != nullptr) {
+            e.ln_gamma = next->ln1.g; e.ln_beta = next->ln1.b; e.ln_eps = cfg_.ln_eps; e.ln_out16 = a16_; e.ld_ln16 = d;
+            lp.next_ln1_fused = true;
+        }
         gemm_prepare(lp.ffn2, h16_, f, w.w_ffn2, f, M, d, f, e);
         plan.layers.push_back(lp);
     };
-    for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i]);
-    for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i]);
+    for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], i + 1 < enc_.size() ? &enc_[i + 1] : nullptr);
+    for (size_t i = 0; i < tp_.size(); ++i) build_layer(tp_[i], i + 1 < tp_.size() ? &tp_[i + 1] : nullptr);
     if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
         GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = ldv();
         gemm_prepare(plan.ctc_head, enc16_, d, w_head_, d, M, cfg_.vocab, d, e);
@@ -464,12 +481,20 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
         GemmEpi e2; e2.out_f32 = t32_; e2.ld_out = d;
         gemm_prepare(g2, hd16_, f, w.w2, f, Md, d, f, e2);
     };
-    for (const DecLayerW& w : dec_) {
+    // norm1 of the next layer (or of decoders3) rides on the cross-attention out-projection's epilogue
+    const bool fuse = ln_fuse_enabled() && gemm_ln_fusable(Md, d);
+    for (size_t i = 0; i < dec_.size(); ++i) {
+        const DecLayerW& w = dec_[i];
         DecLayerPlan lp;
         ffn(w.ffn, lp.w1, lp.w2);
         GemmEpi e; e.bias = w.bq; e.out_f16 = q16_; e.ld_out = d;
         gemm_prepare(lp.q, ad16_, d, w.wq, d, Md, d, d, e);
         GemmEpi o; o.bias = w.bo; o.resid = xd32_; o.ld_resid = d; o.out_f32 = xd32_; o.ld_out = d;
+        if (fuse) {
+            const LnW& nx = i + 1 < dec_.size() ? dec_[i + 1].ffn.ln_in : dec3_.ln_in;
+            o.ln_gamma = nx.g; o.ln_beta = nx.b; o.ln_eps = cfg_.ln_eps; o.ln_out16 = ad16_; o.ld_ln16 = d;
+            lp.next_ln1_fused = true;
+        }
         gemm_prepare(lp.out, ctxd16_, d, w.wo, d, Md, d, d, o);
         plan.layers.push_back(lp);
     }
@@ -682,8 +707,8 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
                            enc_[0].ln1.b, cfg_.ln_eps, a16_, stream_);
     });
     ++launches;
-    auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool first) {
-        if (!first) {
+    auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool have_ln1) {
+        if (!have_ln1) {
             if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
             ++launches;
         }
@@ -695,20 +720,23 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
                                               x32_, d, w.in_size == d, stream_);
         });
         gemm(lp.out);
-        if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
-        ++launches;
+        if (!lp.ln2_fused) {
+            if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
+            ++launches;
+        }
         gemm(lp.ffn1);
         gemm(lp.ffn2);
     };
     size_t li = 0;
-    for (size_t i = 0; i < enc_.size(); ++i, ++li) layer(enc_[i], plan.layers[li], i == 0);
+    // layer 0's norm1 is part of embed_pe_ln; later layers get it from the previous layer's FFN2 epilogue when fused
+    for (size_t i = 0; i < enc_.size(); ++i, ++li) layer(enc_[i], plan.layers[li], i == 0 || plan.layers[li - 1].next_ln1_fused);
     if (tp_.empty()) {
         layernorm_f32_launch(x32_, d, M, d, after_norm_.g, after_norm_.b, cfg_.ln_eps, enc16_, d, enc32_, d, stream_);
         ++launches;
     } else {
         layernorm_f32_launch(x32_, d, M, d, after_norm_.g, after_norm_.b, cfg_.ln_eps, nullptr, 0, x32_, d, stream_);
         ++launches;
-        for (size_t i = 0; i < tp_.size(); ++i, ++li) layer(tp_[i], plan.layers[li], false);
+        for (size_t i = 0; i < tp_.size(); ++i, ++li) layer(tp_[i], plan.layers[li], i > 0 && plan.layers[li - 1].next_ln1_fused);
         layernorm_f32_launch(x32_, d, M, d, tp_norm_.g, tp_norm_.b, cfg_.ln_eps, enc16_, d, enc32_, d, stream_);
         ++launches;
     }
@@ -741,17 +769,20 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
     // Q11 (OnlineModel.cs:222): stack_states hands every layer the stream's LAYER-0 cache; online_flags bit 0 opts out
     const bool per_layer_cache = (cfg_.online_flags & 1) != 0;
     const size_t cache_layer = static_cast<size_t>(cfg_.dec_kernel - 1) * d;
-    auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2) {
-        if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
+    auto ffn = [&](const DecFfnW& w, const GemmOp& g1, const GemmOp& g2, bool have_ln) {
+        if (!have_ln) {                                    // else: ad16_ = LN(x) came out of the previous out-projection
+            if (!(dbg_skip() & 4)) timed("dec_layernorm", [&] { layernorm_f32_launch(xd32_, d, Md, d, w.ln_in.g, w.ln_in.b, eps, ad16_, d, nullptr, 0, stream_); });
+            ++launches;
+        }
         gemm(g1);
         if (!(dbg_skip() & 4)) timed("dec_layernorm_ffn", [&] { layernorm_f32_launch(hd32_, f, Md, f, w.ln_mid.g, w.ln_mid.b, eps, hd16_, f, nullptr, 0, stream_); });
         gemm(g2);
-        launches += 2;
+        ++launches;
     };
     for (size_t i = 0; i < layers.size(); ++i) {
         const DecLayerW& w = layers[i];
         const DecLayerPlan& lp = lps[i];
-        ffn(w.ffn, lp.w1, lp.w2);
+        ffn(w.ffn, lp.w1, lp.w2, i > 0 && lps[i - 1].next_ln1_fused);
         if (!online) {
             // norm2 -> FSMN memory -> residual -> norm3 in one kernel (three launches otherwise)
             if (!(dbg_skip() & 12)) timed("dec_ln_fsmn_ln", [&] {
@@ -774,7 +805,7 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
         gemm(lp.out);
         launches += 4;
     }
-    ffn(d3, d3_w1, d3_w2);
+    ffn(d3, d3_w1, d3_w2, !lps.empty() && lps.back().next_ln1_fused);
 }
 
 void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {

@@ -70,8 +70,15 @@ struct DecLayerW {
     __half* wo = nullptr; float* bo = nullptr;
 };
 
-struct EncLayerPlan { GemmOp qkv, out, ffn1, ffn2; };
-struct DecLayerPlan { GemmOp w1, w2, q, out; };
+struct EncLayerPlan {
+    GemmOp qkv, out, ffn1, ffn2;
+    bool ln2_fused = false;          // norm2 is computed by the out-projection's epilogue
+    bool next_ln1_fused = false;     // the next layer's norm1 is computed by this layer's FFN2 epilogue
+};
+struct DecLayerPlan {
+    GemmOp w1, w2, q, out;
+    bool next_ln1_fused = false;     // norm1 of the next layer / decoders3 is computed by this layer's out-projection epilogue
+};
 struct EncoderPlan {
     std::vector<EncLayerPlan> layers;            // encoders0 + encoders + tp_encoders
     GemmOp pred_conv, kv_all, ctc_head;

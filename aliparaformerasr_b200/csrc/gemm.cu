@@ -507,7 +507,11 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tmem_relinquish<CS>();
     }
     tc_fence_before_sync();
-    if (kPair || kLn) cluster_sync(); else __syncthreads();      // peer barriers are initialised before any remote arrive
+    // peer barriers must be initialised before any remote arrive.  Pair: right away (the first TMA already signals the
+    // leader).  Fused LayerNorm: the first remote access is the statistics exchange at the end of the epilogue, so the
+    // CTA only ARRIVES here and waits much later - it does not stall on its cluster peers becoming resident.
+    if (kPair) cluster_sync();
+    else { if (kLn) cluster_arrive(); __syncthreads(); }
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  The weight tiles do not
@@ -667,6 +671,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     LnFuse f;
                     f.tmL = &tmL; f.gamma_t = ln_gb; f.bnmax = BNMAX; f.part = ln_part; f.part_u32 = smem_u32(ln_part); f.bar_u32 = ln_bar;
                     f.cs = ln_cs; f.rank = ln_rank; f.eps = epi.ln_eps; f.inv_n = 1.0f / static_cast<float>(N);
+                    cluster_wait();                               // (arrived in the prologue) the peers' ln barriers exist
                     ln_publish(f, grp, q * 32 + lane, s1, s2);   // every epilogue thread reports, also the ones without columns
                     if (work) epilogue_ln_pass2<kCpwMax>(f, t_acc + cbase * 32, nchunks, wstage, cbase, q * 32 + lane, row0, colw, lane);
                 }
@@ -696,7 +701,10 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (lane == 0) tma_store_wait_read();                    // staging boxes stay valid until the stores have read them
     }
     tc_fence_before_sync();
-    if (kPair || kLn) cluster_sync(); else __syncthreads();     // no CTA exits while a peer may still signal / write to it
+    // no CTA exits while a peer may still signal / write to it
+    if (kLn) { if (warp < kEpiWarp0) cluster_wait(); cluster_sync(); }
+    else if (kPair) cluster_sync();
+    else __syncthreads();
     if (warp == 2) tmem_dealloc<CS>(tmem_base, C::kTmemCols);
 }
 
@@ -931,8 +939,7 @@ void gemm_launch(const GemmOp& op, cudaStream_t stream) {
 double gemm_flops(const GemmOp& op) { return 2.0 * op.M * static_cast<double>(op.N) * op.K; }
 
 bool gemm_ln_fusable(int M, int N) {
-    static const bool off = [] { const char* e = getenv("PFASR_NO_LN_FUSE"); return e && *e && *e != '0'; }();
-    if (off || N % 32 != 0 || N > kLnMaxCluster * 256) return false;
+    if (N % 32 != 0 || N > kLnMaxCluster * 256) return false;
     for (int w = 128; w <= 256; w += 32)
         if (ceil_div(N, w) <= kLnMaxCluster && ceil_div(M, BM) * ceil_div(N, w) <= num_sms()) return true;
     return false;
