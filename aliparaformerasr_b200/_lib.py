@@ -27,6 +27,7 @@ PF_MODEL_SENSEVOICE_SMALL = 1
 PF_MODEL_SEACO_PARAFORMER = 2
 PF_RUN_WANT_LOGITS = 1
 PF_RUN_WANT_CIF_PEAK = 2
+PF_RUN_WANT_TIMESTAMPS = 4
 
 
 class PfConfig(C.Structure):
@@ -38,7 +39,7 @@ class PfConfig(C.Structure):
         ("smooth_factor", C.c_float), ("noise_threshold", C.c_float), ("fs", C.c_int32), ("n_mels", C.c_int32),
         ("lfr_m", C.c_int32), ("lfr_n", C.c_int32), ("snip_edges", C.c_int32), ("use_itn", C.c_int32),
         ("online_flags", C.c_int32), ("seaco_layers", C.c_int32), ("seaco_ffn", C.c_int32),
-        ("seaco_kernel", C.c_int32), ("seaco_nobias_id", C.c_int32),
+        ("seaco_kernel", C.c_int32), ("seaco_nobias_id", C.c_int32), ("smooth_factor2", C.c_float), ("noise_threshold2", C.c_float),
     ]
 
 
@@ -47,6 +48,7 @@ class PfResult(C.Structure):
         ("batch", C.c_int32), ("max_len", C.c_int32), ("vocab", C.c_int32), ("feat_frames", C.c_int32),
         ("tokens", C.POINTER(C.c_int32)), ("token_num", C.POINTER(C.c_int32)),
         ("logits", C.POINTER(C.c_float)), ("cif_peak", C.POINTER(C.c_float)),
+        ("us_frames", C.c_int32), ("us_alphas", C.POINTER(C.c_float)), ("us_cif_peak", C.POINTER(C.c_float)),
     ]
 
 

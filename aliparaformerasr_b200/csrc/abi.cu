@@ -226,6 +226,9 @@ static void run_all(OfflineHandle* h, uint32_t flags, pf_result* out) {
     h->T = T;
     const bool wl = (flags & PF_RUN_WANT_LOGITS) != 0 && lmax > 0;
     const bool wp = (flags & PF_RUN_WANT_CIF_PEAK) != 0 && lmax > 0 && h->cfg.model_kind != PF_MODEL_SENSEVOICE_SMALL;
+    const bool wt = (flags & PF_RUN_WANT_TIMESTAMPS) != 0 && lmax > 0 && h->devs[active[0]]->us_frames > 0;
+    const int usf = wt ? h->devs[active[0]]->us_frames : 0;
+    out->us_frames = usf;
     out->batch = B;
     out->max_len = lmax;
     out->vocab = V;
@@ -236,12 +239,15 @@ static void run_all(OfflineHandle* h, uint32_t flags, pf_result* out) {
         out->token_num = d->h_token_num;
         out->logits = wl ? d->h_logits : nullptr;
         out->cif_peak = wp ? d->h_peaks : nullptr;
+        out->us_alphas = wt ? d->h_us : nullptr;
+        out->us_cif_peak = wt ? d->h_us + static_cast<size_t>(B) * usf : nullptr;
         return;
     }
     h->tokens.assign(static_cast<size_t>(B) * lmax, 0);
     h->token_num.assign(B, 0);
     if (wl) h->logits.resize(static_cast<size_t>(B) * lmax * V);
     if (wp) h->peaks.resize(static_cast<size_t>(B) * (T + 1));
+    if (wt) h->us.resize(static_cast<size_t>(2) * B * usf);
     for (int i : active) {
         DeviceCtx* d = h->devs[i].get();
         const int b0 = h->shard_begin[i], nb = h->shard_count[i];
@@ -249,7 +255,13 @@ static void run_all(OfflineHandle* h, uint32_t flags, pf_result* out) {
         memcpy(h->token_num.data() + b0, d->h_token_num, static_cast<size_t>(nb) * sizeof(int32_t));
         if (wl) memcpy(h->logits.data() + static_cast<size_t>(b0) * lmax * V, d->h_logits, static_cast<size_t>(nb) * lmax * V * sizeof(float));
         if (wp) memcpy(h->peaks.data() + static_cast<size_t>(b0) * (T + 1), d->h_peaks, static_cast<size_t>(nb) * (T + 1) * sizeof(float));
+        if (wt) {
+            memcpy(h->us.data() + static_cast<size_t>(b0) * usf, d->h_us, static_cast<size_t>(nb) * usf * sizeof(float));
+            memcpy(h->us.data() + static_cast<size_t>(B + b0) * usf, d->h_us + static_cast<size_t>(nb) * usf, static_cast<size_t>(nb) * usf * sizeof(float));
+        }
     }
+    out->us_alphas = wt ? h->us.data() : nullptr;
+    out->us_cif_peak = wt ? h->us.data() + static_cast<size_t>(B) * usf : nullptr;
     out->tokens = h->tokens.data();
     out->token_num = h->token_num.data();
     out->logits = wl ? h->logits.data() : nullptr;

@@ -133,6 +133,8 @@ DeviceCtx::~DeviceCtx() {
     free_pool(wpool_);
     free_pool(apool_);
     free_pool(hpool_);
+    free_pool(tpool_);
+    if (h_us) cudaFreeHost(h_us);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
     if (pcm_) cudaFree(pcm_);
@@ -269,6 +271,40 @@ void DeviceCtx::load_weights(const Blob& b) {
         expect_shape(b.get("predictor.cif_output.weight"), {1, d});
         w_alpha_ = up_f32(b.get("predictor.cif_output.weight"));
         b_alpha_ = up_f32(b.get("predictor.cif_output.bias"));
+    }
+    if (b.has("predictor.upsample_cnn.weight")) {
+        // CifPredictorV3 timestamp branch [EXT]: ConvTranspose1d(d, d, 3, stride 3) weight [in, out, 3] -> GEMM weight
+        // [(j, out), in]; BiLSTM(d) forward | reverse stacked; cif_output2 Linear(2d, 1)
+        const BlobEntry& uw = b.get("predictor.upsample_cnn.weight");
+        expect_shape(uw, {d, d, 3});
+        std::vector<float> re(static_cast<size_t>(3) * d * d), rb(3 * d);
+        const BlobEntry& ub = b.get("predictor.upsample_cnn.bias");
+        expect_shape(ub, {d});
+        for (int j = 0; j < 3; ++j)
+            for (int o = 0; o < d; ++o) {
+                rb[j * d + o] = ub.data[o];
+                for (int c = 0; c < d; ++c) re[(static_cast<size_t>(j) * d + o) * d + c] = uw.data[(static_cast<size_t>(c) * d + o) * 3 + j];
+            }
+        w_up16_ = up_f16(re.data(), re.size());
+        b_up_ = up_f32(rb.data(), rb.size());
+        std::vector<float> wih(static_cast<size_t>(8) * d * d), whh(static_cast<size_t>(8) * d * d), bb(8 * d);
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::string sfx = dir ? "_reverse" : "";
+            const BlobEntry& a = b.get("predictor.blstm.weight_ih_l0" + sfx);
+            const BlobEntry& h = b.get("predictor.blstm.weight_hh_l0" + sfx);
+            const BlobEntry& bi = b.get("predictor.blstm.bias_ih_l0" + sfx);
+            const BlobEntry& bh = b.get("predictor.blstm.bias_hh_l0" + sfx);
+            expect_shape(a, {4 * d, d}); expect_shape(h, {4 * d, d}); expect_shape(bi, {4 * d}); expect_shape(bh, {4 * d});
+            memcpy(wih.data() + static_cast<size_t>(dir) * 4 * d * d, a.data, a.count * sizeof(float));
+            memcpy(whh.data() + static_cast<size_t>(dir) * 4 * d * d, h.data, h.count * sizeof(float));
+            for (int i = 0; i < 4 * d; ++i) bb[dir * 4 * d + i] = bi.data[i] + bh.data[i];
+        }
+        w_ih_bi16_ = up_f16(wih.data(), wih.size());
+        w_hh_bi16_ = up_f16(whh.data(), whh.size());
+        b_bi_ = up_f32(bb.data(), bb.size());
+        expect_shape(b.get("predictor.cif_output2.weight"), {1, 2 * d});
+        w_out2_ = up_f32(b.get("predictor.cif_output2.weight"));
+        b_out2_ = up_f32(b.get("predictor.cif_output2.bias"));
     }
     load_dec_stack(b, "decoder", cfg_.dec_layers, cfg_.dec_ffn, cfg_.dec_kernel, dec_, dec3_, dec_after_, w_kv_all_, b_kv_all_);
     const BlobEntry& wo = b.get("decoder.output_layer.weight");
@@ -829,6 +865,41 @@ void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
     if (seaco) seaco_forward(B, L, plan);
 }
 
+// CifPredictorV3.get_upsample_timestmap (row f1): us_alphas / us_cif_peak [B, 3T] from the encoder output and token_num.
+void DeviceCtx::timestamp_forward(int B, int T) {
+    const int d = cfg_.d_model, M = B * T, T3 = 3 * T;
+    if (B > ts_capB_ || T > ts_capT_) {
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        free_pool(tpool_);
+        ts_capB_ = std::max(ts_capB_, B);
+        ts_capT_ = std::max(ts_capT_, T);
+        const size_t rows = static_cast<size_t>(ts_capB_) * 3 * ts_capT_;
+        gin32_ = dalloc<float>(rows * 8 * d, tpool_);
+        y32_ = dalloc<float>(rows * 2 * d, tpool_);
+        hbuf_ = dalloc<float>(static_cast<size_t>(2) * 2 * kLstmMaxBatch * d, tpool_);
+        lstm_bar_ = dalloc<unsigned int>(2, tpool_);
+        us_alphas_ = dalloc<float>(rows, tpool_);
+        us_peaks_ = dalloc<float>(rows, tpool_);
+    }
+    // ConvTranspose1d(k = stride = 3) == one GEMM: row (b, t) -> its three output frames [3t, 3t+1, 3t+2]; qkv16_ is free by now
+    GemmOp up, gi;
+    GemmEpi e; e.bias = b_up_; e.out_f16 = qkv16_; e.ld_out = 3 * d;
+    gemm_prepare(up, enc16_, d, w_up16_, d, M, 3 * d, d, e);
+    gemm(up);
+    GemmEpi g; g.bias = b_bi_; g.out_f32 = gin32_; g.ld_out = 8 * d;
+    gemm_prepare(gi, qkv16_, d, w_ih_bi16_, d, 3 * M, 8 * d, d, g);          // qkv16_ viewed as [3M, d]
+    gemm(gi);
+    for (int b0 = 0; b0 < B; b0 += kLstmMaxBatch) {
+        const int nb = std::min(kLstmMaxBatch, B - b0);
+        bilstm_launch(gin32_ + static_cast<size_t>(b0) * T3 * 8 * d, w_hh_bi16_, nb, T3, d, y32_ + static_cast<size_t>(b0) * T3 * 2 * d, hbuf_,
+                      lstm_bar_, stream_);
+        ++launches;
+    }
+    us_alphas_peaks_launch(y32_, B, T3, 2 * d, w_out2_, b_out2_, cfg_.smooth_factor2, cfg_.noise_threshold2, token_num_,
+                           cfg_.cif_threshold - 1e-4f, us_alphas_, us_peaks_, stream_);
+    ++launches;
+}
+
 // SeACo bias branch (FunASR SeacoParaformer export [EXT]): the bias decoder attends the hot-word rows
 // twice (queries: CIF embeds, decoder hidden); sum -> hotword_output_layer -> log-softmax dha; rows whose dha pick is
 // NO_BIAS keep the ASR posterior, the others take dha.
@@ -1019,6 +1090,16 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
             if (wl) PF_CUDA(cudaMemcpy2DAsync(h_logits, static_cast<size_t>(cfg_.vocab) * sizeof(float), logits_, static_cast<size_t>(ldv()) * sizeof(float),
                                               static_cast<size_t>(cfg_.vocab) * sizeof(float), ntok, cudaMemcpyDeviceToHost, stream_));
             if (wp) PF_CUDA(cudaMemcpyAsync(h_peaks, peaks_, static_cast<size_t>(B) * (T + 1) * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            us_frames = 0;
+            if ((flags & PF_RUN_WANT_TIMESTAMPS) != 0) {
+                if (!has_timestamps()) throw StatusError{PF_ERR_UNSUPPORTED, "this model has no CifPredictorV3 timestamp branch (predictor.upsample_cnn.* missing)"};
+                timestamp_forward(B, T);
+                const size_t n = static_cast<size_t>(B) * 3 * T;
+                ensure_pinned(reinterpret_cast<void**>(&h_us), &h_us_cap_, 2 * n * sizeof(float));
+                PF_CUDA(cudaMemcpyAsync(h_us, us_alphas_, n * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+                PF_CUDA(cudaMemcpyAsync(h_us + n, us_peaks_, n * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+                us_frames = 3 * T;
+            }
         } else {
             PF_CUDA(cudaEventRecord(ev_[4], stream_));
             PF_CUDA(cudaEventRecord(ev_[5], stream_));

@@ -15,6 +15,7 @@
 #include "gemm.cuh"
 #include "online.cuh"
 #include "ops.cuh"
+#include "timestamp.cuh"
 
 namespace pf {
 
@@ -140,6 +141,9 @@ public:
     int32_t* h_token_num = nullptr;   // [B]
     float* h_logits = nullptr;        // [B, Lmax, V] (on request)
     float* h_peaks = nullptr;         // [B, T+1] (on request)
+    float* h_us = nullptr;            // [2][B, 3T] us_alphas | us_cif_peak (PF_RUN_WANT_TIMESTAMPS, models with the V3 predictor)
+    int us_frames = 0;
+    bool has_timestamps() const { return w_up16_ != nullptr; }
     float timings_ms[6] = {0, 0, 0, 0, 0, 0};
     int64_t launches = 0;
     double gemm_flops = 0.0;
@@ -182,6 +186,7 @@ private:
                    const GemmOp& d3_w2, int ffn_width, int kernel, const __half* kv16, int ldkv, bool kv_shared, int Tk, int B, int L,
                    bool online);
     void seaco_forward(int B, int L, DecoderPlan& plan);
+    void timestamp_forward(int B, int T);
 
     void ensure_workspace(int B, int T);
     void ensure_host(size_t tokens, size_t logits, size_t peaks);
@@ -232,6 +237,16 @@ private:
     __half* bias16_ = nullptr; __half* skv16_ = nullptr;
     std::vector<void*> hpool_;
     float* emb32_ = nullptr; float* hid32_ = nullptr; float* satt32_ = nullptr; float* logits2_ = nullptr; int* tokens2_ = nullptr;
+    // CifPredictorV3 timestamp branch (optional: present when the blob has predictor.upsample_cnn.*)
+    __half* w_up16_ = nullptr; float* b_up_ = nullptr;          // ConvTranspose1d as a [3*d, d] GEMM
+    __half* w_ih_bi16_ = nullptr; float* b_bi_ = nullptr;       // BiLSTM input projections, forward | reverse
+    __half* w_hh_bi16_ = nullptr;                               // [2][4d, d]
+    float* w_out2_ = nullptr; float* b_out2_ = nullptr;         // cif_output2
+    float* gin32_ = nullptr; float* y32_ = nullptr; float* hbuf_ = nullptr; unsigned int* lstm_bar_ = nullptr;
+    float* us_alphas_ = nullptr; float* us_peaks_ = nullptr;
+    std::vector<void*> tpool_;
+    int ts_capB_ = 0, ts_capT_ = 0;
+    size_t h_us_cap_ = 0;
     float* embed_table_ = nullptr;     // SenseVoice prompt table [16, input_size]
     float* inv_ts_ = nullptr;          // PE inverse timescales [input_size/2]
     float* cmvn_shift_ = nullptr; float* cmvn_scale_ = nullptr;
@@ -288,7 +303,7 @@ struct OfflineHandle {
     std::vector<int> shard_begin, shard_count;
     int B = 0, Lmax = 0, T = 0;
     std::vector<int32_t> tokens, token_num;
-    std::vector<float> logits, peaks;
+    std::vector<float> logits, peaks, us;
     bool staged = false;
     bool staged_pcm = false;
 };

@@ -29,6 +29,7 @@ def to_pf_config(cfg: ModelConfig) -> _lib.PfConfig:
         setattr(c, f, float(getattr(cfg, f)))
     c.seaco_layers, c.seaco_ffn, c.seaco_kernel = int(cfg.seaco_layers), int(cfg.seaco_ffn), int(cfg.seaco_kernel)
     c.seaco_nobias_id = int(cfg.nobias_id)
+    c.smooth_factor2, c.noise_threshold2 = float(cfg.smooth_factor2), float(cfg.noise_threshold2)
     c.snip_edges = int(bool(cfg.snip_edges))
     c.use_itn = int(bool(cfg.use_itn))
     return c
@@ -42,6 +43,8 @@ class ModelOutput:
     feat_frames: int
     logits: Optional[np.ndarray] = None      # [B, L, V] log-probs (model_out) when requested
     cif_peak: Optional[np.ndarray] = None
+    us_alphas: Optional[np.ndarray] = None   # [B, 3T] (models with the CifPredictorV3 timestamp branch, on request)
+    us_cif_peak: Optional[np.ndarray] = None
 
 
 class Engine:
@@ -127,6 +130,9 @@ class Engine:
             out.logits = np.ctypeslib.as_array(res.logits, shape=(b, l, v)).copy()
         if want_peak and res.cif_peak:
             out.cif_peak = np.ctypeslib.as_array(res.cif_peak, shape=(b, res.feat_frames + 1)).copy()
+        if res.us_frames > 0 and res.us_cif_peak:
+            out.us_alphas = np.ctypeslib.as_array(res.us_alphas, shape=(b, res.us_frames)).copy()
+            out.us_cif_peak = np.ctypeslib.as_array(res.us_cif_peak, shape=(b, res.us_frames)).copy()
         return out
 
     @staticmethod
@@ -136,18 +142,22 @@ class Engine:
         ns = np.asarray([a.shape[0] for a in arrs], dtype=np.int32)
         return arrs, ptrs, ns
 
-    def run_pcm(self, pcm: Sequence[np.ndarray], want_logits: bool = False, want_cif_peak: bool = False) -> ModelOutput:
+    def run_pcm(self, pcm: Sequence[np.ndarray], want_logits: bool = False, want_cif_peak: bool = False,
+                want_timestamps: bool = False) -> ModelOutput:
         arrs, ptrs, ns = self._pcm_args(pcm)
-        flags = (_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_CIF_PEAK if want_cif_peak else 0)
+        flags = ((_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_CIF_PEAK if want_cif_peak else 0) |
+                 (_lib.PF_RUN_WANT_TIMESTAMPS if want_timestamps else 0))
         res = _lib.PfResult()
         _lib.check(self._lib.pf_offline_run_pcm(self._handle(), ptrs, _lib.iptr(ns), len(arrs), flags, C.byref(res)))
         return self._collect(res, want_logits, want_cif_peak)
 
-    def run_feats(self, speech: np.ndarray, want_logits: bool = False, want_cif_peak: bool = False) -> ModelOutput:
+    def run_feats(self, speech: np.ndarray, want_logits: bool = False, want_cif_peak: bool = False,
+                  want_timestamps: bool = False) -> ModelOutput:
         x = np.ascontiguousarray(speech, dtype=np.float32)
         if x.ndim != 3 or x.shape[2] != self.cfg.input_size:
             raise ValueError("speech must be [B, T, input_size]")
-        flags = (_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_CIF_PEAK if want_cif_peak else 0)
+        flags = ((_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_CIF_PEAK if want_cif_peak else 0) |
+                 (_lib.PF_RUN_WANT_TIMESTAMPS if want_timestamps else 0))
         res = _lib.PfResult()
         _lib.check(self._lib.pf_offline_run_feats(self._handle(), _lib.fptr(x), x.shape[0], x.shape[1], flags, C.byref(res)))
         return self._collect(res, want_logits, want_cif_peak)

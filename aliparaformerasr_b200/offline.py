@@ -212,6 +212,47 @@ class OfflineStream:
     Dispose = dispose
 
 
+def time_stamp_lfr6_onnx(us_cif_peak, tokens, begin_time: float = 0.0, total_offset: float = -1.5) -> List[List[int]]:
+    """``OfflineRecognizer.time_stamp_lfr6_onnx`` (OfflineRecognizer.cs:200-302): host post-processing of the graph's
+    ``us_cif_peak`` row into [start_ms, end_ms] per emitted token (float32 arithmetic, as the C#)."""
+    f32 = np.float32
+    start_end_threshold, max_token_duration = 5, 30
+    time_rate = f32(f32(10.0) * 6 / 1000 / 3)                      # 3 times upsampled
+    us = np.asarray(us_cif_peak, dtype=np.float32)
+    num_frames = us.shape[0]
+    tokens = list(tokens)
+    if tokens and tokens[-1] == 2:
+        tokens = tokens[:-1]
+    fire_place = [f32(i + total_offset) for i in range(num_frames) if float(us[i]) > 1.0 - 1e-4]
+    ts_list: List[List[np.float32]] = []
+    new_char: List[bool] = []
+    if fire_place[0] > start_end_threshold:                         # begin silence
+        ts_list.append([f32(0.0), f32(fire_place[0] * time_rate)])
+        new_char.append(False)
+    for i in range(len(fire_place) - 1):
+        new_char.append(tokens[i] != 1)
+        if i == len(fire_place) - 2 or fire_place[i + 1] - fire_place[i] < max_token_duration:
+            ts_list.append([f32(fire_place[i] * time_rate), f32(fire_place[i + 1] * time_rate)])
+        else:
+            split = f32(fire_place[i] + max_token_duration)
+            ts_list.append([f32(fire_place[i] * time_rate), f32(split * time_rate)])
+            ts_list.append([f32(split * time_rate), f32(fire_place[i + 1] * time_rate)])
+            new_char.append(False)
+    if num_frames - fire_place[-1] > start_end_threshold:           # tail token and end silence
+        end = f32(f32(num_frames + fire_place[-1]) / 2)
+        ts_list[-1][1] = f32(end * time_rate)
+        ts_list.append([f32(end * time_rate), f32(f32(num_frames) * time_rate)])
+        new_char.append(False)
+    else:
+        ts_list[-1][1] = f32(f32(num_frames) * time_rate)
+    if begin_time > 0.0:
+        for t in ts_list:
+            t[0] = f32(t[0] + f32(begin_time) / f32(1000.0))
+            t[1] = f32(t[1] + f32(begin_time) / f32(1000.0))
+    new_char.append(True)
+    return [[int(f32(t[0] * f32(1000))), int(f32(t[1] * f32(1000)))] for c, t in zip(new_char, ts_list) if c]
+
+
 def pad_sequence(feats: Sequence[np.ndarray]) -> np.ndarray:
     """PadHelper.PadSequence (Utils/PadHelper.cs:23-65) on the host, used only when a stream received several
     AddSamples calls: right-pad with 0 to the longest item, then every exact 0.0 -> -23.0258509f*32768 (Q4)."""
@@ -291,14 +332,15 @@ class OfflineRecognizer:
         try:
             if call_hotwords:
                 self._engine.set_hotwords(call_hotwords)
+            want_ts = bool(getattr(self._conf, "timestamps", False))      # 4-output models (OfflineProjOfParaformer.cs:75-79)
             if all(len(s._chunks) == 1 for s in streams):
                 # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
-                out = self._engine.run_pcm([s._chunks[0] for s in streams])
+                out = self._engine.run_pcm([s._chunks[0] for s in streams], want_timestamps=want_ts)
             else:
                 feats = [s.features() for s in streams]
                 if any(f.shape[0] == 0 for f in feats) and max(f.shape[0] for f in feats) == 0:
                     raise ValueError("no input samples")
-                out = self._engine.run_feats(pad_sequence(feats))
+                out = self._engine.run_feats(pad_sequence(feats), want_timestamps=want_ts)
         except _lib.PfError as ex:
             raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
         finally:
@@ -306,7 +348,10 @@ class OfflineRecognizer:
                 self._engine.set_hotwords(self._hotwords)
         for i, s in enumerate(streams):
             s.tokens = [int(t) for t in out.tokens[i]]
-            s.timestamps.extend([[0, 0] for _ in s.tokens])         # 3-output models: {0,0} per token (:151)
+            if out.us_cif_peak is not None:                         # cif_peak_tensor != null (OfflineRecognizer.cs:172-183)
+                s.timestamps.extend(time_stamp_lfr6_onnx(out.us_cif_peak[i], s.tokens))
+            else:
+                s.timestamps.extend([[0, 0] for _ in s.tokens])     # 3-output models: {0,0} per token (:151)
             s.remove_chunk()
 
     # -- OfflineRecognizer.DecodeMulti (OfflineRecognizer.cs:304-418)

@@ -56,6 +56,11 @@ class ModelConfig:
     seaco_ffn: int = 1024
     seaco_kernel: int = 21
     nobias_id: int = 8377
+    # CifPredictorV3 timestamp branch (present in the -timestamp- and SeACo models)
+    timestamps: bool = False
+    upsample_times: int = 3
+    smooth_factor2: float = 0.25
+    noise_threshold2: float = 0.01
 
     def as_dict(self):
         return asdict(self)
@@ -71,13 +76,13 @@ def sensevoice_small() -> ModelConfig:
 
 
 def seaco_paraformer() -> ModelConfig:
-    return ModelConfig(model="seacoparaformer")
+    return ModelConfig(model="seacoparaformer", timestamps=True)
 
 
 def tiny(model: str = "paraformer") -> ModelConfig:
     """Few-layer variant with the real per-layer shapes: the oracle finishes in seconds."""
     if model == "seacoparaformer":
-        return ModelConfig(model=model, enc_layers=3, dec_layers=2, seaco_layers=2)
+        return ModelConfig(model=model, enc_layers=3, dec_layers=2, seaco_layers=2, timestamps=True)
     if model == "sensevoicesmall":
         return ModelConfig(model=model, enc_layers=3, tp_layers=2, dec_layers=0, vocab=25055, ln_eps=1e-5)
     return ModelConfig(model=model, enc_layers=3, dec_layers=2)
@@ -130,6 +135,7 @@ def make_weights(cfg: ModelConfig, seed: int = WEIGHT_SEED) -> Dict[str, np.ndar
     w["predictor.cif_output.bias"] = np.asarray([-1.1], dtype=np.float32)
     # ParaformerSANMDecoder
     _sanm_decoder(w, g, "decoder", cfg.dec_layers, cfg.dec_ffn, cfg.dec_kernel, d)
+    pending_v3 = cfg.timestamps
     w["decoder.output_layer.weight"] = _normal(g, (cfg.vocab, d), 4.0 / math.sqrt(d))
     w["decoder.output_layer.bias"] = _normal(g, (cfg.vocab,), 0.02)
     if cfg.model == "seacoparaformer":
@@ -145,6 +151,17 @@ def make_weights(cfg: ModelConfig, seed: int = WEIGHT_SEED) -> Dict[str, np.ndar
             w[f"bias_encoder.weight_hh_l{layer}"] = _normal(g, (4 * d, d), 1.0 / math.sqrt(d))
             w[f"bias_encoder.bias_ih_l{layer}"] = _normal(g, (4 * d,), 0.05)
             w[f"bias_encoder.bias_hh_l{layer}"] = _normal(g, (4 * d,), 0.05)
+    if pending_v3:
+        # CifPredictorV3 upsampler (drawn last so the other tensors keep their values with or without it)
+        w["predictor.upsample_cnn.weight"] = _normal(g, (d, d, cfg.upsample_times), 1.0 / math.sqrt(d))
+        w["predictor.upsample_cnn.bias"] = _normal(g, (d,), 0.02)
+        for sfx in ("", "_reverse"):
+            w["predictor.blstm.weight_ih_l0" + sfx] = _normal(g, (4 * d, d), 1.0 / math.sqrt(d))
+            w["predictor.blstm.weight_hh_l0" + sfx] = _normal(g, (4 * d, d), 1.0 / math.sqrt(d))
+            w["predictor.blstm.bias_ih_l0" + sfx] = _normal(g, (4 * d,), 0.05)
+            w["predictor.blstm.bias_hh_l0" + sfx] = _normal(g, (4 * d,), 0.05)
+        w["predictor.cif_output2.weight"] = _normal(g, (1, 2 * d), 2.0 / math.sqrt(2 * d))
+        w["predictor.cif_output2.bias"] = np.asarray([0.3], dtype=np.float32)
     return w
 
 

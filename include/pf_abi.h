@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 2
+#define PF_ABI_VERSION 3
 
 typedef int32_t pf_status;
 enum {
@@ -77,6 +77,8 @@ typedef struct pf_config {
     int32_t seaco_ffn;         /* seaco_decoder_conf.linear_units 1024 */
     int32_t seaco_kernel;      /* seaco_decoder_conf.kernel_size 21 */
     int32_t seaco_nobias_id;   /* class id of "no bias" in the hot-word head (8377 for the 8404-token vocabulary) */
+    float smooth_factor2;      /* CifPredictorV3 timestamp branch: predictor_conf.smooth_factor2 0.25 */
+    float noise_threshold2;    /* predictor_conf.noise_threshold2 0.01 */
 } pf_config;
 
 /* ModelOutputEntity (Model/ModelOutputEntity.cs:10-19) plus the greedy ids that OfflineRecognizer.Forward derives
@@ -90,9 +92,14 @@ typedef struct pf_result {
     const int32_t* token_num;  /* [B] model_out_lens */
     const float* logits;       /* [B, L, V] log-softmax, only with PF_RUN_WANT_LOGITS, else NULL */
     const float* cif_peak;     /* [B, T+1] integrate-and-fire trace, only with PF_RUN_WANT_CIF_PEAK, else NULL */
+    /* graph outputs #3 / #4 of the -timestamp- and SeACo models (ModelOutputEntity.cif_peak_tensor = us_cif_peak,
+     * OfflineProjOfParaformer.cs:75-79), only with PF_RUN_WANT_TIMESTAMPS on a model that has the V3 predictor */
+    int32_t us_frames;         /* 3 * T (the predictor upsamples x3), 0 when absent */
+    const float* us_alphas;    /* [B, us_frames] */
+    const float* us_cif_peak;  /* [B, us_frames] consumed by OfflineRecognizer.time_stamp_lfr6_onnx (OfflineRecognizer.cs:200-302) */
 } pf_result;
 
-enum { PF_RUN_WANT_LOGITS = 1, PF_RUN_WANT_CIF_PEAK = 2 };
+enum { PF_RUN_WANT_LOGITS = 1, PF_RUN_WANT_CIF_PEAK = 2, PF_RUN_WANT_TIMESTAMPS = 4 };
 
 typedef struct pf_offline pf_offline;
 

@@ -25,11 +25,11 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in pf_abi.h but not exported by libpfasr.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.pf_abi_version() == 2
+    assert lib.pf_abi_version() == 3
 
 
 def test_config_struct_layout():
-    assert C.sizeof(_lib.PfConfig) == 4 * 29
+    assert C.sizeof(_lib.PfConfig) == 4 * 31
     c = to_pf_config(synth.paraformer_large())
     assert (c.input_size, c.d_model, c.enc_layers, c.dec_layers, c.vocab, c.lfr_m, c.lfr_n) == (560, 512, 50, 16, 8404, 7, 6)
     assert to_pf_config(synth.sensevoice_small()).model_kind == _lib.PF_MODEL_SENSEVOICE_SMALL

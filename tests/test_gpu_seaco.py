@@ -73,3 +73,37 @@ def test_hotwords_rejected_on_plain_paraformer():
     with pytest.raises(_lib.PfError):
         eng.set_hotwords([[5, 6]])
     eng.close()
+
+
+def test_timestamp_branch(tiny_seaco):
+    """Row f1: us_alphas / us_cif_peak of the CifPredictorV3 upsampler (persistent BiLSTM) and the host timestamps."""
+    from aliparaformerasr_b200.offline import time_stamp_lfr6_onnx
+    cfg, w, eng = tiny_seaco
+    eng.set_hotwords([])
+    pcm, speech = _speech(3, seconds=4.0)
+    dims = dims_of(cfg)
+    ref = sanm.paraformer_forward(speech, w, dims)
+    ua, pk = sanm.upsample_timestamp(ref["enc"], ref["token_num"], w, dims)
+    out = eng.run_pcm(pcm, want_timestamps=True)
+    assert out.us_alphas.shape == ua.shape == (3, 3 * speech.shape[1])
+    assert np.abs(out.us_alphas - ua).max() < 3e-3
+    assert np.abs(out.us_cif_peak - pk).max() < 3e-2            # 3T-step running sum of the alphas
+    assert np.allclose(out.us_alphas.sum(1), ref["token_num"], atol=1e-2)
+    for i in range(3):
+        fires_ref = np.nonzero(pk[i] > 1 - 1e-4)[0]
+        fires = np.nonzero(out.us_cif_peak[i] > 1 - 1e-4)[0]
+        assert len(fires) == len(fires_ref) and np.abs(fires - fires_ref).max() <= 1
+        ts = time_stamp_lfr6_onnx(out.us_cif_peak[i], list(out.tokens[i]))
+        ts_ref = sanm.time_stamp_lfr6_onnx(pk[i], list(ref["tokens"][i]))
+        assert len(ts) == len(ts_ref)
+        assert all(abs(a[0] - b[0]) <= 20 and abs(a[1] - b[1]) <= 20 for a, b in zip(ts, ts_ref))      # <= one upsampled frame
+
+
+def test_timestamps_rejected_without_branch():
+    from aliparaformerasr_b200 import _lib
+    cfg = synth.tiny()
+    eng = Engine(cfg, synth.make_weights(cfg))
+    eng.set_cmvn(*synth.make_cmvn())
+    with pytest.raises(_lib.PfError):
+        eng.run_pcm([synth.make_pcm(0, 2.0)], want_timestamps=True)
+    eng.close()

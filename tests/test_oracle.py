@@ -127,3 +127,20 @@ def test_tiny_paraformer_oracle_is_deterministic_and_sane():
     assert a["logits"].shape[:2] == a["tokens"].shape and a["logits"].shape[2] == 8404
     assert np.allclose(np.exp(a["logits"]).sum(-1), 1.0, atol=1e-3)
     assert np.all(a["token_num"] <= a["tokens"].shape[1] + 1)
+
+
+def test_time_stamp_lfr6_host_matches_oracle_restatement():
+    """The host mirror (offline.py) and the oracle restatement of OfflineRecognizer.time_stamp_lfr6_onnx agree, and the
+    documented cases of the C# hold: begin silence dropped, tail split at the midpoint, long tokens split at 30 frames."""
+    import numpy as np
+    from aliparaformerasr_b200.offline import time_stamp_lfr6_onnx
+    from oracle import sanm
+    pk = np.zeros(150, np.float32)
+    for i in (20, 35, 80, 100):
+        pk[i] = 1.0
+    toks = [5, 6, 7, 8, 2]
+    a = time_stamp_lfr6_onnx(pk, toks)
+    assert a == sanm.time_stamp_lfr6_onnx(pk, toks)
+    # hand trace of OfflineRecognizer.cs:200-302: fires at 18.5/33.5/78.5/98.5 (offset -1.5) -> begin silence dropped,
+    # token 2 capped at 30 frames (the split remainder is dropped), token 3 runs to the tail midpoint (150+98.5)/2
+    assert a == [[370, 669], [669, 1270], [1569, 2485]]
