@@ -5,8 +5,9 @@
 // relu(a*0.25 - 0.01) -> rescale to token_num -> cif_wo_hidden(threshold 1 - 1e-4).
 //
 // The BiLSTM is a 3T-step (498 at 10 s) sequential recurrence over a [B,512] state: as per-step GEMM launches it would cost
-// more than the whole recogniser, so it runs as ONE persistent cooperative kernel - W_hh stays in shared memory, the
-// CTAs of a direction synchronise through a global counter once per step.
+// more than the whole recogniser, so it runs as ONE persistent kernel - a 16-CTA cluster per direction keeps W_hh in
+// shared memory, multiplies with mma.sync, exchanges h_t through distributed shared memory and meets at the hardware
+// cluster barrier once per step (a first version with a global-memory barrier and scalar dot products took 16 us / step).
 #include "timestamp.cuh"
 
 #include <math.h>
@@ -15,107 +16,120 @@ namespace pf {
 
 namespace {
 
-constexpr int kWPitch = 512 + 8;      // halfs per staged W_hh row (+16 B: rows of one warp hit different banks)
+constexpr int kPitch = 512 + 8;       // halfs per staged row of W_hh / h (+16 B: ldmatrix rows hit different banks)
+constexpr int kClusterCtas = 16;      // CTAs per direction = one thread-block cluster; each owns 32 hidden units
+constexpr int kUnits = 32;            // hidden units per CTA -> 128 gate rows of W_hh resident in shared memory
+constexpr int kRows = 4 * kUnits;
+constexpr int kMb = 16;               // utterances per launch = M of mma.m16n8k16
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void st_cluster_u128(uint32_t cluster_addr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
-pf_bilstm_persistent(const float* __restrict__ gin, const __half* __restrict__ w_hh, int B, int T3, float* __restrict__ y,
-                     float* hbuf, unsigned int* bar) {
-    constexpr int H = 512, U = kLstmUnitsPerCta, R = 4 * U;      // 32 gate rows per CTA
+// One thread-block cluster (16 CTAs) per direction.  CTA c keeps the 128 rows of W_hh that produce the four gates of
+// hidden units [32c, 32c+32) in shared memory for all T3 steps.  Per step: gates = h_{t-1} W_hh^T (mma.sync, M = 16
+// utterances, N = 128 gate rows, K = 512) + the precomputed input projections; cell update; the CTA's slice of h_t is
+// pushed (fp16) into every peer's shared memory through DSMEM; one hardware cluster barrier.  No global-memory
+// synchronisation, no re-reading of weights.
+__global__ void __launch_bounds__(256, 1)
+pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh, int B, int T3, float* __restrict__ y) {
+    constexpr int H = 512;
     extern __shared__ __align__(16) uint8_t smem_l[];
-    __half* s_w = reinterpret_cast<__half*>(smem_l);                         // [R][kWPitch]
-    float* s_h = reinterpret_cast<float*>(smem_l + R * kWPitch * 2);          // [B][H]
-    float* s_g = s_h + kLstmMaxBatch * H;                                     // [B][R] gate pre-activations
-    const int ctas_per_dir = H / U;
-    const int dir = blockIdx.x / ctas_per_dir;
-    const int u0 = (blockIdx.x % ctas_per_dir) * U;
-    const int tid = threadIdx.x;
-    // stage this CTA's rows of W_hh: row r = gate (r / U), unit u0 + r % U
-    for (int i = tid; i < R * (H / 8); i += blockDim.x) {
+    __half* s_w = reinterpret_cast<__half*>(smem_l);                                  // [kRows][kPitch]
+    __half* s_h = s_w + kRows * kPitch;                                               // [2][kMb][kPitch]  h_{t-1} (all units), double buffered
+    float* s_g = reinterpret_cast<float*>(s_h + 2 * kMb * kPitch);                    // [kMb][kRows] gate pre-activations (recurrent part)
+    __half* s_o = reinterpret_cast<__half*>(s_g + kMb * kRows);                       // [kMb][kUnits] this CTA's h_t slice
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int dir = blockIdx.x / kClusterCtas;
+    const int u0 = rank * kUnits;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // stage W_hh rows: local row r = gate (r / 32) * 32 + unit offset (r % 32)
+    for (int i = tid; i < kRows * (H / 8); i += blockDim.x) {
         const int r = i / (H / 8), c8 = i % (H / 8);
-        const int grow = (r / U) * H + u0 + (r % U);
-        *reinterpret_cast<uint4*>(s_w + r * kWPitch + c8 * 8) =
+        const int grow = (r / kUnits) * H + u0 + (r % kUnits);
+        *reinterpret_cast<uint4*>(s_w + r * kPitch + c8 * 8) =
             *reinterpret_cast<const uint4*>(w_hh + (static_cast<size_t>(dir) * 4 * H + grow) * H + c8 * 8);
     }
-    // thread roles: dot products (row r = tid % 32, batch group tid / 32), cell update (b = tid / U, unit tid % U)
-    const int r = tid & 31, bg = tid >> 5;
-    const int nb_per = (B + 7) / 8;                                          // batches per dot-product thread (<= 4)
-    const int cb = tid / U, cu = tid % U;
-    float cstate = 0.0f;
-    float* hb = hbuf + static_cast<size_t>(dir) * 2 * B * H;
-    unsigned int* my_bar = bar + dir;
-    __syncthreads();
+    for (int i = tid; i < 2 * kMb * kPitch / 8; i += blockDim.x) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);   // h_0 = 0
+    // cell roles: thread -> (utterance cb, units cu, cu + 16)
+    const int cb = tid >> 4, cu = tid & 15;
+    float cstate[2] = {0.0f, 0.0f};
+    cluster_sync();                                                   // every CTA's buffers are initialised before remote writes
+    const uint32_t s_w_u32 = smem_u32(s_w), s_h_u32 = smem_u32(s_h);
+    // input projections of my two cells (4 gates each) are fetched ONE STEP AHEAD: gin (130 MB at 16 x 10 s) streams from
+    // HBM, and a step is far shorter than a DRAM round trip
+    auto load_gi = [&](int step_, float (&dst)[2][4]) {
+        const int t_ = dir == 0 ? step_ : T3 - 1 - step_;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                dst[k][g] = (cb < B && step_ < T3) ? __ldg(gin + (static_cast<size_t>(cb) * T3 + t_) * (8 * H) + dir * 4 * H + g * H + u0 + cu + 16 * k) : 0.0f;
+    };
+    float gi[2][4], gi_next[2][4];
+    load_gi(0, gi_next);
     for (int step = 0; step < T3; ++step) {
         const int t = dir == 0 ? step : T3 - 1 - step;
-        const float* hprev = hb + static_cast<size_t>(step & 1) * B * H;
-        float* hnext = hb + static_cast<size_t>((step & 1) ^ 1) * B * H;
-        // input projections of this step for my (row, batches): issued first, consumed after the dot products
-        float gi[4];
+        const int cur = step & 1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int b = bg * nb_per + j;
-            gi[j] = (j < nb_per && b < B) ? gin[(static_cast<size_t>(b) * T3 + t) * (8 * H) + dir * 4 * H + (r / U) * H + u0 + (r % U)] : 0.0f;
-        }
-        if (step == 0) {
-            for (int i = tid; i < B * H; i += blockDim.x) s_h[i] = 0.0f;
-        } else {
-            for (int i = tid; i < B * H / 4; i += blockDim.x)
-                reinterpret_cast<float4*>(s_h)[i] = __ldcg(reinterpret_cast<const float4*>(hprev) + i);    // L2: written by other SMs
-        }
-        __syncthreads();
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const __half* wr = s_w + r * kWPitch;
-#pragma unroll 4
-        for (int k = 0; k < H; k += 8) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(wr + k);
-            const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
-            float wf[8];
+        for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(w2[i]); wf[2 * i] = f.x; wf[2 * i + 1] = f.y; }
+            for (int g = 0; g < 4; ++g) gi[k][g] = gi_next[k][g];
+        load_gi(step + 1, gi_next);
+        // gates[16 x 128] = h_{t-1}[16 x 512] * W^T: warp w owns gate rows [16w, 16w + 16) = two n-tiles
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const uint32_t a_base = s_h_u32 + static_cast<uint32_t>(((cur * kMb + (lane & 15)) * kPitch + (lane >> 4) * 8) * 2);
+        const uint32_t b_base = s_w_u32 + static_cast<uint32_t>(((warp * 16 + (lane >> 4) * 8 + (lane & 7)) * kPitch + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll 8
+        for (int k0 = 0; k0 < H; k0 += 16) {
+            uint32_t a[4], b0, b1, b2, b3;
+            ldsm_x4(a_base + k0 * 2, a[0], a[1], a[2], a[3]);
+            ldsm_x4(b_base + k0 * 2, b0, b1, b2, b3);
+            mma16816(acc[0], a, b0, b1);
+            mma16816(acc[1], a, b2, b3);
+        }
+        {
+            const int g = lane >> 2, c2 = (lane & 3) * 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bg * nb_per + j;
-                if (j < nb_per && b < B) {
-                    const float4 h0 = *reinterpret_cast<const float4*>(s_h + b * H + k);
-                    const float4 h1 = *reinterpret_cast<const float4*>(s_h + b * H + k + 4);
-                    acc[j] += wf[0] * h0.x + wf[1] * h0.y + wf[2] * h0.z + wf[3] * h0.w + wf[4] * h1.x + wf[5] * h1.y + wf[6] * h1.z + wf[7] * h1.w;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int b = bg * nb_per + j;
-            if (j < nb_per && b < B) s_g[b * R + r] = acc[j] + gi[j];
-        }
-        __syncthreads();
-        if (cb < B) {
-            const float* g = s_g + cb * R;
-            const float ig = 1.0f / (1.0f + expf(-g[cu]));
-            const float fg = 1.0f / (1.0f + expf(-g[U + cu]));
-            const float gg = tanhf(g[2 * U + cu]);
-            const float og = 1.0f / (1.0f + expf(-g[3 * U + cu]));
-            cstate = fg * cstate + ig * gg;
-            const float h = og * tanhf(cstate);
-            hnext[cb * H + u0 + cu] = h;
-            y[(static_cast<size_t>(cb) * T3 + t) * (2 * H) + dir * H + u0 + cu] = h;
-        }
-        // all CTAs of this direction have published h_t before anyone reads it
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(my_bar, 1u);
-            const unsigned int target = static_cast<unsigned int>(ctas_per_dir) * (step + 1);
-            unsigned int spins = 0;
-            while (ld_acquire_u32(my_bar) < target) {
-                if (++spins > (1u << 28)) { printf("pfasr: bilstm grid barrier timeout\n"); __trap(); }
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = warp * 16 + nt * 8 + c2;
+                s_g[g * kRows + col] = acc[nt][0];
+                s_g[g * kRows + col + 1] = acc[nt][1];
+                s_g[(g + 8) * kRows + col] = acc[nt][2];
+                s_g[(g + 8) * kRows + col + 1] = acc[nt][3];
             }
         }
         __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int u = cu + 16 * k;
+            const float* g = s_g + cb * kRows;
+            const float ig = 1.0f / (1.0f + expf(-(g[u] + gi[k][0])));
+            const float fg = 1.0f / (1.0f + expf(-(g[kUnits + u] + gi[k][1])));
+            const float gg = tanhf(g[2 * kUnits + u] + gi[k][2]);
+            const float og = 1.0f / (1.0f + expf(-(g[3 * kUnits + u] + gi[k][3])));
+            cstate[k] = fg * cstate[k] + ig * gg;
+            const float h = og * tanhf(cstate[k]);
+            s_o[cb * kUnits + u] = __float2half_rn(cb < B ? h : 0.0f);
+            if (cb < B) y[(static_cast<size_t>(cb) * T3 + t) * (2 * H) + dir * H + u0 + u] = h;
+        }
+        __syncthreads();
+        // push my [16 x 32] fp16 slice of h_t into the next buffer of every CTA of the cluster (64 x 16-byte pieces x 16 peers)
+        for (int i = tid; i < kMb * (kUnits / 8) * kClusterCtas; i += blockDim.x) {
+            const int peer = i / (kMb * (kUnits / 8)), p = i % (kMb * (kUnits / 8));
+            const int row = p / (kUnits / 8), c8 = p % (kUnits / 8);
+            const uint4 v = *reinterpret_cast<const uint4*>(s_o + row * kUnits + c8 * 8);
+            const uint32_t dst = s_h_u32 + static_cast<uint32_t>((((cur ^ 1) * kMb + row) * kPitch + u0 + c8 * 8) * 2);
+            st_cluster_u128(mapa_shared(dst, peer), v);
+        }
+        cluster_sync();                                               // release / acquire: h_t is complete everywhere
     }
 }
 
@@ -157,9 +171,10 @@ pf_us_alphas_peaks(const float* __restrict__ y, int T3, int D2, const float* __r
 }  // namespace
 
 void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, float* y, float* hbuf, unsigned int* bar, cudaStream_t s) {
+    (void)hbuf; (void)bar;
     if (H != 512) throw CudaError{"bilstm: hidden size must be 512"};
-    if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..32 utterances per launch"};
-    const int smem = 4 * kLstmUnitsPerCta * kWPitch * 2 + kLstmMaxBatch * H * 4 + kLstmMaxBatch * 4 * kLstmUnitsPerCta * 4;
+    if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..16 utterances per launch"};
+    const int smem = kRows * kPitch * 2 + 2 * kMb * kPitch * 2 + kMb * kRows * 4 + kMb * kUnits * 2;
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
@@ -167,16 +182,23 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
         PF_CUDA(cudaGetDevice(&cur));
         for (int d = 0; d < ndev; ++d) {
             PF_CUDA(cudaSetDevice(d));
-            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16-CTA clusters
         }
         PF_CUDA(cudaSetDevice(cur));
         attr_set = true;
     }
-    PF_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned int), s));
-    const int grid = 2 * (H / kLstmUnitsPerCta);
-    void* args[] = {(void*)&gin, (void*)&w_hh, (void*)&B, (void*)&T3, (void*)&y, (void*)&hbuf, (void*)&bar};
-    // cooperative launch: the step barrier needs every CTA resident (128 CTAs, one per SM)
-    PF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pf_bilstm_persistent), dim3(grid), dim3(256), args, static_cast<size_t>(smem), s));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * kClusterCtas);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PF_CUDA(cudaLaunchKernelEx(&cfg, pf_bilstm_cluster, gin, w_hh, B, T3, y));
 }
 
 void us_alphas_peaks_launch(const float* y, int B, int T3, int D2, const float* w2, const float* b2, float smooth, float noise,

@@ -4,15 +4,14 @@
 
 namespace pf {
 
-constexpr int kLstmUnitsPerCta = 8;      // hidden units (x 4 gates) one CTA owns
-constexpr int kLstmMaxBatch = 32;        // utterances per launch (h_{t-1} of the whole batch lives in shared memory)
+constexpr int kLstmMaxBatch = 16;        // utterances per launch (= M of the mma.sync tiles)
 
 // y[b, t, dir*H + u] for t in [0, T3): h_t of a single-layer bidirectional LSTM (PyTorch gate order i|f|g|o).
 //   gin  [B*T3, 2*4H] fp32 : W_ih x_t + b_ih + b_hh for both directions (forward gates first)
 //   w_hh [2][4H, H] fp16   : recurrent weights, forward then reverse
-//   hbuf [2][2][B][H] fp32 : scratch (h double buffer per direction), bar [2] u32 zeroed by the launcher
-// One cooperative launch: 2 * H/8 CTAs, every CTA keeps its 32 rows of W_hh in shared memory for all T3 steps and
-// the CTAs of a direction meet at a global barrier after every step.
+//   hbuf, bar              : unused (kept for ABI stability of the launcher)
+// One launch of two 16-CTA clusters (forward / reverse): every CTA keeps its 128 rows of W_hh in shared memory for all
+// T3 steps, h_t travels through distributed shared memory, one cluster barrier per step.
 void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, float* y, float* hbuf, unsigned int* bar, cudaStream_t s);
 
 // alphas2 = relu(sigmoid(<y[b,t,:], w2> + b2) * smooth - noise); rescaled so that every utterance sums to token_num[b];

@@ -18,7 +18,7 @@ from aliparaformerasr_b200.engine import Engine  # noqa: E402
 from aliparaformerasr_b200.online import OnlineEngine  # noqa: E402
 
 
-def offline(name, cfg, batch, seconds, steps, hotwords=None):
+def offline(name, cfg, batch, seconds, steps, hotwords=None, timestamps=False):
     w = synth.make_weights(cfg)
     eng = Engine(cfg, w, devices=[0])
     eng.set_cmvn(*synth.make_cmvn())
@@ -26,15 +26,16 @@ def offline(name, cfg, batch, seconds, steps, hotwords=None):
         eng.set_hotwords(hotwords)
     pcm = [synth.make_pcm(i, seconds) for i in range(batch)]
     eng.stage_pcm(pcm)
+    run = (lambda: eng.run_pcm(pcm, want_timestamps=True)) if timestamps else eng.run_staged
     for _ in range(3):
-        out = eng.run_staged()
+        out = run()
     ms = []
     for _ in range(steps):
-        eng.run_staged()
+        run()
         ms.append(eng.timings()["total"])
     t0 = time.perf_counter()
     for _ in range(steps):
-        eng.run_pcm(pcm)
+        eng.run_pcm(pcm, want_timestamps=timestamps)
     e2e = (time.perf_counter() - t0) / steps
     dev = float(np.median(ms))
     print(json.dumps({"config": name, "batch": batch, "seconds": seconds, "T": int(out.feat_frames), "Lmax": int(out.tokens.shape[1]),
@@ -86,6 +87,8 @@ def main():
     if "cfg4" in which:
         cfg = synth.seaco_paraformer()
         offline("cfg4 seaco-paraformer 16x10s + 200 hotwords", cfg, 16, 10.0, steps, hotwords=synth.make_hotwords(200, cfg.vocab))
+        offline("cfg4 + timestamps (us_alphas / us_cif_peak, 498-step BiLSTM)", cfg, 16, 10.0, steps, hotwords=synth.make_hotwords(200, cfg.vocab),
+                timestamps=True)
     if "cfg5" in which:
         online("cfg5 streaming 16 streams/GPU (128 over 8 GPUs)", 16, steps)
         online("cfg5 streaming 128 streams on one GPU", 128, steps)
