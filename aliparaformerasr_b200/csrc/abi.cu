@@ -367,10 +367,7 @@ pf_status pf_offline_stage_pcm(pf_offline* hh, const float* const* pcm, const in
         std::lock_guard<std::mutex> g(h->mu);
         stage_pcm_all(h, pcm, nsamp, batch);
         // standalone staging returns only once the PCM is resident in HBM (the caller may free its buffers)
-        for (auto& d : h->devs) {
-            PF_CUDA(cudaSetDevice(d->device()));
-            PF_CUDA(cudaStreamSynchronize(d->stream()));
-        }
+        for (auto& d : h->devs) d->sync_staging();
     });
 }
 

@@ -107,7 +107,10 @@ DeviceCtx::DeviceCtx(int dev, const pf_config& cfg) : dev_(dev), cfg_(cfg) {
         throw StatusError{PF_ERR_CUDA, "device " + std::to_string(dev_) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
                                            std::to_string(prop.minor) + ") is not sm_100: libpfasr has no fallback path"};
     PF_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    PF_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     for (auto& e : ev_) PF_CUDA(cudaEventCreate(&e));
+    for (auto& e : ev_grp_) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    PF_CUDA(cudaEventCreateWithFlags(&ev_compute_, cudaEventDisableTiming));
     fe_tables_ = frontend_tables_create();
     // FunASR SinusoidalPositionEncoder: inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1)), float32 arithmetic
     const int half = cfg_.input_size / 2;
@@ -153,6 +156,9 @@ DeviceCtx::~DeviceCtx() {
     if (ofe_meta_) cudaFree(ofe_meta_);
     free_pool(opool_);
     for (auto& e : ev_) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_grp_) if (e) cudaEventDestroy(e);
+    if (ev_compute_) cudaEventDestroy(ev_compute_);
+    if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
     for (auto& e : prof_pool_) cudaEventDestroy(e);
     for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (stream_) cudaStreamDestroy(stream_);
@@ -675,13 +681,30 @@ void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, 
     ev0_armed_ = true;
     PF_CUDA(cudaMemcpyAsync(d_off_, h_off, static_cast<size_t>(B) * 2 * sizeof(long long), cudaMemcpyHostToDevice, stream_));
     PF_CUDA(cudaMemcpyAsync(d_meta_, h_m, static_cast<size_t>(B) * 3 * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    for (int b = 0; b < B; ++b)
-        if (nsamp[b] > 0)
-            PF_CUDA(cudaMemcpyAsync(pcm_ + h_off[b], pcm[b], static_cast<size_t>(nsamp[b]) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    // PCM travels on a second stream in up to kCopyGroups groups of utterances; the compute stream waits per group, so the
+    // front-end of group g runs while the copy engine still moves group g+1 (the encoder needs them all)
+    PF_CUDA(cudaEventRecord(ev_compute_, stream_));                       // pcm_ may still be read by the previous run
+    PF_CUDA(cudaStreamWaitEvent(copy_stream_, ev_compute_, 0));
+    staged_groups_ = std::min(kCopyGroups, B);
+    for (int g = 0; g < staged_groups_; ++g) {
+        const int b0 = static_cast<int>(static_cast<long long>(B) * g / staged_groups_);
+        const int b1 = static_cast<int>(static_cast<long long>(B) * (g + 1) / staged_groups_);
+        for (int b = b0; b < b1; ++b)
+            if (nsamp[b] > 0)
+                PF_CUDA(cudaMemcpyAsync(pcm_ + h_off[b], pcm[b], static_cast<size_t>(nsamp[b]) * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
+        PF_CUDA(cudaEventRecord(ev_grp_[g], copy_stream_));
+    }
     staged_B_ = B;
     staged_T_ = tmax_lfr;
     staged_maxframes_ = maxframes;
     staged_is_pcm_ = true;
+}
+
+void DeviceCtx::sync_staging() {
+    PF_CUDA(cudaSetDevice(dev_));
+    PF_CUDA(cudaStreamSynchronize(copy_stream_));
+    PF_CUDA(cudaStreamSynchronize(stream_));
+    if (staged_groups_ > 1) staged_groups_ = 1;      // everything is resident: one front-end launch for the whole batch
 }
 
 void DeviceCtx::stage_feats(const float* speech, int B, int T) {
@@ -1009,12 +1032,17 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
     // ---- front-end
     if (staged_is_pcm_) {
         float* dst = sv ? feats_raw_ : feats_;
-        if (T > 0) {
+        for (int g = 0; g < staged_groups_; ++g) {
+            const int b0 = static_cast<int>(static_cast<long long>(B) * g / staged_groups_);
+            const int b1 = static_cast<int>(static_cast<long long>(B) * (g + 1) / staged_groups_);
+            PF_CUDA(cudaStreamWaitEvent(stream_, ev_grp_[g], 0));          // this group's PCM has landed
+            if (T <= 0 || b1 <= b0) continue;
             FrontendLaunch a;
-            a.tables = fe_tables_; a.pcm = pcm_; a.pcm_off = d_off_; a.nsamp = d_meta_; a.nframes = d_meta_ + B; a.nlfr = d_meta_ + 2 * B;
+            a.tables = fe_tables_; a.pcm = pcm_; a.pcm_off = d_off_ + b0; a.nsamp = d_meta_ + b0; a.nframes = d_meta_ + B + b0;
+            a.nlfr = d_meta_ + 2 * B + b0;
             a.add_shift = cmvn_shift_; a.rescale = cmvn_scale_;
-            a.feats_out = dst; a.feats_off = d_off_ + B;
-            a.batch = B; a.max_frames = staged_maxframes_; a.tmax_lfr = T; a.lfr_m = cfg_.lfr_m; a.lfr_n = cfg_.lfr_n;
+            a.feats_out = dst; a.feats_off = d_off_ + B + b0;
+            a.batch = b1 - b0; a.max_frames = staged_maxframes_; a.tmax_lfr = T; a.lfr_m = cfg_.lfr_m; a.lfr_n = cfg_.lfr_n;
             a.snip_edges = cfg_.snip_edges != 0;
             a.pad_quirk = true; a.pad_fill = true;
             a.pad_value = -23.025850929940457f * 32768.0f;      // Utils/PadHelper.cs:63

@@ -169,6 +169,7 @@ public:
 
     void get_tensor(const std::string& name, float* dst, size_t capacity, int32_t* dims4, int32_t* ndim);
     cudaStream_t stream() const { return stream_; }
+    void sync_staging();               // staged inputs are resident: the caller may release its host buffers
     int device() const { return dev_; }
     int ldv() const { return (cfg_.vocab + 3) & ~3; }   // fp32 logits row pitch (16-byte aligned rows)
 
@@ -210,8 +211,13 @@ private:
 
     int dev_;
     pf_config cfg_;
+    static constexpr int kCopyGroups = 4;
     cudaStream_t stream_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr;      // H2D of the PCM, overlapped with the front-end of earlier utterance groups
     cudaEvent_t ev_[7] = {};
+    cudaEvent_t ev_grp_[kCopyGroups] = {};
+    cudaEvent_t ev_compute_ = nullptr;
+    int staged_groups_ = 0;
     std::vector<void*> wpool_, apool_;
     std::vector<void*> tmp_;           // upload staging, freed after load
 
