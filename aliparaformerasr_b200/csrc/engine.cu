@@ -151,6 +151,7 @@ DeviceCtx::~DeviceCtx() {
     if (h_peaks) cudaFreeHost(h_peaks);
     if (h_online_counts) cudaFreeHost(h_online_counts);
     if (h_ostage_) cudaFreeHost(h_ostage_);
+    if (h_push_ring_) cudaFreeHost(h_push_ring_);
     for (float* p : {ofifo_, opcm_, osplice_, ocache_, ocif_a_, ocif_h_, ofsmn_}) if (p) cudaFree(p);
     if (ofe_off_) cudaFree(ofe_off_);
     if (ofe_meta_) cudaFree(ofe_meta_);
@@ -1225,7 +1226,18 @@ void DeviceCtx::online_push_chunk(int slot, const float* samples, int nsamp) {
     if (s.pushed - c_min >= od_.nslot)
         throw StatusError{PF_ERR_SHAPE, "stream backlog exceeds " + std::to_string(od_.nslot) + " chunks: call the recognizer's GetResults"};
     float* dst = opcm_ + (static_cast<size_t>(slot) * od_.nslot + static_cast<size_t>(s.pushed % od_.nslot)) * chunk;
-    PF_CUDA(cudaMemcpyAsync(dst, samples, static_cast<size_t>(chunk) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    // bounce through a pinned ring: the caller's buffer is pageable (a managed float[] in the reference) and a pageable
+    // cudaMemcpyAsync stalls the host for the whole staged copy; from pinned memory the push returns after a 38 KB memcpy
+    constexpr int kRing = 256;
+    if (!h_push_ring_) PF_CUDA(cudaMallocHost(&h_push_ring_, static_cast<size_t>(kRing) * chunk * sizeof(float)));
+    if (push_ring_pos_ == kRing) {                       // wrapped: the copies issued from the ring have to be done
+        PF_CUDA(cudaStreamSynchronize(copy_stream_));
+        push_ring_pos_ = 0;
+    }
+    float* bounce = h_push_ring_ + static_cast<size_t>(push_ring_pos_++) * chunk;
+    memcpy(bounce, samples, static_cast<size_t>(chunk) * sizeof(float));
+    PF_CUDA(cudaMemcpyAsync(dst, bounce, static_cast<size_t>(chunk) * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
+    push_pending_ = true;
     ++s.pushed;
 }
 
@@ -1253,6 +1265,11 @@ void DeviceCtx::online_step_impl(const std::vector<int>& slots, uint32_t flags, 
     online_working.clear();
     Lmax_ = 0; Lpad_ = 0; B_ = 0; T_ = 0;
     PF_CUDA(cudaEventRecord(ev_[0], stream_));
+    if (push_pending_) {                                  // pushed chunks travel on the copy stream
+        PF_CUDA(cudaEventRecord(ev_grp_[0], copy_stream_));
+        PF_CUDA(cudaStreamWaitEvent(stream_, ev_grp_[0], 0));
+        push_pending_ = false;
+    }
     const int chunk = 160 * od_.chunk_len;
     // ---- per-chunk fbank (InputSpeech, OnlineStream.cs:114-167) for everything pushed since the last step, one launch
     int npend = 0;

@@ -292,6 +292,7 @@ private:
     float* ofresh_ = nullptr; float* ocache_new_ = nullptr; int* otab_ = nullptr; int owork_cap_ = 0;
     long long* ofe_off_ = nullptr; int* ofe_meta_ = nullptr; int ofe_cap_ = 0;
     void* h_ostage_ = nullptr; size_t h_ostage_bytes_ = 0;
+    float* h_push_ring_ = nullptr; int push_ring_pos_ = 0; bool push_pending_ = false;   // pinned bounce ring of pushed chunks
     size_t h_ocounts_cap_ = 0;
     std::vector<void*> opool_;
     size_t fsmn_state_stride() const { return static_cast<size_t>(cfg_.dec_layers) * (cfg_.dec_kernel - 1) * cfg_.d_model; }

@@ -169,7 +169,7 @@ pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, floa
 // operand of the cross-attention query projection.  Replaces three launches per decoder layer (LayerNorm, pf_fsmn,
 // LayerNorm) - the decoder is launch-latency bound at M = B * L ~ 1600 rows.
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const float* __restrict__ g2, const float* __restrict__ b2,
                   const float* __restrict__ w, const float* __restrict__ g3, const float* __restrict__ b3,
                   const int* __restrict__ lens, int L, float eps, __half* __restrict__ out16) {
@@ -185,7 +185,7 @@ pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const fl
     pdl_wait();
     const int len = min(lens[b], L);
     const size_t rowbase = static_cast<size_t>(b) * L;
-    for (int r = warp; r < ROWS; r += 8) {
+    for (int r = warp; r < ROWS; r += 16) {
         const int t = t0 - LEFT + r;
         float4* dst = reinterpret_cast<float4*>(s_v + r * D);
         if (t < 0 || t >= len) {
@@ -216,9 +216,8 @@ pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const fl
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int c = threadIdx.x + half * 256;
+    {
+        const int c = threadIdx.x;                                  // one channel per thread (512 threads)
         float wk[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) wk[j] = __ldg(w + c * K + j);
@@ -239,7 +238,7 @@ pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const fl
     __syncthreads();
     const float4* g3v = reinterpret_cast<const float4*>(g3);
     const float4* b3v = reinterpret_cast<const float4*>(b3);
-    for (int i = warp; i < TT; i += 8) {
+    for (int i = warp; i < TT; i += 16) {
         const int t = t0 + i;
         if (t >= L) break;
         const float4* src = reinterpret_cast<const float4*>(s_x + i * D);
@@ -612,7 +611,7 @@ static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2,
         PF_CUDA(cudaSetDevice(cur));
         attr_set = true;
     }
-    launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, 16), B), dim3(256), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
+    launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, 16), B), dim3(512), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
 }
 
 void dec_ln_fsmn_ln_launch(const float* t32, float* x, const float* g2, const float* b2, const float* w, int K, const float* g3,
