@@ -113,3 +113,49 @@ def test_sensevoice_matches_oracle():
     safe = margins(ref["logits"]) > TOKEN_MARGIN
     assert np.array_equal(out.tokens[safe], ref["tokens"][safe])
     eng.close()
+
+
+def test_ragged_batch_with_pad_quirk(tiny_paraformer):
+    """Different lengths in one batch: short items are right-padded, every exact zero becomes -23.0258509*32768 (Q4) and
+    the padded frames are attended to because speech_lengths = T_max for all items (Q3)."""
+    cfg, w, eng = tiny_paraformer
+    pcm = [synth.make_pcm(20, 5.0), synth.make_pcm(21, 2.3), synth.make_pcm(22, 3.71), np.zeros(16000, np.float32)]
+    ref = sanm.paraformer_forward(_oracle_feats(pcm, cfg), w, dims_of(cfg))
+    out = eng.run_pcm(pcm, want_logits=True)
+    _compare(out, ref, cfg)
+
+
+def test_long_utterance_takes_the_streaming_attention_path(tiny_paraformer):
+    """T_lfr > 192 frames (11.5 s): the single-pass tcgen05 attention does not apply; FSMN kernel + streaming attention."""
+    cfg, w, eng = tiny_paraformer
+    pcm = [synth.make_pcm(30, 14.0), synth.make_pcm(31, 12.5)]
+    speech = _oracle_feats(pcm, cfg)
+    assert speech.shape[1] > 192
+    ref = sanm.paraformer_forward(speech, w, dims_of(cfg))
+    out = eng.run_pcm(pcm, want_logits=True)
+    assert np.abs(eng.tensor("enc") - ref["enc"]).max() < 1e-2
+    _compare(out, ref, cfg)
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (paraformer-large, 32 x 10 s), checked through size-independent properties: the step is
+    deterministic, ids are valid, and an utterance decodes to the same ids alone or inside the batch (equal lengths =>
+    no cross-utterance coupling) wherever the batch run's top-1/top-2 margin is not within rounding."""
+    cfg = synth.paraformer_large()
+    eng = Engine(cfg, synth.make_weights(cfg))
+    eng.set_cmvn(*synth.make_cmvn())
+    pcm = [synth.make_pcm(i, 10.0) for i in range(32)]
+    a = eng.run_pcm(pcm, want_logits=True)
+    b = eng.run_pcm(pcm)
+    assert a.feat_frames == 166 and a.tokens.shape[0] == 32
+    assert np.array_equal(a.tokens, b.tokens) and np.array_equal(a.token_num, b.token_num)
+    assert a.tokens.min() >= 0 and a.tokens.max() < cfg.vocab
+    assert (a.token_num <= a.tokens.shape[1]).all() and (a.token_num >= 1).all() and a.token_num.max() == a.tokens.shape[1]
+    assert np.allclose(np.exp(a.logits.astype(np.float64)).sum(-1), 1.0, atol=1e-3)        # log-softmax rows
+    sub = eng.run_pcm(pcm[:5], want_logits=True)
+    assert np.array_equal(sub.token_num, a.token_num[:5])
+    L = sub.tokens.shape[1]
+    safe = margins(a.logits[:5, :L]) > 0.1
+    assert safe.mean() > 0.8
+    assert np.array_equal(sub.tokens[safe], a.tokens[:5, :L][safe])
+    eng.close()
