@@ -1,6 +1,9 @@
-// Hand-written sm_100a GEMM (v2): persistent CTAs, TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring ->
-// tcgen05.mma (single issuing thread, fp32 accumulators double-buffered in TMEM) -> tcgen05.ld epilogue that
-// transposes through shared memory so every global load/store of the fused epilogue is a coalesced row segment.
+// Hand-written sm_100a GEMM: persistent CTAs, TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring ->
+// tcgen05.mma (single issuing thread, fp32 accumulators double-buffered in TMEM) -> asynchronous epilogue: tcgen05.ld
+// rows -> bias / ReLU / residual in registers -> swizzled staging boxes -> TMA store (the fp32 residual is TMA-prefetched
+// into the same boxes).  A smem-transposing epilogue with per-thread global accesses remains for the cases the TMA path
+// does not cover (two fp32 addends, unaligned pitches).  Optional variants: CTA-pair MMA (cta_group::2) and a fused
+// LayerNorm second pass across the CTAs of a cluster - both parity-green, both measured slower on this path.
 //
 // Replaces the MLAS GEMMs that OnnxRuntime runs for the reference at
 // /root/reference/AliParaformerAsr/OfflineProjOfParaformer.cs:68 (InferenceSession.Run).
@@ -79,22 +82,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // -> row-segment layout (fp32 out: 8 lanes x float4 per row, 4 rows per instruction; fp16 out: 4 lanes x 8 halfs per
 // row, 8 rows per instruction) -> bias / addends / ReLU -> 16-byte coalesced stores.  kAdds = number of fp32 tensors
 // added to the product (FSMN memory, residual); the adds of a chunk are all issued before the first use.
-// fp32 addend rows of one 32x32 chunk in the layout the fp32-output path consumes (lane: column group lane & 7, rows
-// (lane >> 3) + 4 * it): loaded one chunk ahead so their L2 latency overlaps the previous chunk's work.
-__device__ __forceinline__ void load_addend_chunk(float4 (&x)[8], const float* add, int ld, int lane, int row0, int col0, int M) {
-    const int jj = lane & 7, rsub = lane >> 3;
-    const float* p = add + static_cast<size_t>(row0 + rsub) * ld + col0 + jj * 4;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + it * 4 + rsub < M) x[it] = *reinterpret_cast<const float4*>(p + static_cast<size_t>(it) * 4 * ld);
-    }
-}
-
-template <bool kOutHalf, int kAdds, bool kPre = false>
+template <bool kOutHalf, int kAdds>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* stage, int lane, int row0, int col0,
-                                               int M, int N, const GemmEpi& e, bool vec_ok, const float* bias_t, int n0,
-                                               const float4* pre = nullptr) {
+                                               int M, int N, const GemmEpi& e, bool vec_ok, const float* bias_t, int n0) {
     float4* st4 = reinterpret_cast<float4*>(stage);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -153,8 +143,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], float* s
                 const bool ok = row0 + it * 4 + rsub < M;
                 x0[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                 x1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kPre) x0[it] = pre[it];
-                else if (kAdds > 0 && ok) x0[it] = *reinterpret_cast<const float4*>(e.add0 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add0 + col);
+                if (kAdds > 0 && ok) x0[it] = *reinterpret_cast<const float4*>(e.add0 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add0 + col);
                 if (kAdds > 1 && ok) x1[it] = *reinterpret_cast<const float4*>(e.add1 + static_cast<size_t>(row0 + it * 4 + rsub) * e.ld_add1 + col);
             }
 #pragma unroll
