@@ -60,6 +60,16 @@ class PfOnlineResult(C.Structure):
     ]
 
 
+class PfTextResult(C.Structure):
+    _fields_ = [
+        ("text", C.c_void_p), ("text_capacity", C.c_size_t), ("text_bytes", C.c_size_t),
+        ("text_len", C.c_int32), ("n_tokens", C.c_int32), ("n_timestamps", C.c_int32), ("reserved", C.c_int32),
+        ("tokens", C.c_void_p), ("tokens_capacity", C.c_size_t), ("tokens_bytes", C.c_size_t),
+        ("ts", C.POINTER(C.c_int32)), ("ts_capacity", C.c_size_t), ("ts_count", C.c_size_t),
+        ("ts_offsets", C.POINTER(C.c_int32)), ("ts_offsets_capacity", C.c_size_t),
+    ]
+
+
 class PfError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libpfasr error {code}: {message}")
@@ -105,6 +115,15 @@ SIGNATURES = {
     "pf_online_get_timings": (C.c_int32, [C.c_void_p, _F, C.c_int32]),
     "pf_online_get_launch_count": (C.c_int64, [C.c_void_p]),
     "pf_online_get_gemm_flops": (C.c_double, [C.c_void_p]),
+    "pf_tokens_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "pf_tokens_create_from_memory": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "pf_tokens_destroy": (C.c_int, [C.c_void_p]),
+    "pf_tokens_count": (C.c_int32, [C.c_void_p]),
+    "pf_tokens_get": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]),
+    "pf_timestamps_lfr6": (C.c_int, [_F, C.c_int32, _I, C.c_int32, C.c_float, C.c_float, _I, C.c_int32, _I]),
+    "pf_decode_offline": (C.c_int, [C.c_void_p, _I, C.c_int32, _I, C.c_int32, C.POINTER(PfTextResult)]),
+    "pf_decode_offline_result": (C.c_int, [C.c_void_p, C.POINTER(PfResult), C.c_int32, C.POINTER(PfTextResult)]),
+    "pf_decode_online": (C.c_int, [C.c_void_p, _I, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),
     "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),

@@ -50,8 +50,11 @@ def read_tokens(path: str) -> Optional[List[str]]:
     """Utils/PreloadHelper.cs:120-141 ``ReadTokens``: one token per line; empty path -> null."""
     if not path:
         return None
-    with open(path, "r", encoding="utf-8") as f:
-        return f.read().splitlines()
+    with open(path, "rb") as f:
+        lines = re.split(r"\r\n|\r|\n", f.read().decode("utf-8-sig"))   # File.ReadAllLines: CR / LF / CRLF, BOM dropped
+    if lines and lines[-1] == "":
+        lines.pop()
+    return lines
 
 
 def load_cmvn(path: str):
@@ -212,45 +215,7 @@ class OfflineStream:
     Dispose = dispose
 
 
-def time_stamp_lfr6_onnx(us_cif_peak, tokens, begin_time: float = 0.0, total_offset: float = -1.5) -> List[List[int]]:
-    """``OfflineRecognizer.time_stamp_lfr6_onnx`` (OfflineRecognizer.cs:200-302): host post-processing of the graph's
-    ``us_cif_peak`` row into [start_ms, end_ms] per emitted token (float32 arithmetic, as the C#)."""
-    f32 = np.float32
-    start_end_threshold, max_token_duration = 5, 30
-    time_rate = f32(f32(10.0) * 6 / 1000 / 3)                      # 3 times upsampled
-    us = np.asarray(us_cif_peak, dtype=np.float32)
-    num_frames = us.shape[0]
-    tokens = list(tokens)
-    if tokens and tokens[-1] == 2:
-        tokens = tokens[:-1]
-    fire_place = [f32(i + total_offset) for i in range(num_frames) if float(us[i]) > 1.0 - 1e-4]
-    ts_list: List[List[np.float32]] = []
-    new_char: List[bool] = []
-    if fire_place[0] > start_end_threshold:                         # begin silence
-        ts_list.append([f32(0.0), f32(fire_place[0] * time_rate)])
-        new_char.append(False)
-    for i in range(len(fire_place) - 1):
-        new_char.append(tokens[i] != 1)
-        if i == len(fire_place) - 2 or fire_place[i + 1] - fire_place[i] < max_token_duration:
-            ts_list.append([f32(fire_place[i] * time_rate), f32(fire_place[i + 1] * time_rate)])
-        else:
-            split = f32(fire_place[i] + max_token_duration)
-            ts_list.append([f32(fire_place[i] * time_rate), f32(split * time_rate)])
-            ts_list.append([f32(split * time_rate), f32(fire_place[i + 1] * time_rate)])
-            new_char.append(False)
-    if num_frames - fire_place[-1] > start_end_threshold:           # tail token and end silence
-        end = f32(f32(num_frames + fire_place[-1]) / 2)
-        ts_list[-1][1] = f32(end * time_rate)
-        ts_list.append([f32(end * time_rate), f32(f32(num_frames) * time_rate)])
-        new_char.append(False)
-    else:
-        ts_list[-1][1] = f32(f32(num_frames) * time_rate)
-    if begin_time > 0.0:
-        for t in ts_list:
-            t[0] = f32(t[0] + f32(begin_time) / f32(1000.0))
-            t[1] = f32(t[1] + f32(begin_time) / f32(1000.0))
-    new_char.append(True)
-    return [[int(f32(t[0] * f32(1000))), int(f32(t[1] * f32(1000)))] for c, t in zip(new_char, ts_list) if c]
+from .text import TokenTable, time_stamp_lfr6_onnx  # noqa: E402  (native post-processing, csrc/text.cu)
 
 
 def pad_sequence(feats: Sequence[np.ndarray]) -> np.ndarray:
@@ -265,9 +230,6 @@ def pad_sequence(feats: Sequence[np.ndarray]) -> np.ndarray:
     return out
 
 
-_CHINESE = re.compile(r"^[一-龥]+$")
-
-
 class OfflineRecognizer:
     """OfflineRecognizer.cs:23 — same constructor arguments; ``model_file_path`` is the PFW1 weight blob that replaces
     ``model.onnx``.  ``threads_num`` is accepted and ignored (it only set ORT inter-op threads, Q17)."""
@@ -280,6 +242,7 @@ class OfflineRecognizer:
         self._tokens = read_tokens(tokens_file_path)
         if not self._tokens:
             raise Exception("tokens invalid")                      # OfflineRecognizer.cs:30-33
+        self._token_table = TokenTable(path=tokens_file_path)      # the same file, held by libpfasr for DecodeMulti
         self._mvn_file_path = mvn_file_path
         self._engine = Engine(self._conf, weights if weights is not None else model_file_path, devices=devices)
         if mvn_file_path:
@@ -312,6 +275,7 @@ class OfflineRecognizer:
     def dispose(self) -> None:
         if not self._disposed:
             self._engine.close()
+            self._token_table.close()
             self._tokens = None
             self._disposed = True
 
@@ -354,55 +318,11 @@ class OfflineRecognizer:
                 s.timestamps.extend([[0, 0] for _ in s.tokens])     # 3-output models: {0,0} per token (:151)
             s.remove_chunk()
 
-    # -- OfflineRecognizer.DecodeMulti (OfflineRecognizer.cs:304-418)
+    # -- OfflineRecognizer.DecodeMulti (OfflineRecognizer.cs:304-418), native: pf_decode_offline (csrc/text.cu)
     def _decode_multi(self, streams: List[OfflineStream]) -> List[OfflineRecognizerResultEntity]:
         results = []
         for s in streams:
             ent = OfflineRecognizerResultEntity()
-            text = ""
-            last_token = ""
-            last_ts = None
-            for token, ts in zip(s.tokens, s.timestamps):
-                if token == 2:
-                    break
-                cur = self._tokens[token].split("\t")[0] if 0 <= token < len(self._tokens) else "<unk>"
-                if cur in ("</s>", "<s>", "<blank>", "<unk>"):
-                    continue
-                if _CHINESE.match(cur):
-                    text += cur
-                    ent.tokens.append(cur)
-                    ent.timestamps.append(ts)
-                    continue
-                text += "▁" + cur + "▁"
-                joined = last_token + "▁" + cur + "▁"
-                if joined.find("@@▁▁") > 0:
-                    cur_token = joined.replace("@@▁▁", "")
-                    cur_ts = ts if last_ts is None else list(last_ts) + list(ts)
-                    if ent.tokens:
-                        ent.tokens.pop()
-                        ent.timestamps.pop()
-                    ent.tokens.append(cur_token.replace("▁", ""))
-                    ent.timestamps.append(cur_ts)
-                    last_token, last_ts = cur_token, cur_ts
-                elif joined.count("▁") in (3, 5) and joined.find("▁▁▁") < 0:
-                    cur_token = joined.replace("▁▁", "")
-                    cur_ts = ts if last_ts is None else list(last_ts) + list(ts)
-                    if ent.tokens:
-                        ent.tokens.pop()
-                    ent.tokens.append(cur_token.replace("▁", ""))
-                    if ent.timestamps:
-                        ent.timestamps.pop()
-                    ent.timestamps.append(cur_ts)
-                    last_token, last_ts = cur_token, cur_ts
-                else:
-                    ent.tokens.append(cur.replace("▁", ""))
-                    ent.timestamps.append(ts)
-                    last_token, last_ts = "▁" + cur + "▁", ts
-            if text.find("@@▁▁") > 0 or text.find("▁▁▁") < 0:
-                text = text.replace("@@▁▁", "").replace("▁▁", " ").replace("@@", " ").replace("▁", " ")
-            else:
-                text = text.replace("▁▁▁", " ").replace("▁▁", "").replace("▁", "")
-            ent.text = text
-            ent.text_len = len(text)
+            ent.text, ent.text_len, ent.tokens, ent.timestamps = self._token_table.decode_offline(s.tokens, s.timestamps)
             results.append(ent)
         return results

@@ -11,7 +11,6 @@ the handle; this module keeps only what the reference's host keeps for the user:
 from __future__ import annotations
 
 import ctypes as C
-import re
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -20,10 +19,10 @@ import numpy as np
 from . import _lib
 from .engine import to_pf_config
 from .offline import ObjectDisposedError, load_cmvn, load_conf, read_tokens
+from .text import TokenTable
 from .synth import ModelConfig
 from .weights import pack
 
-_CHINESE = re.compile(r"^[一-龥]+$")
 
 
 @dataclass
@@ -178,6 +177,8 @@ class OnlineRecognizer:
         self._disposed = False
         self._conf = config if config is not None else load_conf(config_file_path)
         self._tokens = read_tokens(tokens_file_path)
+        # null when the path is empty: the reference then fails inside DecodeMulti (NullReferenceException)
+        self._token_table = TokenTable(path=tokens_file_path) if self._tokens else None
         self._engine = OnlineEngine(self._conf, weights if weights is not None else encoder_file_path, devices=devices,
                                     per_layer_cache=per_layer_cache)
         if mvn_file_path:
@@ -199,6 +200,8 @@ class OnlineRecognizer:
     def dispose(self) -> None:
         if not self._disposed:
             self._engine.close()
+            if self._token_table is not None:
+                self._token_table.close()
             self._disposed = True
 
     CreateOnlineStream = create_online_stream
@@ -217,18 +220,8 @@ class OnlineRecognizer:
         for i, s in enumerate(streams):
             s.tokens.extend(int(t) for t in out.new_tokens[i, : int(out.appended[i])])
 
-    # OnlineRecognizer.DecodeMulti (OnlineRecognizer.cs:403-436)
+    # OnlineRecognizer.DecodeMulti (OnlineRecognizer.cs:403-436), native: pf_decode_online (csrc/text.cu)
     def _decode_multi(self, streams: List[OnlineStream]) -> List[OnlineRecognizerResultEntity]:
-        results = []
-        for s in streams:
-            text = ""
-            for token in s.tokens:
-                if token == 2:
-                    break
-                cur = self._tokens[token] if self._tokens and 0 <= token < len(self._tokens) else "<unk>"
-                if cur in ("</s>", "<s>", "<blank>", "<unk>"):
-                    continue
-                text += cur if _CHINESE.match(cur) else "▁" + cur + "▁"
-            text = text.replace("@@▁▁", "").replace("@@▁", "").replace("▁▁", " ").replace("▁", "").lower()
-            results.append(OnlineRecognizerResultEntity(text=text))
-        return results
+        if self._token_table is None:
+            raise TypeError("tokens table is null")
+        return [OnlineRecognizerResultEntity(text=self._token_table.decode_online(s.tokens)) for s in streams]

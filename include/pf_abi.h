@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 3
+#define PF_ABI_VERSION 4
 
 typedef int32_t pf_status;
 enum {
@@ -208,6 +208,53 @@ pf_status pf_online_get_state(pf_online* h, int32_t stream_id, const char* name,
 int32_t pf_online_get_timings(pf_online* h, float* ms, int32_t capacity);
 int64_t pf_online_get_launch_count(pf_online* h);
 double pf_online_get_gemm_flops(pf_online* h);
+
+/* ================= host post-processing (consumer half of f1) =================
+ * Native equivalents of the string / timestamp loops that follow the graph in the reference, for callers that want the
+ * whole GetResults in one library.  Pure host code; UTF-8 in and out. */
+typedef struct pf_tokens pf_tokens;
+
+typedef struct pf_text_result {
+    char* text;                 /* caller buffer (may be NULL to query sizes): UTF-8, NUL-terminated on return */
+    size_t text_capacity;       /* bytes available in text */
+    size_t text_bytes;          /* out: bytes of the text, excluding the NUL */
+    int32_t text_len;           /* out: OfflineRecognizerResultEntity.TextLen = string.Length (UTF-16 code units) */
+    int32_t n_tokens;           /* out: entries of OfflineRecognizerResultEntity.Tokens */
+    int32_t n_timestamps;       /* out: entries of .Timestamps (equals n_tokens unless the Remove-by-value quirk fired) */
+    int32_t reserved;
+    char* tokens;               /* caller buffer or NULL: the merged tokens, each NUL-terminated, back to back */
+    size_t tokens_capacity;
+    size_t tokens_bytes;        /* out: bytes needed for tokens (terminators included) */
+    int32_t* ts;                /* caller buffer or NULL: all timestamp ints back to back (a merged token owns 2, 4, ... ) */
+    size_t ts_capacity;         /* int32 elements available in ts */
+    size_t ts_count;            /* out: int32 elements needed */
+    int32_t* ts_offsets;        /* caller buffer, required with ts: [n_timestamps + 1], entry i spans ts[off[i] .. off[i+1]) */
+    size_t ts_offsets_capacity;
+} pf_text_result;
+
+/* Utils/PreloadHelper.ReadTokens (PreloadHelper.cs:120-141): File.ReadAllLines of tokens.txt; an empty table is the
+ * reference's "invalid tokens file" (OfflineRecognizer.cs:30) -> PF_ERR_BAD_ARG */
+pf_status pf_tokens_create(const char* path, pf_tokens** out);
+pf_status pf_tokens_create_from_memory(const char* utf8, size_t bytes, pf_tokens** out);
+pf_status pf_tokens_destroy(pf_tokens* t);
+int32_t pf_tokens_count(const pf_tokens* t);
+/* copies line `id` (NUL-terminated, truncated to capacity), returns its byte length or -1 */
+int32_t pf_tokens_get(const pf_tokens* t, int32_t id, char* buf, size_t capacity);
+/* OfflineRecognizer.time_stamp_lfr6_onnx (OfflineRecognizer.cs:200-302): one us_cif_peak row + the picked ids ->
+ * [start_ms, end_ms] pairs.  out_pairs may be NULL to query n_pairs.  PF_ERR_SHAPE where the C# would throw. */
+pf_status pf_timestamps_lfr6(const float* us_cif_peak, int32_t num_frames, const int32_t* token_ids, int32_t n_ids,
+                             float begin_time, float total_offset, int32_t* out_pairs, int32_t capacity_pairs,
+                             int32_t* n_pairs);
+/* OfflineRecognizer.DecodeMulti for one stream (OfflineRecognizer.cs:304-418): ids + [n_timestamps][2] stamps (NULL =
+ * the {0,0} per id of the 3-output models) -> Text, Tokens, Timestamps.  PF_ERR_BAD_ARG with the required sizes filled
+ * in when a buffer is too small; PF_ERR_SHAPE for an id outside the table (IndexOutOfRangeException in the C#). */
+pf_status pf_decode_offline(const pf_tokens* t, const int32_t* token_ids, int32_t n_ids, const int32_t* timestamps,
+                            int32_t n_timestamps, pf_text_result* out);
+/* the same straight from a run: row `utt` of res->tokens, timestamps from res->us_cif_peak when the run produced it */
+pf_status pf_decode_offline_result(const pf_tokens* t, const pf_result* res, int32_t utt, pf_text_result* out);
+/* OnlineRecognizer.DecodeMulti for one stream (OnlineRecognizer.cs:403-436), lower-cased */
+pf_status pf_decode_online(const pf_tokens* t, const int32_t* token_ids, int32_t n_ids, char* text, size_t capacity,
+                           size_t* text_bytes);
 
 const char* pf_last_error(void);
 int32_t pf_abi_version(void);

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in pf_abi.h but not exported by libpfasr.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.pf_abi_version() == 3
+    assert lib.pf_abi_version() == 4
 
 
 def test_config_struct_layout():

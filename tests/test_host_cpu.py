@@ -56,7 +56,8 @@ def test_host_pad_sequence_equals_reference_padhelper():
 
 def test_decode_multi_text_rules():
     rec = offline.OfflineRecognizer.__new__(offline.OfflineRecognizer)
-    rec._tokens = ["<blank>", "<s>", "</s>", "你", "好", "hel@@", "lo", "world", "<unk>"]
+    from aliparaformerasr_b200.text import TokenTable
+    rec._token_table = TokenTable(lines=["<blank>", "<s>", "</s>", "你", "好", "hel@@", "lo", "world", "<unk>"])
     s = offline.OfflineStream.__new__(offline.OfflineStream)
     s.tokens = [3, 4, 5, 6, 7, 2, 3]
     s.timestamps = [[0, 0]] * 7
