@@ -60,6 +60,14 @@ class PfOnlineResult(C.Structure):
     ]
 
 
+PF_AUDIO_U8, PF_AUDIO_S16, PF_AUDIO_S24, PF_AUDIO_S32, PF_AUDIO_F32 = range(5)
+
+
+class PfAudio(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n_values", C.c_int64), ("format", C.c_int32), ("channels", C.c_int32),
+                ("sample_rate", C.c_int32), ("reserved", C.c_int32)]
+
+
 class PfTextResult(C.Structure):
     _fields_ = [
         ("text", C.c_void_p), ("text_capacity", C.c_size_t), ("text_bytes", C.c_size_t),
@@ -115,6 +123,10 @@ SIGNATURES = {
     "pf_online_get_timings": (C.c_int32, [C.c_void_p, _F, C.c_int32]),
     "pf_online_get_launch_count": (C.c_int64, [C.c_void_p]),
     "pf_online_get_gemm_flops": (C.c_double, [C.c_void_p]),
+    "pf_wav_parse": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(PfAudio)]),
+    "pf_audio_num_samples": (C.c_int64, [C.POINTER(PfAudio)]),
+    "pf_offline_run_audio": (C.c_int, [C.c_void_p, C.POINTER(PfAudio), C.c_int32, C.c_uint32, C.POINTER(PfResult)]),
+    "pf_dbg_audio_convert": (C.c_int, [C.POINTER(PfAudio), _F, C.c_int64, C.POINTER(C.c_int64)]),
     "pf_tokens_create": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "pf_tokens_create_from_memory": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "pf_tokens_destroy": (C.c_int, [C.c_void_p]),

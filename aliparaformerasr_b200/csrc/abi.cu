@@ -283,6 +283,23 @@ static void stage_pcm_all(OfflineHandle* h, const float* const* pcm, const int32
     h->staged = true;
 }
 
+static void stage_audio_all(OfflineHandle* h, const pf_audio* utts, int32_t B) {
+    if (!utts || B <= 0) throw StatusError{PF_ERR_BAD_ARG, "utterance table null or empty batch"};
+    std::vector<int32_t> nsamp(B);
+    int tmax = 0;
+    for (int b = 0; b < B; ++b) {
+        nsamp[b] = static_cast<int32_t>(audio_num_samples(utts[b]));
+        tmax = std::max(tmax, frontend_num_frames(nsamp[b], h->cfg.snip_edges != 0) / h->cfg.lfr_n);
+    }
+    const int n = static_cast<int>(h->devs.size());
+    split_batch(B, n, h->shard_begin, h->shard_count);
+    for (int i = 0; i < n; ++i)
+        if (h->shard_count[i] > 0)
+            h->devs[i]->stage_pcm(nullptr, nsamp.data() + h->shard_begin[i], h->shard_count[i], tmax, utts + h->shard_begin[i]);
+    h->B = B;
+    h->staged = true;
+}
+
 }  // namespace pf
 
 using namespace pf;
@@ -390,6 +407,18 @@ pf_status pf_offline_run_pcm(pf_offline* hh, const float* const* pcm, const int3
         std::lock_guard<std::mutex> g(h->mu);
         memset(out, 0, sizeof(*out));
         stage_pcm_all(h, pcm, nsamp, batch);
+        run_all(h, flags, out);
+    });
+}
+
+pf_status pf_offline_run_audio(pf_offline* hh, const pf_audio* utts, int32_t batch, uint32_t flags, pf_result* out) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
+        OfflineHandle* h = reinterpret_cast<OfflineHandle*>(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        memset(out, 0, sizeof(*out));
+        stage_audio_all(h, utts, batch);
         run_all(h, flags, out);
     });
 }

@@ -7,6 +7,7 @@
 #include "../../include/pf_abi.h"
 #include "attention.cuh"
 #include "common.cuh"
+#include "engine.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
 
@@ -51,6 +52,9 @@ pf_status guarded(F&& f) {
     try {
         f();
         return PF_OK;
+    } catch (const StatusError& e) {
+        set_last_error(e.what);
+        return e.code;
     } catch (const CudaError& e) {
         set_last_error(e.what);
         cudaGetLastError();
@@ -162,6 +166,32 @@ pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const 
             cudaEventDestroy(a);
             cudaEventDestroy(b);
         }
+    });
+}
+
+pf_status pf_dbg_audio_convert(const pf_audio* a, float* out, int64_t capacity, int64_t* n) {
+    return guarded([&] {
+        if (!a || !n) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
+        const long long ns = audio_num_samples(*a);
+        *n = ns;
+        if (ns == 0 || !out || capacity <= 0) return;
+        Scratch s;
+        const size_t nb = static_cast<size_t>(a->n_values) * audio_bytes_per_value(a->format);
+        unsigned char* raw = s.alloc<unsigned char>(nb + 16);
+        PF_CUDA(cudaMemcpy(raw, a->data, nb, cudaMemcpyHostToDevice));
+        const AudioItem item{0, a->n_values, a->format, a->channels, a->sample_rate, 0};
+        AudioItem* d_item = s.alloc<AudioItem>(1);
+        PF_CUDA(cudaMemcpy(d_item, &item, sizeof(item), cudaMemcpyHostToDevice));
+        const long long off = 0;
+        const int cnt = static_cast<int>(ns);
+        long long* d_off = s.alloc<long long>(1);
+        int* d_n = s.alloc<int>(1);
+        PF_CUDA(cudaMemcpy(d_off, &off, sizeof(off), cudaMemcpyHostToDevice));
+        PF_CUDA(cudaMemcpy(d_n, &cnt, sizeof(cnt), cudaMemcpyHostToDevice));
+        float* pcm = s.alloc<float>(static_cast<size_t>(ns));
+        audio_convert_launch(raw, d_item, pcm, d_off, d_n, 1, cnt, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        PF_CUDA(cudaMemcpy(out, pcm, static_cast<size_t>(std::min<long long>(ns, capacity)) * sizeof(float), cudaMemcpyDeviceToHost));
     });
 }
 

@@ -141,6 +141,9 @@ DeviceCtx::~DeviceCtx() {
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
     if (pcm_) cudaFree(pcm_);
+    if (raw_) cudaFree(raw_);
+    if (d_audio_) cudaFree(d_audio_);
+    if (h_audio_) cudaFreeHost(h_audio_);
     if (d_off_) cudaFree(d_off_);
     if (d_meta_) cudaFree(d_meta_);
     if (h_stage_) cudaFreeHost(h_stage_);
@@ -641,7 +644,7 @@ void DeviceCtx::finish_profile() {
 }
 
 // ------------------------------------------------------------------ staging
-void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr) {
+void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr, const pf_audio* audio) {
     PF_CUDA(cudaSetDevice(dev_));
     const bool sv = cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL;
     const int Tenc = tmax_lfr + (sv ? 4 : 0);
@@ -660,8 +663,33 @@ void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, 
     int* h_m = reinterpret_cast<int*>(h_off + 2 * B);
     size_t total = 0;
     int maxframes = 0;
+    int max_nsamp = 0;
     const int dim = cfg_.lfr_m * cfg_.n_mels;
+    AudioItem* h_items = nullptr;
+    if (audio) {
+        ensure_pinned(&h_audio_, &h_audio_bytes_, static_cast<size_t>(B) * sizeof(AudioItem));
+        h_items = static_cast<AudioItem*>(h_audio_);
+        if (B > audio_capB_) {
+            if (d_audio_) cudaFree(d_audio_);
+            d_audio_ = nullptr;
+            PF_CUDA(cudaMalloc(&d_audio_, static_cast<size_t>(B) * sizeof(AudioItem)));
+            audio_capB_ = B;
+        }
+        size_t raw_total = 0;
+        for (int b = 0; b < B; ++b) {
+            h_items[b] = AudioItem{static_cast<long long>(raw_total), audio[b].n_values, audio[b].format, audio[b].channels, audio[b].sample_rate, 0};
+            raw_total += static_cast<size_t>(audio[b].n_values) * audio_bytes_per_value(audio[b].format);
+            raw_total = (raw_total + 15) & ~static_cast<size_t>(15);
+        }
+        if (raw_total > raw_cap_) {
+            if (raw_) cudaFree(raw_);
+            raw_ = nullptr;
+            PF_CUDA(cudaMalloc(&raw_, std::max<size_t>(raw_total, 16)));
+            raw_cap_ = raw_total;
+        }
+    }
     for (int b = 0; b < B; ++b) {
+        max_nsamp = std::max(max_nsamp, nsamp[b]);
         h_off[b] = static_cast<long long>(total);
         h_off[B + b] = static_cast<long long>(b) * tmax_lfr * dim;
         const int nf = frontend_num_frames(nsamp[b], cfg_.snip_edges != 0);
@@ -682,6 +710,7 @@ void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, 
     ev0_armed_ = true;
     PF_CUDA(cudaMemcpyAsync(d_off_, h_off, static_cast<size_t>(B) * 2 * sizeof(long long), cudaMemcpyHostToDevice, stream_));
     PF_CUDA(cudaMemcpyAsync(d_meta_, h_m, static_cast<size_t>(B) * 3 * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    if (audio) PF_CUDA(cudaMemcpyAsync(d_audio_, h_items, static_cast<size_t>(B) * sizeof(AudioItem), cudaMemcpyHostToDevice, stream_));
     // PCM travels on a second stream in up to kCopyGroups groups of utterances; the compute stream waits per group, so the
     // front-end of group g runs while the copy engine still moves group g+1 (the encoder needs them all)
     PF_CUDA(cudaEventRecord(ev_compute_, stream_));                       // pcm_ may still be read by the previous run
@@ -690,11 +719,18 @@ void DeviceCtx::stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, 
     for (int g = 0; g < staged_groups_; ++g) {
         const int b0 = static_cast<int>(static_cast<long long>(B) * g / staged_groups_);
         const int b1 = static_cast<int>(static_cast<long long>(B) * (g + 1) / staged_groups_);
-        for (int b = b0; b < b1; ++b)
-            if (nsamp[b] > 0)
+        for (int b = b0; b < b1; ++b) {
+            if (audio) {
+                const size_t nb = static_cast<size_t>(audio[b].n_values) * audio_bytes_per_value(audio[b].format);
+                if (nb > 0) PF_CUDA(cudaMemcpyAsync(raw_ + h_items[b].raw_off, audio[b].data, nb, cudaMemcpyHostToDevice, copy_stream_));
+            } else if (nsamp[b] > 0) {
                 PF_CUDA(cudaMemcpyAsync(pcm_ + h_off[b], pcm[b], static_cast<size_t>(nsamp[b]) * sizeof(float), cudaMemcpyHostToDevice, copy_stream_));
+            }
+        }
         PF_CUDA(cudaEventRecord(ev_grp_[g], copy_stream_));
     }
+    staged_audio_ = audio != nullptr;
+    staged_max_nsamp_ = max_nsamp;
     staged_B_ = B;
     staged_T_ = tmax_lfr;
     staged_maxframes_ = maxframes;
@@ -1038,6 +1074,10 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
             const int b1 = static_cast<int>(static_cast<long long>(B) * (g + 1) / staged_groups_);
             PF_CUDA(cudaStreamWaitEvent(stream_, ev_grp_[g], 0));          // this group's PCM has landed
             if (T <= 0 || b1 <= b0) continue;
+            if (staged_audio_) {       // raw file samples -> float mono 16 kHz PCM (AudioHelper.GetFileSample), csrc/audio.cu
+                audio_convert_launch(raw_, d_audio_ + b0, pcm_, d_off_ + b0, d_meta_ + b0, b1 - b0, staged_max_nsamp_, stream_);
+                ++launches;
+            }
             FrontendLaunch a;
             a.tables = fe_tables_; a.pcm = pcm_; a.pcm_off = d_off_ + b0; a.nsamp = d_meta_ + b0; a.nframes = d_meta_ + B + b0;
             a.nlfr = d_meta_ + 2 * B + b0;

@@ -10,6 +10,7 @@
 
 #include "../../include/pf_abi.h"
 #include "attention.cuh"
+#include "audio.cuh"
 #include "common.cuh"
 #include "frontend.cuh"
 #include "gemm.cuh"
@@ -126,7 +127,9 @@ public:
     void set_hotwords(const int32_t* ids, int n);      // SeACo: [n, 10] padded ids -> bias rows + their K|V (n = 0 clears)
 
     // inputs
-    void stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr);
+    // audio != null: raw interleaved samples (pf_audio) travel instead of float PCM and are converted on the device;
+    // nsamp then holds the converted lengths (audio_num_samples)
+    void stage_pcm(const float* const* pcm, const int32_t* nsamp, int B, int tmax_lfr, const pf_audio* audio = nullptr);
     void stage_feats(const float* speech, int B, int T);
     // front-end only (single utterance); returns frames written
     int extract(const float* samples, int nsamp, float* out, int capacity_frames, bool raw_fbank);
@@ -276,6 +279,12 @@ private:
     void* h_stage_ = nullptr; size_t h_stage_bytes_ = 0;
     int staged_B_ = 0, staged_T_ = 0, staged_maxframes_ = 0;
     bool staged_is_pcm_ = false;
+    // staged raw audio (row f4): bytes as read from the file + one AudioItem per utterance
+    unsigned char* raw_ = nullptr; size_t raw_cap_ = 0;
+    AudioItem* d_audio_ = nullptr; int audio_capB_ = 0;
+    void* h_audio_ = nullptr; size_t h_audio_bytes_ = 0;
+    bool staged_audio_ = false;
+    int staged_max_nsamp_ = 0;
 
     // host results
     int* h_meta_ = nullptr;

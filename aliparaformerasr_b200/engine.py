@@ -151,6 +151,17 @@ class Engine:
         _lib.check(self._lib.pf_offline_run_pcm(self._handle(), ptrs, _lib.iptr(ns), len(arrs), flags, C.byref(res)))
         return self._collect(res, want_logits, want_cif_peak)
 
+    def run_audio(self, clips: Sequence["Audio"], want_logits: bool = False, want_cif_peak: bool = False,
+                  want_timestamps: bool = False) -> ModelOutput:
+        """GetFileSample + AddSamples + Forward on raw file samples (``audio.Audio``): conversion to float, the
+        stereo down-mix and the resample to 16 kHz run on the device (csrc/audio.cu)."""
+        table = (_lib.PfAudio * len(clips))(*[c.as_pf_audio() for c in clips])
+        flags = ((_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_CIF_PEAK if want_cif_peak else 0) |
+                 (_lib.PF_RUN_WANT_TIMESTAMPS if want_timestamps else 0))
+        res = _lib.PfResult()
+        _lib.check(self._lib.pf_offline_run_audio(self._handle(), table, len(clips), flags, C.byref(res)))
+        return self._collect(res, want_logits, want_cif_peak)
+
     def run_feats(self, speech: np.ndarray, want_logits: bool = False, want_cif_peak: bool = False,
                   want_timestamps: bool = False) -> ModelOutput:
         x = np.ascontiguousarray(speech, dtype=np.float32)

@@ -254,6 +254,19 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = BATCH * nsamp * 4 + BATCH * 28
+    # the same call fed with the file's own 16-bit samples (pf_offline_run_audio: conversion on the device, half the H2D)
+    from aliparaformerasr_b200 import _lib, audio as pf_audio
+    host16 = torch.empty((BATCH, nsamp), dtype=torch.int16).pin_memory()
+    host16.copy_((host * 32768.0).round().clamp(-32768, 32767).to(torch.int16))
+    clips = [pf_audio.Audio(host16[i].numpy(), _lib.PF_AUDIO_S16, 1, 16000) for i in range(BATCH)]
+    for _ in range(3):
+        eng.run_audio(clips)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run_audio(clips)
+    barrier()
+    e2e16_s = time.perf_counter() - t0
     d2h = int(out.tokens.size * 4 + BATCH * 4 + 16)
 
     # -------- roofline leg: one profiled step (per-launch CUDA events on the GEMM kernel)
@@ -292,7 +305,10 @@ def main():
                        "l2": "256 MB buffer written between timed steps (L2 flush); weights alone (0.43 GB) also exceed L2",
                        "parallelism": f"dp{world} (utterances sharded, weights replicated, no data-path collective)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "api": "pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids)"},
+                    "ms_per_step": e2e_ms / args.steps, "api": "pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids)",
+                    "s16_input": {"api": "pf_offline_run_audio (16-bit file samples, converted on the device; rank 0, no gather)",
+                                  "ms_per_step": e2e16_s * 1e3 / args.steps, "value": BATCH * SECONDS * args.steps / e2e16_s,
+                                  "h2d_bytes_per_step": BATCH * nsamp * 2 + BATCH * 52}},
             "gpu_launches": int(launches_per_step * args.steps * world),
             "launches_per_step": int(launches_per_step),
             "rtf": (total_ms / 1e3) / (audio_per_step * args.steps),

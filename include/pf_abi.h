@@ -209,6 +209,30 @@ int32_t pf_online_get_timings(pf_online* h, float* ms, int32_t capacity);
 int64_t pf_online_get_launch_count(pf_online* h);
 double pf_online_get_gemm_flops(pf_online* h);
 
+/* ================= audio ingestion =================
+ * Replaces AliParaformerAsr.Examples/Utils/AudioHelper.cs:12-32 (GetFileSample: NAudio AudioFileReader -> float) and
+ * :223-279 (Resample: stereo -> mono average, linear interpolation to 16 kHz).  The caller passes the file's raw sample
+ * bytes; conversion, down-mix and resampling run on the device in front of the fbank kernel, bit-identical to the C#.
+ * As in the reference, a 16 kHz file is passed through without down-mixing (AudioHelper.cs:27-30). */
+enum { PF_AUDIO_U8 = 0, PF_AUDIO_S16 = 1, PF_AUDIO_S24 = 2, PF_AUDIO_S32 = 3, PF_AUDIO_F32 = 4 };
+
+typedef struct pf_audio {
+    const void* data;        /* interleaved little-endian samples */
+    int64_t n_values;        /* frames * channels */
+    int32_t format;          /* PF_AUDIO_* */
+    int32_t channels;
+    int32_t sample_rate;
+    int32_t reserved;
+} pf_audio;
+
+/* locate the fmt / data chunks of a RIFF/WAVE image (PCM 8/16/24/32, IEEE float 32, WAVE_FORMAT_EXTENSIBLE);
+ * out->data points into `file`.  PF_ERR_UNSUPPORTED for other containers / codecs. */
+pf_status pf_wav_parse(const void* file, size_t bytes, pf_audio* out);
+/* samples GetFileSample would return for this audio (after the optional resample), -1 on invalid input */
+int64_t pf_audio_num_samples(const pf_audio* a);
+/* OfflineRecognizer.GetResults on a batch of files: GetFileSample + AddSamples + Forward in one call */
+pf_status pf_offline_run_audio(pf_offline* h, const pf_audio* utts, int32_t batch, uint32_t flags, pf_result* out);
+
 /* ================= host post-processing (consumer half of f1) =================
  * Native equivalents of the string / timestamp loops that follow the graph in the reference, for callers that want the
  * whole GetResults in one library.  Pure host code; UTF-8 in and out. */
@@ -267,6 +291,8 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
 /* x = A W^T + bias + resid (fp32) and LN(x) * gamma + beta (fp16) from the fused-LayerNorm GEMM epilogue */
 pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                          const float* resid, const float* gamma, const float* beta, float eps, float* out, float* out_ln);
+/* one utterance through the device audio converter: out receives min(capacity, n) samples, *n the converted length */
+pf_status pf_dbg_audio_convert(const pf_audio* a, float* out, int64_t capacity, int64_t* n);
 pf_status pf_dbg_layernorm(int32_t M, int32_t D, const float* x, const float* gamma, const float* beta, float eps,
                            float* out);
 pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats, float scale, const float* gamma,
