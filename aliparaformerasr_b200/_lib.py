@@ -92,6 +92,9 @@ _I = C.POINTER(C.c_int32)
 SIGNATURES = {
     "pf_offline_create": (C.c_int32, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.POINTER(C.c_void_p)]),
     "pf_offline_create_from_memory": (C.c_int32, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_offline_create_mt": (C.c_int, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_offline_create_from_memory_mt": (C.c_int, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_offline_lanes": (C.c_int32, [C.c_void_p]),
     "pf_offline_destroy": (C.c_int32, [C.c_void_p]),
     "pf_offline_set_cmvn": (C.c_int32, [C.c_void_p, _F, _F, C.c_int32]),
     "pf_offline_set_hotwords": (C.c_int32, [C.c_void_p, _I, C.c_int32]),
@@ -139,6 +142,7 @@ SIGNATURES = {
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),
     "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),
+    "pf_dbg_ffn_chain": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, _F, _F, _F, C.c_int32]),
     "pf_dbg_gemm_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, _F, C.c_float, _F, _F]),
     "pf_dbg_layernorm": (C.c_int32, [C.c_int32, C.c_int32, _F, _F, _F, C.c_float, _F]),
     "pf_dbg_embed_pe_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, C.c_float, _F, _F, C.c_float, _F]),

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libpfasr.so"
-SOURCES = ["gemm.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
+SOURCES = ["gemm.cu", "ffn_chain.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

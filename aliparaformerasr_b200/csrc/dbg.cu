@@ -117,6 +117,43 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
     });
 }
 
+pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* x, float* out, float* elapsed_ms, int32_t iters) {
+    return guarded([&] {
+        Scratch s;
+        static FfnChainScratch sc;               // test hook: legacy stream of the current device
+        if (!sc.flags) ffn_chain_scratch_create(sc);
+        if (!ffn_chain_supported(M, D, F, sc)) throw CudaError{"shape cannot run as a feed-forward chain"};
+        __half* da = s.up_half(a, static_cast<size_t>(M) * D);
+        __half* dw1 = s.up_half(w1, static_cast<size_t>(F) * D);
+        __half* dw2 = s.up_half(w2, static_cast<size_t>(D) * F);
+        float* db1 = s.up(b1, F);
+        float* db2 = s.up(b2, D);
+        float* dx = s.up(x, static_cast<size_t>(M) * D);
+        __half* h = s.alloc<__half>(static_cast<size_t>(M) * F);
+        FfnChainOp op;
+        ffn_chain_prepare(op, da, D, dw1, db1, h, F, dw2, db2, dx, D, M, D, F, sc);
+        ffn_chain_launch(op, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        PF_CUDA(cudaMemcpy(out, dx, static_cast<size_t>(M) * D * sizeof(float), cudaMemcpyDeviceToHost));
+        if (elapsed_ms && iters > 0) {
+            cudaEvent_t e0, e1;
+            PF_CUDA(cudaEventCreate(&e0));
+            PF_CUDA(cudaEventCreate(&e1));
+            for (int i = 0; i < 3; ++i) ffn_chain_launch(op, 0);
+            PF_CUDA(cudaEventRecord(e0, 0));
+            for (int i = 0; i < iters; ++i) ffn_chain_launch(op, 0);
+            PF_CUDA(cudaEventRecord(e1, 0));
+            PF_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            PF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            *elapsed_ms = ms / iters;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
+    });
+}
+
 pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, const float* resid,
                          const float* gamma, const float* beta, float eps, float* out, float* out_ln) {
     return guarded([&] {

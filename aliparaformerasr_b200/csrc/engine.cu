@@ -112,6 +112,7 @@ DeviceCtx::DeviceCtx(int dev, const pf_config& cfg) : dev_(dev), cfg_(cfg) {
     for (auto& e : ev_grp_) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     PF_CUDA(cudaEventCreateWithFlags(&ev_compute_, cudaEventDisableTiming));
     fe_tables_ = frontend_tables_create();
+    ffn_chain_scratch_create(chain_);
     // FunASR SinusoidalPositionEncoder: inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1)), float32 arithmetic
     const int half = cfg_.input_size / 2;
     std::vector<float> inv(half);
@@ -140,6 +141,7 @@ DeviceCtx::~DeviceCtx() {
     if (h_us) cudaFreeHost(h_us);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
+    ffn_chain_scratch_destroy(chain_);
     if (pcm_) cudaFree(pcm_);
     if (raw_) cudaFree(raw_);
     if (d_audio_) cudaFree(d_audio_);
@@ -498,6 +500,8 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
             lp.next_ln1_fused = true;
         }
         gemm_prepare(lp.ffn2, h16_, f, w.w_ffn2, f, M, d, f, e);
+        if (!lp.next_ln1_fused && ffn_chain_enabled() && ffn_chain_supported(M, d, f, chain_))
+            ffn_chain_prepare(lp.chain, a16_, d, w.w_ffn1, w.b_ffn1, h16_, f, w.w_ffn2, w.b_ffn2, x32_, d, M, d, f, chain_);
         plan.layers.push_back(lp);
     };
     for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], i + 1 < enc_.size() ? &enc_[i + 1] : nullptr);
@@ -587,6 +591,25 @@ void DeviceCtx::gemm(const GemmOp& op) {
     }
     ++launches;
     gemm_flops += pf::gemm_flops(op);
+}
+
+void DeviceCtx::ffn_chain(const FfnChainOp& op) {
+    if (profile_) {
+        // one row for both GEMMs: 2 M (2F) D flops = the sum of the two
+        ProfRec r{op.M, 2 * op.F, op.D, 256 + 1000 * 11, nullptr, nullptr, nullptr};
+        for (cudaEvent_t* e : {&r.a, &r.b}) {
+            if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
+            else PF_CUDA(cudaEventCreate(e));
+        }
+        PF_CUDA(cudaEventRecord(r.a, stream_));
+        ffn_chain_launch(op, stream_);
+        PF_CUDA(cudaEventRecord(r.b, stream_));
+        prof_.push_back(r);
+    } else {
+        ffn_chain_launch(op, stream_);
+    }
+    ++launches;
+    gemm_flops += ffn_chain_flops(op);
 }
 
 template <typename F>
@@ -820,8 +843,12 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
             if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
             ++launches;
         }
-        gemm(lp.ffn1);
-        gemm(lp.ffn2);
+        if (lp.chain.valid) {
+            ffn_chain(lp.chain);
+        } else {
+            gemm(lp.ffn1);
+            gemm(lp.ffn2);
+        }
     };
     size_t li = 0;
     // layer 0's norm1 is part of embed_pe_ln; later layers get it from the previous layer's FFN2 epilogue when fused

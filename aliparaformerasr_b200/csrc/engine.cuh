@@ -12,6 +12,7 @@
 #include "attention.cuh"
 #include "audio.cuh"
 #include "common.cuh"
+#include "ffn_chain.cuh"
 #include "frontend.cuh"
 #include "gemm.cuh"
 #include "online.cuh"
@@ -74,6 +75,7 @@ struct DecLayerW {
 
 struct EncLayerPlan {
     GemmOp qkv, out, ffn1, ffn2;
+    FfnChainOp chain;                // valid: ffn1 + ffn2 run as one persistent kernel (csrc/ffn_chain.cu)
     bool ln2_fused = false;          // norm2 is computed by the out-projection's epilogue
     bool next_ln1_fused = false;     // the next layer's norm1 is computed by this layer's FFN2 epilogue
 };
@@ -273,6 +275,8 @@ private:
     float* t32_ = nullptr; float* tn32_ = nullptr; __half* q16_ = nullptr; __half* ctxd16_ = nullptr;
     float* logits_ = nullptr; int* tokens_ = nullptr;
     int* prompt_ids_ = nullptr;
+    FfnChainScratch chain_;                  // dependency flags of the fused feed-forward kernel (this device's compute stream)
+    void ffn_chain(const FfnChainOp& op);
     // staged PCM
     float* pcm_ = nullptr; size_t pcm_cap_ = 0;
     long long* d_off_ = nullptr; int* d_meta_ = nullptr; int meta_capB_ = 0;   // per-utterance tables

@@ -55,5 +55,8 @@ double gemm_flops(const GemmOp& op);
 bool gemm_ln_fusable(int M, int N);
 // cuTensorMapEncodeTiled entry point (resolved through the runtime, no libcuda link dependency); throws if missing
 void* tensormap_encode_fn();
+// 2-D row-major tensor map (fp16 or fp32), box = [box_rows, box_bytes of columns], 128B (or 64B) swizzle
+void gemm_make_tmap(CUtensorMap* tm, const void* ptr, bool f32, int rows, int cols, int ld, int box_rows, int box_bytes = 128);
+int gemm_num_sms();
 
 }  // namespace pf

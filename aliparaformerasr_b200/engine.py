@@ -51,7 +51,7 @@ class Engine:
     """One ``pf_offline`` handle."""
 
     def __init__(self, cfg: ModelConfig, weights: Union[str, Dict[str, np.ndarray], np.ndarray],
-                 devices: Optional[Sequence[int]] = None):
+                 devices: Optional[Sequence[int]] = None, lanes: int = 1):
         self._lib = _lib.load()
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -61,12 +61,13 @@ class Engine:
         if devices is not None:
             dev_np = np.asarray(list(devices), dtype=np.int32)
             dev_arr, ndev = _lib.iptr(dev_np), len(dev_np)
+        # lanes > 1: calls from different host threads run concurrently on the GPU (pf_offline_create_mt)
         if isinstance(weights, str):
-            st = self._lib.pf_offline_create(C.byref(pcfg), weights.encode(), dev_arr, ndev, C.byref(self._h))
+            st = self._lib.pf_offline_create_mt(C.byref(pcfg), weights.encode(), dev_arr, ndev, int(lanes), C.byref(self._h))
         else:
             blob = pack(weights) if isinstance(weights, dict) else np.ascontiguousarray(weights, dtype=np.uint8)
-            st = self._lib.pf_offline_create_from_memory(C.byref(pcfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
-                                                         dev_arr, ndev, C.byref(self._h))
+            st = self._lib.pf_offline_create_from_memory_mt(C.byref(pcfg), blob.ctypes.data_as(C.c_void_p), blob.nbytes,
+                                                            dev_arr, ndev, int(lanes), C.byref(self._h))
         _lib.check(st)
 
     # -- lifecycle

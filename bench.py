@@ -7,10 +7,13 @@
 One "step" = one pass of the hot path over one batch: PCM -> fbank/LFR/CMVN -> SAN-M encoder -> CIF -> decoder ->
 log-softmax -> greedy ids (what OfflineRecognizer.GetResults does for 32 streams, OfflineRecognizer.cs:110-198).
 
-* value  : whole-job audio-s/s with the PCM already resident in HBM (pf_offline_run_staged), device-timed per step
-           with CUDA events on the engine's stream, L2 flushed between steps, max over ranks.
-* e2e    : the same metric through the public call a user makes (pf_offline_run_pcm) with pinned HOST buffers:
-           H2D of the PCM and D2H of the token ids are inside the timed region.
+* value  : whole-job audio-s/s with the PCM already resident in HBM (pf_offline_run_staged), device-timed with CUDA
+           events on the engine's streams, max over ranks.  --lanes L (default 3) keeps L batches in flight per GPU,
+           one host thread and one execution lane each (pf_offline_create_mt); the K steps are split over the lanes
+           and timed from the first lane's start to the last lane's end.  --lanes 1: one batch at a time, L2 flushed
+           between steps.
+* e2e    : the same metric through the public call a user makes (pf_offline_run_pcm) with pinned HOST buffers, from
+           the same L host threads: H2D of the PCM and D2H of the token ids are inside the timed region.
 * roofline: dominant kernel = the tcgen05 GEMM; achieved = algorithmic GEMM FLOPs / summed per-launch CUDA-event
            durations of one profiled step; peak = MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step).
 * cpu_baseline: the oracle (a port of the reference's CPU path; OnnxRuntime/dotnet are not available) on a bounded
@@ -144,6 +147,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3,
+                    help="batches in flight per GPU (pf_offline_create_mt): one host thread + one execution lane each")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
@@ -188,101 +193,145 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     weights = synth.make_weights(cfg)
-    eng = Engine(cfg, weights, devices=[local_rank])
+    L = max(1, min(args.lanes, 8))
+    eng = Engine(cfg, weights, devices=[local_rank], lanes=L)
     eng.set_cmvn(*synth.make_cmvn())
     nsamp = int(SECONDS * cfg.fs)
-    # pinned host PCM for this rank's shard (global utterance index = rank * BATCH + i)
-    host = torch.empty((BATCH, nsamp), dtype=torch.float32, pin_memory=True)
-    for i in range(BATCH):
-        host[i].copy_(torch.from_numpy(synth.make_pcm(rank * BATCH + i, SECONDS)))
-    pcm = [host[i].numpy() for i in range(BATCH)]
-    stream = torch.cuda.ExternalStream(eng.stream_ptr(0), device=local_rank)
+    # pinned host PCM: every lane works on its own batch (global utterance index = (rank * L + lane) * BATCH + i)
+    host = torch.empty((L, BATCH, nsamp), dtype=torch.float32, pin_memory=True)
+    for l in range(L):
+        for i in range(BATCH):
+            host[l, i].copy_(torch.from_numpy(synth.make_pcm((rank * L + l) * BATCH + i, SECONDS)))
+    pcm = [[host[l, i].numpy() for i in range(BATCH)] for l in range(L)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # 2x the 126 MB L2
-    tok_dev = torch.zeros((BATCH, 256), dtype=torch.int32, device="cuda")
+    steps_of = [args.steps // L + (1 if l < args.steps % L else 0) for l in range(L)]
+
+    # one long-lived host thread per lane: libpfasr binds a thread to a lane on its first call, so lane l's staging,
+    # warm-up and timed steps all come from worker l
+    import concurrent.futures as cf
+    pools = [cf.ThreadPoolExecutor(max_workers=1) for _ in range(L)]
+
+    def on_lanes(fn):
+        futs = [pools[l].submit(fn, l) for l in range(L)]
+        return [f.result() for f in futs]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def flush_l2():
-        with torch.cuda.stream(stream):
-            flush.zero_()
-
     # -------- value: inputs resident in HBM
-    eng.stage_pcm(pcm)
-    out = None
-    for _ in range(args.warmup):
-        out = eng.run_staged()
-    launches_per_step = eng.launch_count()
+    def lane_setup(l):
+        torch.cuda.set_device(local_rank)
+        eng.stage_pcm(pcm[l])
+        o = None
+        for _ in range(args.warmup):
+            o = eng.run_staged()
+        return o, eng.launch_count(), torch.cuda.ExternalStream(eng.stream_ptr(0), device=local_rank)
+
+    setup = on_lanes(lane_setup)
+    out = setup[0][0]
+    launches_per_step = setup[0][1]
+    streams = [x[2] for x in setup]
+
+    single = []                             # L == 1: per-step (start, end) events
+
+    def lane_resident(l):
+        st = streams[l]
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps_of[l]):
+            if L == 1:                      # one batch at a time: explicit L2 flush between steps, outside the step's events
+                with torch.cuda.stream(st):
+                    flush.zero_()
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                eng.run_staged()
+                b.record(st)
+                single.append((a, b))
+            else:
+                eng.run_staged()
+        e1.record(st)
+        return e0, e1
+
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
-    dev_ms = []
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush_l2()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        out = eng.run_staged()
-        e1.record(stream)
-        e1.synchronize()
-        dev_ms.append(e0.elapsed_time(e1))
+    evs = on_lanes(lane_resident)
     barrier()
     wall_resident = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(dev_ms)
-    stage_ms = eng.timings()
+    if L == 1:
+        total_ms = sum(a.elapsed_time(b) for a, b in single)
+    else:
+        # device time from the earliest lane start to the latest lane end (events of different streams share the device clock)
+        first = min(range(L), key=lambda l: evs[0][0].elapsed_time(evs[l][0]))
+        total_ms = max(evs[first][0].elapsed_time(evs[l][1]) for l in range(L))
+    stage_ms = pools[0].submit(eng.timings).result()
 
-    # -------- e2e: host PCM -> host token ids through the public call
-    def e2e_step():
-        o = eng.run_pcm(pcm)
-        if world > 1:   # C1: gather the ids on rank 0 (NCCL over NVLink), padded to a fixed width
-            tok_dev.zero_()
-            tok_dev[:, : o.tokens.shape[1]].copy_(torch.from_numpy(o.tokens), non_blocking=True)
-            gl = [torch.empty_like(tok_dev) for _ in range(world)] if rank == 0 else None
-            dist.gather(tok_dev, gl, dst=0)
+    # -------- e2e: host PCM -> host token ids through the public call, every lane fed by its own host thread
+    tok_host = [np.zeros((max(1, steps_of[l]), BATCH, 256), np.int32) for l in range(L)]
 
-    for _ in range(3):      # includes the first gather: NCCL builds its communicator lazily
-        e2e_step()
+    def lane_e2e(l, n=None):
+        for k in range(steps_of[l] if n is None else n):
+            o = eng.run_pcm(pcm[l])
+            tok_host[l][k % tok_host[l].shape[0], :, : o.tokens.shape[1]] = o.tokens
+        return None
+
+    def gather_ids():
+        if world > 1:   # C1: the ids of all timed steps reach rank 0 over NCCL (NVLink), one padded gather
+            t = torch.from_numpy(np.concatenate(tok_host, axis=0)).cuda(non_blocking=True)
+            gl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+            dist.gather(t, gl, dst=0)
+
+    on_lanes(lambda l: lane_e2e(l, 3))
+    gather_ids()            # includes the first gather: NCCL builds its communicator lazily
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    on_lanes(lane_e2e)
+    gather_ids()
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = BATCH * nsamp * 4 + BATCH * 28
+    d2h = int(out.tokens.size * 4 + BATCH * 4 + 16)
     # the same call fed with the file's own 16-bit samples (pf_offline_run_audio: conversion on the device, half the H2D)
     from aliparaformerasr_b200 import _lib, audio as pf_audio
-    host16 = torch.empty((BATCH, nsamp), dtype=torch.int16).pin_memory()
+    host16 = torch.empty((L, BATCH, nsamp), dtype=torch.int16).pin_memory()
     host16.copy_((host * 32768.0).round().clamp(-32768, 32767).to(torch.int16))
-    clips = [pf_audio.Audio(host16[i].numpy(), _lib.PF_AUDIO_S16, 1, 16000) for i in range(BATCH)]
-    for _ in range(3):
-        eng.run_audio(clips)
+    clips = [[pf_audio.Audio(host16[l, i].numpy(), _lib.PF_AUDIO_S16, 1, 16000) for i in range(BATCH)] for l in range(L)]
+
+    def lane_s16(l, n=None):
+        for _ in range(steps_of[l] if n is None else n):
+            eng.run_audio(clips[l])
+
+    on_lanes(lambda l: lane_s16(l, 3))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.run_audio(clips)
+    on_lanes(lane_s16)
     barrier()
     e2e16_s = time.perf_counter() - t0
-    d2h = int(out.tokens.size * 4 + BATCH * 4 + 16)
 
-    # -------- roofline leg: one profiled step (per-launch CUDA events on the GEMM kernel)
-    eng.set_profile(True)
-    eng.run_staged()
-    gemm_ms = eng.gemm_ms()
-    gemm_flops = eng.gemm_flops()
-    prof = [p for p in eng.profile() if p.get("name", "gemm") == "gemm"]
+    # -------- roofline leg: one profiled step on lane 0 (per-launch CUDA events on the GEMM kernel)
+    def lane_profile():
+        eng.set_profile(True)
+        eng.run_staged()
+        g_ms, g_fl = eng.gemm_ms(), eng.gemm_flops()
+        pr = [p for p in eng.profile() if p.get("name", "gemm") == "gemm"]
+        # in-situ (warm, stream-ordered, no PDL overlap) time of every kernel family of the layers
+        eng.set_profile(2)
+        eng.run_staged()
+        k_ms = {}
+        for p in eng.profile():
+            k_ms[p.get("name", "gemm")] = k_ms.get(p.get("name", "gemm"), 0.0) + p["ms"]
+        eng.set_profile(0)
+        return g_ms, g_fl, pr, k_ms
+
+    gemm_ms, gemm_flops, prof, kernel_ms = pools[0].submit(lane_profile).result()
     n_gemm = sum(p["launches"] for p in prof) or 1
-    # in-situ (warm, stream-ordered, no PDL overlap) time of every kernel family of the layers
-    eng.set_profile(2)
-    eng.run_staged()
-    kernel_ms = {}
-    for p in eng.profile():
-        kernel_ms[p.get("name", "gemm")] = kernel_ms.get(p.get("name", "gemm"), 0.0) + p["ms"]
-    eng.set_profile(0)
 
     # -------- reduce over ranks (max time)
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -302,10 +351,14 @@ def main():
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "audio_seconds_per_utt": SECONDS,
                        "T_lfr": int(out.feat_frames), "Lmax": int(out.tokens.shape[1]), "weights": "random-init paraformer-large (seed 20260917), fp16 operands / fp32 accumulate",
-                       "l2": "256 MB buffer written between timed steps (L2 flush); weights alone (0.43 GB) also exceed L2",
+                       "lanes": L,
+                       "l2": ("256 MB buffer written between timed steps (L2 flush); weights alone (0.43 GB) also exceed L2" if L == 1 else
+                              f"{L} batches in flight on {L} streams: every step streams its lane's 0.43 GB weight copy plus activations, "
+                              "far more than the 126 MB L2, so no explicit flush between the (overlapping) steps"),
                        "parallelism": f"dp{world} (utterances sharded, weights replicated, no data-path collective)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "api": "pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids)",
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": f"pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids), {L} host threads on {L} lanes",
                     "s16_input": {"api": "pf_offline_run_audio (16-bit file samples, converted on the device; rank 0, no gather)",
                                   "ms_per_step": e2e16_s * 1e3 / args.steps, "value": BATCH * SECONDS * args.steps / e2e16_s,
                                   "h2d_bytes_per_step": BATCH * nsamp * 2 + BATCH * 52}},
@@ -325,12 +378,14 @@ def main():
         }
         if not args.no_cpu_baseline:
             nb = max(1, min(args.cpu_sample, BATCH))
-            ts, cores = time_cpu(pcm[:nb], weights, cfg, 3, 1)
+            ts, cores = time_cpu(pcm[0][:nb], weights, cfg, 3, 1)
             sec = statistics.mean(ts)
             line["cpu_baseline"] = {"value": nb * SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{nb} of the {BATCH} utterances per pass, 1 warm-up + 3 timed passes; oracle port of the reference CPU path "
                                               f"(OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"}
         print(json.dumps(line))
+    for pl in pools:
+        pl.shutdown()
     eng.close()
     if world > 1:
         dist.barrier()

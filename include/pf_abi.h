@@ -111,6 +111,17 @@ pf_status pf_offline_create(const pf_config* cfg, const char* weights_path, cons
 pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes,
                                         const int32_t* devices, int32_t ndev, pf_offline** out);
 /* replaces IOfflineProj.Dispose / InferenceSession.Dispose (OfflineProjOfParaformer.cs:88-101) */
+/* Concurrent callers: the same handle with `lanes` (1..8) independent execution lanes (own streams, staging buffers,
+ * activations and weight copy per lane).  A host thread is bound to a lane on its first call; calls from different
+ * threads then overlap on the GPU (one batch's kernel tails, launch gaps and PCIe copies are filled with another
+ * batch's work).  Results returned to a thread stay valid until that thread's next call on the handle.  The plain
+ * create functions use one lane (or $PFASR_LANES).  Replaces nothing in the reference: OfflineRecognizer.GetResults
+ * may be called from several threads there too, and they queue on the one ORT session. */
+pf_status pf_offline_create_mt(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev,
+                               int32_t lanes, pf_offline** out);
+pf_status pf_offline_create_from_memory_mt(const pf_config* cfg, const void* blob, size_t blob_bytes, const int32_t* devices,
+                                           int32_t ndev, int32_t lanes, pf_offline** out);
+int32_t pf_offline_lanes(const pf_offline* h);
 pf_status pf_offline_destroy(pf_offline* h);
 
 /* SeACo hot words: replaces EmbedSeacoModel.Forward (EmbedSeacoModel.cs:70-108, model_eb.onnx = Embedding + 2-layer
@@ -289,6 +300,9 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
                       const float* resid, const float* addend, int32_t relu, int32_t out_half, int32_t tile_n,
                       float* out, float* elapsed_ms, int32_t iters);
 /* x = A W^T + bias + resid (fp32) and LN(x) * gamma + beta (fp16) from the fused-LayerNorm GEMM epilogue */
+/* x + relu(a W1^T + b1) W2^T + b2 through the fused feed-forward kernel (csrc/ffn_chain.cu); D, F multiples of 256 */
+pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* x, float* out, float* elapsed_ms, int32_t iters);
 pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                          const float* resid, const float* gamma, const float* beta, float eps, float* out, float* out_ln);
 /* one utterance through the device audio converter: out receives min(capacity, n) samples, *n the converted length */

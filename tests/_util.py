@@ -35,3 +35,14 @@ def dbg_gemm(lib, A, W, bias=None, resid=None, addend=None, relu=0, out_half=0, 
 def margins(logp):
     s = np.sort(logp, axis=-1)
     return s[..., -1] - s[..., -2]
+
+
+def dbg_ffn_chain(lib, a, w1, b1, w2, b2, x, iters=0):
+    M, D = a.shape
+    F = w1.shape[0]
+    out = np.zeros((M, D), dtype=np.float32)
+    ms = C.c_float(0)
+    a, w1, b1, w2, b2, x = (f(v) for v in (a, w1, b1, w2, b2, x))
+    _lib.check(lib.pf_dbg_ffn_chain(M, D, F, _lib.fptr(a), _lib.fptr(w1), _lib.fptr(b1), _lib.fptr(w2), _lib.fptr(b2), _lib.fptr(x),
+                                    _lib.fptr(out), C.byref(ms), iters))
+    return out, ms.value

@@ -7,7 +7,7 @@ import torch
 
 from aliparaformerasr_b200 import _lib
 from oracle import sanm
-from _util import dbg_gemm, f, half_round
+from _util import dbg_ffn_chain, dbg_gemm, f, half_round
 
 pytestmark = pytest.mark.gpu
 
@@ -72,6 +72,25 @@ def test_gemm_fused_layernorm(lib, M, N, K):
     assert np.abs(out - ref).max() < 2e-3
     ref_ln = torch.nn.functional.layer_norm(torch.from_numpy(out), (N,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
     assert np.abs(out_ln - ref_ln).max() < 6e-3      # fp16 output of O(1..4) values
+
+
+@pytest.mark.parametrize("M,D,F", [(5344, 512, 2048), (8768, 512, 2048), (1328, 512, 2048), (320, 512, 2048), (100, 512, 1024), (1, 256, 256),
+                                   (20000, 512, 2048)])
+def test_ffn_chain(lib, M, D, F):
+    """Feed-forward block as one persistent kernel (csrc/ffn_chain.cu): x + relu(a W1^T + b1) W2^T + b2 with the fp16
+    hidden activations handed from the first tile set to the second through flags.  Run twice: the flags carry an epoch."""
+    rng = np.random.default_rng(M + D + F)
+    a = rng.standard_normal((M, D)).astype(np.float32)
+    w1 = (rng.standard_normal((F, D)) / np.sqrt(D)).astype(np.float32)
+    b1 = (0.3 * rng.standard_normal(F)).astype(np.float32)
+    w2 = (rng.standard_normal((D, F)) / np.sqrt(F)).astype(np.float32)
+    b2 = (0.3 * rng.standard_normal(D)).astype(np.float32)
+    x = (rng.standard_normal((M, D)) * 2).astype(np.float32)
+    h = half_round(np.maximum(half_round(a) @ half_round(w1).T + b1, 0.0))
+    ref = x + h.astype(np.float64) @ half_round(w2).astype(np.float64).T + b2
+    for _ in range(2):
+        out, _ms = dbg_ffn_chain(lib, a, w1, b1, w2, b2, x)
+        assert np.abs(out - ref).max() < 4e-3
 
 
 @pytest.mark.parametrize("M,D", [(7, 512), (1000, 512), (333, 2048)])
