@@ -181,6 +181,10 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    # stdout carries exactly one JSON line: anything libraries print to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -383,7 +387,7 @@ def main():
             line["cpu_baseline"] = {"value": nb * SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{nb} of the {BATCH} utterances per pass, 1 warm-up + 3 timed passes; oracle port of the reference CPU path "
                                               f"(OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     for pl in pools:
         pl.shutdown()
     eng.close()
