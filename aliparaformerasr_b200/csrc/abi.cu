@@ -61,7 +61,8 @@ static void validate_config(const pf_config& c) {
 }
 
 template <typename Handle>
-static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev) {
+static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev,
+                               const Handle* share = nullptr) {
     if (!cfg || !blob) throw StatusError{PF_ERR_BAD_ARG, "null config or weights"};
     validate_config(*cfg);
     int count = 0;
@@ -82,9 +83,9 @@ static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t by
     b.parse(blob, bytes);
     std::unique_ptr<Handle> h(new Handle());
     h->cfg = *cfg;
-    for (int d : devs) {
-        std::unique_ptr<DeviceCtx> ctx(new DeviceCtx(d, *cfg));
-        ctx->load_weights(b);
+    for (size_t i = 0; i < devs.size(); ++i) {
+        std::unique_ptr<DeviceCtx> ctx(new DeviceCtx(devs[i], *cfg));
+        ctx->load_weights(b, share ? share->devs.at(i).get() : nullptr);     // lanes of one handle read the same device weights
         h->devs.push_back(std::move(ctx));
     }
     return h.release();
@@ -97,6 +98,7 @@ static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t by
 // reference serialises concurrent GetResults calls on the single ORT session's intra-op pool; results stay valid until
 // the calling thread's next call on the handle.
 struct OfflinePool {
+    ~OfflinePool() { while (!lanes.empty()) lanes.pop_back(); }     // lane 0 owns the device weights: it goes last
     std::vector<std::unique_ptr<OfflineHandle>> lanes;
     std::mutex mu;
     std::map<std::thread::id, int> lane_of_thread;
@@ -113,7 +115,8 @@ static int default_lanes() {
 static OfflinePool* create_pool(const pf_config* cfg, const void* blob, size_t bytes, const int32_t* devices, int32_t ndev, int lanes) {
     if (lanes < 1 || lanes > 8) throw StatusError{PF_ERR_BAD_ARG, "lanes must be in [1, 8]"};
     std::unique_ptr<OfflinePool> pool(new OfflinePool());
-    for (int l = 0; l < lanes; ++l) pool->lanes.emplace_back(create_handle_t<OfflineHandle>(cfg, blob, bytes, devices, ndev));
+    for (int l = 0; l < lanes; ++l)
+        pool->lanes.emplace_back(create_handle_t<OfflineHandle>(cfg, blob, bytes, devices, ndev, l ? pool->lanes[0].get() : nullptr));
     pool->cfg = *cfg;
     return pool.release();
 }

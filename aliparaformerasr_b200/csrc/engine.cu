@@ -183,6 +183,8 @@ T* DeviceCtx::dalloc(size_t n, std::vector<void*>& pool) {
 }
 
 float* DeviceCtx::up_f32(const float* host, size_t n) {
+    // a lane that shares another lane's weights walks that lane's upload log instead of uploading again
+    if (share_from_) return static_cast<float*>(share_from_->wpool_.at(share_idx_++));
     float* d = dalloc<float>(n, wpool_);
     PF_CUDA(cudaMemcpyAsync(d, host, n * sizeof(float), cudaMemcpyHostToDevice, stream_));
     PF_CUDA(cudaStreamSynchronize(stream_));   // host buffer may be a temporary
@@ -191,6 +193,7 @@ float* DeviceCtx::up_f32(const float* host, size_t n) {
 float* DeviceCtx::up_f32(const BlobEntry& e) { return up_f32(e.data, e.count); }
 
 __half* DeviceCtx::up_f16(const float* host, size_t n) {
+    if (share_from_) return static_cast<__half*>(share_from_->wpool_.at(share_idx_++));
     float* t = dalloc<float>(n, tmp_);
     PF_CUDA(cudaMemcpyAsync(t, host, n * sizeof(float), cudaMemcpyHostToDevice, stream_));
     __half* d = dalloc<__half>(n, wpool_);
@@ -249,8 +252,13 @@ void DeviceCtx::load_dec_ffn(const Blob& b, const std::string& p, DecFfnW& w, in
     w.w2 = up_f16(w2.data, w2.count);
 }
 
-void DeviceCtx::load_weights(const Blob& b) {
+void DeviceCtx::load_weights(const Blob& b, const DeviceCtx* share) {
     PF_CUDA(cudaSetDevice(dev_));
+    if (share && share->dev_ != dev_) throw StatusError{PF_ERR_BAD_ARG, "weights can only be shared with an owning context on the same device"};
+    wload_begin_ = wpool_.size();                 // the constructor's own uploads (PE table, default CMVN) come first
+    share_from_ = share;
+    share_idx_ = share ? share->wload_begin_ : 0;
+    struct Done { DeviceCtx* c; ~Done() { c->share_from_ = nullptr; } } done{this};   // later uploads (CMVN, hot words) are this lane's own
     const int d = cfg_.d_model;
     enc_.resize(cfg_.enc_layers);
     load_enc_layer(b, "encoder.encoders0.0", cfg_.input_size, enc_[0]);

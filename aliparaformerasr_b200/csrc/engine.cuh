@@ -124,7 +124,8 @@ class DeviceCtx {
 public:
     DeviceCtx(int dev, const pf_config& cfg);
     ~DeviceCtx();
-    void load_weights(const Blob& blob);
+    // share == another context on the same device that already loaded this blob: reuse its device weights (read-only)
+    void load_weights(const Blob& blob, const DeviceCtx* share = nullptr);
     void set_cmvn(const float* shift, const float* scale, int dim);
     void set_hotwords(const int32_t* ids, int n);      // SeACo: [n, 10] padded ids -> bias rows + their K|V (n = 0 clears)
 
@@ -223,7 +224,8 @@ private:
     cudaEvent_t ev_grp_[kCopyGroups] = {};
     cudaEvent_t ev_compute_ = nullptr;
     int staged_groups_ = 0;
-    std::vector<void*> wpool_, apool_;
+    std::vector<void*> wpool_, apool_;      // wpool_: every weight upload, in load order
+    const DeviceCtx* share_from_ = nullptr; size_t share_idx_ = 0, wload_begin_ = 0;
     std::vector<void*> tmp_;           // upload staging, freed after load
 
     // weights
