@@ -118,6 +118,9 @@ static OfflinePool* create_pool(const pf_config* cfg, const void* blob, size_t b
     for (int l = 0; l < lanes; ++l)
         pool->lanes.emplace_back(create_handle_t<OfflineHandle>(cfg, blob, bytes, devices, ndev, l ? pool->lanes[0].get() : nullptr));
     pool->cfg = *cfg;
+    if (lanes > 1)
+        for (auto& lane : pool->lanes)
+            for (auto& d : lane->devs) d->throughput_mode = true;
     return pool.release();
 }
 

@@ -483,6 +483,7 @@ void DeviceCtx::ensure_host(size_t tokens, size_t logits, size_t peaks) {
 
 // ------------------------------------------------------------------ plans (TMA descriptors are baked per shape)
 EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
+    gemm_set_policy(throughput_mode);
     auto key = std::make_pair(B, T);
     auto it = enc_plans_.find(key);
     if (it != enc_plans_.end()) return it->second;
@@ -527,6 +528,7 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
 }
 
 DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
+    gemm_set_policy(throughput_mode);
     if (dec_plan_T_ != T) { dec_plans_.clear(); dec_plan_T_ = T; }
     auto key = std::make_pair(B, L);
     auto it = dec_plans_.find(key);

@@ -126,6 +126,7 @@ public:
     ~DeviceCtx();
     // share == another context on the same device that already loaded this blob: reuse its device weights (read-only)
     void load_weights(const Blob& blob, const DeviceCtx* share = nullptr);
+    bool throughput_mode = false;    // several lanes share this device: GEMM tiles are picked for least SM time, not shortest kernel
     void set_cmvn(const float* shift, const float* scale, int dim);
     void set_hotwords(const int32_t* ids, int n);      // SeACo: [n, 10] padded ids -> bias rows + their K|V (n = 0 clears)
 

@@ -606,7 +606,10 @@ struct Launcher {
         const int tiles_n = ceil_div(op.N, op.bn);
         const int num_tiles = tiles_n * ceil_div(op.M, BM * CS);
         // fused LayerNorm: one tile per CTA, the column tiles of a row tile form a cluster
-        const int grid = kLn ? num_tiles : std::min(num_tiles, max_units) * CS;
+        // persistent grid, balanced: with r = ceil(tiles / SMs) rounds, ceil(tiles / r) CTAs finish at the same time as a
+        // full grid would, and the SMs left over start the next kernel (PDL) or another lane's CTAs
+        const int rounds = ceil_div(num_tiles, max_units);     // (more rounds on fewer CTAs measured slower, also with lanes)
+        const int grid = kLn ? num_tiles : ceil_div(num_tiles, rounds) * CS;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kThreads);
@@ -661,6 +664,12 @@ bool pair_enabled() {
 // and the kernel costs waves(bn) * t_wave.  What it captures: M = 5312 is 41.5 row tiles, so the number of waves jumps
 // with the column-tile count - 224-wide tiles cover N = 1536 / 2048 in 294 / 420 tiles (2 / 3 waves of 0.875-size tiles)
 // where 256-wide ones need 252 / 336 tiles (2 / 3 waves of full-size tiles), and N = 512 fits one wave at 192.
+// Two objectives.  Latency (one batch at a time): kernel time = waves x t_wave.  Throughput (several batches in flight,
+// execution lanes): other work fills idle SMs, so what counts is the SM time a launch occupies = CTAs x fixed cost
+// (launch, prologue, first loads, exposed last epilogue, ~3 us) + tiles x t_tile - e.g. N = 512, K = 2048 prefers 84 full
+// 256-wide tiles (1460 SM-us) over one wave of 126 192-wide ones (1890 SM-us).
+thread_local int g_policy = 0;      // 0 latency, 1 throughput
+
 void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
     const int mt = ceil_div(M, BM), kb = ceil_div(K, BK), sms = num_sms();
     cn_out = 1;
@@ -671,7 +680,7 @@ void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
             const int tiles = ceil_div(mt, cm) * ceil_div(N, bn);
             const int waves = ceil_div(tiles, sms / cm);
             const double t_wave = 0.3 + 0.004 * bn + kb * (0.13 + 0.0011 * bn) + (cm > 1 ? 0.1 * kb : 0.0);
-            const double cost = waves * t_wave;
+            const double cost = g_policy == 1 ? cm * (std::min(tiles, sms / cm) * 3.0 + tiles * t_wave) : waves * t_wave;
             if (cost < best_cost) { best_cost = cost; bn_out = bn; cm_out = cm; }
         }
     }
@@ -680,6 +689,10 @@ void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
 }  // namespace
 
 void* tensormap_encode_fn() { return reinterpret_cast<void*>(get_encode_fn()); }
+void gemm_set_policy(int throughput) {
+    static const int forced = [] { const char* e = getenv("PFASR_GEMM_POLICY"); return e ? (*e == 't' ? 1 : 0) : -1; }();
+    g_policy = forced >= 0 ? forced : (throughput ? 1 : 0);
+}
 void gemm_make_tmap(CUtensorMap* tm, const void* ptr, bool f32, int rows, int cols, int ld, int box_rows, int box_bytes) {
     make_tmap_any(tm, ptr, f32, rows, cols, ld, box_rows, box_bytes);
 }
@@ -707,6 +720,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and the 2x1 CTA pair are instantiated)"};
     if (cm == 2 && bn % 64 != 0) throw CudaError{"gemm: the CTA-pair MMA needs an N tile that is a multiple of 64"};
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
+    op.throughput = g_policy;
     // the kernel adds up to two fp32 tensors in a fixed order: FSMN memory first, then the residual
     op.n_adds = 0;
     op.epi.add0 = op.epi.add1 = nullptr;

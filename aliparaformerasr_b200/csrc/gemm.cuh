@@ -41,6 +41,7 @@ struct GemmOp {
     int M = 0, N = 0, K = 0;
     int bn = 128;    // N tile: 64, 128 or 256
     int cm = 1, cn = 1;   // cm = 2: CTA pair (cluster of 2 along M) driving cta_group::2 MMAs on a 256 x bn tile; cn is always 1
+    int throughput = 0;   // prepared under the throughput objective (gemm_set_policy)
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
     int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
@@ -50,6 +51,9 @@ struct GemmOp {
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
+// tile-selection objective of the ops this thread prepares from now on: 0 = shortest kernel (one batch at a time),
+// 1 = least SM time (several batches in flight); PFASR_GEMM_POLICY=latency|throughput overrides
+void gemm_set_policy(int throughput);
 double gemm_flops(const GemmOp& op);
 // can a [M, N] fp32 + residual GEMM carry the fused LayerNorm epilogue (row inside one cluster, one wave)?
 bool gemm_ln_fusable(int M, int N);
