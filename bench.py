@@ -93,8 +93,8 @@ class ClockSampler:
 
 def _gemm_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/gemm_traffic_r01.json: launch-weighted mean over the four GEMMs of an encoder layer)."""
-    path = os.path.join(ROOT, "profiles", "gemm_traffic_r01.json")
+    (profiles/gemm_traffic_r01_v11.json: launch-weighted mean over the four GEMMs of an encoder layer)."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic_r01_v11.json")
     try:
         return int(json.load(open(path))["avg_dram_bytes_per_launch"])
     except Exception:
@@ -372,7 +372,7 @@ def main():
             "stage_ms": stage_ms,
             "kernel_ms_profiled_step": kernel_ms,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r01.json)",
+                         "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r01_v11.json)",
                          "kernel": "pf_gemm_f16_tn_tcgen05", "peak_source": peak_src,
                          "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
                          "gemm_share_of_step": gemm_ms / (total_ms / args.steps) if total_ms else None,
