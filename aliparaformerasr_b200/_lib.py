@@ -98,6 +98,7 @@ SIGNATURES = {
     "pf_offline_destroy": (C.c_int32, [C.c_void_p]),
     "pf_offline_set_cmvn": (C.c_int32, [C.c_void_p, _F, _F, C.c_int32]),
     "pf_offline_set_hotwords": (C.c_int32, [C.c_void_p, _I, C.c_int32]),
+    "pf_offline_set_hotwords_local": (C.c_int32, [C.c_void_p, _I, C.c_int32]),
     "pf_frontend_extract": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
     "pf_frontend_fbank": (C.c_int32, [C.c_void_p, _F, C.c_int32, _F, C.c_int32, _I]),
     "pf_frontend_num_frames": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -131,6 +131,7 @@ static OfflineHandle* lane_of(pf_offline* hh) {
     std::lock_guard<std::mutex> g(pool->mu);
     auto it = pool->lane_of_thread.find(std::this_thread::get_id());
     if (it == pool->lane_of_thread.end()) {
+        if (pool->lane_of_thread.size() > 4096) pool->lane_of_thread.clear();    // thread-per-request callers: forget exited threads
         it = pool->lane_of_thread.emplace(std::this_thread::get_id(), pool->next).first;
         pool->next = (pool->next + 1) % static_cast<int>(pool->lanes.size());
     }
@@ -422,6 +423,16 @@ pf_status pf_offline_set_hotwords(pf_offline* hh, const int32_t* ids, int32_t n)
             std::lock_guard<std::mutex> g(h->mu);
             for (auto& d : h->devs) d->set_hotwords(ids, n);
         }
+    });
+}
+
+pf_status pf_offline_set_hotwords_local(pf_offline* hh, const int32_t* ids, int32_t n) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        if (n < 0 || (n > 0 && !ids)) throw StatusError{PF_ERR_BAD_ARG, "ids is null"};
+        OfflineHandle* h = lane_of(hh);
+        std::lock_guard<std::mutex> g(h->mu);
+        for (auto& d : h->devs) d->set_hotwords(ids, n);
     });
 }
 

@@ -92,14 +92,16 @@ class Engine:
         b = np.ascontiguousarray(rescale, dtype=np.float32)
         _lib.check(self._lib.pf_offline_set_cmvn(self._handle(), _lib.fptr(a), _lib.fptr(b), a.shape[0]))
 
-    def set_hotwords(self, hotwords: Sequence[Sequence[int]]) -> None:
+    def set_hotwords(self, hotwords: Sequence[Sequence[int]], local: bool = False) -> None:
         """``EmbedSeacoModel.Forward`` + the Q8 bias_embed assembly; ``hotwords`` = id lists (PadList applied here:
         truncate to 10, pad with 0, EmbedSeacoModel.cs:110-123).  Empty list clears them."""
         ids = np.zeros((len(hotwords), 10), dtype=np.int32)
         for i, h in enumerate(hotwords):
             h = list(h)[:10]
             ids[i, : len(h)] = h
-        _lib.check(self._lib.pf_offline_set_hotwords(self._handle(), _lib.iptr(ids) if len(hotwords) else None, len(hotwords)))
+        # local: only the calling thread's execution lane (per-call hot words while other threads use the handle)
+        fn = self._lib.pf_offline_set_hotwords_local if local else self._lib.pf_offline_set_hotwords
+        _lib.check(fn(self._handle(), _lib.iptr(ids) if len(hotwords) else None, len(hotwords)))
 
     # -- front-end only (OfflineStream.AddSamples)
     def num_frames(self, nsamp: int) -> int:

@@ -232,11 +232,12 @@ def pad_sequence(feats: Sequence[np.ndarray]) -> np.ndarray:
 
 class OfflineRecognizer:
     """OfflineRecognizer.cs:23 — same constructor arguments; ``model_file_path`` is the PFW1 weight blob that replaces
-    ``model.onnx``.  ``threads_num`` is accepted and ignored (it only set ORT inter-op threads, Q17)."""
+    ``model.onnx``.  ``threads_num`` is accepted and ignored (it only set ORT inter-op threads, Q17).  ``lanes`` > 1 lets
+    ``get_results`` calls from different host threads run concurrently on the GPU (pf_offline_create_mt)."""
 
     def __init__(self, model_file_path: str, config_file_path: str, mvn_file_path: str, tokens_file_path: str,
                  modeleb_file_path: str = "", hotword_file_path: str = "", batch_size: int = 1, threads_num: int = 1,
-                 devices: Optional[Sequence[int]] = None, weights=None, config: Optional[ModelConfig] = None):
+                 devices: Optional[Sequence[int]] = None, weights=None, config: Optional[ModelConfig] = None, lanes: int = 1):
         self._disposed = False
         self._conf = config if config is not None else load_conf(config_file_path)
         self._tokens = read_tokens(tokens_file_path)
@@ -244,7 +245,7 @@ class OfflineRecognizer:
             raise Exception("tokens invalid")                      # OfflineRecognizer.cs:30-33
         self._token_table = TokenTable(path=tokens_file_path)      # the same file, held by libpfasr for DecodeMulti
         self._mvn_file_path = mvn_file_path
-        self._engine = Engine(self._conf, weights if weights is not None else model_file_path, devices=devices)
+        self._engine = Engine(self._conf, weights if weights is not None else model_file_path, devices=devices, lanes=lanes)
         if mvn_file_path:
             shift, scale = load_cmvn(mvn_file_path)
             self._engine.set_cmvn(shift, scale)
@@ -295,7 +296,7 @@ class OfflineRecognizer:
         call_hotwords = [list(h) for s in streams for h in (s.hotwords or [])] if self._seaco else []
         try:
             if call_hotwords:
-                self._engine.set_hotwords(call_hotwords)
+                self._engine.set_hotwords(call_hotwords, local=True)
             want_ts = bool(getattr(self._conf, "timestamps", False))      # 4-output models (OfflineProjOfParaformer.cs:75-79)
             if all(len(s._chunks) == 1 for s in streams):
                 # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
@@ -309,7 +310,7 @@ class OfflineRecognizer:
             raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
         finally:
             if call_hotwords:
-                self._engine.set_hotwords(self._hotwords)
+                self._engine.set_hotwords(self._hotwords, local=True)
         for i, s in enumerate(streams):
             s.tokens = [int(t) for t in out.tokens[i]]
             if out.us_cif_peak is not None:                         # cif_peak_tensor != null (OfflineRecognizer.cs:172-183)

@@ -49,7 +49,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (every 25 ms)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -60,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -268,7 +268,6 @@ def main():
     evs = on_lanes(lane_resident)
     barrier()
     wall_resident = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
     if L == 1:
         total_ms = sum(a.elapsed_time(b) for a, b in single)
     else:
@@ -318,6 +317,7 @@ def main():
     on_lanes(lane_s16)
     barrier()
     e2e16_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None       # sampled across the three timed loops (resident, e2e, e2e 16-bit)
 
     # -------- roofline leg: one profiled step on lane 0 (per-launch CUDA events on the GEMM kernel)
     def lane_profile():

@@ -129,6 +129,9 @@ pf_status pf_offline_destroy(pf_offline* h);
  * Q8).  ids: [n, 10] int32, already truncated / zero padded as EmbedSeacoModel.PadList does (:110-123).  n = 0 clears
  * the hot words (the bias branch is skipped).  Valid for PF_MODEL_SEACO_PARAFORMER handles only. */
 pf_status pf_offline_set_hotwords(pf_offline* h, const int32_t* ids, int32_t n);
+/* the same for the calling thread's execution lane only: per-call hot words of the streams in one GetResults
+ * (OfflineProjOfSeacoParaformer.cs:51-60) when several threads share the handle */
+pf_status pf_offline_set_hotwords_local(pf_offline* h, const int32_t* hotword_ids, int32_t n_hotwords);
 
 /* am.mvn vectors parsed by WavFrontend.LoadCmvn (WavFrontend.cs:112-153): <AddShift> and <Rescale>, dim = 560 */
 pf_status pf_offline_set_cmvn(pf_offline* h, const float* add_shift, const float* rescale, int32_t dim);
