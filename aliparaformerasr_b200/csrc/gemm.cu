@@ -617,7 +617,7 @@ struct Launcher {
         cfg.stream = stream;
         cudaLaunchAttribute at[2];
         int na = 0;
-        if (pdl_enabled()) {
+        if (pdl_enabled()) {      // (GEMMs without PDL: 4.18 vs 3.82 ms/step with three lanes - early residency is worth it)
             at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[na].val.programmaticStreamSerializationAllowed = 1;
             ++na;
