@@ -112,6 +112,7 @@ SIGNATURES = {
     "pf_offline_get_gemm_flops": (C.c_double, [C.c_void_p]),
     "pf_offline_set_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pf_offline_get_gemm_ms": (C.c_double, [C.c_void_p]),
+    "pf_offline_replay_gemms": (C.c_double, [C.c_void_p, C.c_int32]),
     "pf_offline_get_profile_json": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int32]),
     "pf_offline_get_stream": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "pf_online_create": (C.c_int32, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.POINTER(C.c_void_p)]),

@@ -574,6 +574,17 @@ double pf_offline_get_gemm_ms(pf_offline* hh) {
     return lane_of(hh)->devs[0]->gemm_ms;
 }
 
+double pf_offline_replay_gemms(pf_offline* hh, int32_t iters) {
+    if (!hh) return 0;
+    OfflineHandle* h = lane_of(hh);
+    std::lock_guard<std::mutex> g(h->mu);
+    try {
+        return h->devs[0]->replay_gemms(iters);
+    } catch (...) {
+        return 0;
+    }
+}
+
 int32_t pf_offline_get_profile_json(pf_offline* hh, char* buf, int32_t capacity) {
     if (!hh || !buf || capacity <= 0) return 0;
     const std::string& js = lane_of(hh)->devs[0]->profile_json;

@@ -585,7 +585,27 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
     return dec_plans_.emplace(key, std::move(plan)).first->second;
 }
 
+double DeviceCtx::replay_gemms(int iters) {
+    PF_CUDA(cudaSetDevice(dev_));
+    if (replay_.empty() || iters <= 0) return 0.0;
+    cudaEvent_t a, b;
+    PF_CUDA(cudaEventCreate(&a));
+    PF_CUDA(cudaEventCreate(&b));
+    for (const GemmOp& op : replay_) gemm_launch(op, stream_);            // warm pass
+    PF_CUDA(cudaEventRecord(a, stream_));
+    for (int i = 0; i < iters; ++i)
+        for (const GemmOp& op : replay_) gemm_launch(op, stream_);
+    PF_CUDA(cudaEventRecord(b, stream_));
+    PF_CUDA(cudaEventSynchronize(b));
+    float ms = 0.0f;
+    PF_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return ms / iters;
+}
+
 void DeviceCtx::gemm(const GemmOp& op) {
+    if (profile_ == 1) replay_.push_back(op);
     if (profile_) {
         ProfRec r{op.M, op.N, op.K, op.bn + 1000 * (op.cm * 10 + op.cn), nullptr, nullptr, nullptr};
         for (cudaEvent_t* e : {&r.a, &r.b}) {
@@ -1082,6 +1102,7 @@ void DeviceCtx::set_hotwords(const int32_t* ids, int n) {
 
 void DeviceCtx::run(uint32_t flags, SharedRun* shared, int idx) {
     arrived_ = false;
+    if (profile_ == 1) replay_.clear();
     try {
         run_impl(flags, shared, idx);
     } catch (...) {

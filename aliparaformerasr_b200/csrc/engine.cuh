@@ -157,6 +157,11 @@ public:
 
     // per-launch CUDA-event profiling of the GEMM kernel (bench.py roofline leg); adds two events per launch
     void set_profile(int level) { profile_ = level; }   // 0 off, 1 GEMM launches, 2 every kernel (labelled)
+    // Re-launch the GEMMs of the last profiled run back to back (PDL-chained, as inside the step) `iters` times between two
+    // CUDA events: ms per pass.  The per-launch events of set_profile(1) break the programmatic launch chain and add an
+    // event round trip to every launch; this measures the kernel's launch duration the way the step experiences it.
+    double replay_gemms(int iters);
+    std::vector<GemmOp> replay_;
     double gemm_ms = 0.0;              // sum of GEMM launch durations of the last profiled run
     std::string profile_json;          // per-shape breakdown of the last profiled run
 

@@ -209,6 +209,10 @@ class Engine:
     def gemm_ms(self) -> float:
         return float(self._lib.pf_offline_get_gemm_ms(self._handle()))
 
+    def replay_gemms(self, iters: int = 5) -> float:
+        """ms per pass over the GEMMs of the last ``set_profile(1)`` run, launched back to back (see pf_abi.h)."""
+        return float(self._lib.pf_offline_replay_gemms(self._handle(), int(iters)))
+
     def profile(self):
         import json
         buf = C.create_string_buffer(1 << 16)

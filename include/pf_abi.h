@@ -178,6 +178,9 @@ double pf_offline_get_gemm_flops(pf_offline* h);
 pf_status pf_offline_set_profile(pf_offline* h, int32_t on);
 double pf_offline_get_gemm_ms(pf_offline* h);
 int32_t pf_offline_get_profile_json(pf_offline* h, char* buf, int32_t capacity);
+/* after a run with pf_offline_set_profile(h, 1): re-launch that run's GEMMs back to back (programmatic-launch chained,
+ * as inside the step) `iters` times between two CUDA events on device 0's stream; returns ms per pass (0 on error) */
+double pf_offline_replay_gemms(pf_offline* h, int32_t iters);
 /* CUDA stream of device dev_index (as a cudaStream_t), so callers can bracket runs with their own events */
 void* pf_offline_get_stream(pf_offline* h, int32_t dev_index);
 
