@@ -52,3 +52,55 @@ def test_lanes_match_single_lane_results():
         t.join()
     assert len(extra) == 5 and all(np.array_equal(tok, ref[k % 3].tokens) for k, tok in extra)
     eng.close()
+
+
+def test_lane_local_hotwords_do_not_leak_between_threads():
+    """Per-call hot words (OfflineProjOfSeacoParaformer.cs:51-60) set through pf_offline_set_hotwords_local only touch the
+    calling thread's lane: a thread biased with hot words and a thread without them keep their own results."""
+    cfg = synth.tiny("seacoparaformer")
+    w = synth.make_weights(cfg)
+    pcm = [synth.make_pcm(i, 1.5) for i in range(3)]
+    hot = synth.make_hotwords(4, cfg.vocab)
+    one = Engine(cfg, w)
+    one.set_cmvn(*synth.make_cmvn())
+    plain = one.run_pcm(pcm, want_logits=True)
+    one.set_hotwords(hot)
+    biased = one.run_pcm(pcm, want_logits=True)
+    one.close()
+    assert not np.array_equal(plain.logits, biased.logits)
+    eng = Engine(cfg, w, lanes=2)
+    eng.set_cmvn(*synth.make_cmvn())
+    res = {}
+    start = threading.Barrier(2)
+
+    def worker(name, hotwords):
+        eng.set_hotwords(hotwords, local=True)
+        start.wait()
+        for _ in range(4):
+            res[name] = eng.run_pcm(pcm, want_logits=True)
+
+    ths = [threading.Thread(target=worker, args=("plain", [])), threading.Thread(target=worker, args=("biased", hot))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert np.array_equal(res["plain"].logits, plain.logits)
+    assert np.array_equal(res["biased"].logits, biased.logits)
+    eng.close()
+
+
+def test_gemm_replay_measures_the_profiled_step():
+    cfg = synth.tiny()
+    eng = Engine(cfg, synth.make_weights(cfg))
+    eng.set_cmvn(*synth.make_cmvn())
+    pcm = [synth.make_pcm(i, 2.0) for i in range(4)]
+    ref = eng.run_pcm(pcm)
+    assert eng.replay_gemms(2) == 0.0                      # nothing recorded without a profiled run
+    eng.set_profile(1)
+    eng.run_pcm(pcm)
+    n = sum(p["launches"] for p in eng.profile() if p.get("name", "gemm") == "gemm")
+    ms = eng.replay_gemms(3)
+    assert n > 0 and 0.0 < ms < 50.0
+    eng.set_profile(0)
+    assert np.array_equal(eng.run_pcm(pcm).tokens, ref.tokens)   # the replay only scribbles over activations
+    eng.close()
