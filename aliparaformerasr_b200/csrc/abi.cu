@@ -537,7 +537,7 @@ pf_status pf_offline_get_tensor(pf_offline* hh, int32_t dev_index, const char* n
 int32_t pf_offline_get_timings(pf_offline* hh, float* ms, int32_t capacity) {
     if (!hh || !ms) return 0;
     OfflineHandle* h = lane_of(hh);
-    const int n = std::min(capacity, 6);
+    const int n = std::min(capacity, 10);
     for (int i = 0; i < n; ++i) ms[i] = h->devs[0]->timings_ms[i];
     return n;
 }

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 namespace pf {
 
@@ -1114,8 +1115,13 @@ void DeviceCtx::run(uint32_t flags, SharedRun* shared, int idx) {
     ev0_armed_ = false;
 }
 
+static double host_ms_since(const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
     PF_CUDA(cudaSetDevice(dev_));
+    const auto host_t0 = std::chrono::steady_clock::now();     // host-side view: enqueue vs blocked time (timings_ms[6..9])
     if (!ev0_armed_) PF_CUDA(cudaEventRecord(ev_[0], stream_));   // run_staged: time from here, not from staging
     const bool sv = cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL;
     const int B = staged_B_;
@@ -1197,7 +1203,9 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
         PF_CUDA(cudaMemcpyAsync(h_meta_, meta_, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         PF_CUDA(cudaMemcpyAsync(h_token_num, token_num_, static_cast<size_t>(B) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         PF_CUDA(cudaEventRecord(ev_[3], stream_));
+        timings_ms[6] = static_cast<float>(host_ms_since(host_t0));           // front-end + encoder + predictor enqueued
         PF_CUDA(cudaStreamSynchronize(stream_));
+        timings_ms[7] = static_cast<float>(host_ms_since(host_t0));           // ... and finished (token counts on the host)
         int lmax = h_meta_[0];
         if (shared) {
             shared->lmax[idx] = lmax;
@@ -1232,7 +1240,9 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
             PF_CUDA(cudaEventRecord(ev_[5], stream_));
         }
         PF_CUDA(cudaEventRecord(ev_[6], stream_));
+        timings_ms[8] = static_cast<float>(host_ms_since(host_t0));           // decoder enqueued
         PF_CUDA(cudaStreamSynchronize(stream_));
+        timings_ms[9] = static_cast<float>(host_ms_since(host_t0));           // results on the host
     }
     finish_profile();
     float ms = 0.0f;

@@ -151,7 +151,7 @@ public:
     float* h_us = nullptr;            // [2][B, 3T] us_alphas | us_cif_peak (PF_RUN_WANT_TIMESTAMPS, models with the V3 predictor)
     int us_frames = 0;
     bool has_timestamps() const { return w_up16_ != nullptr; }
-    float timings_ms[6] = {0, 0, 0, 0, 0, 0};
+    float timings_ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [0..5] device (events), [6..9] host clock since the run began
     int64_t launches = 0;
     double gemm_flops = 0.0;
 

@@ -198,9 +198,10 @@ class Engine:
         return out
 
     def timings(self) -> Dict[str, float]:
-        ms = (C.c_float * 6)()
-        self._lib.pf_offline_get_timings(self._handle(), ms, 6)
-        keys = ["h2d_frontend", "encoder", "predictor_cif", "decoder", "head_pick", "total"]
+        ms = (C.c_float * 10)()
+        self._lib.pf_offline_get_timings(self._handle(), ms, 10)
+        keys = ["h2d_frontend", "encoder", "predictor_cif", "decoder", "head_pick", "total",
+                "host_enqueued_1", "host_counts_ready", "host_enqueued_2", "host_done"]
         return {k: float(ms[i]) for i, k in enumerate(keys)}
 
     def set_profile(self, on: int) -> None:

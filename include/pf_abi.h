@@ -166,7 +166,9 @@ pf_status pf_offline_run_staged(pf_offline* h, uint32_t flags, pf_result* out);
 pf_status pf_offline_get_tensor(pf_offline* h, int32_t dev_index, const char* name, float* dst, size_t capacity,
                                 int32_t* dims4, int32_t* ndim);
 /* per-stage device times of the last run (ms, CUDA events, device 0 of the handle):
- * [0] h2d+frontend [1] encoder [2] predictor+cif [3] decoder [4] head+pick [5] total.  Returns count written. */
+ * [0] h2d+frontend [1] encoder [2] predictor+cif [3] decoder [4] head+pick [5] total; then host clock since the run
+ * began (ms): [6] first half enqueued [7] token counts on the host [8] decoder enqueued [9] results on the host.
+ * Returns count written (at most 10). */
 int32_t pf_offline_get_timings(pf_offline* h, float* ms, int32_t capacity);
 /* kernels launched by the last run (all devices), algorithmic GEMM flops of the last run */
 int64_t pf_offline_get_launch_count(pf_offline* h);
