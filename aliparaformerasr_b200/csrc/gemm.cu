@@ -29,14 +29,15 @@ namespace {
 // launch parameter, so one instantiation serves every width that shares its shared-memory / TMEM layout.
 constexpr int kLnMaxCluster = 4;       // column tiles (CTAs of one cluster) a fused-LayerNorm row may span
 
-template <int BNMAX, bool kPair, bool kOutHalf, bool kLn = false>
+template <int BNMAX, bool kPair, bool kOutHalf, bool kLn = false, int kEW = kEpiWarps>
 struct Cfg {
+    static constexpr int kThreadsCta = kEpiWarp0 * 32 + kEW * 32;    // producer, MMA, TMEM, spare warp + kEW epilogue warps
     static constexpr int kBRows = kPair ? BNMAX / 2 : BNMAX;        // W-tile rows a stage slot can hold
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     // per-warp staging: fp16 output = two 32 x 32 boxes (2 KiB each); fp32 output = two 32 x 32 boxes (4 KiB each)
     static constexpr int kWarpStageBytes = kOutHalf ? 4096 : 8192;
-    static constexpr int kEpiBytes = kEpiWarps * kWarpStageBytes;
+    static constexpr int kEpiBytes = kEW * kWarpStageBytes;
     static constexpr int kBarBytes = 512;
     static constexpr int kBiasBytes = 2 * BNMAX * 4;                 // two tiles' bias columns
     // fused LayerNorm: gamma | beta tiles and the per-row partial sums of every CTA of the cluster
@@ -241,8 +242,10 @@ __device__ __forceinline__ void epilogue_ln_pass2(const LnFuse& f, uint32_t t_ac
 // (the leader alone arms it with the pair's total bytes); the leader's tcgen05.commit multicasts the "stage free"
 // and "accumulator complete" arrivals to both CTAs; epilogue warps of both CTAs arrive on the leader's
 // tmem_empty barrier (the peer through a mapa-translated shared::cluster address).
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// kEW = epilogue warps: 8 (two column groups per TMEM quadrant) or 16 (four groups: half the chunks per warp; 640
+// threads cap the kernel at 96 registers per thread; opt-in, see launch_cl).
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps>
+__global__ void __launch_bounds__(kEpiWarp0 * 32 + kEW * 32, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                        const __grid_constant__ CUtensorMap tmL, const GemmEpi epi, const int M, const int N, const int K,
@@ -250,8 +253,9 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     static_assert(!kLn || (!kPair && !kOutHalf && kAdds == 1), "fused LayerNorm rides on the fp32 + residual epilogue");
     const int vec_ok = vec_ok_flags & 1;
     const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
-    using C = Cfg<BNMAX, kPair, kOutHalf, kLn>;
+    using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
     constexpr int STAGES = C::kStages;
+    constexpr int kGroups = kEW / 4;                             // column groups (warps per TMEM quadrant)
     constexpr int CS = kPair ? 2 : 1;
     const int brows = bn / CS;                                   // W rows this CTA stages per k-block
     const uint32_t stage_tx = kABytes + static_cast<uint32_t>(brows) * BK * 2;
@@ -272,7 +276,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     float* bias_s = reinterpret_cast<float*>(smem + kBarOff + C::kBarBytes);       // [2][BNMAX] bias of the current tiles
     float* ln_gb = bias_s + 2 * BNMAX;                                             // kLn: [2][BNMAX] gamma | beta of this tile
     float* ln_part = ln_gb + 2 * BNMAX;                                            // kLn: [cluster][2][BM][2] partial sums
-    const uint32_t ln_bar = bar_base + 8u * (2 * STAGES + 5 + 2 * kEpiWarps);
+    const uint32_t ln_bar = bar_base + 8u * (2 * STAGES + 5 + 2 * kEW);
     const int ln_cs = kLn ? static_cast<int>(cluster_nctarank()) : 1;
     const int ln_rank = kLn ? static_cast<int>(cluster_ctarank()) : 0;
 
@@ -305,13 +309,13 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), kEpiWarps * CS);        // pair: the leader's barrier collects both CTAs' warps
+            mbar_init(tmem_empty_bar(a), kEW * CS);        // pair: the leader's barrier collects both CTAs' warps
         }
-        for (int w = 0; w < kEpiWarps; ++w) {
+        for (int w = 0; w < kEW; ++w) {
             mbar_init(resid_bar(w, 0), 1);
             mbar_init(resid_bar(w, 1), 1);
         }
-        if (kLn) mbar_init(ln_bar, ln_cs * kEpiWarps * 32);      // every epilogue thread of every CTA of the cluster arrives
+        if (kLn) mbar_init(ln_bar, ln_cs * kEW * 32);      // every epilogue thread of every CTA of the cluster arrives
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -419,9 +423,9 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* wstage = smem + kEpiOff + ew * C::kWarpStageBytes;
         float* stage = reinterpret_cast<float*>(wstage);         // legacy path: 32 x 32 fp32 transpose buffer
         constexpr bool kTmaOk = kOutHalf ? (kAdds == 0) : (kAdds <= 1);     // shapes the asynchronous epilogue covers
-        constexpr int kCpwMax = BNMAX / 64;                                  // 32-column chunks per warp (TMA epilogue), at most
+        constexpr int kCpwMax = (BNMAX / 32 + kGroups - 1) / kGroups;        // 32-column chunks per warp (TMA epilogue), at most
         const int nch = bn / 32;                                             // chunks of this tile width
-        const int cpw = (nch + 1) / 2;                                       // left / right warpgroup share
+        const int cpw = (nch + kGroups - 1) / kGroups;                       // share of every column group
         const int cbase = grp * cpw;
         ResidPipe rp;
         rp.bar[0] = resid_bar(ew, 0); rp.bar[1] = resid_bar(ew, 1);
@@ -438,10 +442,10 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             // bias of this tile's columns -> shared memory (zeros past N / without bias), one L2 round trip per tile
             // taken while the MMAs still run; two buffers so a fast warp may already fill the next tile's
             float* bias_t = bias_s + (local & 1u) * BNMAX;
-            for (int i = ew * 32 + lane; i < bn; i += kEpiWarps * 32)
+            for (int i = ew * 32 + lane; i < bn; i += kEW * 32)
                 bias_t[i] = (epi.bias != nullptr && n0 + i < N) ? __ldg(epi.bias + n0 + i) : 0.0f;
             if (kLn) {                                            // gamma | beta of this tile's columns (fused LayerNorm)
-                for (int i = ew * 32 + lane; i < bn; i += kEpiWarps * 32) {
+                for (int i = ew * 32 + lane; i < bn; i += kEW * 32) {
                     const bool ok = n0 + i < N;
                     ln_gb[i] = ok ? __ldg(epi.ln_gamma + n0 + i) : 0.0f;
                     ln_gb[BNMAX + i] = ok ? __ldg(epi.ln_beta + n0 + i) : 0.0f;
@@ -466,7 +470,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 tc_fence_after_sync();
-                epi_bar_sync();                                   // bias tile visible to all epilogue warps
+                epi_bar_sync_n<kEW>();                                   // bias tile visible to all epilogue warps
                 if (work) {
                     if constexpr (kOutHalf && kAdds == 0)
                         epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
@@ -490,10 +494,10 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             } else {
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 tc_fence_after_sync();
-                epi_bar_sync();
+                epi_bar_sync_n<kEW>();
                 if (m0 < M && !dbg_no_epi) {
 #pragma unroll 1
-                    for (int c = grp; c < nch; c += 2) {
+                    for (int c = grp; c < nch; c += kGroups) {
                         const int col0 = n0 + c * 32;
                         if (col0 >= N) break;                    // warp-uniform
                         uint32_t r[32];
@@ -570,14 +574,14 @@ int num_sms() {
     return n;
 }
 
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps>
 struct Launcher {
     static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
-        using C = Cfg<BNMAX, kPair, kOutHalf, kLn>;
+        using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
         constexpr int CS = kPair ? 2 : 1;
-        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn>;
+        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>;
         static std::once_flag once;
         std::call_once(once, [&] {
             int ndev = 0, cur = 0;
@@ -592,7 +596,7 @@ struct Launcher {
             if (kPair) {
                 cudaLaunchConfig_t q{};
                 q.gridDim = dim3(num_sms() / CS * CS);
-                q.blockDim = dim3(kThreads);
+                q.blockDim = dim3(C::kThreadsCta);
                 q.dynamicSmemBytes = C::kSmemBytes;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
@@ -612,7 +616,7 @@ struct Launcher {
         const int grid = kLn ? num_tiles : ceil_div(num_tiles, rounds) * CS;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(C::kThreadsCta);
         cfg.dynamicSmemBytes = C::kSmemBytes;
         cfg.stream = stream;
         cudaLaunchAttribute at[2];
@@ -632,11 +636,18 @@ struct Launcher {
         PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.tmL, op.epi, op.M, op.N, op.K, op.bn, tiles_n, num_tiles, op.vec_ok));
     }
 };
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn>
-int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn>::max_units = 1;
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn, int kEW>
+int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>::max_units = 1;
 
 template <int BNMAX, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
+    if constexpr (kOutHalf && kAdds == 0) {
+        // fp16 output without addends (QKV, FFN1, K/V projections) with sixteen epilogue warps: opt-in (PFASR_GEMM_EPI16=1).
+        // Measured slower - 5.22 vs 5.12 ms/step (one lane), 3.92 vs 3.87 (three lanes), GEMM replay 587 vs 606 TFLOP/s:
+        // the extra staging costs the fourth operand stage and 640 threads cap the kernel at 96 registers.
+        static const bool epi16 = [] { const char* e = getenv("PFASR_GEMM_EPI16"); return e && *e == '1'; }();
+        if ((epi16 || op.epi16) && op.cm == 1 && op.cn == 1 && (op.vec_ok & 2)) { Launcher<BNMAX, false, true, 0, false, 16>::run(op, stream); return; }
+    }
     if (op.cm == 2 && op.cn == 1) Launcher<BNMAX, true, kOutHalf, kAdds>::run(op, stream);
     else if (op.cm == 1 && op.cn == 1) Launcher<BNMAX, false, kOutHalf, kAdds>::run(op, stream);
     else throw CudaError{"gemm: cluster shape not instantiated"};
@@ -703,7 +714,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if ((epi.out_f32 != nullptr) == (epi.out_f16 != nullptr)) throw CudaError{"gemm: exactly one output pointer must be set"};
     if (M <= 0 || N <= 0 || K <= 0) throw CudaError{"gemm: empty problem"};
     int bn = tile_code & 0xFFF, cm = (tile_code >> 12) & 0xF, cn = (tile_code >> 16) & 0xF;
-    if (tile_code == 0) pick_config(M, N, K, bn, cm, cn);
+    if ((tile_code & 0xFFFFF) == 0) pick_config(M, N, K, bn, cm, cn);
     op.ln_cluster = 0;
     if (epi.ln_out16 != nullptr) {
         // fused LayerNorm: narrowest tile whose column tiles (<= 4) cover a row inside one cluster and the grid in one wave
@@ -721,6 +732,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if (cm == 2 && bn % 64 != 0) throw CudaError{"gemm: the CTA-pair MMA needs an N tile that is a multiple of 64"};
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
     op.throughput = g_policy;
+    op.epi16 = (tile_code >> 22) & 1;
     // the kernel adds up to two fp32 tensors in a fixed order: FSMN memory first, then the residual
     op.n_adds = 0;
     op.epi.add0 = op.epi.add1 = nullptr;

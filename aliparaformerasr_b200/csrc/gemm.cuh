@@ -42,12 +42,14 @@ struct GemmOp {
     int bn = 128;    // N tile: 64, 128 or 256
     int cm = 1, cn = 1;   // cm = 2: CTA pair (cluster of 2 along M) driving cta_group::2 MMAs on a 256 x bn tile; cn is always 1
     int throughput = 0;   // prepared under the throughput objective (gemm_set_policy)
+    int epi16 = 0;        // sixteen epilogue warps (fp16 output without addends; tile_code bit 22 or PFASR_GEMM_EPI16=1)
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
     int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
 
 // Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).
-// tile_code = 0 picks tile width and pairing from the problem shape; otherwise bn | (cm << 12).
+// tile_code = 0 picks tile width and pairing from the problem shape; otherwise bn | (cm << 12); bit 22 asks for the
+// sixteen-epilogue-warp variant (fp16 output without addends).
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);

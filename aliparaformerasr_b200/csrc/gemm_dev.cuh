@@ -56,7 +56,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32(taddr, r); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+template <int kWarps>
+__device__ __forceinline__ void epi_bar_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { epi_bar_sync_n<kEpiWarps>(); }
 
 // fp16 output: this warp's rows [row0, row0+32) x columns [colw, colw + 32*nchunks) of the tile.  One 32 x 32 box
 // (64-byte rows, SWIZZLE_64B) per chunk, two alternating 2 KiB staging boxes, so a box is rewritten two chunks after

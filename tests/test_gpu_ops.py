@@ -31,6 +31,18 @@ def test_gemm_plain(lib, M, N, K, tile):
     assert err < 2e-3, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("M,N,K,tile", [(5344, 1536, 512, 256), (5344, 2048, 512, 0), (300, 520, 192, 128), (129, 96, 64, 0)])
+def test_gemm_f16_sixteen_epilogue_warps(lib, M, N, K, tile):
+    """fp16 + ReLU output through the 640-thread variant (tile_code bit 22; opt-in on the product path)."""
+    rng = np.random.default_rng(M + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out, _ = dbg_gemm(lib, A, W, bias, relu=1, out_half=1, tile_n=tile | (1 << 22))
+    ref = np.maximum(half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias, 0.0)
+    assert np.abs(out - ref).max() < 6e-3
+
+
 @pytest.mark.parametrize("out_half,relu", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("adds", [0, 1, 2])
 @pytest.mark.parametrize("N", [520, 517])          # 517: unaligned pitch -> scalar epilogue path
