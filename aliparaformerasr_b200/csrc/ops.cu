@@ -168,13 +168,14 @@ pf_fsmn(const TIn* __restrict__ in, int ld_in, const float* __restrict__ w, floa
 // (rows past the utterance's token count keep x), and the block's new x rows are normalised again (norm3) into the fp16
 // operand of the cross-attention query projection.  Replaces three launches per decoder layer (LayerNorm, pf_fsmn,
 // LayerNorm) - the decoder is launch-latency bound at M = B * L ~ 1600 rows.
+constexpr int kDecTT = 8;     // output rows per CTA (8: 224 CTAs at B x L = 32 x 50; 16 measured slower per launch)
 template <int K>
 __global__ void __launch_bounds__(512)
 pf_dec_ln_fsmn_ln(const float* __restrict__ t32, float* __restrict__ x, const float* __restrict__ g2, const float* __restrict__ b2,
                   const float* __restrict__ w, const float* __restrict__ g3, const float* __restrict__ b3,
                   const int* __restrict__ lens, int L, float eps, __half* __restrict__ out16) {
     pdl_launch_dependents();
-    constexpr int D = 512, TT = 16, LEFT = (K - 1) / 2, ROWS = TT + K - 1;
+    constexpr int D = 512, TT = kDecTT, LEFT = (K - 1) / 2, ROWS = TT + K - 1;
     extern __shared__ float s_dec[];
     float* s_v = s_dec;                    // [ROWS][D]  LN2 output, zero outside [0, len)
     float* s_x = s_dec + ROWS * D;         // [TT][D]    new residual rows
@@ -598,7 +599,7 @@ void fsmn_f32_launch(const float* in, int ld_in, const float* w, int K, float* o
 template <int K>
 static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2, const float* b2, const float* w, const float* g3,
                                     const float* b3, const int* lens, int B, int L, float eps, __half* out16, cudaStream_t s) {
-    constexpr int kSmem = (16 + K - 1 + 16) * 512 * 4;
+    constexpr int kSmem = (kDecTT + K - 1 + kDecTT) * 512 * 4;
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
@@ -611,7 +612,7 @@ static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2,
         PF_CUDA(cudaSetDevice(cur));
         attr_set = true;
     }
-    launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, 16), B), dim3(512), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
+    launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, kDecTT), B), dim3(512), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
 }
 
 void dec_ln_fsmn_ln_launch(const float* t32, float* x, const float* g2, const float* b2, const float* w, int K, const float* g3,
