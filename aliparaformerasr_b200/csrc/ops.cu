@@ -314,38 +314,69 @@ pf_alpha_head(const float* __restrict__ h, int B, int T, int D, const float* __r
     }
 }
 
-// CIF scalar recurrence, one thread per utterance (the recurrence is inherently sequential in t; T1 <= ~1000).
-__global__ void pf_cif_scan(const float* __restrict__ alphas, int B, int T1, float threshold, float* __restrict__ w_cur,
-                            float* __restrict__ w_rem, int* __restrict__ fire_idx, float* __restrict__ peaks,
-                            int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta) {
+// CIF scalar recurrence (inherently sequential in t).  One CTA per 32 utterances: the alphas of a chunk of frames are
+// staged in shared memory with coalesced loads, 32 threads (one per utterance) run the recurrence on shared memory, and
+// the four per-frame outputs leave coalesced again - a thread walking global memory frame by frame paid an L2 round trip
+// per step (32 us for T = 167; 5 us now).  Same fp32 operation order as before (OnlineRecognizer.cs:149-200).
+constexpr int kCifChunk = 64;      // frames per staged chunk (4 arrays x 32 x 65 x 4 B = 33 KB of static shared memory)
+__global__ void __launch_bounds__(256)
+pf_cif_scan(const float* __restrict__ alphas, int B, int T1, float threshold, float* __restrict__ w_cur,
+            float* __restrict__ w_rem, int* __restrict__ fire_idx, float* __restrict__ peaks,
+            int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta) {
     pdl_launch_dependents();
     pdl_wait();
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    __shared__ float s_a[32][kCifChunk + 1];       // in: alpha; out: w_cur          (+1: conflict-free column walks)
+    __shared__ float s_rem[32][kCifChunk + 1];
+    __shared__ float s_peak[32][kCifChunk + 1];
+    __shared__ int s_idx[32][kCifChunk + 1];
+    const int b0 = blockIdx.x * 32;
+    const int nb = min(32, B - b0);
     float integrate = 0.0f, total = 0.0f;
     int nf = 0;
-    const size_t base = static_cast<size_t>(b) * T1;
-    for (int t = 0; t < T1; ++t) {
-        const float a = alphas[base + t];
-        total = __fadd_rn(total, a);
-        const float completion = __fsub_rn(1.0f, integrate);
-        integrate = __fadd_rn(integrate, a);
-        if (peaks) peaks[base + t] = integrate;
-        const bool fire = integrate >= threshold;
-        const float cur = fire ? completion : a;
-        w_cur[base + t] = cur;
-        if (fire) {
-            integrate = __fsub_rn(integrate, 1.0f);
-            w_rem[base + t] = __fsub_rn(a, cur);
-            fire_idx[base + t] = nf++;
-        } else {
-            w_rem[base + t] = 0.0f;
-            fire_idx[base + t] = -1;
+    for (int c0 = 0; c0 < T1; c0 += kCifChunk) {
+        const int nt = min(kCifChunk, T1 - c0);
+        for (int i = threadIdx.x; i < nb * nt; i += blockDim.x) {
+            const int u = i / nt, t = i - u * nt;
+            s_a[u][t] = alphas[static_cast<size_t>(b0 + u) * T1 + c0 + t];
         }
+        __syncthreads();
+        if (threadIdx.x < nb) {
+            const int u = threadIdx.x;
+            for (int t = 0; t < nt; ++t) {
+                const float a = s_a[u][t];
+                total = __fadd_rn(total, a);
+                const float completion = __fsub_rn(1.0f, integrate);
+                integrate = __fadd_rn(integrate, a);
+                s_peak[u][t] = integrate;
+                const bool fire = integrate >= threshold;
+                const float cur = fire ? completion : a;
+                s_a[u][t] = cur;
+                if (fire) {
+                    integrate = __fsub_rn(integrate, 1.0f);
+                    s_rem[u][t] = __fsub_rn(a, cur);
+                    s_idx[u][t] = nf++;
+                } else {
+                    s_rem[u][t] = 0.0f;
+                    s_idx[u][t] = -1;
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * nt; i += blockDim.x) {
+            const int u = i / nt, t = i - u * nt;
+            const size_t o = static_cast<size_t>(b0 + u) * T1 + c0 + t;
+            w_cur[o] = s_a[u][t];
+            w_rem[o] = s_rem[u][t];
+            fire_idx[o] = s_idx[u][t];
+            if (peaks) peaks[o] = s_peak[u][t];
+        }
+        __syncthreads();
     }
-    token_num[b] = static_cast<int>(floorf(total));
-    fires[b] = nf;
-    atomicMax(meta, nf);
+    if (threadIdx.x < nb) {
+        token_num[b0 + threadIdx.x] = static_cast<int>(floorf(total));
+        fires[b0 + threadIdx.x] = nf;
+        atomicMax(meta, nf);
+    }
 }
 
 // One CTA per (token l, utterance b): the frames between the previous fire and this one, accumulated in the same order
@@ -637,7 +668,7 @@ void alpha_head_launch(const float* h, int B, int T, int D, const float* w, cons
 
 void cif_scan_launch(const float* alphas, int B, int T1, float threshold, float* w_cur, float* w_rem, int* fire_idx,
                      float* peaks, int* token_num, int* fires, int* meta, cudaStream_t s) {
-    launch_k(pf_cif_scan, dim3(ceil_div(B, 32)), dim3(32), 0, s, alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
+    launch_k(pf_cif_scan, dim3(ceil_div(B, 32)), dim3(256), 0, s, alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
 }
 
 void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_cur, const float* w_rem,
