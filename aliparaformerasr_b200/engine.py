@@ -61,6 +61,13 @@ class Engine:
         if devices is not None:
             dev_np = np.asarray(list(devices), dtype=np.int32)
             dev_arr, ndev = _lib.iptr(dev_np), len(dev_np)
+        if isinstance(weights, str) and weights.lower().endswith(".onnx"):
+            # the reference's own model file (OfflineModel.cs:35-70 loads model.onnx / model.int8.onnx into ORT): read the
+            # initialisers, de-quantise, map them to FunASR names (onnx_weights.py) and hand the blob to the library
+            from . import onnx_weights
+            if pcfg.model_kind != _lib.PF_MODEL_PARAFORMER:
+                raise NotImplementedError("ONNX ingestion is mapped for the paraformer export only; convert other models to a PFW1 blob")
+            weights = onnx_weights.paraformer_state_dict(onnx_weights.read_onnx(weights), cfg.enc_layers, cfg.dec_layers)
         # lanes > 1: calls from different host threads run concurrently on the GPU (pf_offline_create_mt)
         if isinstance(weights, str):
             st = self._lib.pf_offline_create_mt(C.byref(pcfg), weights.encode(), dev_arr, ndev, int(lanes), C.byref(self._h))

@@ -46,3 +46,59 @@ def dbg_ffn_chain(lib, a, w1, b1, w2, b2, x, iters=0):
     _lib.check(lib.pf_dbg_ffn_chain(M, D, F, _lib.fptr(a), _lib.fptr(w1), _lib.fptr(b1), _lib.fptr(w2), _lib.fptr(b2), _lib.fptr(x),
                                     _lib.fptr(out), C.byref(ms), iters))
     return out, ms.value
+
+
+# ---------------------------------------------------------------- minimal ONNX (protobuf) writer for the ingestion tests
+def _pb_varint(x):
+    out = b""
+    while True:
+        b = x & 0x7F
+        x >>= 7
+        out += bytes([b | (0x80 if x else 0)])
+        if not x:
+            return out
+
+
+def _pb_ld(num, payload):
+    return _pb_varint((num << 3) | 2) + _pb_varint(len(payload)) + payload
+
+
+def onnx_tensor(name, arr):
+    dt = {np.dtype(np.float32): 1, np.dtype(np.uint8): 2, np.dtype(np.int8): 3, np.dtype(np.int64): 7}[arr.dtype]
+    return (b"".join(_pb_varint((1 << 3) | 0) + _pb_varint(int(d)) for d in arr.shape) + _pb_varint((2 << 3) | 0) + _pb_varint(dt) +
+            _pb_ld(8, name.encode()) + _pb_ld(9, np.ascontiguousarray(arr).tobytes()))
+
+
+def onnx_model(tensors, nodes):
+    def node(op, ins, outs):
+        return b"".join(_pb_ld(1, i.encode()) for i in ins) + b"".join(_pb_ld(2, o.encode()) for o in outs) + _pb_ld(4, op.encode())
+    graph = b"".join(_pb_ld(1, node(*n)) for n in nodes) + _pb_ld(2, b"g") + b"".join(_pb_ld(5, t) for t in tensors)
+    return _pb_varint((1 << 3) | 0) + _pb_varint(8) + _pb_ld(7, graph)
+
+
+def export_paraformer_onnx(weights, enc_layers, dec_layers):
+    """A model.onnx image in the FunASR export convention for a synthetic paraformer state dict: Linear weights become
+    anonymous ``onnx::MatMul_N`` initialisers ([in, out]) consumed by MatMul nodes in execution order, everything else
+    keeps its module name."""
+    order = []
+    for i in range(enc_layers):
+        p = "encoder.encoders0.0" if i == 0 else f"encoder.encoders.{i - 1}"
+        order += [p + ".self_attn.linear_q_k_v.weight", p + ".self_attn.linear_out.weight", p + ".feed_forward.w_1.weight",
+                  p + ".feed_forward.w_2.weight"]
+    order.append("predictor.cif_output.weight")
+    for i in range(dec_layers):
+        p = f"decoder.decoders.{i}"
+        order += [p + ".feed_forward.w_1.weight", p + ".feed_forward.w_2.weight", p + ".src_attn.linear_q.weight",
+                  p + ".src_attn.linear_k_v.weight", p + ".src_attn.linear_out.weight"]
+    order += ["decoder.decoders3.0.feed_forward.w_1.weight", "decoder.decoders3.0.feed_forward.w_2.weight"]
+    tensors, nodes = [], []
+    anon = {}
+    for k, name in enumerate(order):
+        anon[name] = f"onnx::MatMul_{1000 + 7 * k}"
+        tensors.append(onnx_tensor(anon[name], np.ascontiguousarray(weights[name].T)))
+        nodes.append(("MatMul", [f"x{k}", anon[name]], [f"y{k}"]))
+        nodes.append(("Add", [f"y{k}", "some.bias"], [f"x{k + 1}"]))
+    for name, arr in weights.items():
+        if name not in anon:
+            tensors.append(onnx_tensor(name, np.asarray(arr, np.float32)))
+    return onnx_model(tensors, nodes)

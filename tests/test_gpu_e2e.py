@@ -159,3 +159,19 @@ def test_full_size_properties():
     assert safe.mean() > 0.8
     assert np.array_equal(sub.tokens[safe], a.tokens[:5, :L][safe])
     eng.close()
+
+
+def test_engine_loads_the_reference_model_file_format(tmp_path, tiny_paraformer):
+    """Engine(cfg, "model.onnx"): the ONNX initialisers are read, mapped and packed on the fly (row f3) and give the same
+    ids and logits as the state dict they were exported from."""
+    from _util import export_paraformer_onnx
+    cfg, w, eng = tiny_paraformer
+    path = tmp_path / "model.onnx"
+    path.write_bytes(export_paraformer_onnx(w, cfg.enc_layers, cfg.dec_layers))
+    eng2 = Engine(cfg, str(path))
+    eng2.set_cmvn(*synth.make_cmvn())
+    pcm = [synth.make_pcm(i, 2.0) for i in range(3)]
+    a = eng.run_pcm(pcm, want_logits=True)
+    b = eng2.run_pcm(pcm, want_logits=True)
+    assert np.array_equal(a.tokens, b.tokens) and np.array_equal(a.logits, b.logits)
+    eng2.close()

@@ -92,3 +92,18 @@ def test_real_embed_onnx_matches_golden():
     assert np.array_equal(ow.sensevoice_embed_table(REAL), np.load(GOLD))
     g = ow.read_onnx(REAL)
     assert g.nodes == [("Gather", ["weight", "x"], ["y"])]
+
+
+def test_paraformer_export_maps_back_to_the_state_dict():
+    """model.onnx ingestion end to end on the host: a synthetic paraformer state dict written in the FunASR export
+    convention (anonymous MatMul weights in graph order) maps back to the same names and values."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from _util import export_paraformer_onnx
+    from aliparaformerasr_b200 import synth
+    cfg = synth.tiny()
+    w = synth.make_weights(cfg)
+    sd = ow.paraformer_state_dict(ow.read_onnx(export_paraformer_onnx(w, cfg.enc_layers, cfg.dec_layers)), cfg.enc_layers, cfg.dec_layers)
+    assert set(sd) == set(w)
+    for k in w:
+        assert sd[k].shape == w[k].shape and np.array_equal(sd[k], w[k]), k
