@@ -101,7 +101,9 @@ long long audio_num_samples(const pf_audio& a) {
         if (n == 0) return 0;
         const long long mono = a.channels == 2 ? n / 2 : n;
         const double ratio = static_cast<double>(a.sample_rate) / 16000.0;
-        n = static_cast<long long>(static_cast<int>(nearbyint(static_cast<double>(mono) / ratio)));   // Math.Round: half to even
+        const double rounded = nearbyint(static_cast<double>(mono) / ratio);                          // Math.Round: half to even
+        if (rounded > 2147483647.0) throw StatusError{PF_ERR_SHAPE, "utterance longer than Int32.MaxValue samples"};
+        n = static_cast<long long>(rounded);
     }
     if (n > 0x7fffffffLL) throw StatusError{PF_ERR_SHAPE, "utterance longer than Int32.MaxValue samples"};
     return n;
