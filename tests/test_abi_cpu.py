@@ -80,3 +80,26 @@ def test_blob_roundtrip():
     assert set(back) == set(w)
     for k in w:
         assert back[k].shape == w[k].shape and np.array_equal(back[k], w[k])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pf_abi.h is what a foreign-function binding reads: it must compile as C99 on its own (no C++-isms, no
+    missing includes) and its structs must have the sizes the ctypes mirror uses."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_check.c"
+    src.write_text(
+        '#include "pf_abi.h"\n#include <stdio.h>\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %d\\n", sizeof(pf_config), sizeof(pf_result), sizeof(pf_online_result),\n'
+        '                        sizeof(pf_text_result), sizeof(pf_audio), PF_ABI_VERSION); return 0; }\n')
+    exe = tmp_path / "abi_check"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert sizes[:5] == [C.sizeof(_lib.PfConfig), C.sizeof(_lib.PfResult), C.sizeof(_lib.PfOnlineResult), C.sizeof(_lib.PfTextResult),
+                         C.sizeof(_lib.PfAudio)]
+    assert sizes[5] == 4
