@@ -103,3 +103,30 @@ def test_header_is_plain_c(tmp_path):
     assert sizes[:5] == [C.sizeof(_lib.PfConfig), C.sizeof(_lib.PfResult), C.sizeof(_lib.PfOnlineResult), C.sizeof(_lib.PfTextResult),
                          C.sizeof(_lib.PfAudio)]
     assert sizes[5] == 4
+
+
+def _build_example(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "offline_wav"
+    libdir = os.path.join(ROOT, "aliparaformerasr_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "offline_wav.c"), "-L", libdir, "-lpfasr", f"-Wl,-rpath,{libdir}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_consumer_links_and_reports_errors(tmp_path):
+    """examples/offline_wav.c: a C99 program linked against libpfasr.so through include/pf_abi.h only."""
+    import subprocess
+    exe = _build_example(tmp_path)
+    tok = tmp_path / "tokens.txt"
+    tok.write_text("<blank>\n<s>\n</s>\n")
+    r = subprocess.run([str(exe), "/nonexistent/model.pfw", str(tok), "/nonexistent/a.wav"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open weights file" in r.stderr
+    r = subprocess.run([str(exe), "/nonexistent/model.pfw", "/nonexistent/tokens.txt", "a.wav"], capture_output=True, text=True)
+    assert r.returncode == 1 and "tokens" in r.stderr

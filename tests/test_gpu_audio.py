@@ -81,3 +81,52 @@ def test_run_audio_equals_run_pcm_of_converted_samples():
     c = eng.run_audio(clips[:2])
     assert np.array_equal(c.tokens[:, : c.tokens.shape[1]], eng.run_pcm(pcm[:2]).tokens)
     eng.close()
+
+
+def test_plain_c_consumer_end_to_end(tmp_path):
+    """The C example (WAV files -> text through the C-ABI alone) prints what the Python host mirror decodes."""
+    import shutil
+    import struct
+    import subprocess
+    import os
+    from aliparaformerasr_b200 import weights as W
+    from aliparaformerasr_b200.text import TokenTable
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "aliparaformerasr_b200")
+    exe = tmp_path / "offline_wav"
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "offline_wav.c"), "-L", libdir,
+                        "-lpfasr", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cfg = synth.tiny()
+    w = synth.make_weights(cfg)
+    blob = tmp_path / "model.pfw"
+    W.pack(w).tofile(str(blob))
+    vocab = ["<blank>", "<s>", "</s>"] + [chr(0x4E00 + i) if i % 3 else f"w{i}@@" for i in range(cfg.vocab - 3)]
+    tok = tmp_path / "tokens.txt"
+    tok.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    wavs, clips = [], []
+    for i, (rate, ch) in enumerate(((16000, 1), (44100, 2))):
+        pcm = synth.make_pcm(i, 1.5)
+        n = int(1.5 * rate)
+        x = np.interp(np.arange(n) * 16000.0 / rate, np.arange(pcm.size), pcm)
+        s16 = np.clip(x * 32767, -32768, 32767).astype(np.int16)
+        data = np.repeat(s16, ch) if ch == 2 else s16
+        hdr = struct.pack("<4sI4s4sIHHIIHH4sI", b"RIFF", 36 + data.nbytes, b"WAVE", b"fmt ", 16, 1, ch, rate, rate * ch * 2, ch * 2, 16,
+                          b"data", data.nbytes)
+        path = tmp_path / f"u{i}.wav"
+        path.write_bytes(hdr + data.tobytes())
+        wavs.append(str(path))
+        clips.append(audio.Audio(data, _lib.PF_AUDIO_S16, ch, rate))
+    env = dict(os.environ, PFASR_EXAMPLE_LAYERS=f"{cfg.enc_layers},{cfg.dec_layers}")
+    r = subprocess.run([str(exe), str(blob), str(tok)] + wavs, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    got = [line.split("\t", 1)[1] for line in r.stdout.splitlines()]
+    eng = Engine(cfg, w)                                  # default CMVN (shift 0, scale 1), as the example uses
+    out = eng.run_audio(clips)
+    table = TokenTable(lines=vocab)
+    want = [table.decode_offline(out.tokens[i])[0] for i in range(2)]
+    assert got == want and any(len(t) > 0 for t in want)
+    eng.close()
