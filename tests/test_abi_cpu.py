@@ -130,3 +130,38 @@ def test_plain_c_consumer_links_and_reports_errors(tmp_path):
     assert r.returncode == 1 and "cannot open weights file" in r.stderr
     r = subprocess.run([str(exe), "/nonexistent/model.pfw", "/nonexistent/tokens.txt", "a.wav"], capture_output=True, text=True)
     assert r.returncode == 1 and "tokens" in r.stderr
+
+
+def test_library_sass_uses_tcgen05_and_tma():
+    """What the hot kernels are made of, read from the built library itself (cuobjdump -sass, sm_100a): 5th-generation
+    tensor-core MMAs (UTCHMMA), TMEM loads / stores (LDTM / STTM), TMA loads, stores and reduce-adds (UTMALDG / UTMASTG /
+    UTMAREDG) - not mma.sync re-compiles."""
+    import shutil
+    import subprocess
+    from collections import Counter
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([cuobjdump, "-sass", "-arch", "sm_100a", str(_lib.LIB_PATH)], capture_output=True, text=True)
+    if r.returncode != 0 or not r.stdout:
+        r = subprocess.run([cuobjdump, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    per_kernel, cur = {}, None
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = per_kernel.setdefault(m.group(1), Counter())
+            continue
+        if cur is not None:
+            for op in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "HMMA"):
+                if re.search(r"\b" + op + r"(\b|\.)", line):
+                    cur[op] += 1
+    gemm = [c for k, c in per_kernel.items() if "pf_gemm_f16_tn_tcgen05" in k]
+    attn = [c for k, c in per_kernel.items() if "pf_sanm_attention_tc" in k]
+    chain = [c for k, c in per_kernel.items() if "pf_ffn_chain_tcgen05" in k]
+    assert gemm and attn and chain
+    for c in gemm + chain:
+        assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["HMMA"] == 0
+    assert any(c["UTMASTG"] > 0 for c in gemm)                       # asynchronous TMA-store epilogue
+    for c in attn:
+        assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["UTMAREDG"] > 0   # FSMN memory leaves by TMA reduce-add
