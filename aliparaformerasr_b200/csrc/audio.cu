@@ -159,7 +159,7 @@ pf_status pf_wav_parse(const void* file, size_t bytes, pf_audio* out) {
             else if (tag == 1 && bits == 32) format = PF_AUDIO_S32;
             else if (tag == 3 && bits == 32) format = PF_AUDIO_F32;
             if (format < 0) return fail(PF_ERR_UNSUPPORTED, "only PCM 8/16/24/32-bit and 32-bit IEEE float WAV data is decoded on the device");
-            if (channels == 0 || rate == 0) return fail(PF_ERR_UNSUPPORTED, "fmt chunk without channels / sample rate");
+            if (channels == 0 || rate == 0 || rate > 0x7fffffffu) return fail(PF_ERR_UNSUPPORTED, "fmt chunk without a usable channel count / sample rate");
             const size_t data_bytes = size < avail ? size : avail;        // a streamed file may overstate the length
             const size_t frame = static_cast<size_t>(channels) * (bits / 8);
             (void)align;

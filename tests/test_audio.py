@@ -96,3 +96,30 @@ def test_oracle_resample_hand_cases():
     assert oaudio.to_float(np.asarray([0, 128, 255], np.uint8), oaudio.U8).tolist() == [-1.0, 0.0, 127 / 128]
     assert oaudio.to_float(np.asarray([0, 0, 0x80, 0, 0, 0x40], np.uint8), oaudio.S24).tolist() == [-1.0, 0.5]
     assert oaudio.to_float(np.asarray([-2**31, 2**30], np.int32), oaudio.S32).tolist() == [-1.0, 0.5]
+
+
+def test_wav_parse_survives_corrupted_images():
+    """Truncations and random byte flips of valid files: the parser may accept or refuse, but what it returns always lies
+    inside the image (it reads untrusted files)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    base = [make_wav(rng.integers(-3000, 3000, 400, dtype=np.int16).tobytes(), 1, 16, 2, 44100, junk_before=True),
+            make_wav(rng.standard_normal(100).astype(np.float32).tobytes(), 3, 32, 1, 8000, extensible=True),
+            make_wav(bytes(range(90)), 1, 24, 1, 16000)]
+    width = {_lib.PF_AUDIO_U8: 1, _lib.PF_AUDIO_S16: 2, _lib.PF_AUDIO_S24: 3, _lib.PF_AUDIO_S32: 4, _lib.PF_AUDIO_F32: 4}
+    for _ in range(3000):
+        blob = bytearray(base[int(rng.integers(0, len(base)))])
+        if rng.random() < 0.5:
+            blob = blob[: int(rng.integers(0, len(blob) + 1))]
+        for _ in range(int(rng.integers(0, 6))):
+            if blob:
+                blob[int(rng.integers(0, len(blob)))] = int(rng.integers(0, 256))
+        buf = np.frombuffer(bytes(blob) + b"\0", dtype=np.uint8)[: len(blob)]
+        out = _lib.PfAudio()
+        st = lib.pf_wav_parse(buf.ctypes.data if len(blob) else None, len(blob), C.byref(out))
+        if st == _lib.PF_OK:
+            off = out.data - buf.ctypes.data
+            assert out.format in width and out.channels >= 1 and out.sample_rate >= 1 and out.n_values >= 0
+            assert 0 <= off and off + out.n_values * width[out.format] <= len(blob)
+        else:
+            assert st in (_lib.PF_ERR_UNSUPPORTED, _lib.PF_ERR_BAD_ARG)

@@ -173,3 +173,45 @@ def test_timestamps_native_matches_oracle_and_hand_trace():
         pk = np.zeros(50, np.float32)
         pk[[5, 10, 15, 20]] = 1.0
         time_stamp_lfr6_onnx(pk, [3])
+
+
+def test_decode_survives_arbitrary_bytes_in_the_tokens_table():
+    """tokens.txt is user data: lines with invalid UTF-8, stray bars / '@@' fragments and truncated sequences must decode
+    without faults (the text functions work on bytes)."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    frag = [b"\xe2\x96\x81", b"@@", b"\xe4\xbd", b"\xe4\xbd\xa0", b"\xf0\x9d\x84", b"\xc3", b"A", b"\t", b"</s>", b"\xff", b""]
+    for _ in range(300):
+        lines = []
+        for _ in range(int(rng.integers(3, 40))):
+            lines.append(b"".join(frag[int(k)] for k in rng.integers(0, len(frag), int(rng.integers(0, 5)))))
+        blob = b"\n".join(lines)
+        h = C.c_void_p()
+        st = lib.pf_tokens_create_from_memory(blob, len(blob), C.byref(h))
+        if st != _lib.PF_OK:
+            continue
+        n = lib.pf_tokens_count(h)
+        ids = rng.integers(0, max(n, 1), int(rng.integers(0, 30))).astype(np.int32)
+        res = _lib.PfTextResult()
+        p = ids.ctypes.data_as(C.POINTER(C.c_int32))
+        st = lib.pf_decode_offline(h, p, ids.size, None, 0, C.byref(res))
+        # PF_ERR_SHAPE: a table line such as "@@▁" makes the C# call Last() on an empty list (InvalidOperationException)
+        assert st in (_lib.PF_OK, _lib.PF_ERR_SHAPE)
+        if st != _lib.PF_OK:
+            lib.pf_tokens_destroy(h)
+            continue
+        text = C.create_string_buffer(res.text_bytes + 1)
+        toks = C.create_string_buffer(max(1, res.tokens_bytes))
+        ts = np.zeros(max(1, res.ts_count), np.int32)
+        off = np.zeros(res.n_timestamps + 1, np.int32)
+        res.text, res.text_capacity = C.cast(text, C.c_void_p), len(text)
+        res.tokens, res.tokens_capacity = C.cast(toks, C.c_void_p), len(toks)
+        res.ts, res.ts_capacity = ts.ctypes.data_as(C.POINTER(C.c_int32)), ts.size
+        res.ts_offsets, res.ts_offsets_capacity = off.ctypes.data_as(C.POINTER(C.c_int32)), off.size
+        assert lib.pf_decode_offline(h, p, ids.size, None, 0, C.byref(res)) == _lib.PF_OK
+        assert off[res.n_timestamps] == res.ts_count and len(text.value) <= res.text_bytes
+        need = C.c_size_t(0)
+        assert lib.pf_decode_online(h, p, ids.size, None, 0, C.byref(need)) == _lib.PF_OK
+        buf = C.create_string_buffer(need.value + 1)
+        assert lib.pf_decode_online(h, p, ids.size, buf, len(buf), C.byref(need)) == _lib.PF_OK
+        lib.pf_tokens_destroy(h)
