@@ -100,7 +100,17 @@ class OnnxGraph:
 
 
 def read_onnx(path_or_bytes) -> OnnxGraph:
+    """Initialisers and node list of an ONNX file.  A truncated or corrupted file raises ``ValueError``."""
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray, memoryview)) else open(path_or_bytes, "rb").read()
+    try:
+        return _read_onnx(data)
+    except ValueError:
+        raise
+    except (IndexError, TypeError, UnicodeDecodeError, OverflowError, struct.error) as ex:
+        raise ValueError(f"corrupt ONNX file: {type(ex).__name__}: {ex}") from ex
+
+
+def _read_onnx(data) -> OnnxGraph:
     g = OnnxGraph()
     for num, wt, val in _fields(memoryview(data)):
         if num != 7 or wt != 2:                        # ModelProto.graph

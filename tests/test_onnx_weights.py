@@ -107,3 +107,23 @@ def test_paraformer_export_maps_back_to_the_state_dict():
     assert set(sd) == set(w)
     for k in w:
         assert sd[k].shape == w[k].shape and np.array_equal(sd[k], w[k]), k
+
+
+def test_corrupted_files_raise_value_error():
+    rng = np.random.default_rng(0)
+    base = _model([_tensor("onnx::MatMul_1", rng.standard_normal((4, 6)).astype(np.float32)), _tensor("b", rng.standard_normal(6).astype(np.float32))],
+                  [("MatMul", ["x", "onnx::MatMul_1"], ["y"]), ("Add", ["y", "b"], ["z"])])
+    ok = 0
+    for _ in range(3000):
+        blob = bytearray(base)
+        if rng.random() < 0.5:
+            blob = blob[: int(rng.integers(0, len(blob) + 1))]
+        for _ in range(int(rng.integers(0, 5))):
+            if blob:
+                blob[int(rng.integers(0, len(blob)))] = int(rng.integers(0, 256))
+        try:
+            ow.read_onnx(bytes(blob))
+            ok += 1
+        except ValueError:
+            pass
+    assert ok > 0
