@@ -65,6 +65,8 @@ static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t by
                                const Handle* share = nullptr) {
     if (!cfg || !blob) throw StatusError{PF_ERR_BAD_ARG, "null config or weights"};
     validate_config(*cfg);
+    Blob b;
+    b.parse(blob, bytes);            // a bad weights file is reported as such, with or without a device
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -79,8 +81,6 @@ static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t by
         devs.push_back(cur);
     }
     for (int d : devs) if (d < 0 || d >= count) throw StatusError{PF_ERR_BAD_ARG, "device ordinal out of range"};
-    Blob b;
-    b.parse(blob, bytes);
     std::unique_ptr<Handle> h(new Handle());
     h->cfg = *cfg;
     for (size_t i = 0; i < devs.size(); ++i) {

@@ -66,13 +66,17 @@ void Blob::parse(const void* data, size_t bytes) {
         memcpy(&e, p + 16 + static_cast<size_t>(i) * sizeof(RawEntry), sizeof(RawEntry));
         e.name[95] = 0;
         if (e.dtype != 0 || e.ndim > 4) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad entry ") + e.name};
-        if (e.offset + e.nbytes > bytes || (e.offset & 3)) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad extent ") + e.name};
+        if (e.offset > bytes || e.nbytes > bytes - e.offset || (e.offset & 3))      // (no offset + nbytes: it can wrap)
+            throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad extent ") + e.name};
         BlobEntry be;
         be.name = e.name;
         be.ndim = static_cast<int>(e.ndim);
         size_t cnt = 1;
         for (int d = 0; d < 4; ++d) {
+            if (d < be.ndim && e.dims[d] > (1ull << 40)) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad shape ") + e.name};
             be.dims[d] = d < be.ndim ? static_cast<int64_t>(e.dims[d]) : 1;
+            if (be.dims[d] != 0 && cnt > (~static_cast<size_t>(0) / 8) / static_cast<size_t>(be.dims[d]))
+                throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: bad shape ") + e.name};
             cnt *= static_cast<size_t>(be.dims[d]);
         }
         if (cnt * 4 != e.nbytes) throw StatusError{PF_ERR_WEIGHTS, std::string("weights blob: size mismatch ") + e.name};

@@ -165,3 +165,28 @@ def test_library_sass_uses_tcgen05_and_tma():
     assert any(c["UTMASTG"] > 0 for c in gemm)                       # asynchronous TMA-store epilogue
     for c in attn:
         assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["UTMAREDG"] > 0   # FSMN memory leaves by TMA reduce-add
+
+
+def test_corrupted_weight_blobs_are_refused():
+    """PFW1 files are untrusted input: truncations and byte flips end in PF_ERR_WEIGHTS (or, when the table still parses,
+    in whatever comes next - no device here, a missing tensor on a GPU box), never in a fault."""
+    import torch
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    base = weights.pack({"a.weight": rng.standard_normal((3, 5)).astype(np.float32), "b": rng.standard_normal(7).astype(np.float32)})
+    cfg = to_pf_config(synth.tiny())
+    seen = set()
+    for _ in range(2000):
+        blob = bytearray(base.tobytes())
+        if rng.random() < 0.4:
+            blob = blob[: int(rng.integers(0, len(blob) + 1))]
+        for _ in range(int(rng.integers(1, 8))):
+            if blob:
+                blob[int(rng.integers(0, min(len(blob), 400)))] = int(rng.integers(0, 256))     # header + entry table
+        buf = np.frombuffer(bytes(blob) + b"\0", dtype=np.uint8)
+        h = C.c_void_p()
+        st = lib.pf_offline_create_from_memory(C.byref(cfg), buf.ctypes.data_as(C.c_void_p), len(blob), None, 0, C.byref(h))
+        seen.add(st)
+        assert st != _lib.PF_OK and not h
+    allowed = {_lib.PF_ERR_WEIGHTS, _lib.PF_ERR_CUDA} if not torch.cuda.is_available() else {_lib.PF_ERR_WEIGHTS}
+    assert _lib.PF_ERR_WEIGHTS in seen and seen <= allowed | {_lib.PF_ERR_BAD_ARG}
