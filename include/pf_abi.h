@@ -114,7 +114,8 @@ pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, 
 /* Concurrent callers: the same handle with `lanes` (1..8) independent execution lanes (own streams, staging buffers,
  * activations and weight copy per lane).  A host thread is bound to a lane on its first call; calls from different
  * threads then overlap on the GPU (one batch's kernel tails, launch gaps and PCIe copies are filled with another
- * batch's work).  Results returned to a thread stay valid until that thread's next call on the handle.  The plain
+ * batch's work).  Results returned to a thread stay valid until that thread's next call on the handle; a batch staged
+ * with pf_offline_stage_pcm must be run (pf_offline_run_staged) by the thread that staged it.  The plain
  * create functions use one lane (or $PFASR_LANES).  Replaces nothing in the reference: OfflineRecognizer.GetResults
  * may be called from several threads there too, and they queue on the one ORT session. */
 pf_status pf_offline_create_mt(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev,
