@@ -1545,6 +1545,18 @@ void DeviceCtx::get_tensor(const std::string& name, float* dst, size_t capacity,
     else if (name == "logits") { src = logits_; dims[0] = B_; dims[1] = Lpad_; dims[2] = ldv(); nd = 3; }   // padded row pitch
     else if (name == "x") { src = x32_; dims[0] = B_; dims[1] = T_; dims[2] = d; nd = 3; }
     else if (name == "dec_x") { src = xd32_; dims[0] = B_; dims[1] = Lpad_; dims[2] = d; nd = 3; }
+    else if (name == "acoustic_embeds") {
+        // test hook: the decoder overwrites its input in place, so the CIF frames are gathered again from the tensors the
+        // run left behind (encoder output, integrate-and-fire weights) into a scratch buffer
+        if (!wcur_ || !tn32_ || Lpad_ <= 0 || dst == nullptr) {
+            src = wcur_ && Lpad_ > 0 ? tn32_ : nullptr;
+        } else {
+            PF_CUDA(cudaMemsetAsync(tn32_, 0, static_cast<size_t>(B_) * Lpad_ * d * sizeof(float), stream_));
+            cif_gather_launch(enc32_, B_, T_, d, wcur_, wrem_, fire_idx_, T_ + 1, tn32_, Lpad_, stream_);
+            src = tn32_;
+        }
+        dims[0] = B_; dims[1] = Lpad_; dims[2] = d; nd = 3;
+    }
     else throw StatusError{PF_ERR_BAD_ARG, "unknown tensor '" + name + "'"};
     if (!src) throw StatusError{PF_ERR_BAD_ARG, "tensor '" + name + "' not available for this model / before a run"};
     size_t n = 1;

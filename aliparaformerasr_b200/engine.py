@@ -65,9 +65,20 @@ class Engine:
             # the reference's own model file (OfflineModel.cs:35-70 loads model.onnx / model.int8.onnx into ORT): read the
             # initialisers, de-quantise, map them to FunASR names (onnx_weights.py) and hand the blob to the library
             from . import onnx_weights
-            if pcfg.model_kind != _lib.PF_MODEL_PARAFORMER:
-                raise NotImplementedError("ONNX ingestion is mapped for the paraformer export only; convert other models to a PFW1 blob")
-            weights = onnx_weights.paraformer_state_dict(onnx_weights.read_onnx(weights), cfg.enc_layers, cfg.dec_layers)
+            graph = onnx_weights.read_onnx(weights)
+            if pcfg.model_kind == _lib.PF_MODEL_PARAFORMER:
+                weights = onnx_weights.paraformer_state_dict(graph, cfg.enc_layers, cfg.dec_layers, cfg.d_model, cfg.ffn, cfg.input_size,
+                                                             cfg.dec_ffn, cfg.vocab)
+            elif pcfg.model_kind == _lib.PF_MODEL_SENSEVOICE_SMALL:
+                weights = onnx_weights.sensevoice_state_dict(graph, cfg.enc_layers, cfg.tp_layers, cfg.d_model, cfg.ffn, cfg.input_size, cfg.vocab)
+            else:
+                raise NotImplementedError("ONNX ingestion is mapped for the paraformer and SenseVoiceSmall exports; convert SeACo models to a PFW1 blob")
+        if pcfg.model_kind == _lib.PF_MODEL_SENSEVOICE_SMALL and isinstance(weights, dict) and "embed.weight" not in weights:
+            # split-embed export: the prompt rows come from the reference's own data/embed.onnx (EmbedSVModel.cs:45-77,
+            # OfflineProjOfSenseVoiceSmall.cs:84-100), shipped as sha256-pinned package data
+            from . import onnx_weights
+            weights = dict(weights)
+            weights["embed.weight"] = onnx_weights.packaged_sensevoice_embed()
         # lanes > 1: calls from different host threads run concurrently on the GPU (pf_offline_create_mt)
         if isinstance(weights, str):
             st = self._lib.pf_offline_create_mt(C.byref(pcfg), weights.encode(), dev_arr, ndev, int(lanes), C.byref(self._h))

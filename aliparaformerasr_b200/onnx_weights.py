@@ -176,27 +176,126 @@ def sensevoice_embed_table(path_or_bytes) -> np.ndarray:
     return tabs[0]
 
 
-def paraformer_state_dict(g: OnnxGraph, enc_layers: int = 50, dec_layers: int = 16) -> Dict[str, np.ndarray]:
-    """[EXT, unpinned] FunASR paraformer export -> FunASR state-dict names.  Named initialisers (biases, LayerNorm, FSMN
-    and conv kernels, output layer) keep their module names in the export; the anonymous MatMul weights are assigned by
-    graph order - per encoder layer linear_q_k_v, linear_out, w_1, w_2; predictor cif_output; per decoder layer w_1,
-    w_2, linear_q, linear_k_v, linear_out; decoders3 w_1, w_2 - and transposed from [in, out] to torch's [out, in]."""
+# sha256 of the float32 payload of the reference's AliParaformerAsr/data/embed.onnx (file sha256 5c69dceb...52f9b1)
+SENSEVOICE_EMBED_SHA256 = "9d27e2547e90d9a0348ad97cfc1d86ce2ae7453c03f8f9d96e86b7aecca801a8"
+
+
+def packaged_sensevoice_embed() -> np.ndarray:
+    """The reference's own prompt table, shipped as package data (``data/sensevoice_embed.npy``): EmbedSVModel loads
+    ``data/embed.onnx`` as an embedded resource of the assembly (EmbedSVModel.cs:20-43), so a split-embed SenseVoice
+    ``model.onnx`` carries no ``embed.weight``.  The bytes are checked against the pinned digest on every load."""
+    import hashlib
+    import os
+    tab = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "sensevoice_embed.npy"))
+    tab = np.ascontiguousarray(tab, dtype=np.float32)
+    if tab.shape != (16, 560) or hashlib.sha256(tab.tobytes()).hexdigest() != SENSEVOICE_EMBED_SHA256:
+        raise ValueError("packaged SenseVoice prompt table does not match the reference's data/embed.onnx")
+    return tab
+
+
+def _enc_slots(prefix_layers, d_in0: int, d: int, f: int):
+    """(name, (out, in)) of the four Linear weights of every SAN-M encoder layer, in execution order."""
+    out = []
+    for k, p in enumerate(prefix_layers):
+        din = d_in0 if k == 0 and d_in0 else d
+        out += [(p + ".self_attn.linear_q_k_v.weight", (3 * d, din)), (p + ".self_attn.linear_out.weight", (d, d)),
+                (p + ".feed_forward.w_1.weight", (f, d)), (p + ".feed_forward.w_2.weight", (d, f))]
+    return out
+
+
+def _assign_matmul_weights(g: OnnxGraph, init: Dict[str, np.ndarray], slots, sd: Dict[str, np.ndarray]) -> Dict[str, str]:
+    """Give every anonymous MatMul weight its FunASR name.  torch.onnx exports ``nn.Linear`` on a 3-D input as
+    ``MatMul(x, onnx::MatMul_N)`` followed by ``Add(bias, y)`` where the bias KEEPS its module name, so the weight's
+    name is read off the bias of the Add that consumes the MatMul output ("<module>.bias" -> "<module>.weight").  Only
+    bias-less layers (the decoder's feed_forward.w_2) fall back to graph order: they take the first still-unassigned
+    slot that follows the slot of the previous MatMul.  Every assignment is checked against the slot's [out, in] shape,
+    so two same-sized tensors cannot be swapped silently."""
+    shape_of = dict(slots)
+    consumers: Dict[str, List[Tuple[str, List[str]]]] = {}
+    for op, ins, outs in g.nodes:
+        for x in ins:
+            consumers.setdefault(x, []).append((op, ins))
+    order = [s for s, _ in slots]
+    pos = {s: i for i, s in enumerate(order)}
+    assigned: Dict[str, str] = {}
+    last = -1
+    for op, ins, outs in g.nodes:
+        if op not in ("MatMul", "Gemm", "MatMulInteger", "DynamicQuantizeMatMul") or len(ins) < 2:
+            continue
+        w = ins[1]
+        stem = w[: -len("_quantized")] if w.endswith("_quantized") else w
+        if stem not in init or init[stem].ndim != 2:
+            continue
+        if not stem.startswith("onnx::") and stem in shape_of:          # the export kept the module name
+            last = pos[stem]
+            continue
+        name = None
+        if op == "Gemm" and len(ins) >= 3 and ins[2].endswith(".bias"):
+            name = ins[2][: -len("bias")] + "weight"
+        for cop, cins in consumers.get(outs[0], []) if outs else []:
+            if cop == "Add":
+                for b in cins:
+                    if b.endswith(".bias") and b in init:
+                        name = b[: -len("bias")] + "weight"
+        if name is None or name not in shape_of or name in assigned.values():
+            nxt = [s for s in order[last + 1:] if s not in assigned.values() and s not in sd]
+            cand = [s for s in nxt if tuple(init[stem].shape) == shape_of[s][::-1]]
+            if not cand:
+                continue                                                  # not one of ours (e.g. a helper MatMul)
+            name = cand[0]
+        want = shape_of[name]
+        if tuple(init[stem].shape) != want[::-1]:
+            raise ValueError(f"{name}: MatMul weight {stem} has shape {tuple(init[stem].shape)}, expected [in, out] = {want[::-1]}")
+        assigned[stem] = name
+        last = pos[name]
+    return assigned
+
+
+def _finish_state_dict(g: OnnxGraph, slots, what: str) -> Dict[str, np.ndarray]:
     init = dequantize(g.initializers)
     sd = {k: v for k, v in init.items() if not k.startswith("onnx::") and v.dtype == np.float32}
-    order = [n for n in matmul_weights_in_order(g) if n.startswith("onnx::")]
-    want: List[str] = []
-    for i in range(enc_layers):
-        p = "encoder.encoders0.0" if i == 0 else f"encoder.encoders.{i - 1}"
-        want += [p + ".self_attn.linear_q_k_v.weight", p + ".self_attn.linear_out.weight", p + ".feed_forward.w_1.weight",
-                 p + ".feed_forward.w_2.weight"]
-    want.append("predictor.cif_output.weight")
+    for name, arr in list(sd.items()):
+        want = dict(slots).get(name)
+        if want is not None and tuple(arr.shape) == want[::-1] and want[0] != want[1]:
+            sd[name] = np.ascontiguousarray(arr.T)                        # a named weight stored [in, out]
+    assigned = _assign_matmul_weights(g, init, slots, sd)
+    for src, name in assigned.items():
+        sd[name] = np.ascontiguousarray(init[src].T)
+    missing = [s for s, _ in slots if s not in sd]
+    if missing:
+        raise ValueError(f"{what}: {len(missing)} Linear weights could not be located in the graph, first: {missing[0]}")
+    for name, want in slots:
+        if tuple(sd[name].shape) != want:
+            raise ValueError(f"{what}: {name} has shape {tuple(sd[name].shape)}, expected {want}")
+    return sd
+
+
+def paraformer_state_dict(g: OnnxGraph, enc_layers: int = 50, dec_layers: int = 16, d: int = 512, f: int = 2048, din: int = 560,
+                          dec_f: int = 2048, vocab: int = 0) -> Dict[str, np.ndarray]:
+    """[EXT, EXPERIMENTAL until pinned against a real export] FunASR paraformer ``model.onnx`` -> FunASR state-dict names.
+    Named initialisers (biases, LayerNorm, FSMN and conv kernels) keep their module names in the export; the anonymous
+    ``onnx::MatMul_N`` weights ([in, out]) get theirs from the named bias of the Add behind them, bias-less ones by
+    order, all shape-checked (see ``_assign_matmul_weights``)."""
+    enc = ["encoder.encoders0.0"] + [f"encoder.encoders.{i}" for i in range(enc_layers - 1)]
+    slots = _enc_slots(enc, din, d, f)
+    slots.append(("predictor.cif_output.weight", (1, d)))
     for i in range(dec_layers):
         p = f"decoder.decoders.{i}"
-        want += [p + ".feed_forward.w_1.weight", p + ".feed_forward.w_2.weight", p + ".src_attn.linear_q.weight",
-                 p + ".src_attn.linear_k_v.weight", p + ".src_attn.linear_out.weight"]
-    want += ["decoder.decoders3.0.feed_forward.w_1.weight", "decoder.decoders3.0.feed_forward.w_2.weight"]
-    if len(order) < len(want):
-        raise ValueError(f"graph has {len(order)} anonymous MatMul weights, the paraformer layout needs {len(want)}")
-    for name, src in zip(want, order):
-        sd[name] = np.ascontiguousarray(init[src].T)
-    return sd
+        slots += [(p + ".feed_forward.w_1.weight", (dec_f, d)), (p + ".feed_forward.w_2.weight", (d, dec_f)),
+                  (p + ".src_attn.linear_q.weight", (d, d)), (p + ".src_attn.linear_k_v.weight", (2 * d, d)),
+                  (p + ".src_attn.linear_out.weight", (d, d))]
+    slots += [("decoder.decoders3.0.feed_forward.w_1.weight", (dec_f, d)), ("decoder.decoders3.0.feed_forward.w_2.weight", (d, dec_f))]
+    if vocab:
+        slots.append(("decoder.output_layer.weight", (vocab, d)))
+    return _finish_state_dict(g, slots, "paraformer model.onnx")
+
+
+def sensevoice_state_dict(g: OnnxGraph, enc_layers: int = 50, tp_layers: int = 20, d: int = 512, f: int = 2048, din: int = 560,
+                          vocab: int = 25055) -> Dict[str, np.ndarray]:
+    """[EXT, EXPERIMENTAL] SenseVoiceSmall ``model.onnx`` -> state-dict names: encoders0 + encoders + tp_encoders (four
+    Linear weights each) and the CTC head.  A split-embed export has no ``embed.weight``; the caller adds the reference's
+    own table (``packaged_sensevoice_embed``), which is what EmbedSVModel does with data/embed.onnx."""
+    enc = ["encoder.encoders0.0"] + [f"encoder.encoders.{i}" for i in range(enc_layers - 1)]
+    slots = _enc_slots(enc, din, d, f) + _enc_slots([f"encoder.tp_encoders.{i}" for i in range(tp_layers)], 0, d, f)
+    slots.append(("ctc.ctc_lo.weight", (vocab, d)))
+    return _finish_state_dict(g, slots, "sensevoice model.onnx")

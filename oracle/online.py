@@ -174,15 +174,15 @@ def online_decoder(enc: np.ndarray, embeds: np.ndarray, embeds_len: np.ndarray, 
             out_caches.append(oc.numpy())
             x = x + y
             h = sanm._ln(x, w, p + ".norm3", dims.ln_eps)
-            q = Fn.linear(h, sanm._t(w, p + ".src_attn.linear_q.weight"), sanm._t(w, p + ".src_attn.linear_q.bias"))
-            kv = Fn.linear(memory, sanm._t(w, p + ".src_attn.linear_k_v.weight"), sanm._t(w, p + ".src_attn.linear_k_v.bias"))
+            q = sanm._lin(h, w, p + ".src_attn.linear_q.weight", p + ".src_attn.linear_q.bias", "dec.q")
+            kv = sanm._lin(memory, w, p + ".src_attn.linear_k_v.weight", p + ".src_attn.linear_k_v.bias", "dec.kv")
             k, v = torch.split(kv, d, dim=-1)
-            ctx = sanm._mha(q, k, v, dims.heads)
-            x = x + Fn.linear(ctx, sanm._t(w, p + ".src_attn.linear_out.weight"), sanm._t(w, p + ".src_attn.linear_out.bias"))
+            ctx = sanm._mha(q, k, v, dims.heads, "dec.att")
+            x = x + sanm._lin(ctx, w, p + ".src_attn.linear_out.weight", p + ".src_attn.linear_out.bias", "dec.out")
         p = "decoder.decoders3.0"
         x = sanm._dec_ffn(sanm._ln(x, w, p + ".norm1", dims.ln_eps), w, p + ".feed_forward", dims)
         x = sanm._ln(x, w, "decoder.after_norm", dims.ln_eps)
-        logits = Fn.linear(x, sanm._t(w, "decoder.output_layer.weight"), sanm._t(w, "decoder.output_layer.bias"))
+        logits = sanm._lin(x, w, "decoder.output_layer.weight", "decoder.output_layer.bias", "head")
     return logits.numpy(), out_caches
 
 

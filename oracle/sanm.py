@@ -66,6 +66,53 @@ def _ln(x: torch.Tensor, w, name: str, eps: float) -> torch.Tensor:
     return Fn.layer_norm(x, (x.shape[-1],), _t(w, name + ".weight"), _t(w, name + ".bias"), eps)
 
 
+# --------------------------------------------------------------------------- operand-rounding model (test aid)
+class OperandRounding:
+    """Where a half-precision tensor-core implementation rounds: GEMM / attention OPERANDS go to IEEE fp16 (weights and
+    activations), everything else (accumulation, bias, residual stream, LayerNorm, softmax, CIF) stays float32.  Used as
+    a context manager it turns this float32 oracle into the "same arithmetic, fp16 operands" model that
+    tests/test_gpu_fulldepth.py uses to PROVE where the distance between the CUDA path and the float32 graph comes from:
+
+        with OperandRounding(weights=True, activations=False): ...   # the fp32 graph merely GIVEN fp16-rounded weights
+        with OperandRounding(): ...                                  # every tensor-core operand rounded
+
+    ``skip`` names sites that stay float32 (e.g. {"pred.conv", "head"}); sites: enc.qkv enc.att enc.out enc.ffn1
+    enc.ffn2 pred.conv dec.kv dec.ffn1 dec.ffn2 dec.q dec.att dec.out head hw.lstm (SeACo stacks use the dec.* names)."""
+    current: "Optional[OperandRounding]" = None
+
+    def __init__(self, weights: bool = True, activations: bool = True, skip=()):
+        self.weights, self.activations, self.skip = weights, activations, frozenset(skip)
+
+    def __enter__(self):
+        self._prev = OperandRounding.current
+        OperandRounding.current = self
+        return self
+
+    def __exit__(self, *exc):
+        OperandRounding.current = self._prev
+        return False
+
+
+def _h(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.float16).to(torch.float32)
+
+
+def _ra(x: torch.Tensor, site: str) -> torch.Tensor:
+    """activation operand of ``site``"""
+    r = OperandRounding.current
+    return _h(x) if r is not None and r.activations and site not in r.skip else x
+
+
+def _rw(x: torch.Tensor, site: str) -> torch.Tensor:
+    """weight operand of ``site``"""
+    r = OperandRounding.current
+    return _h(x) if r is not None and r.weights and site not in r.skip else x
+
+
+def _lin(x: torch.Tensor, w, wname: str, bname: Optional[str], site: str) -> torch.Tensor:
+    return Fn.linear(_ra(x, site), _rw(_t(w, wname), site), _t(w, bname) if bname else None)
+
+
 def sinusoidal_pe(t: int, depth: int, start: int = 1) -> torch.Tensor:
     """FunASR ``SinusoidalPositionEncoder``: positions start..start+t-1, [sin | cos] halves,
     ``inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1))``."""
@@ -92,11 +139,21 @@ def _fsmn(v: torch.Tensor, weight: torch.Tensor, mask: Optional[torch.Tensor]) -
     return x
 
 
-def _mha(q, k, v, heads: int) -> torch.Tensor:
+def _mha(q, k, v, heads: int, site: str = "att") -> torch.Tensor:
     """softmax(q k^T / sqrt(d_k)) v over [B,Tq,D] x [B,Tk,D]; masks are all-ones (Q3)."""
     b, tq, d = q.shape
     tk = k.shape[1]
     dk = d // heads
+    r = OperandRounding.current
+    if r is not None and r.activations and site not in r.skip:
+        # tensor-core form: q, k, v are fp16 operands; the scale is applied to the fp32 scores; the un-normalised
+        # probabilities exp(s - max) are the fp16 operand of the second product and the row sum divides its fp32 result
+        qh = _h(q).view(b, tq, heads, dk).transpose(1, 2)
+        kh = _h(k).view(b, tk, heads, dk).transpose(1, 2)
+        vh = _h(v).view(b, tk, heads, dk).transpose(1, 2)
+        sc = (qh @ kh.transpose(-2, -1)) * (dk ** -0.5)
+        e = torch.exp(sc - sc.max(dim=-1, keepdim=True).values)
+        return ((_h(e) @ vh) / e.sum(dim=-1, keepdim=True)).transpose(1, 2).reshape(b, tq, d)
     qh = q.view(b, tq, heads, dk).transpose(1, 2) * (dk ** -0.5)
     kh = k.view(b, tk, heads, dk).transpose(1, 2)
     vh = v.view(b, tk, heads, dk).transpose(1, 2)
@@ -109,15 +166,15 @@ def encoder_layer(x: torch.Tensor, w, p: str, dims: ModelDims) -> torch.Tensor:
     in_size = x.shape[-1]
     d = dims.d_model
     h = _ln(x, w, p + ".norm1", dims.ln_eps)
-    qkv = Fn.linear(h, _t(w, p + ".self_attn.linear_q_k_v.weight"), _t(w, p + ".self_attn.linear_q_k_v.bias"))
+    qkv = _lin(h, w, p + ".self_attn.linear_q_k_v.weight", p + ".self_attn.linear_q_k_v.bias", "enc.qkv")
     q, k, v = torch.split(qkv, d, dim=-1)
-    mem = _fsmn(v, _t(w, p + ".self_attn.fsmn_block.weight"), None)
-    ctx = _mha(q, k, v, dims.heads)
-    att = Fn.linear(ctx, _t(w, p + ".self_attn.linear_out.weight"), _t(w, p + ".self_attn.linear_out.bias")) + mem
+    mem = _fsmn(_ra(v, "enc.att"), _t(w, p + ".self_attn.fsmn_block.weight"), None)      # the memory reads the stored V
+    ctx = _mha(q, k, v, dims.heads, "enc.att")
+    att = _lin(ctx, w, p + ".self_attn.linear_out.weight", p + ".self_attn.linear_out.bias", "enc.out") + mem
     x = att + x if in_size == d else att
     h = _ln(x, w, p + ".norm2", dims.ln_eps)
-    h = torch.relu(Fn.linear(h, _t(w, p + ".feed_forward.w_1.weight"), _t(w, p + ".feed_forward.w_1.bias")))
-    h = Fn.linear(h, _t(w, p + ".feed_forward.w_2.weight"), _t(w, p + ".feed_forward.w_2.bias"))
+    h = torch.relu(_lin(h, w, p + ".feed_forward.w_1.weight", p + ".feed_forward.w_1.bias", "enc.ffn1"))
+    h = _lin(h, w, p + ".feed_forward.w_2.weight", p + ".feed_forward.w_2.bias", "enc.ffn2")
     return x + h
 
 
@@ -128,8 +185,11 @@ def encoder(speech: torch.Tensor, w, dims: ModelDims, collect: Optional[dict] = 
     x = encoder_layer(x, w, "encoder.encoders0.0", dims)
     if collect is not None:
         collect["enc_layer0"] = x.clone()
+        collect["enc_after_1"] = x.numpy().copy()
     for i in range(dims.enc_layers - 1):
         x = encoder_layer(x, w, f"encoder.encoders.{i}", dims)
+        if collect is not None and (i + 2) in collect.get("tap_layers", ()):
+            collect[f"enc_after_{i + 2}"] = x.numpy().copy()          # residual stream after i+2 layers
     x = _ln(x, w, "encoder.after_norm", dims.ln_eps)
     if dims.tp_layers:
         for i in range(dims.tp_layers):
@@ -140,8 +200,8 @@ def encoder(speech: torch.Tensor, w, dims: ModelDims, collect: Optional[dict] = 
 
 def predictor_alphas(enc: torch.Tensor, w, dims: ModelDims) -> torch.Tensor:
     """CifPredictorV2 alpha head + tail: returns alphas [B, T+1] (last column = tail_threshold)."""
-    ctx = Fn.pad(enc.transpose(1, 2), (1, 1))
-    out = torch.relu(Fn.conv1d(ctx, _t(w, "predictor.cif_conv1d.weight"), _t(w, "predictor.cif_conv1d.bias")))
+    ctx = Fn.pad(_ra(enc, "pred.conv").transpose(1, 2), (1, 1))
+    out = torch.relu(Fn.conv1d(ctx, _rw(_t(w, "predictor.cif_conv1d.weight"), "pred.conv"), _t(w, "predictor.cif_conv1d.bias")))
     out = Fn.linear(out.transpose(1, 2), _t(w, "predictor.cif_output.weight"), _t(w, "predictor.cif_output.bias"))
     alphas = torch.sigmoid(out).squeeze(-1)
     alphas = torch.relu(alphas * dims.smooth_factor - dims.noise_threshold)
@@ -195,9 +255,9 @@ def cif(hidden: np.ndarray, alphas: np.ndarray, threshold: float = 1.0):
 
 def _dec_ffn(x: torch.Tensor, w, p: str, dims: ModelDims) -> torch.Tensor:
     """PositionwiseFeedForwardDecoderSANM: w_2(LN(relu(w_1 x))), w_2 has no bias."""
-    h = torch.relu(Fn.linear(x, _t(w, p + ".w_1.weight"), _t(w, p + ".w_1.bias")))
+    h = torch.relu(_lin(x, w, p + ".w_1.weight", p + ".w_1.bias", "dec.ffn1"))
     h = _ln(h, w, p + ".norm", dims.ln_eps)
-    return Fn.linear(h, _t(w, p + ".w_2.weight"), None)
+    return _lin(h, w, p + ".w_2.weight", None, "dec.ffn2")
 
 
 def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w, dims: ModelDims,
@@ -215,11 +275,11 @@ def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w,
         tn = _ln(t, w, p + ".norm2", dims.ln_eps)
         x = x + _fsmn(tn, _t(w, p + ".self_attn.fsmn_block.weight"), tgt_mask)
         h = _ln(x, w, p + ".norm3", dims.ln_eps)
-        q = Fn.linear(h, _t(w, p + ".src_attn.linear_q.weight"), _t(w, p + ".src_attn.linear_q.bias"))
-        kv = Fn.linear(enc, _t(w, p + ".src_attn.linear_k_v.weight"), _t(w, p + ".src_attn.linear_k_v.bias"))
+        q = _lin(h, w, p + ".src_attn.linear_q.weight", p + ".src_attn.linear_q.bias", "dec.q")
+        kv = _lin(enc, w, p + ".src_attn.linear_k_v.weight", p + ".src_attn.linear_k_v.bias", "dec.kv")
         k, v = torch.split(kv, d, dim=-1)
-        ctx = _mha(q, k, v, dims.heads)
-        x = x + Fn.linear(ctx, _t(w, p + ".src_attn.linear_out.weight"), _t(w, p + ".src_attn.linear_out.bias"))
+        ctx = _mha(q, k, v, dims.heads, "dec.att")
+        x = x + _lin(ctx, w, p + ".src_attn.linear_out.weight", p + ".src_attn.linear_out.bias", "dec.out")
         if collect is not None and i == 0:
             collect["dec_layer0"] = x.clone()
     p = f"{prefix}.decoders3.0"
@@ -227,7 +287,7 @@ def decoder(enc: torch.Tensor, embeds: torch.Tensor, token_num: torch.Tensor, w,
     x = _ln(x, w, f"{prefix}.after_norm", dims.ln_eps)
     if prefix != "decoder":
         return x
-    logits = Fn.linear(x, _t(w, "decoder.output_layer.weight"), _t(w, "decoder.output_layer.bias"))
+    logits = _lin(x, w, "decoder.output_layer.weight", "decoder.output_layer.bias", "head")
     return (logits, x) if return_hidden else logits
 
 
@@ -305,7 +365,7 @@ def sensevoice_forward(speech: np.ndarray, w, dims: ModelDims):
     with torch.no_grad():
         x = torch.from_numpy(np.ascontiguousarray(speech, dtype=np.float32))
         enc = encoder(x, w, dims)
-        logits = Fn.linear(enc, _t(w, "ctc.ctc_lo.weight"), _t(w, "ctc.ctc_lo.bias"))
+        logits = _lin(enc, w, "ctc.ctc_lo.weight", "ctc.ctc_lo.bias", "head")
         logp = torch.log_softmax(logits, dim=-1).numpy()
     return {"logits": logp, "tokens": greedy_pick(logp), "enc": enc.numpy(),
             "token_num": np.full(speech.shape[0], speech.shape[1], dtype=np.int32)}
@@ -351,7 +411,7 @@ def hotword_embed(hotword: np.ndarray, w) -> np.ndarray:
             c = torch.zeros(n, hdim)
             outs = []
             for t in range(x.shape[0]):
-                gates = Fn.linear(x[t], wih, bih) + Fn.linear(h, whh, bhh)
+                gates = Fn.linear(_ra(x[t], "hw.lstm"), _rw(wih, "hw.lstm"), bih) + Fn.linear(_ra(h, "hw.lstm"), _rw(whh, "hw.lstm"), bhh)
                 i, f, g, o = gates.chunk(4, dim=1)                                    # PyTorch gate order
                 c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
                 h = torch.sigmoid(o) * torch.tanh(c)
@@ -388,7 +448,7 @@ def seaco_forward(speech: np.ndarray, w, dims: ModelDims, bias_rows: np.ndarray)
         cif_att = decoder(mem, embeds, tn, w, sdims, prefix="seaco_decoder", layers=dims.seaco_layers)
         dec_att = decoder(mem, dec_hidden, tn, w, sdims, prefix="seaco_decoder", layers=dims.seaco_layers)
         merged = cif_att + dec_att
-        dha = torch.log_softmax(Fn.linear(merged, _t(w, "hotword_output_layer.weight"), _t(w, "hotword_output_layer.bias")), dim=-1)
+        dha = torch.log_softmax(_lin(merged, w, "hotword_output_layer.weight", "hotword_output_layer.bias", "head"), dim=-1)
         dha_ids = dha.argmax(dim=-1)
         keep_asr = (dha_ids == dims.nobias_id)[..., None]
         out = torch.where(keep_asr, asr, dha).numpy()

@@ -76,29 +76,51 @@ def onnx_model(tensors, nodes):
     return _pb_varint((1 << 3) | 0) + _pb_varint(8) + _pb_ld(7, graph)
 
 
-def export_paraformer_onnx(weights, enc_layers, dec_layers):
-    """A model.onnx image in the FunASR export convention for a synthetic paraformer state dict: Linear weights become
-    anonymous ``onnx::MatMul_N`` initialisers ([in, out]) consumed by MatMul nodes in execution order, everything else
-    keeps its module name."""
-    order = []
-    for i in range(enc_layers):
-        p = "encoder.encoders0.0" if i == 0 else f"encoder.encoders.{i - 1}"
-        order += [p + ".self_attn.linear_q_k_v.weight", p + ".self_attn.linear_out.weight", p + ".feed_forward.w_1.weight",
-                  p + ".feed_forward.w_2.weight"]
-    order.append("predictor.cif_output.weight")
-    for i in range(dec_layers):
-        p = f"decoder.decoders.{i}"
-        order += [p + ".feed_forward.w_1.weight", p + ".feed_forward.w_2.weight", p + ".src_attn.linear_q.weight",
-                  p + ".src_attn.linear_k_v.weight", p + ".src_attn.linear_out.weight"]
-    order += ["decoder.decoders3.0.feed_forward.w_1.weight", "decoder.decoders3.0.feed_forward.w_2.weight"]
+def _export_linears(weights, linears, extra_nodes=()):
+    """FunASR / torch.onnx convention: ``nn.Linear`` on a 3-D input becomes ``MatMul(x, onnx::MatMul_N)`` with the weight
+    stored [in, out] under an anonymous name, followed by ``Add(<module>.bias, y)`` whose bias keeps its module name;
+    a bias-less Linear is a bare MatMul.  ``linears``: module names in the order the nodes are written."""
     tensors, nodes = [], []
-    anon = {}
-    for k, name in enumerate(order):
-        anon[name] = f"onnx::MatMul_{1000 + 7 * k}"
-        tensors.append(onnx_tensor(anon[name], np.ascontiguousarray(weights[name].T)))
-        nodes.append(("MatMul", [f"x{k}", anon[name]], [f"y{k}"]))
-        nodes.append(("Add", [f"y{k}", "some.bias"], [f"x{k + 1}"]))
+    anon = set()
+    for k, mod in enumerate(linears):
+        a = f"onnx::MatMul_{1000 + 7 * k}"
+        anon.add(mod + ".weight")
+        tensors.append(onnx_tensor(a, np.ascontiguousarray(weights[mod + ".weight"].T)))
+        nodes.append(("MatMul", [f"x{k}", a], [f"y{k}"]))
+        if mod + ".bias" in weights:
+            nodes.append(("Add", [mod + ".bias", f"y{k}"], [f"x{k + 1}"]))
+        else:
+            nodes.append(("Relu", [f"y{k}"], [f"x{k + 1}"]))
+    nodes += list(extra_nodes)
     for name, arr in weights.items():
         if name not in anon:
             tensors.append(onnx_tensor(name, np.asarray(arr, np.float32)))
     return onnx_model(tensors, nodes)
+
+
+def export_paraformer_onnx(weights, enc_layers, dec_layers, anonymous_head=True):
+    """A model.onnx image in the FunASR export convention for a synthetic paraformer state dict.  The node order is
+    deliberately NOT the order onnx_weights lists its slots in (the cross-attention K/V projection is written before the
+    query projection, the alpha head after the decoder), so the round trip only succeeds if names are derived from the
+    graph (the bias of the Add behind each MatMul), not from position."""
+    order = []
+    for i in range(enc_layers):
+        p = "encoder.encoders0.0" if i == 0 else f"encoder.encoders.{i - 1}"
+        order += [p + ".self_attn.linear_q_k_v", p + ".self_attn.linear_out", p + ".feed_forward.w_1", p + ".feed_forward.w_2"]
+    for i in range(dec_layers):
+        p = f"decoder.decoders.{i}"
+        order += [p + ".src_attn.linear_k_v", p + ".feed_forward.w_1", p + ".feed_forward.w_2", p + ".src_attn.linear_q", p + ".src_attn.linear_out"]
+    order += ["decoder.decoders3.0.feed_forward.w_1", "decoder.decoders3.0.feed_forward.w_2", "predictor.cif_output"]
+    if anonymous_head:
+        order.append("decoder.output_layer")
+    return _export_linears(weights, order)
+
+
+def export_sensevoice_onnx(weights, enc_layers, tp_layers):
+    """Split-embed SenseVoiceSmall export: encoder + tp_encoder Linears and the CTC head, no ``embed.weight``."""
+    order = []
+    for p in ["encoder.encoders0.0"] + [f"encoder.encoders.{i}" for i in range(enc_layers - 1)] + [f"encoder.tp_encoders.{i}" for i in range(tp_layers)]:
+        order += [p + ".self_attn.linear_q_k_v", p + ".self_attn.linear_out", p + ".feed_forward.w_1", p + ".feed_forward.w_2"]
+    order.append("ctc.ctc_lo")
+    w = {k: v for k, v in weights.items() if k != "embed.weight"}
+    return _export_linears(w, order)

@@ -96,17 +96,72 @@ def test_real_embed_onnx_matches_golden():
 
 def test_paraformer_export_maps_back_to_the_state_dict():
     """model.onnx ingestion end to end on the host: a synthetic paraformer state dict written in the FunASR export
-    convention (anonymous MatMul weights in graph order) maps back to the same names and values."""
+    convention (anonymous MatMul weights, named biases, node order different from the mapper's slot order) maps back to
+    the same names and values - names come from the bias behind each MatMul, bias-less w_2 from its position."""
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
     from _util import export_paraformer_onnx
     from aliparaformerasr_b200 import synth
     cfg = synth.tiny()
     w = synth.make_weights(cfg)
-    sd = ow.paraformer_state_dict(ow.read_onnx(export_paraformer_onnx(w, cfg.enc_layers, cfg.dec_layers)), cfg.enc_layers, cfg.dec_layers)
-    assert set(sd) == set(w)
+    for anon_head in (True, False):
+        g = ow.read_onnx(export_paraformer_onnx(w, cfg.enc_layers, cfg.dec_layers, anonymous_head=anon_head))
+        sd = ow.paraformer_state_dict(g, cfg.enc_layers, cfg.dec_layers, cfg.d_model, cfg.ffn, cfg.input_size, cfg.dec_ffn, cfg.vocab)
+        assert set(sd) == set(w)
+        for k in w:
+            assert sd[k].shape == w[k].shape and np.array_equal(sd[k], w[k]), k
+
+
+def test_same_shaped_weights_cannot_be_swapped_silently():
+    """linear_out and linear_q are both [512, 512]: writing them in swapped node order still maps each to its own name
+    (bias-derived), and a weight whose shape does not fit its slot is an error, not a silent mis-assignment."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from _util import _export_linears
+    from aliparaformerasr_b200 import synth
+    cfg = synth.tiny()
+    w = synth.make_weights(cfg)
+    mods = sorted({k[: -len(".weight")] for k in w if k.endswith(".weight") and w[k].ndim == 2 and
+                   ("linear" in k or ".w_" in k or k.startswith("predictor.cif_output"))})
+    # bias-less w_2 must still follow its w_1; everything else is shuffled
+    rng = np.random.default_rng(3)
+    rest = [m for m in mods if not (m.startswith("decoder.") and m.endswith("feed_forward.w_2"))]
+    rng.shuffle(rest)
+    order = []
+    for m in rest:
+        order.append(m)
+        if m.startswith("decoder.") and m.endswith("feed_forward.w_1"):
+            order.append(m[:-1] + "2")
+    sd = ow.paraformer_state_dict(ow.read_onnx(_export_linears(w, order)), cfg.enc_layers, cfg.dec_layers, cfg.d_model, cfg.ffn,
+                                  cfg.input_size, cfg.dec_ffn)
     for k in w:
-        assert sd[k].shape == w[k].shape and np.array_equal(sd[k], w[k]), k
+        assert np.array_equal(sd[k], w[k]), k
+    bad = dict(w)
+    bad["encoder.encoders.0.self_attn.linear_out.weight"] = np.zeros((512, 256), np.float32)
+    with pytest.raises(ValueError):
+        ow.paraformer_state_dict(ow.read_onnx(_export_linears(bad, order)), cfg.enc_layers, cfg.dec_layers, cfg.d_model, cfg.ffn,
+                                 cfg.input_size, cfg.dec_ffn)
+
+
+def test_sensevoice_split_embed_export_and_packaged_prompt_table():
+    """A split-embed SenseVoice model.onnx has no embed.weight: the mapper finds the 70 x 4 + 1 Linear weights and the
+    packaged table is the reference's data/embed.onnx payload (sha256-pinned, EmbedSVModel.cs:20-43)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from _util import export_sensevoice_onnx
+    from aliparaformerasr_b200 import synth
+    cfg = synth.tiny("sensevoicesmall")
+    w = synth.make_weights(cfg)
+    sd = ow.sensevoice_state_dict(ow.read_onnx(export_sensevoice_onnx(w, cfg.enc_layers, cfg.tp_layers)), cfg.enc_layers, cfg.tp_layers,
+                                  cfg.d_model, cfg.ffn, cfg.input_size, cfg.vocab)
+    assert "embed.weight" not in sd
+    for k in w:
+        if k != "embed.weight":
+            assert np.array_equal(sd[k], w[k]), k
+    tab = ow.packaged_sensevoice_embed()
+    assert tab.shape == (16, 560) and np.array_equal(tab, np.load(GOLD))
+    if os.path.exists(REAL):
+        assert np.array_equal(tab, ow.sensevoice_embed_table(REAL))
 
 
 def test_corrupted_files_raise_value_error():
