@@ -3,9 +3,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <fstream>
 #include <map>
 #include <thread>
+#include <unordered_map>
 
 #include "engine.cuh"
 
@@ -91,20 +93,68 @@ static Handle* create_handle_t(const pf_config* cfg, const void* blob, size_t by
     return h.release();
 }
 
-// pf_offline = a pool of independent lanes (each a full OfflineHandle: own streams, staging, activations, weight copy).
-// A host thread is bound to one lane on its first call, so calls from different threads run concurrently on the GPU:
-// the kernels of two batches interleave at CTA granularity and one batch's kernel tails, launch gaps and PCIe copies
-// are filled with the other's work (measured +13 % resident / +30 % end to end with two lanes at 32 x 10 s).  The
-// reference serialises concurrent GetResults calls on the single ORT session's intra-op pool; results stay valid until
-// the calling thread's next call on the handle.
+// pf_offline = a pool of independent lanes (each a full OfflineHandle: own streams, staging, activations; the device
+// weights are shared).  Calls from different host threads run concurrently on the GPU: the kernels of two batches
+// interleave at CTA granularity and one batch's kernel tails, launch gaps and PCIe copies are filled with the other's
+// work.  The reference serialises concurrent GetResults calls on the single ORT session's intra-op pool.
+//
+// Isolation between threads (what pf_abi.h promises):
+//   * thread -> lane binding is a pure function of a process-wide thread ordinal (assigned at the thread's first call
+//     into the library) modulo the lane count: it never changes, so a batch staged by a thread is run by the same lane,
+//     and no table has to be pruned.  More threads than lanes simply share lanes; every call holds the lane's mutex.
+//   * pf_result never points into lane-owned buffers: before the lane mutex is released the outputs are copied into
+//     storage owned by the CALLING THREAD (per handle), valid until that thread's next run on the handle.
+//   * a sequence of calls that must not be interleaved with another thread sharing the lane (per-call hot words:
+//     set_hotwords_local -> run -> restore) is wrapped in pf_offline_lane_acquire / pf_offline_lane_release.
 struct OfflinePool {
     ~OfflinePool() { while (!lanes.empty()) lanes.pop_back(); }     // lane 0 owns the device weights: it goes last
     std::vector<std::unique_ptr<OfflineHandle>> lanes;
-    std::mutex mu;
-    std::map<std::thread::id, int> lane_of_thread;
-    int next = 0;
     pf_config cfg;
+    uint64_t serial = 0;               // distinguishes a new pool that reuses a destroyed pool's address
 };
+
+static std::atomic<int> g_thread_ordinals{0};
+static std::atomic<uint64_t> g_pool_serials{1};
+static int thread_ordinal() {
+    thread_local int ord = g_thread_ordinals.fetch_add(1);
+    return ord;
+}
+
+// outputs of the calling thread's last run on a handle
+struct ThreadResults {
+    uint64_t serial = 0;
+    std::vector<int32_t> tokens, token_num;
+    std::vector<float> logits, peaks, us;
+};
+static ThreadResults& thread_results(const OfflinePool* pool) {
+    thread_local std::unordered_map<const OfflinePool*, ThreadResults> store;
+    ThreadResults& r = store[pool];
+    if (r.serial != pool->serial) { r = ThreadResults{}; r.serial = pool->serial; }
+    return r;
+}
+
+// pf_result as filled by run_all points into lane-owned (pinned) buffers: re-home it into the calling thread's storage
+static void own_results(const OfflinePool* pool, pf_result* out) {
+    ThreadResults& r = thread_results(pool);
+    const size_t B = static_cast<size_t>(std::max(out->batch, 0)), L = static_cast<size_t>(std::max(out->max_len, 0));
+    auto take = [](auto& vec, auto*& ptr, size_t n) {
+        if (!ptr) { return; }
+        vec.assign(ptr, ptr + n);
+        ptr = vec.data();
+    };
+    take(r.tokens, out->tokens, B * L);
+    take(r.token_num, out->token_num, B);
+    take(r.logits, out->logits, B * L * static_cast<size_t>(out->vocab));
+    take(r.peaks, out->cif_peak, B * static_cast<size_t>(out->feat_frames + 1));
+    if (out->us_alphas && out->us_cif_peak && out->us_frames > 0) {
+        const size_t n = B * static_cast<size_t>(out->us_frames);
+        r.us.resize(2 * n);
+        memcpy(r.us.data(), out->us_alphas, n * sizeof(float));
+        memcpy(r.us.data() + n, out->us_cif_peak, n * sizeof(float));
+        out->us_alphas = r.us.data();
+        out->us_cif_peak = r.us.data() + n;
+    }
+}
 
 static int default_lanes() {
     const char* e = getenv("PFASR_LANES");
@@ -118,6 +168,7 @@ static OfflinePool* create_pool(const pf_config* cfg, const void* blob, size_t b
     for (int l = 0; l < lanes; ++l)
         pool->lanes.emplace_back(create_handle_t<OfflineHandle>(cfg, blob, bytes, devices, ndev, l ? pool->lanes[0].get() : nullptr));
     pool->cfg = *cfg;
+    pool->serial = g_pool_serials.fetch_add(1);
     if (lanes > 1)
         for (auto& lane : pool->lanes)
             for (auto& d : lane->devs) d->throughput_mode = true;
@@ -128,14 +179,7 @@ static OfflinePool* create_pool(const pf_config* cfg, const void* blob, size_t b
 static OfflineHandle* lane_of(pf_offline* hh) {
     OfflinePool* pool = reinterpret_cast<OfflinePool*>(hh);
     if (pool->lanes.size() == 1) return pool->lanes[0].get();
-    std::lock_guard<std::mutex> g(pool->mu);
-    auto it = pool->lane_of_thread.find(std::this_thread::get_id());
-    if (it == pool->lane_of_thread.end()) {
-        if (pool->lane_of_thread.size() > 4096) pool->lane_of_thread.clear();    // thread-per-request callers: forget exited threads
-        it = pool->lane_of_thread.emplace(std::this_thread::get_id(), pool->next).first;
-        pool->next = (pool->next + 1) % static_cast<int>(pool->lanes.size());
-    }
-    return pool->lanes[it->second].get();
+    return pool->lanes[static_cast<size_t>(thread_ordinal()) % pool->lanes.size()].get();
 }
 
 static std::vector<char> read_file(const char* path) {
@@ -402,13 +446,29 @@ pf_status pf_offline_destroy(pf_offline* hh) {
     });
 }
 
+int32_t pf_offline_lane_acquire(pf_offline* hh) {
+    if (!hh) return -1;
+    OfflinePool* pool = reinterpret_cast<OfflinePool*>(hh);
+    OfflineHandle* h = lane_of(hh);
+    h->mu.lock();
+    for (size_t i = 0; i < pool->lanes.size(); ++i) if (pool->lanes[i].get() == h) return static_cast<int32_t>(i);
+    return 0;
+}
+
+pf_status pf_offline_lane_release(pf_offline* hh) {
+    return guarded([&] {
+        if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
+        lane_of(hh)->mu.unlock();
+    });
+}
+
 pf_status pf_offline_set_cmvn(pf_offline* hh, const float* add_shift, const float* rescale, int32_t dim) {
     return guarded([&] {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!add_shift || !rescale) throw StatusError{PF_ERR_BAD_ARG, "null cmvn vectors"};
         for (auto& lane : reinterpret_cast<OfflinePool*>(hh)->lanes) {
             OfflineHandle* h = lane.get();
-            std::lock_guard<std::mutex> g(h->mu);
+            std::lock_guard<std::recursive_mutex> g(h->mu);
             for (auto& d : h->devs) d->set_cmvn(add_shift, rescale, dim);
         }
     });
@@ -420,7 +480,7 @@ pf_status pf_offline_set_hotwords(pf_offline* hh, const int32_t* ids, int32_t n)
         if (n < 0 || (n > 0 && !ids)) throw StatusError{PF_ERR_BAD_ARG, "ids is null"};
         for (auto& lane : reinterpret_cast<OfflinePool*>(hh)->lanes) {
             OfflineHandle* h = lane.get();
-            std::lock_guard<std::mutex> g(h->mu);
+            std::lock_guard<std::recursive_mutex> g(h->mu);
             for (auto& d : h->devs) d->set_hotwords(ids, n);
         }
     });
@@ -431,7 +491,7 @@ pf_status pf_offline_set_hotwords_local(pf_offline* hh, const int32_t* ids, int3
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (n < 0 || (n > 0 && !ids)) throw StatusError{PF_ERR_BAD_ARG, "ids is null"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         for (auto& d : h->devs) d->set_hotwords(ids, n);
     });
 }
@@ -442,7 +502,7 @@ static pf_status extract_common(pf_offline* hh, const float* samples, int32_t ns
         if (!samples) throw StatusError{PF_ERR_BAD_ARG, "samples is null (ArgumentNullException 'source' in the reference, WavFrontend.cs:34)"};
         if (nsamp < 0 || !out_frames || (!out && cap > 0)) throw StatusError{PF_ERR_BAD_ARG, "bad arguments"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         *out_frames = h->devs[0]->extract(samples, nsamp, out, cap, raw);
     });
 }
@@ -463,7 +523,7 @@ pf_status pf_offline_stage_pcm(pf_offline* hh, const float* const* pcm, const in
     return guarded([&] {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         stage_pcm_all(h, pcm, nsamp, batch);
         // standalone staging returns only once the PCM is resident in HBM (the caller may free its buffers)
         for (auto& d : h->devs) d->sync_staging();
@@ -475,9 +535,10 @@ pf_status pf_offline_run_staged(pf_offline* hh, uint32_t flags, pf_result* out) 
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         memset(out, 0, sizeof(*out));
         run_all(h, flags, out);
+        own_results(reinterpret_cast<OfflinePool*>(hh), out);
     });
 }
 
@@ -486,10 +547,11 @@ pf_status pf_offline_run_pcm(pf_offline* hh, const float* const* pcm, const int3
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         memset(out, 0, sizeof(*out));
         stage_pcm_all(h, pcm, nsamp, batch);
         run_all(h, flags, out);
+        own_results(reinterpret_cast<OfflinePool*>(hh), out);
     });
 }
 
@@ -498,10 +560,11 @@ pf_status pf_offline_run_audio(pf_offline* hh, const pf_audio* utts, int32_t bat
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!out) throw StatusError{PF_ERR_BAD_ARG, "out is null"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         memset(out, 0, sizeof(*out));
         stage_audio_all(h, utts, batch);
         run_all(h, flags, out);
+        own_results(reinterpret_cast<OfflinePool*>(hh), out);
     });
 }
 
@@ -511,7 +574,7 @@ pf_status pf_offline_run_feats(pf_offline* hh, const float* speech, int32_t batc
         if (!out || !speech) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
         if (batch <= 0 || frames <= 0) throw StatusError{PF_ERR_SHAPE, "speech must be [B>0, T>0, input_size]"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         memset(out, 0, sizeof(*out));
         const int n = static_cast<int>(h->devs.size());
         split_batch(batch, n, h->shard_begin, h->shard_count);
@@ -521,6 +584,7 @@ pf_status pf_offline_run_feats(pf_offline* hh, const float* speech, int32_t batc
         h->B = batch;
         h->staged = true;
         run_all(h, flags, out);
+        own_results(reinterpret_cast<OfflinePool*>(hh), out);
     });
 }
 
@@ -528,7 +592,7 @@ pf_status pf_offline_get_tensor(pf_offline* hh, int32_t dev_index, const char* n
     return guarded([&] {
         if (!hh || !name) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
         OfflineHandle* h = lane_of(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         if (dev_index < 0 || dev_index >= static_cast<int>(h->devs.size())) throw StatusError{PF_ERR_BAD_ARG, "dev_index out of range"};
         h->devs[dev_index]->get_tensor(name, dst, capacity, dims4, ndim);
     });
@@ -563,7 +627,7 @@ pf_status pf_offline_set_profile(pf_offline* hh, int32_t on) {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         for (auto& lane : reinterpret_cast<OfflinePool*>(hh)->lanes) {
             OfflineHandle* h = lane.get();
-            std::lock_guard<std::mutex> g(h->mu);
+            std::lock_guard<std::recursive_mutex> g(h->mu);
             for (auto& d : h->devs) d->set_profile(on);
         }
     });
@@ -577,7 +641,7 @@ double pf_offline_get_gemm_ms(pf_offline* hh) {
 double pf_offline_replay_gemms(pf_offline* hh, int32_t iters) {
     if (!hh) return 0;
     OfflineHandle* h = lane_of(hh);
-    std::lock_guard<std::mutex> g(h->mu);
+    std::lock_guard<std::recursive_mutex> g(h->mu);
     try {
         return h->devs[0]->replay_gemms(iters);
     } catch (...) {
@@ -637,7 +701,7 @@ pf_status pf_online_set_cmvn(pf_online* hh, const float* add_shift, const float*
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!add_shift || !rescale) throw StatusError{PF_ERR_BAD_ARG, "null cmvn vectors"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         for (auto& d : h->devs) d->set_cmvn(add_shift, rescale, dim);
     });
 }
@@ -647,7 +711,7 @@ pf_status pf_online_stream_open(pf_online* hh, int32_t* stream_id) {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         if (!stream_id) throw StatusError{PF_ERR_BAD_ARG, "stream_id is null"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         int id = -1;
         for (size_t i = 0; i < h->streams.size(); ++i) if (!h->streams[i].open) { id = static_cast<int>(i); break; }
         if (id < 0) { id = static_cast<int>(h->streams.size()); h->streams.emplace_back(); }
@@ -664,7 +728,7 @@ pf_status pf_online_stream_close(pf_online* hh, int32_t stream_id) {
     return guarded([&] {
         if (!hh) throw StatusError{PF_ERR_DISPOSED, "handle is null"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         OnlineStreamHost& st = stream_of(h, stream_id);
         h->devs[st.dev]->online_close(st.slot);
         st.open = false;
@@ -679,7 +743,7 @@ pf_status pf_online_stream_push(pf_online* hh, int32_t stream_id, const float* s
         if (!samples && nsamp != 0) throw StatusError{PF_ERR_BAD_ARG, "samples is null (NullReferenceException in OnlineStream.AddSamples)"};
         if (nsamp < 0) throw StatusError{PF_ERR_BAD_ARG, "negative sample count"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         OnlineStreamHost& st = stream_of(h, stream_id);
         st.cache_samples.insert(st.cache_samples.end(), samples, samples + nsamp);
         if (static_cast<int>(st.cache_samples.size()) > kChunkSamples) {          // strictly more than one chunk (OnlineStream.cs:102)
@@ -692,7 +756,7 @@ pf_status pf_online_stream_push(pf_online* hh, int32_t stream_id, const float* s
 int32_t pf_online_stream_ready(pf_online* hh, int32_t stream_id) {
     if (!hh) return -1;
     OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-    std::lock_guard<std::mutex> g(h->mu);
+    std::lock_guard<std::recursive_mutex> g(h->mu);
     if (stream_id < 0 || stream_id >= static_cast<int>(h->streams.size()) || !h->streams[stream_id].open) return -1;
     const OnlineStreamHost& st = h->streams[stream_id];
     return h->devs[st.dev]->online_ready(st.slot) ? 1 : 0;
@@ -706,7 +770,7 @@ pf_status pf_online_step(pf_online* hh, const int32_t* stream_ids, int32_t n, ui
         if (n == 0) return;                                            // streams.Count == 0 (OnlineRecognizer.cs:343-346)
         if (!stream_ids || n < 0) throw StatusError{PF_ERR_BAD_ARG, "stream_ids is null"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         online_step_all(h, stream_ids, n, flags, out);
     });
 }
@@ -715,7 +779,7 @@ pf_status pf_online_get_state(pf_online* hh, int32_t stream_id, const char* name
     return guarded([&] {
         if (!hh || !name) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
         OnlineHandle* h = reinterpret_cast<OnlineHandle*>(hh);
-        std::lock_guard<std::mutex> g(h->mu);
+        std::lock_guard<std::recursive_mutex> g(h->mu);
         OnlineStreamHost& st = stream_of(h, stream_id);
         h->devs[st.dev]->online_get_state(st.slot, name, dst, capacity);
     });

@@ -1282,6 +1282,9 @@ void DeviceCtx::online_grow(int min_slots) {
     }
     int cap = std::max(16, ocap_);
     while (cap < min_slots) cap *= 2;
+    // pushed chunks travel on copy_stream_ into the OLD opcm_: they have to land before the buffers are copied and freed
+    PF_CUDA(cudaStreamSynchronize(copy_stream_));
+    push_pending_ = false;
     PF_CUDA(cudaStreamSynchronize(stream_));
     const size_t dim = static_cast<size_t>(cfg_.lfr_m) * cfg_.n_mels;
     const size_t per[7] = {static_cast<size_t>(od_.nslot) * (od_.nf + 1) * od_.mel, static_cast<size_t>(od_.nslot) * 160 * od_.chunk_len,

@@ -326,7 +326,7 @@ private:
 struct OfflineHandle {
     pf_config cfg;
     std::vector<std::unique_ptr<DeviceCtx>> devs;
-    std::mutex mu;
+    std::recursive_mutex mu;          // recursive: a thread that leased the lane (pf_offline_lane_acquire) keeps calling into it
     // last run layout
     std::vector<int> shard_begin, shard_count;
     int B = 0, Lmax = 0, T = 0;
@@ -345,7 +345,7 @@ struct OnlineStreamHost {             // host half of OnlineStream: the sample c
 struct OnlineHandle {
     pf_config cfg;
     std::vector<std::unique_ptr<DeviceCtx>> devs;
-    std::mutex mu;
+    std::recursive_mutex mu;
     std::vector<OnlineStreamHost> streams;
     // last step
     std::vector<int32_t> appended, new_tokens, embeds_len;

@@ -105,6 +105,21 @@ class Engine:
             raise _lib.PfError(_lib.PF_ERR_DISPOSED, "engine disposed")
         return self._h
 
+    def lease(self):
+        """Context manager: the calling thread's execution lane stays locked for the enclosed calls (per-call hot words:
+        set -> run -> restore must not interleave with another thread sharing the lane; pf_offline_lane_acquire)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def _lease():
+            if self._lib.pf_offline_lane_acquire(self._handle()) < 0:
+                raise _lib.PfError(_lib.PF_ERR_DISPOSED, "engine disposed")
+            try:
+                yield self
+            finally:
+                self._lib.pf_offline_lane_release(self._handle())
+        return _lease()
+
     def set_cmvn(self, add_shift: np.ndarray, rescale: np.ndarray) -> None:
         a = np.ascontiguousarray(add_shift, dtype=np.float32)
         b = np.ascontiguousarray(rescale, dtype=np.float32)

@@ -121,6 +121,17 @@ def load_conf(path: str) -> ModelConfig:
     cfg.lfr_n = int(fe.get("lfr_n", cfg.lfr_n))
     cfg.snip_edges = bool(fe.get("snip_edges", cfg.snip_edges))
     cfg.input_size = cfg.lfr_m * cfg.n_mels
+    # the reference forwards window / frame sizes / dither to the fbank (WavFrontend.cs:21-26, FrontendConfEntity.cs:7-15);
+    # the device front-end is built for the values every published model uses, so anything else is an error here
+    # instead of silently different features
+    window = str(fe.get("window", "hamming")).lower()
+    frame_length, frame_shift = int(fe.get("frame_length", 25)), int(fe.get("frame_shift", 10))
+    if window != "hamming" or frame_length != 25 or frame_shift != 10:
+        raise NotImplementedError(f"frontend_conf window={window!r} frame_length={frame_length} frame_shift={frame_shift}: the device "
+                                  "front-end computes Hamming windows of 25 ms every 10 ms (PF_ERR_UNSUPPORTED)")
+    # dither: the C# entity defaults to 1.0, which makes the reference non-deterministic; the device path never dithers
+    # (pf_abi.h), so a non-zero value is accepted and recorded, not applied
+    cfg.dither = float(fe.get("dither", 0.0))
     sd = raw.get("seaco_decoder_conf") or {}
     cfg.seaco_layers = int(sd.get("num_blocks", cfg.seaco_layers))
     cfg.seaco_ffn = int(sd.get("linear_units", cfg.seaco_ffn))
@@ -195,6 +206,23 @@ class OfflineStream:
         self._chunks.append(np.ascontiguousarray(samples, dtype=np.float32).reshape(-1))
 
     AddSamples = add_samples
+
+    # C#-style member names (OfflineStream.cs:30-34)
+    @property
+    def Hotwords(self):
+        return self.hotwords
+
+    @Hotwords.setter
+    def Hotwords(self, value):
+        self.hotwords = value
+
+    @property
+    def Tokens(self):
+        return self.tokens
+
+    @property
+    def Timestamps(self):
+        return self.timestamps
 
     def features(self) -> np.ndarray:
         """What ``OfflineInputEntity.Speech`` holds: per-call fbank->LFR->CMVN, concatenated (Q10)."""
@@ -294,23 +322,25 @@ class OfflineRecognizer:
             raise ObjectDisposedError("OfflineRecognizer")
         # per-stream hot words replace the file hot words for this call (OfflineProjOfSeacoParaformer.cs:51-60)
         call_hotwords = [list(h) for s in streams for h in (s.hotwords or [])] if self._seaco else []
-        try:
-            if call_hotwords:
-                self._engine.set_hotwords(call_hotwords, local=True)
-            want_ts = bool(getattr(self._conf, "timestamps", False))      # 4-output models (OfflineProjOfParaformer.cs:75-79)
-            if all(len(s._chunks) == 1 for s in streams):
-                # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
-                out = self._engine.run_pcm([s._chunks[0] for s in streams], want_timestamps=want_ts)
-            else:
-                feats = [s.features() for s in streams]
-                if any(f.shape[0] == 0 for f in feats) and max(f.shape[0] for f in feats) == 0:
-                    raise ValueError("no input samples")
-                out = self._engine.run_feats(pad_sequence(feats), want_timestamps=want_ts)
-        except _lib.PfError as ex:
-            raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
-        finally:
-            if call_hotwords:
-                self._engine.set_hotwords(self._hotwords, local=True)
+        # set -> run -> restore is one leased section: another thread sharing the lane cannot run with these hot words
+        with self._engine.lease():
+            try:
+                if call_hotwords:
+                    self._engine.set_hotwords(call_hotwords, local=True)
+                want_ts = bool(getattr(self._conf, "timestamps", False))      # 4-output models (OfflineProjOfParaformer.cs:75-79)
+                if all(len(s._chunks) == 1 for s in streams):
+                    # one AddSamples per stream: fused fbank+LFR+CMVN+PadSequence on the device
+                    out = self._engine.run_pcm([s._chunks[0] for s in streams], want_timestamps=want_ts)
+                else:
+                    feats = [s.features() for s in streams]
+                    if max(f.shape[0] for f in feats) == 0:
+                        raise ValueError("no input samples")
+                    out = self._engine.run_feats(pad_sequence(feats), want_timestamps=want_ts)
+            except _lib.PfError as ex:
+                raise Exception("Offline recognition failed") from ex   # OfflineRecognizer.cs:194-197
+            finally:
+                if call_hotwords:
+                    self._engine.set_hotwords(self._hotwords, local=True)
         for i, s in enumerate(streams):
             s.tokens = [int(t) for t in out.tokens[i]]
             if out.us_cif_peak is not None:                         # cif_peak_tensor != null (OfflineRecognizer.cs:172-183)

@@ -50,6 +50,7 @@ class ModelConfig:
     lfr_m: int = 7
     lfr_n: int = 6
     snip_edges: bool = False
+    dither: float = 0.0          # parsed for completeness; the device front-end never dithers (reference default 1.0 is random)
     use_itn: bool = True
     # SeACo bias decoder (seaco_decoder_conf [EXT]) and NO_BIAS class id; unused by the other models
     seaco_layers: int = 4

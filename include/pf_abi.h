@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 4
+#define PF_ABI_VERSION 5
 
 typedef int32_t pf_status;
 enum {
@@ -111,18 +111,26 @@ pf_status pf_offline_create(const pf_config* cfg, const char* weights_path, cons
 pf_status pf_offline_create_from_memory(const pf_config* cfg, const void* blob, size_t blob_bytes,
                                         const int32_t* devices, int32_t ndev, pf_offline** out);
 /* replaces IOfflineProj.Dispose / InferenceSession.Dispose (OfflineProjOfParaformer.cs:88-101) */
-/* Concurrent callers: the same handle with `lanes` (1..8) independent execution lanes (own streams, staging buffers,
- * activations and weight copy per lane).  A host thread is bound to a lane on its first call; calls from different
- * threads then overlap on the GPU (one batch's kernel tails, launch gaps and PCIe copies are filled with another
- * batch's work).  Results returned to a thread stay valid until that thread's next call on the handle; a batch staged
- * with pf_offline_stage_pcm must be run (pf_offline_run_staged) by the thread that staged it.  The plain
- * create functions use one lane (or $PFASR_LANES).  Replaces nothing in the reference: OfflineRecognizer.GetResults
- * may be called from several threads there too, and they queue on the one ORT session. */
+/* Concurrent callers: the same handle with `lanes` (1..8) independent execution lanes (own streams, staging buffers and
+ * activations per lane; the device weights are shared).  A host thread is bound to lane (thread ordinal mod lanes), the
+ * ordinal being assigned at the thread's first call into the library, so the binding never changes: calls from
+ * different threads overlap on the GPU (one batch's kernel tails, launch gaps and PCIe copies are filled with another
+ * batch's work) and more threads than lanes share lanes, every call holding its lane's lock.
+ *   - pf_result points into storage owned by the CALLING THREAD: it stays valid until that thread's next run on the
+ *     handle, whatever other threads do (also with one lane).
+ *   - a batch staged with pf_offline_stage_pcm must be run (pf_offline_run_staged) by the thread that staged it; wrap
+ *     the pair - and any other sequence that another thread sharing the lane must not interleave with, such as
+ *     set_hotwords_local / run / restore - in pf_offline_lane_acquire ... pf_offline_lane_release.
+ * The plain create functions use one lane (or $PFASR_LANES).  Replaces nothing in the reference: there
+ * OfflineRecognizer.GetResults may be called from several threads too, and they queue on the one ORT session. */
 pf_status pf_offline_create_mt(const pf_config* cfg, const char* weights_path, const int32_t* devices, int32_t ndev,
                                int32_t lanes, pf_offline** out);
 pf_status pf_offline_create_from_memory_mt(const pf_config* cfg, const void* blob, size_t blob_bytes, const int32_t* devices,
                                            int32_t ndev, int32_t lanes, pf_offline** out);
 int32_t pf_offline_lanes(const pf_offline* h);
+/* lease the calling thread's lane (re-entrant lock; returns the lane index, -1 on a null handle) / give it back */
+int32_t pf_offline_lane_acquire(pf_offline* h);
+pf_status pf_offline_lane_release(pf_offline* h);
 pf_status pf_offline_destroy(pf_offline* h);
 
 /* SeACo hot words: replaces EmbedSeacoModel.Forward (EmbedSeacoModel.cs:70-108, model_eb.onnx = Embedding + 2-layer
@@ -139,7 +147,11 @@ pf_status pf_offline_set_cmvn(pf_offline* h, const float* add_shift, const float
 
 /* -------- front-end only: replaces WavFrontend.GetFbank + LfrCmvn as called by OfflineStream.AddSamples
  * (OfflineStream.cs:40-41).  samples: float PCM in [-1, 1].  feats: [capacity_frames, 560] out; *out_frames = T_lfr.
- * No Q4 substitution here (the reference applies it later, in PadHelper). */
+ * No Q4 substitution here (the reference applies it later, in PadHelper).
+ * Fixed fbank settings: Hamming window, 25 ms frames every 10 ms, 80 mel bins, 16 kHz, and NO dither (the reference
+ * forwards frontend_conf.dither, C# default 1.0, to OnlineFbank, WavFrontend.cs:21-26: that makes its features random;
+ * every published model sets dither 0 or is evaluated without it).  A caller whose asr.yaml asks for another window or
+ * frame size must not use this library (the Python host raises; the C# shim should do the same). */
 pf_status pf_frontend_extract(pf_offline* h, const float* samples, int32_t nsamp, float* feats,
                               int32_t capacity_frames, int32_t* out_frames);
 /* raw Kaldi fbank [T, 80] of one utterance (x32768 scaling included), for parity checks of OnlineFbank.GetFbank */

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in pf_abi.h but not exported by libpfasr.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.pf_abi_version() == 4
+    assert lib.pf_abi_version() == 5
 
 
 def test_config_struct_layout():
@@ -102,7 +102,7 @@ def test_header_is_plain_c(tmp_path):
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
     assert sizes[:5] == [C.sizeof(_lib.PfConfig), C.sizeof(_lib.PfResult), C.sizeof(_lib.PfOnlineResult), C.sizeof(_lib.PfTextResult),
                          C.sizeof(_lib.PfAudio)]
-    assert sizes[5] == 4
+    assert sizes[5] == 5
 
 
 def _build_example(tmp_path):
