@@ -18,8 +18,14 @@ log-softmax -> greedy ids (what OfflineRecognizer.GetResults does for 32 streams
            that step's GEMM launches re-issued back to back on the engine's stream (average launch duration x launches);
            the per-launch event pairs of the profiled step are reported beside it (they serialise the launch chain);
            peak = MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a step).
-* cpu_baseline: the oracle (a port of the reference's CPU path; OnnxRuntime/dotnet are not available) on a bounded
-           sample of the same workload, all host cores.
+* cpu_baseline: the oracle (a port of the reference's CPU path; OnnxRuntime/dotnet are not available) on the SAME
+           32-utterance batch, all host cores, N = 1 only (1 warm-up + 2 timed passes).
+* latency_single_lane: one batch at a time on a one-lane handle, L2 flushed between steps (the latency a lone caller sees).
+* strong_scaling: global batch 32 through ONE multi-device handle over the N GPUs of the job (pf_offline_create with N
+           devices, rank 0 drives it while the other ranks sit in a CPU-side barrier).
+* shard_check (N > 1): rank 0 recomputes rank 1's lane-0 batch on its own GPU and compares with the ids gathered over NCCL.
+Every timed loop runs for at least ~1 s: the K steps are repeated for `passes` passes and the figures are per step.
+The SURVEY 8(d) metric (host PCM -> host ids) is `e2e`; `value` is the same loop with the PCM already resident in HBM.
 """
 from __future__ import annotations
 
@@ -40,6 +46,15 @@ UNIT = "audio-s/s"
 BATCH = 32
 SECONDS = 10.0
 WORKLOAD = "paraformer-large-zh-en offline, batch=32x10 s synthetic 16 kHz per GPU (BASELINE configs[1])"
+
+
+def workload_config(world: int):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "audio_seconds_per_utt": SECONDS, "T_lfr": 166,
+            "weights": "random-init paraformer-large 50+16 (seed 20260917)",
+            "l2": "every step streams 0.43 GB of weights plus activations, far more than the 126 MB L2; the single-lane latency leg "
+                  "additionally writes a 256 MB buffer between steps",
+            "parallelism": f"dp{world} (utterances sharded, weights replicated, no data-path collective)"}
 
 
 def _peaks():
@@ -117,18 +132,26 @@ def cpu_reference_step(pcm, weights, cfg):
     return sanm.paraformer_forward(speech, weights, _oracle_dims(cfg))["tokens"]
 
 
-def time_cpu(pcm_sample, weights, cfg, steps, warmup):
+def time_cpu(pcm_sample, weights, cfg, steps, warmup, budget_s=None):
+    """Times the CPU path with a pinned thread count (all host cores).  budget_s bounds the whole call: the number of
+    timed steps is cut (never below 2) so that warm-up + steps fit."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    for _ in range(warmup):
+    t0 = time.perf_counter()
+    cpu_reference_step(pcm_sample, weights, cfg)               # first warm-up doubles as the calibration
+    first = time.perf_counter() - t0
+    if budget_s is not None:
+        warmup = min(warmup, max(1, int(0.2 * budget_s / max(first, 1e-3))))
+        steps = max(2, min(steps, int((budget_s - warmup * first) / max(first, 1e-3))))
+    for _ in range(max(0, warmup - 1)):
         cpu_reference_step(pcm_sample, weights, cfg)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
         cpu_reference_step(pcm_sample, weights, cfg)
         ts.append(time.perf_counter() - t0)
-    return ts, cores
+    return ts, cores, warmup
 
 
 def cpu_model_name():
@@ -147,7 +170,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=BATCH, help="utterances per CPU pass (default: the full batch, same config as the GPU arm)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds the --impl reference run may take (steps are cut to fit)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="every timed loop repeats its K steps until it lasted this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=3,
                     help="batches in flight per GPU (pf_offline_create_mt): one host thread + one execution lane each")
@@ -168,14 +193,17 @@ def main():
         weights = synth.make_weights(cfg)
         nb = max(1, min(args.cpu_sample, BATCH))
         pcm = [synth.make_pcm(i, SECONDS) for i in range(nb)]
-        ts, cores = time_cpu(pcm, weights, cfg, max(1, args.steps), args.warmup)
-        sec = statistics.mean(ts)
+        ts, cores, warm = time_cpu(pcm, weights, cfg, max(1, args.steps), args.warmup, budget_s=args.ref_budget)
+        sec = statistics.median(ts)
         val = nb * SECONDS / sec
-        sample = f"{nb} of the {BATCH} utterances (10 s each) per step; oracle port of the reference CPU path (OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"
+        sample = (f"the full batch: {nb} utterances x 10 s per step, {len(ts)} timed steps after {warm} warm-up (cut from --steps {args.steps} to fit "
+                  f"{args.ref_budget:.0f} s); torch threads pinned to {cores}; oracle port of the reference CPU path (OnnxRuntime/dotnet unavailable); "
+                  f"CPU: {cpu_model_name()}")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(max(1, args.gpus)),
+            "ms_per_step_min_median_max": [min(ts) * 1e3, sec * 1e3, max(ts) * 1e3],
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -195,8 +223,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")       # host-side waits that must not spin on a GPU
 
     weights = synth.make_weights(cfg)
     L = max(1, min(args.lanes, 8))
@@ -212,10 +242,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # 2x the 126 MB L2
     steps_of = [args.steps // L + (1 if l < args.steps % L else 0) for l in range(L)]
 
-    # one long-lived host thread per lane: libpfasr binds a thread to a lane on its first call, so lane l's staging,
-    # warm-up and timed steps all come from worker l
+    # one long-lived host thread per lane: libpfasr binds a thread to lane (thread ordinal mod lanes), the ordinal being
+    # taken at the thread's first call into the library - the L workers make that call one after the other, so they own
+    # L consecutive ordinals = L distinct lanes
     import concurrent.futures as cf
     pools = [cf.ThreadPoolExecutor(max_workers=1) for _ in range(L)]
+    lane_ids = [pools[l].submit(lambda: (eng._lib.pf_offline_lane_acquire(eng._handle()), eng._lib.pf_offline_lane_release(eng._handle()))[0]).result()
+                for l in range(L)]
+    assert sorted(lane_ids) == list(range(L)), lane_ids
 
     def on_lanes(fn):
         futs = [pools[l].submit(fn, l) for l in range(L)]
@@ -240,64 +274,70 @@ def main():
     launches_per_step = setup[0][1]
     streams = [x[2] for x in setup]
 
-    single = []                             # L == 1: per-step (start, end) events
-
-    def lane_resident(l):
+    def lane_resident(l, passes):
         st = streams[l]
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        for _ in range(steps_of[l]):
-            if L == 1:                      # one batch at a time: explicit L2 flush between steps, outside the step's events
-                with torch.cuda.stream(st):
-                    flush.zero_()
-                a = torch.cuda.Event(enable_timing=True)
-                b = torch.cuda.Event(enable_timing=True)
-                a.record(st)
-                eng.run_staged()
-                b.record(st)
-                single.append((a, b))
-            else:
-                eng.run_staged()
+        for _ in range(steps_of[l] * passes):
+            eng.run_staged()
         e1.record(st)
         return e0, e1
 
+    def resident_pass(passes):
+        evs = on_lanes(lambda l: lane_resident(l, passes))
+        torch.cuda.synchronize()
+        # device time from the earliest lane start to the latest lane end (events of different streams share the device clock)
+        first = min(range(L), key=lambda l: evs[0][0].elapsed_time(evs[l][0]))
+        return max(evs[first][0].elapsed_time(evs[l][1]) for l in range(L))
+
+    def agree_passes(ms_one_pass):
+        """Passes needed for the loop to last --min-seconds, the same on every rank."""
+        p = max(1, int(np.ceil(args.min_seconds * 1e3 / max(ms_one_pass, 1e-3))))
+        if world > 1:
+            t = torch.tensor([p], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p = int(t[0])
+        return min(p, 200)
+
+    passes = agree_passes(resident_pass(1))               # calibration pass (also more warm-up)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     t_wall0 = time.perf_counter()
-    evs = on_lanes(lane_resident)
+    total_ms = resident_pass(passes)
     barrier()
     wall_resident = time.perf_counter() - t_wall0
-    if L == 1:
-        total_ms = sum(a.elapsed_time(b) for a, b in single)
-    else:
-        # device time from the earliest lane start to the latest lane end (events of different streams share the device clock)
-        first = min(range(L), key=lambda l: evs[0][0].elapsed_time(evs[l][0]))
-        total_ms = max(evs[first][0].elapsed_time(evs[l][1]) for l in range(L))
     stage_ms = pools[0].submit(eng.timings).result()
 
     # -------- e2e: host PCM -> host token ids through the public call, every lane fed by its own host thread
     tok_host = [np.zeros((max(1, steps_of[l]), BATCH, 256), np.int32) for l in range(L)]
 
-    def lane_e2e(l, n=None):
-        for k in range(steps_of[l] if n is None else n):
+    def lane_e2e(l, n):
+        for k in range(n):
             o = eng.run_pcm(pcm[l])
             tok_host[l][k % tok_host[l].shape[0], :, : o.tokens.shape[1]] = o.tokens
         return None
 
+    gathered = []
+
     def gather_ids():
-        if world > 1:   # C1: the ids of all timed steps reach rank 0 over NCCL (NVLink), one padded gather
+        if world > 1:   # C1: the ids of the timed steps reach rank 0 over NCCL (NVLink), one padded gather
             t = torch.from_numpy(np.concatenate(tok_host, axis=0)).cuda(non_blocking=True)
             gl = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
             dist.gather(t, gl, dst=0)
+            gathered[:] = gl or []
 
     on_lanes(lambda l: lane_e2e(l, 3))
     gather_ids()            # includes the first gather: NCCL builds its communicator lazily
     barrier()
     t0 = time.perf_counter()
-    on_lanes(lane_e2e)
+    on_lanes(lambda l: lane_e2e(l, steps_of[l]))
+    e2e_passes = agree_passes((time.perf_counter() - t0) * 1e3)
+    barrier()
+    t0 = time.perf_counter()
+    on_lanes(lambda l: lane_e2e(l, steps_of[l] * e2e_passes))
     gather_ids()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -309,17 +349,27 @@ def main():
     host16.copy_((host * 32768.0).round().clamp(-32768, 32767).to(torch.int16))
     clips = [[pf_audio.Audio(host16[l, i].numpy(), _lib.PF_AUDIO_S16, 1, 16000) for i in range(BATCH)] for l in range(L)]
 
-    def lane_s16(l, n=None):
-        for _ in range(steps_of[l] if n is None else n):
+    def lane_s16(l, n):
+        for _ in range(n):
             eng.run_audio(clips[l])
 
     on_lanes(lambda l: lane_s16(l, 3))
     barrier()
     t0 = time.perf_counter()
-    on_lanes(lane_s16)
+    on_lanes(lambda l: lane_s16(l, steps_of[l] * e2e_passes))
     barrier()
     e2e16_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None       # sampled across the three timed loops (resident, e2e, e2e 16-bit)
+
+    # -------- shard equivalence (N > 1): rank 0 recomputes rank 1's lane-0 batch on its own GPU; make_pcm is keyed by the
+    # global utterance index, so the ids must equal what rank 1 computed and sent over NCCL
+    shard_check = None
+    if world > 1 and rank == 0:
+        other = [synth.make_pcm((1 * L + 0) * BATCH + i, SECONDS) for i in range(BATCH)]
+        mine = pools[0].submit(lambda: eng.run_pcm(other)).result()
+        theirs = gathered[1][0].cpu().numpy()[:, : mine.tokens.shape[1]]
+        shard_check = {"rank": 1, "lane": 0, "utterances": BATCH, "ids_identical": bool(np.array_equal(mine.tokens, theirs)),
+                       "mismatching_ids": int((mine.tokens != theirs).sum())}
 
     # -------- roofline leg: one profiled step on lane 0 (per-launch CUDA events on the GEMM kernel)
     def lane_profile():
@@ -342,6 +392,53 @@ def main():
     if gemm_ms <= 0:
         gemm_ms = gemm_ms_events
     n_gemm = sum(p["launches"] for p in prof) or 1
+    for pl in pools:
+        pl.shutdown()
+    eng.close()
+
+    # -------- latency of a lone caller: one-lane handle, one batch at a time, L2 flushed between steps
+    def single_lane_leg(devices, tag):
+        e1 = Engine(cfg, weights, devices=devices, lanes=1)
+        e1.set_cmvn(*synth.make_cmvn())
+        st = torch.cuda.ExternalStream(e1.stream_ptr(0), device=devices[0])
+        for _ in range(args.warmup):
+            e1.run_pcm(pcm[0])
+        res, e2e = [], []
+        e1.stage_pcm(pcm[0])
+        for _ in range(args.steps):
+            for d in devices:                              # flush every device's L2, outside the step's events
+                with torch.cuda.device(d):
+                    torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{d}").zero_()
+                    torch.cuda.synchronize(d)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            e1.run_staged()
+            b.record(st)
+            b.synchronize()
+            res.append(a.elapsed_time(b))
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            e1.run_pcm(pcm[0])
+            e2e.append((time.perf_counter() - t0) * 1e3)
+        e1.close()
+        audio = BATCH * SECONDS
+        return {"handle": tag, "global_batch": BATCH, "n_gpus": len(devices), "steps": args.steps,
+                "resident_ms_min_median_max": [min(res), statistics.median(res), max(res)],
+                "e2e_ms_min_median_max": [min(e2e), statistics.median(e2e), max(e2e)],
+                "resident_value": audio / (statistics.median(res) * 1e-3), "e2e_value": audio / (statistics.median(e2e) * 1e-3), "unit": UNIT}
+
+    latency = strong = None
+    if rank == 0:
+        latency = single_lane_leg([local_rank], "one lane on one GPU, L2 flushed between steps (device events around pf_offline_run_staged; "
+                                                "host clock around pf_offline_run_pcm)")
+    if world > 1:
+        dist.barrier(group=cpu_group)                      # the other ranks wait on the CPU: their GPUs are idle from here on
+        if rank == 0:
+            strong = single_lane_leg(list(range(world)), f"ONE handle over {world} GPUs (pf_offline_create, devices 0..{world - 1}): the batch of 32 is "
+                                                         "split contiguously, one host thread per device, Lmax exchanged on the host")
+        dist.barrier(group=cpu_group)
+    elif rank == 0:
+        strong = dict(latency, handle="1 GPU: identical to latency_single_lane")
 
     # -------- reduce over ranks (max time)
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -351,30 +448,33 @@ def main():
 
     if rank == 0:
         audio_per_step = BATCH * SECONDS * world
-        value = audio_per_step * args.steps / (total_ms / 1e3)
-        e2e_val = audio_per_step * args.steps / (e2e_ms / 1e3)
+        nsteps, nsteps_e2e = args.steps * passes, args.steps * e2e_passes
+        value = audio_per_step * nsteps / (total_ms / 1e3)
+        e2e_val = audio_per_step * nsteps_e2e / (e2e_ms / 1e3)
         peak, peak_src = _peaks()
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        config = workload_config(world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "audio_seconds_per_utt": SECONDS,
-                       "T_lfr": int(out.feat_frames), "Lmax": int(out.tokens.shape[1]), "weights": "random-init paraformer-large (seed 20260917), fp16 operands / fp32 accumulate",
-                       "lanes": L,
-                       "l2": ("256 MB buffer written between timed steps (L2 flush); weights alone (0.43 GB) also exceed L2" if L == 1 else
-                              f"{L} batches in flight on {L} streams: every step streams its lane's 0.43 GB weight copy plus activations, "
-                              "far more than the 126 MB L2, so no explicit flush between the (overlapping) steps"),
-                       "parallelism": f"dp{world} (utterances sharded, weights replicated, no data-path collective)"},
+            "ms_per_step": total_ms / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "config": config,
+            "headline_note": "e2e is the SURVEY 8(d) metric (host PCM -> host token ids through pf_offline_run_pcm); value is the same loop with "
+                             "the PCM already resident in HBM (pf_offline_run_staged)",
+            "run": {"lanes": L, "passes": passes, "timed_steps": nsteps, "timed_seconds": total_ms / 1e3, "Lmax": int(out.tokens.shape[1]),
+                    "T_lfr": int(out.feat_frames), "operands": "fp16 operands / fp32 accumulate",
+                    "in_flight": f"{L} batches on {L} lanes (one host thread each)"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / nsteps_e2e, "timed_steps": nsteps_e2e, "timed_seconds": e2e_ms / 1e3,
                     "api": f"pf_offline_run_pcm (C-ABI, pinned host PCM -> host token ids), {L} host threads on {L} lanes",
                     "s16_input": {"api": "pf_offline_run_audio (16-bit file samples, converted on the device; rank 0, no gather)",
-                                  "ms_per_step": e2e16_s * 1e3 / args.steps, "value": BATCH * SECONDS * args.steps / e2e16_s,
+                                  "ms_per_step": e2e16_s * 1e3 / nsteps_e2e, "value": BATCH * SECONDS * nsteps_e2e / e2e16_s,
                                   "h2d_bytes_per_step": BATCH * nsamp * 2 + BATCH * 52}},
-            "gpu_launches": int(launches_per_step * args.steps * world),
+            "latency_single_lane": latency,
+            "strong_scaling": strong,
+            "shard_check": shard_check,
+            "gpu_launches": int(launches_per_step * nsteps * world),
             "launches_per_step": int(launches_per_step),
-            "rtf": (total_ms / 1e3) / (audio_per_step * args.steps),
+            "rtf": (total_ms / 1e3) / (audio_per_step * nsteps),
             "stage_ms": stage_ms,
             "kernel_ms_profiled_step": kernel_ms,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
@@ -385,24 +485,24 @@ def main():
                          "achieved_per_launch_events": gemm_flops / (gemm_ms_events * 1e-3) / 1e12 if gemm_ms_events > 0 else None,
                          "per_launch_events_note": "an event pair around every launch breaks the launch chain and adds an event round trip per launch; by_shape uses these",
                          "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
-                         "gemm_share_of_step": gemm_ms / (total_ms / args.steps) if total_ms else None,
+                         "gemm_share_of_step": gemm_ms / (total_ms / nsteps) if total_ms else None,
                          "avg_launch_us": gemm_ms * 1e3 / n_gemm, "by_shape": prof},
             "clocks": clocks,
             "wall_s_resident_loop": wall_resident,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             nb = max(1, min(args.cpu_sample, BATCH))
-            ts, cores = time_cpu(pcm[0][:nb], weights, cfg, 3, 1)
-            sec = statistics.mean(ts)
+            ts, cores, warm = time_cpu(pcm[0][:nb], weights, cfg, 2, 1, budget_s=60.0)
+            sec = statistics.median(ts)
             line["cpu_baseline"] = {"value": nb * SECONDS / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{nb} of the {BATCH} utterances per pass, 1 warm-up + 3 timed passes; oracle port of the reference CPU path "
-                                              f"(OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"}
+                                    "ms_per_pass_min_median_max": [min(ts) * 1e3, sec * 1e3, max(ts) * 1e3],
+                                    "sample": f"the same {nb}-utterance batch, {warm} warm-up + {len(ts)} timed passes, torch threads pinned to {cores}; "
+                                              f"oracle port of the reference CPU path (OnnxRuntime/dotnet unavailable); CPU: {cpu_model_name()}"}
+        elif not args.no_cpu_baseline:
+            line["cpu_baseline"] = {"skipped": "reported at N = 1 only (and by --impl reference): at N > 1 the other ranks would have to wait for it"}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    for pl in pools:
-        pl.shutdown()
-    eng.close()
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
 
 
