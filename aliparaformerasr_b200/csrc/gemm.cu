@@ -475,7 +475,8 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if constexpr (kOutHalf && kAdds == 0)
                         epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
                     else if constexpr (!kOutHalf && kAdds == 0)
-                        epilogue_tma_f32<kCpwMax, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0);
+                        epilogue_tma_f32<kCpwMax, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0,
+                                                         nullptr, nullptr, (vec_ok_flags & 0x2000) != 0);
                     else if constexpr (!kOutHalf && kAdds == 1 && !kLn)
                         epilogue_tma_f32<kCpwMax, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
                 }
@@ -742,6 +743,14 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
         else { op.epi.add1 = epi.resid; op.epi.ld_add1 = epi.ld_resid; }
         ++op.n_adds;
     }
+    // in-place residual update (x += A W^T + b: out-projection, FFN2, decoder out-projection): the epilogue hands
+    // acc + bias to the TMA engine as an fp32 REDUCE-ADD into x instead of loading x, adding and storing - one rounding
+    // for acc + bias and one for the sum either way, so the result is bit-identical, but the residual never travels
+    // to the SM and the staging boxes are never waited on for a load.  PFASR_GEMM_NO_REDADD=1 keeps the load-add-store path.
+    static const bool no_redadd = [] { const char* e = getenv("PFASR_GEMM_NO_REDADD"); return e && *e && *e != '0'; }();
+    const bool red_add = !no_redadd && op.ln_cluster == 0 && epi.resid != nullptr && epi.addend == nullptr && epi.out_f32 != nullptr &&
+                         epi.resid == epi.out_f32 && epi.ld_resid == epi.ld_out && !epi.relu;
+    if (red_add) { op.n_adds = 0; op.epi.add0 = nullptr; }
     // vector epilogue: 16-byte row segments of every fp32 tensor (8-byte for the fp16 output) must be aligned
     auto al = [](const void* p, int ld, int bytes) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % bytes) == 0 && ld % 4 == 0); };
     op.vec_ok = (al(epi.bias, 0, 16) && al(epi.resid, epi.ld_resid, 16) && al(epi.addend, epi.ld_addend, 16) &&
@@ -756,6 +765,11 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
                                          (op.n_adds == 0 || row_ok(op.epi.add0, op.epi.ld_add0, 4))));
     op.tmC = CUtensorMap{};
     op.tmR = CUtensorMap{};
+    if (red_add && !tma_epi) {                                    // the reduce needs the TMA epilogue: fall back to load-add-store
+        op.epi.add0 = epi.resid; op.epi.ld_add0 = epi.ld_resid; op.n_adds = 1;
+    }
+    op.red_add = red_add && tma_epi ? 1 : 0;
+    if (op.red_add) op.vec_ok |= 0x2000;
     if (tma_epi) {
         op.vec_ok |= 2;
         if (epi.out_f16) make_tmap_any(&op.tmC, epi.out_f16, false, M, N, epi.ld_out, 32, 64);   // 32 x 32 fp16 boxes

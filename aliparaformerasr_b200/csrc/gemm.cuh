@@ -44,6 +44,7 @@ struct GemmOp {
     int throughput = 0;   // prepared under the throughput objective (gemm_set_policy)
     int epi16 = 0;        // sixteen epilogue warps (fp16 output without addends; tile_code bit 22 or PFASR_GEMM_EPI16=1)
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
+    int red_add = 0; // the residual aliases the output: added by a TMA fp32 reduce-add instead of load + add + store
     int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
 

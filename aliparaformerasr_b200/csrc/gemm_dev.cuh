@@ -52,6 +52,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t s
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
                  : "memory");
 }
+// fp32 tile += staging box, performed by the L2 reduction units (cp.reduce.async.bulk): the in-place residual update
+// x += A W^T + b needs no residual load at all
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -126,7 +133,8 @@ __device__ __forceinline__ void resid_issue(ResidPipe& rp, int buf, uint32_t stg
 template <int kMaxChunks, bool kResid, bool kLn = false>
 __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, uint8_t* stg, ResidPipe& rp, const CUtensorMap* tmC,
                                                  const CUtensorMap* tmR, const float* bias_w, float lo, int row0,
-                                                 int colw, int lane, int prefetched, float* ln_s1 = nullptr, float* ln_s2 = nullptr) {
+                                                 int colw, int lane, int prefetched, float* ln_s1 = nullptr, float* ln_s2 = nullptr,
+                                                 bool red_add = false) {
     float s1 = 0.0f, s2 = 0.0f;                                    // kLn: this row's sum / sum of squares over the warp's columns
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t ra[32], rb[32];
@@ -147,8 +155,8 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
             if (kResid) {
                 mbar_wait(rp.bar[buf], rp.count[buf] & 1u);
                 rp.count[buf]++;
-            } else if (k >= 2) {                                   // buffer reuse without a residual load in between
-                if (lane == 0) tma_store_wait_read();
+            } else if (k >= 2) {                                   // buffer reuse without a residual load in between:
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // only the previous chunk's store may be pending
                 __syncwarp();
             }
             uint8_t* box = stg + buf * 4096 + lane * 128;
@@ -177,7 +185,8 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                tma_store_2d(tmC, stg_u32 + buf * 4096, col, row0);
+                if (!kResid && red_add) tma_reduce_add_2d(tmC, stg_u32 + buf * 4096, col, row0);
+                else tma_store_2d(tmC, stg_u32 + buf * 4096, col, row0);
                 tma_store_commit();
                 if (kResid && k + 2 < nchunks) tma_store_wait_read();     // box k is read before chunk k+2 lands in it
             }

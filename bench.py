@@ -388,6 +388,18 @@ def main():
         eng.set_profile(0)
         return g_ms, g_fl, pr, k_ms, rp_ms
 
+    # all lanes replay their step's GEMMs at the same time (the way the timed loops run them): aggregate tensor throughput
+    conc = None
+    if L > 1:
+        eng.set_profile(True)
+        fl = on_lanes(lambda l: (eng.run_staged(), eng.gemm_flops())[1])
+        gate = threading.Barrier(L)
+        ms = on_lanes(lambda l: (gate.wait(), eng.replay_gemms(5))[1])
+        eng.set_profile(0)
+        if min(ms) > 0:
+            conc = {"tflops": sum(fl) / (max(ms) * 1e-3) / 1e12, "ms_per_pass_per_lane": ms,
+                    "method": f"{L} lanes re-launch the GEMMs of their own step concurrently (5 passes each, started together); "
+                              "sum of the lanes' algorithmic FLOPs / the slowest lane's time per pass"}
     gemm_ms_events, gemm_flops, prof, kernel_ms, gemm_ms = pools[0].submit(lane_profile).result()
     if gemm_ms <= 0:
         gemm_ms = gemm_ms_events
@@ -486,7 +498,8 @@ def main():
                          "per_launch_events_note": "an event pair around every launch breaks the launch chain and adds an event round trip per launch; by_shape uses these",
                          "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
                          "gemm_share_of_step": gemm_ms / (total_ms / nsteps) if total_ms else None,
-                         "avg_launch_us": gemm_ms * 1e3 / n_gemm, "by_shape": prof},
+                         "avg_launch_us": gemm_ms * 1e3 / n_gemm,
+                         "concurrent_lanes": dict(conc, frac=conc["tflops"] / peak) if conc else None, "by_shape": prof},
             "clocks": clocks,
             "wall_s_resident_loop": wall_resident,
         }
