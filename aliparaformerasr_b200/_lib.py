@@ -94,6 +94,7 @@ SIGNATURES = {
     "pf_offline_create_from_memory": (C.c_int32, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.POINTER(C.c_void_p)]),
     "pf_offline_create_mt": (C.c_int, [C.POINTER(PfConfig), C.c_char_p, _I, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "pf_offline_create_from_memory_mt": (C.c_int, [C.POINTER(PfConfig), C.c_void_p, C.c_size_t, _I, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pf_build_experiments": (C.c_int32, []),
     "pf_offline_lanes": (C.c_int32, [C.c_void_p]),
     "pf_offline_lane_acquire": (C.c_int32, [C.c_void_p]),
     "pf_offline_lane_release": (C.c_int32, [C.c_void_p]),

@@ -16,12 +16,19 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libpfasr.so"
-SOURCES = ["gemm.cu", "ffn_chain.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
+# PFASR_BUILD_EXPERIMENTS=1 additionally compiles the variants that were measured SLOWER than the selected path and are kept
+# for A/B work only: the fused FFN1->FFN2 kernel (ffn_chain.cu), the CTA-pair (cta_group::2) GEMM, the
+# sixteen-epilogue-warp GEMM and the fused-LayerNorm GEMM epilogue.  The product library carries only the selected path.
+EXPERIMENTS = os.environ.get("PFASR_BUILD_EXPERIMENTS", "0") == "1"
+SOURCES = ["gemm.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if EXPERIMENTS:
+    SOURCES.insert(1, "ffn_chain.cu")
+    NVCC_FLAGS.append("-DPFASR_EXPERIMENTS=1")
 
 
 def _nvcc() -> str:
@@ -33,6 +40,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
+    h.update(b"experiments" if EXPERIMENTS else b"product")
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "pf_abi.h", Path(__file__)]):
         h.update(p.name.encode())
         h.update(p.read_bytes())

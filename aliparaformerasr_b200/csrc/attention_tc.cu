@@ -287,110 +287,79 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
         uint8_t* tile = smem + 2 * p.kv_bytes + g * p.tile_bytes;
         float inv_sum = 0.0f;
-        // warps whose 32 rows all lie past the last query (the second tile of a 166-frame utterance has 38 valid rows of
-        // 128: two of its four warps) do no softmax work: their P rows keep whatever the Q tile held (finite fp16), their
-        // O rows are clipped by the store map.  Warp-uniform on purpose: tcgen05.ld is a warp-collective instruction.
-        const bool row_ok = g * BQ + q * 32 < p.Tq;
         if (active) {
             mbar_wait(bar_s(g), 0);
             tc_fence_after_sync();
-            if (row_ok) {
-                // pass 1: row maximum over the valid keys (only the last chunk can hold padded keys); the next chunk's
-                // tcgen05.ld is in flight while this one is reduced
-                float mx = -INFINITY;
-                uint32_t va[32], vb[32];
-                const int n0 = min(32, p.Tkp);
-                if (n0 == 32) tmem_ld_32x32(trow, va); else tmem_ld_32x32b_x16(trow, va);
-                for (int c0 = 0; c0 < p.Tkp; c0 += 64) {
+            // pass 1: row maximum over the valid keys (only the last chunk can hold padded keys)
+            float mx = -INFINITY;
+            for (int c0 = 0; c0 < p.Tkp; c0 += 32) {
+                uint32_t v[32];
+                const int n = min(32, p.Tkp - c0);                // 32 or 16 (Tkp % 16 == 0)
+                if (n == 32) tmem_ld_32x32(trow + c0, v); else tmem_ld_32x32b_x16(trow + c0, v);
+                tmem_ld_wait();
+                if (c0 + 32 <= p.Tk) {
+                    float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int c = c0 + 32 * half;
-                        if (c < p.Tkp) {
-                            uint32_t (&v)[32] = half ? vb : va;
-                            uint32_t (&nx)[32] = half ? va : vb;
-                            tmem_ld_wait();
-                            const int cn = c + 32;
-                            if (cn < p.Tkp) {
-                                if (p.Tkp - cn >= 32) tmem_ld_32x32(trow + cn, nx); else tmem_ld_32x32b_x16(trow + cn, nx);
-                            }
-                            const int n = min(32, p.Tkp - c);
-                            if (c + 32 <= p.Tk) {
-                                float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-                                for (int i = 0; i < 32; i += 4) {
-                                    m0 = fmaxf(m0, __uint_as_float(v[i]));
-                                    m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-                                    m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-                                    m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-                                }
-                                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (i < n && c + i < p.Tk) mx = fmaxf(mx, __uint_as_float(v[i]));
-                            }
-                        }
+                    for (int i = 0; i < 32; i += 4) {
+                        m0 = fmaxf(m0, __uint_as_float(v[i]));
+                        m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                        m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+                        m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
                     }
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < n && c0 + i < p.Tk) mx = fmaxf(mx, __uint_as_float(v[i]));
                 }
-                const float mxs = mx * p.scale_log2e;
-                // pass 2: p = exp2(s * scale - max * scale); fp32 row sum; fp16 P into the A-operand layout
-                float sum = 0.0f;
-                if (n0 == 32) tmem_ld_32x32(trow, va); else tmem_ld_32x32b_x16(trow, va);
-                for (int c0 = 0; c0 < p.Tkp; c0 += 64) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        const int c = c0 + 32 * half;
-                        if (c < p.Tkp) {
-                            uint32_t (&v)[32] = half ? vb : va;
-                            uint32_t (&nx)[32] = half ? va : vb;
-                            tmem_ld_wait();
-                            const int cn = c + 32;
-                            if (cn < p.Tkp) {
-                                if (p.Tkp - cn >= 32) tmem_ld_32x32(trow + cn, nx); else tmem_ld_32x32b_x16(trow + cn, nx);
-                            }
-                            const int n = min(32, p.Tkp - c);
-                            float e[32];
-                            if (c + 32 <= p.Tk) {
-                                float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-                                for (int i = 0; i < 32; i += 4) {
-                                    e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs));
-                                    e[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -mxs));
-                                    e[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, -mxs));
-                                    e[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, -mxs));
-                                    s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
-                                }
-                                sum += (s0 + s1) + (s2 + s3);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const bool ok = i < n && c + i < p.Tk;
-                                    e[i] = ok ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs)) : 0.0f;
-                                    sum += e[i];
-                                }
-                            }
-                            uint8_t* kblk = tile + (c >> 6) * 16384;          // 64 keys per 16 KiB k-block
-                            const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (j * 8 < n) {
-                                    uint4 pk;
-                                    __half2 h0 = __floats2half2_rn(e[8 * j], e[8 * j + 1]);
-                                    __half2 h1 = __floats2half2_rn(e[8 * j + 2], e[8 * j + 3]);
-                                    __half2 h2 = __floats2half2_rn(e[8 * j + 4], e[8 * j + 5]);
-                                    __half2 h3 = __floats2half2_rn(e[8 * j + 6], e[8 * j + 7]);
-                                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                    *reinterpret_cast<uint4*>(kblk + sw128_off(r, chunk0 + j)) = pk;
-                                }
-                            }
-                        }
-                    }
-                }
-                inv_sum = 1.0f / sum;
             }
+            const float mxs = mx * p.scale_log2e;
+            // pass 2: p = exp2(s * scale - max * scale); fp32 row sum; fp16 P into the A-operand layout
+            float sum = 0.0f;
+            for (int c0 = 0; c0 < p.Tkp; c0 += 32) {
+                uint32_t v[32];
+                const int n = min(32, p.Tkp - c0);
+                if (n == 32) tmem_ld_32x32(trow + c0, v); else tmem_ld_32x32b_x16(trow + c0, v);
+                tmem_ld_wait();
+                float e[32];
+                if (c0 + 32 <= p.Tk) {
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs));
+                        e[i + 1] = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -mxs));
+                        e[i + 2] = ex2_approx(fmaf(__uint_as_float(v[i + 2]), p.scale_log2e, -mxs));
+                        e[i + 3] = ex2_approx(fmaf(__uint_as_float(v[i + 3]), p.scale_log2e, -mxs));
+                        s0 += e[i]; s1 += e[i + 1]; s2 += e[i + 2]; s3 += e[i + 3];
+                    }
+                    sum += (s0 + s1) + (s2 + s3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const bool ok = i < n && c0 + i < p.Tk;
+                        e[i] = ok ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mxs)) : 0.0f;
+                        sum += e[i];
+                    }
+                }
+                uint8_t* kblk = tile + (c0 >> 6) * 16384;         // 64 keys per 16 KiB k-block
+                const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j * 8 < n) {
+                        uint4 pk;
+                        __half2 h0 = __floats2half2_rn(e[8 * j], e[8 * j + 1]);
+                        __half2 h1 = __floats2half2_rn(e[8 * j + 2], e[8 * j + 3]);
+                        __half2 h2 = __floats2half2_rn(e[8 * j + 4], e[8 * j + 5]);
+                        __half2 h3 = __floats2half2_rn(e[8 * j + 6], e[8 * j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(kblk + sw128_off(r, chunk0 + j)) = pk;
+                    }
+                }
+            }
+            inv_sum = 1.0f / sum;
             fence_proxy_async();                                  // generic-proxy smem writes -> visible to tcgen05.mma
             tc_fence_before_sync();
             mbar_arrive(bar_p(g));
@@ -398,32 +367,26 @@ pf_sanm_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (active) {
             mbar_wait(bar_o(g), 0);
             tc_fence_after_sync();
-            // O row / sum -> fp16 -> swizzled staging (two 64-column boxes) -> TMA store (clipped at Tq by the map);
-            // the next 32-column chunk is in flight while this one is converted
-            if (row_ok) {
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(trow, va);
+            // O row / sum -> fp16 -> swizzled staging (two 64-column boxes) -> TMA store (clipped at Tq by the map)
+#pragma unroll 1
+            for (int c0 = 0; c0 < HD; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + c0, v);
+                tmem_ld_wait();
+                uint8_t* box = tile + (c0 >> 6) * (BQ * 128);
+                const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
-                for (int c0 = 0; c0 < HD; c0 += 32) {
-                    uint32_t (&v)[32] = (c0 & 32) ? vb : va;
-                    uint32_t (&nx)[32] = (c0 & 32) ? va : vb;
-                    tmem_ld_wait();
-                    if (c0 + 32 < HD) tmem_ld_32x32(trow + c0 + 32, nx);
-                    uint8_t* box = tile + (c0 >> 6) * (BQ * 128);
-                    const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 pk;
-                        __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * j]) * inv_sum, __uint_as_float(v[8 * j + 1]) * inv_sum);
-                        __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * j + 2]) * inv_sum, __uint_as_float(v[8 * j + 3]) * inv_sum);
-                        __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * j + 4]) * inv_sum, __uint_as_float(v[8 * j + 5]) * inv_sum);
-                        __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * j + 6]) * inv_sum, __uint_as_float(v[8 * j + 7]) * inv_sum);
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(box + sw128_off(r, chunk0 + j)) = pk;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * j]) * inv_sum, __uint_as_float(v[8 * j + 1]) * inv_sum);
+                    __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * j + 2]) * inv_sum, __uint_as_float(v[8 * j + 3]) * inv_sum);
+                    __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * j + 4]) * inv_sum, __uint_as_float(v[8 * j + 5]) * inv_sum);
+                    __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * j + 6]) * inv_sum, __uint_as_float(v[8 * j + 7]) * inv_sum);
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                    pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(box + sw128_off(r, chunk0 + j)) = pk;
                 }
             }
             fence_proxy_async();

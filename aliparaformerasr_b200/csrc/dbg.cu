@@ -119,6 +119,10 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
 
 pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* x, float* out, float* elapsed_ms, int32_t iters) {
+#ifndef PFASR_EXPERIMENTS
+    (void)M; (void)D; (void)F; (void)a; (void)w1; (void)b1; (void)w2; (void)b2; (void)x; (void)out; (void)elapsed_ms; (void)iters;
+    return guarded([&] { throw StatusError{PF_ERR_UNSUPPORTED, "the fused feed-forward kernel is an experiment: build with PFASR_BUILD_EXPERIMENTS=1"}; });
+#else
     return guarded([&] {
         Scratch s;
         static FfnChainScratch sc;               // test hook: legacy stream of the current device
@@ -152,11 +156,21 @@ pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, cons
             cudaEventDestroy(e1);
         }
     });
+#endif
+}
+
+int32_t pf_build_experiments(void) {
+#ifdef PFASR_EXPERIMENTS
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 pf_status pf_dbg_gemm_ln(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, const float* resid,
                          const float* gamma, const float* beta, float eps, float* out, float* out_ln) {
     return guarded([&] {
+        if (!pf_build_experiments()) throw StatusError{PF_ERR_UNSUPPORTED, "the fused-LayerNorm GEMM epilogue is an experiment: build with PFASR_BUILD_EXPERIMENTS=1"};
         if (!gemm_ln_fusable(M, N)) throw CudaError{"shape cannot carry the fused LayerNorm epilogue"};
         Scratch s;
         __half* dA = s.up_half(A, static_cast<size_t>(M) * K);

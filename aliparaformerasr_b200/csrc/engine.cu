@@ -26,8 +26,12 @@ static int dbg_skip() {
 // vs 5.17 ms): the second pass runs on 8 warps per SM where the stand-alone LayerNorm spreads 5312 rows over every warp
 // slot of the chip.  It therefore stays opt-in (PFASR_LN_FUSE=1).
 static bool ln_fuse_enabled() {
+#ifdef PFASR_EXPERIMENTS
     static const bool on = [] { const char* e = getenv("PFASR_LN_FUSE"); return e && *e && *e != '0'; }();
     return on;
+#else
+    return false;                 // the product build carries only the selected path (build.py: PFASR_BUILD_EXPERIMENTS)
+#endif
 }
 
 bool pdl_enabled() {
@@ -117,7 +121,9 @@ DeviceCtx::DeviceCtx(int dev, const pf_config& cfg) : dev_(dev), cfg_(cfg) {
     for (auto& e : ev_grp_) PF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     PF_CUDA(cudaEventCreateWithFlags(&ev_compute_, cudaEventDisableTiming));
     fe_tables_ = frontend_tables_create();
+#ifdef PFASR_EXPERIMENTS
     ffn_chain_scratch_create(chain_);
+#endif
     // FunASR SinusoidalPositionEncoder: inv_timescale_i = exp(-i * ln(1e4) / (depth/2 - 1)), float32 arithmetic
     const int half = cfg_.input_size / 2;
     std::vector<float> inv(half);
@@ -146,7 +152,9 @@ DeviceCtx::~DeviceCtx() {
     if (h_us) cudaFreeHost(h_us);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
+#ifdef PFASR_EXPERIMENTS
     ffn_chain_scratch_destroy(chain_);
+#endif
     if (pcm_) cudaFree(pcm_);
     if (raw_) cudaFree(raw_);
     if (d_audio_) cudaFree(d_audio_);
@@ -514,8 +522,10 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
             lp.next_ln1_fused = true;
         }
         gemm_prepare(lp.ffn2, h16_, f, w.w_ffn2, f, M, d, f, e);
+#ifdef PFASR_EXPERIMENTS
         if (!lp.next_ln1_fused && ffn_chain_enabled() && ffn_chain_supported(M, d, f, chain_))
             ffn_chain_prepare(lp.chain, a16_, d, w.w_ffn1, w.b_ffn1, h16_, f, w.w_ffn2, w.b_ffn2, x32_, d, M, d, f, chain_);
+#endif
         plan.layers.push_back(lp);
     };
     for (size_t i = 0; i < enc_.size(); ++i) build_layer(enc_[i], i + 1 < enc_.size() ? &enc_[i + 1] : nullptr);
@@ -628,6 +638,7 @@ void DeviceCtx::gemm(const GemmOp& op) {
     gemm_flops += pf::gemm_flops(op);
 }
 
+#ifdef PFASR_EXPERIMENTS
 void DeviceCtx::ffn_chain(const FfnChainOp& op) {
     if (profile_) {
         // one row for both GEMMs: 2 M (2F) D flops = the sum of the two
@@ -646,6 +657,8 @@ void DeviceCtx::ffn_chain(const FfnChainOp& op) {
     ++launches;
     gemm_flops += ffn_chain_flops(op);
 }
+
+#endif
 
 template <typename F>
 void DeviceCtx::timed(const char* label, F&& f) {
@@ -878,9 +891,12 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
             if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
             ++launches;
         }
+#ifdef PFASR_EXPERIMENTS
         if (lp.chain.valid) {
             ffn_chain(lp.chain);
-        } else {
+        } else
+#endif
+        {
             gemm(lp.ffn1);
             gemm(lp.ffn2);
         }

@@ -12,7 +12,9 @@
 #include "attention.cuh"
 #include "audio.cuh"
 #include "common.cuh"
+#ifdef PFASR_EXPERIMENTS
 #include "ffn_chain.cuh"
+#endif
 #include "frontend.cuh"
 #include "gemm.cuh"
 #include "online.cuh"
@@ -75,7 +77,9 @@ struct DecLayerW {
 
 struct EncLayerPlan {
     GemmOp qkv, out, ffn1, ffn2;
+#ifdef PFASR_EXPERIMENTS
     FfnChainOp chain;                // valid: ffn1 + ffn2 run as one persistent kernel (csrc/ffn_chain.cu)
+#endif
     bool ln2_fused = false;          // norm2 is computed by the out-projection's epilogue
     bool next_ln1_fused = false;     // the next layer's norm1 is computed by this layer's FFN2 epilogue
 };
@@ -283,8 +287,10 @@ private:
     float* t32_ = nullptr; float* tn32_ = nullptr; __half* q16_ = nullptr; __half* ctxd16_ = nullptr;
     float* logits_ = nullptr; int* tokens_ = nullptr;
     int* prompt_ids_ = nullptr;
+#ifdef PFASR_EXPERIMENTS
     FfnChainScratch chain_;                  // dependency flags of the fused feed-forward kernel (this device's compute stream)
     void ffn_chain(const FfnChainOp& op);
+#endif
     // staged PCM
     float* pcm_ = nullptr; size_t pcm_cap_ = 0;
     long long* d_off_ = nullptr; int* d_meta_ = nullptr; int meta_capB_ = 0;   // per-utterance tables

@@ -642,6 +642,7 @@ int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>::max_units = 1;
 
 template <int BNMAX, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
+#ifdef PFASR_EXPERIMENTS
     if constexpr (kOutHalf && kAdds == 0) {
         // fp16 output without addends (QKV, FFN1, K/V projections) with sixteen epilogue warps: opt-in (PFASR_GEMM_EPI16=1).
         // Measured slower - 5.22 vs 5.12 ms/step (one lane), 3.92 vs 3.87 (three lanes), GEMM replay 587 vs 606 TFLOP/s:
@@ -649,14 +650,22 @@ void launch_cl(const GemmOp& op, cudaStream_t stream) {
         static const bool epi16 = [] { const char* e = getenv("PFASR_GEMM_EPI16"); return e && *e == '1'; }();
         if ((epi16 || op.epi16) && op.cm == 1 && op.cn == 1 && (op.vec_ok & 2)) { Launcher<BNMAX, false, true, 0, false, 16>::run(op, stream); return; }
     }
-    if (op.cm == 2 && op.cn == 1) Launcher<BNMAX, true, kOutHalf, kAdds>::run(op, stream);
-    else if (op.cm == 1 && op.cn == 1) Launcher<BNMAX, false, kOutHalf, kAdds>::run(op, stream);
-    else throw CudaError{"gemm: cluster shape not instantiated"};
+    if (op.cm == 2 && op.cn == 1) { Launcher<BNMAX, true, kOutHalf, kAdds>::run(op, stream); return; }
+#endif
+    if (op.cm == 1 && op.cn == 1) Launcher<BNMAX, false, kOutHalf, kAdds>::run(op, stream);
+    else throw CudaError{"gemm: cluster shape not instantiated (CTA pairs need a PFASR_BUILD_EXPERIMENTS=1 build)"};
 }
 
 template <int BNMAX>
 void launch_bn(const GemmOp& op, cudaStream_t stream) {
-    if (op.ln_cluster > 0) { Launcher<BNMAX, false, false, 1, true>::run(op, stream); return; }
+    if (op.ln_cluster > 0) {
+#ifdef PFASR_EXPERIMENTS
+        Launcher<BNMAX, false, false, 1, true>::run(op, stream);
+        return;
+#else
+        throw CudaError{"gemm: the fused-LayerNorm epilogue needs a PFASR_BUILD_EXPERIMENTS=1 build"};
+#endif
+    }
     const bool h = op.epi.out_f16 != nullptr;
     switch (op.n_adds) {
         case 0:  h ? launch_cl<BNMAX, true, 0>(op, stream) : launch_cl<BNMAX, false, 0>(op, stream); break;
@@ -666,8 +675,12 @@ void launch_bn(const GemmOp& op, cudaStream_t stream) {
 }
 
 bool pair_enabled() {
+#ifdef PFASR_EXPERIMENTS
     static const bool on = [] { const char* e = getenv("PFASR_GEMM_PAIR"); return e && *e && *e != '0'; }();
     return on;
+#else
+    return false;
+#endif
 }
 
 // Tile width (any multiple of 32 up to 256) and pairing from a wave model fitted to scripts/gemm_probe.py on B200
@@ -730,6 +743,9 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     cn = std::max(cn, 1);
     if (bn < 32 || bn > 256 || bn % 32 != 0) throw CudaError{"gemm: the N tile must be a multiple of 32 in [32, 256]"};
     if (cm > 2 || cn != 1) throw CudaError{"gemm: unsupported cluster shape (1x1 and the 2x1 CTA pair are instantiated)"};
+#ifndef PFASR_EXPERIMENTS
+    if (cm == 2 || ((tile_code >> 22) & 1)) throw CudaError{"gemm: CTA pairs / sixteen epilogue warps need a PFASR_BUILD_EXPERIMENTS=1 build"};
+#endif
     if (cm == 2 && bn % 64 != 0) throw CudaError{"gemm: the CTA-pair MMA needs an N tile that is a multiple of 64"};
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
     op.throughput = g_policy;
@@ -795,6 +811,10 @@ void gemm_launch(const GemmOp& op, cudaStream_t stream) {
 double gemm_flops(const GemmOp& op) { return 2.0 * op.M * static_cast<double>(op.N) * op.K; }
 
 bool gemm_ln_fusable(int M, int N) {
+#ifndef PFASR_EXPERIMENTS
+    (void)M; (void)N;
+    return false;
+#endif
     if (N % 32 != 0 || N > kLnMaxCluster * 256) return false;
     for (int w = 128; w <= 256; w += 32)
         if (ceil_div(N, w) <= kLnMaxCluster && ceil_div(M, BM) * ceil_div(N, w) <= num_sms()) return true;

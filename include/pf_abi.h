@@ -314,6 +314,9 @@ pf_status pf_decode_online(const pf_tokens* t, const int32_t* token_ids, int32_t
 
 const char* pf_last_error(void);
 int32_t pf_abi_version(void);
+/* 1 when the library was built with PFASR_BUILD_EXPERIMENTS=1 (slower A/B variants compiled in: fused FFN kernel, CTA-pair
+ * and sixteen-epilogue-warp GEMMs, fused-LayerNorm GEMM epilogue); the product build returns 0 */
+int32_t pf_build_experiments(void);
 
 /* -------- op-level test hooks (device 0 of the process; fp32 host in/out, the library converts to its compute
  * types).  Not used by the product path; they let tests/ check each kernel against the oracle through the C-ABI. */

@@ -159,12 +159,18 @@ def test_library_sass_uses_tcgen05_and_tma():
     gemm = [c for k, c in per_kernel.items() if "pf_gemm_f16_tn_tcgen05" in k]
     attn = [c for k, c in per_kernel.items() if "pf_sanm_attention_tc" in k]
     chain = [c for k, c in per_kernel.items() if "pf_ffn_chain_tcgen05" in k]
-    assert gemm and attn and chain
+    assert gemm and attn
+    assert bool(chain) == bool(lib_experiments()), "the fused feed-forward kernel ships only in PFASR_BUILD_EXPERIMENTS=1 builds"
     for c in gemm + chain:
         assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["HMMA"] == 0
     assert any(c["UTMASTG"] > 0 for c in gemm)                       # asynchronous TMA-store epilogue
+    assert any(c["UTMAREDG"] > 0 for c in gemm)                      # in-place residual: fp32 reduce-add by the TMA engine
     for c in attn:
         assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["UTMAREDG"] > 0   # FSMN memory leaves by TMA reduce-add
+
+
+def lib_experiments():
+    return _lib.load().pf_build_experiments()
 
 
 def test_corrupted_weight_blobs_are_refused():

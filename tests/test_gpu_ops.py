@@ -22,6 +22,8 @@ pytestmark = pytest.mark.gpu
     (1000, 520, 72, 128 | (2 << 12)), (129, 256, 64, 256 | (2 << 12)), (1600, 2048, 512, 256 | (2 << 12)), (200, 25055, 512, 256),
 ])
 def test_gemm_plain(lib, M, N, K, tile):
+    if (tile >> 12) & 0xF == 2 and not lib.pf_build_experiments():
+        tile &= 0xFFF                       # CTA pairs exist in PFASR_BUILD_EXPERIMENTS=1 builds only: same shape, one CTA per tile
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
@@ -34,6 +36,8 @@ def test_gemm_plain(lib, M, N, K, tile):
 @pytest.mark.parametrize("M,N,K,tile", [(5344, 1536, 512, 256), (5344, 2048, 512, 0), (300, 520, 192, 128), (129, 96, 64, 0)])
 def test_gemm_f16_sixteen_epilogue_warps(lib, M, N, K, tile):
     """fp16 + ReLU output through the 640-thread variant (tile_code bit 22; opt-in on the product path)."""
+    if not lib.pf_build_experiments():
+        pytest.skip("measured-slower A/B variant: compiled only with PFASR_BUILD_EXPERIMENTS=1 (build.py)")
     rng = np.random.default_rng(M + N)
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
@@ -69,6 +73,8 @@ def test_gemm_epilogue(lib, out_half, relu, adds, N):
 @pytest.mark.parametrize("M,N,K", [(5312, 512, 512), (5312, 512, 2048), (1600, 512, 512), (333, 512, 512), (83, 512, 64), (700, 1024, 256)])
 def test_gemm_fused_layernorm(lib, M, N, K):
     """out-projection / FFN2 epilogue: residual add + LayerNorm of the new rows across the CTAs of a cluster."""
+    if not lib.pf_build_experiments():
+        pytest.skip("measured-slower A/B variant: compiled only with PFASR_BUILD_EXPERIMENTS=1 (build.py)")
     rng = np.random.default_rng(M + N + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
@@ -91,6 +97,8 @@ def test_gemm_fused_layernorm(lib, M, N, K):
 def test_ffn_chain(lib, M, D, F):
     """Feed-forward block as one persistent kernel (csrc/ffn_chain.cu): x + relu(a W1^T + b1) W2^T + b2 with the fp16
     hidden activations handed from the first tile set to the second through flags.  Run twice: the flags carry an epoch."""
+    if not lib.pf_build_experiments():
+        pytest.skip("measured-slower A/B variant: compiled only with PFASR_BUILD_EXPERIMENTS=1 (build.py)")
     rng = np.random.default_rng(M + D + F)
     a = rng.standard_normal((M, D)).astype(np.float32)
     w1 = (rng.standard_normal((F, D)) / np.sqrt(D)).astype(np.float32)
