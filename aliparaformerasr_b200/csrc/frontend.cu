@@ -6,10 +6,16 @@
 //   WavFrontend.ApplyCmvn  WavFrontend.cs:53-71
 //   PadHelper.PadSequence  Utils/PadHelper.cs:23-65 (Q4: every exact 0.0 -> -23.0258509f*32768)
 //
-// One warp per fbank frame: reflect-indexed window load, DC removal, pre-emphasis, Hamming, 512-point real FFT
-// (256-point complex radix-2 in shared memory + split post-pass), 80 triangular mel bins, log, then the frame is
-// scattered straight into every LFR slot that references it, with CMVN applied on the way out.  HBM traffic =
-// read PCM once + write features once.
+// One CTA per chunk of 32 consecutive frames of one utterance; the chunk's samples (reflect-indexed at the utterance
+// edges, x32768) are staged ONCE in shared memory - frames overlap by 240 of 400 samples, so this removes the 2.5x
+// re-read of the PCM - together with the window, twiddle, mel and CMVN tables.  A warp then takes frames of the chunk in
+// turn and keeps the whole 256-point complex FFT (the 512-point real transform, even/odd packed) in REGISTERS: lane L
+// holds positions r*32 + L (r = 0..7), radix-2 DIT stages 1..5 pair lanes (shuffle-xor butterflies), stages 6..8 pair
+// registers, the split post-pass fetches Z[256-k] with one more shuffle.  Shared memory is touched for the 17 input
+// samples a lane needs (consecutive: bit-reversed position r*32+L <-> samples 16*rev5(L) .. +15), for the power spectrum
+// handed to the mel filters and for nothing else; the one-pad-word-per-32 layout makes the 64-byte-strided sample and
+// window reads conflict-free.  The frame leaves through every LFR slot that references it, CMVN applied on the way out.
+// HBM traffic = read PCM once + write features once.
 #include "frontend.cuh"
 
 #include <math.h>
@@ -46,6 +52,17 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
     return i;
 }
 
+constexpr int kChunkFrames = 32;                                             // frames per CTA
+constexpr int kChunkSamples = kFrameShift * (kChunkFrames - 1) + kFrameLen;  // 5360 staged samples
+constexpr int kMelNnzSmem = 512;                                             // Kaldi's 80 triangles over 256 bins: 501 taps
+constexpr int kMaxCmvnDim = 640;
+
+__device__ __forceinline__ int padi(int a) { return a + (a >> 5); }          // one pad word per 32: stride-16 reads hit 32 banks
+
+__device__ __forceinline__ float2 cmul_tw(const float2 w, const float2 a) {  // same expression as the butterfly of the first kernel
+    return make_float2(w.x * a.x - w.y * a.y, w.x * a.y + w.y * a.x);
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 pf_frontend_fbank_lfr_cmvn(const FrontendTables* __restrict__ tab, const float* __restrict__ pcm,
                            const long long* __restrict__ pcm_off, const int* __restrict__ nsamp,
@@ -56,145 +73,194 @@ pf_frontend_fbank_lfr_cmvn(const FrontendTables* __restrict__ tab, const float* 
                            int lfr_m, int lfr_n, int snip_edges, int pad_quirk, float pad_value) {
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ float s_x[kChunkSamples + kChunkSamples / 32 + 2];
+    __shared__ float s_win[kFrameLen + kFrameLen / 32 + 2];
     __shared__ float2 s_tw[256];
-    __shared__ float s_win[kFrameLen];
-    __shared__ float2 s_z[kWarps][256];
-    __shared__ float s_tmp[kWarps][kFft];
-    __shared__ unsigned char s_rev[256];
+    __shared__ float s_p[kWarps][256];
+    __shared__ float s_melw[kMelNnzSmem];
+    __shared__ short s_mst[kMel], s_mln[kMel], s_mof[kMel];
+    __shared__ float s_shift[kMaxCmvnDim], s_scale[kMaxCmvnDim];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        s_tw[i] = tab->tw[i];
-        s_rev[i] = tab->bitrev[i];
-    }
-    for (int i = threadIdx.x; i < kFrameLen; i += blockDim.x) s_win[i] = tab->window[i];
-    __syncthreads();
-
-    const int f = blockIdx.x * kWarps + warp;
     const int T = nframes[b];
-    if (f >= T) return;                       // whole warp exits together
+    const int f0 = blockIdx.x * kChunkFrames;
+    if (f0 >= T) return;                                   // the whole CTA leaves before any barrier
     const int n = nsamp[b];
     const float* x = pcm + pcm_off[b];
-    const int start = snip_edges ? f * kFrameShift : f * kFrameShift + (kFrameShift / 2 - kFrameLen / 2);
+    const int nfr = min(kChunkFrames, T - f0);
+    const int start0 = snip_edges ? f0 * kFrameShift : f0 * kFrameShift + (kFrameShift / 2 - kFrameLen / 2);
+    const int ns = kFrameShift * (nfr - 1) + kFrameLen;
 
-    float* tmp = s_tmp[warp];
-    float2* z = s_z[warp];
-
-    // 1. load + scale (WavFrontend.cs:34 multiplies by 32768f in float32), accumulate the frame mean
-    float sum = 0.0f;
-    for (int j = lane; j < kFrameLen; j += 32) {
-        int idx = start + j;
+    // stage the chunk: scale by 32768 in float32 like WavFrontend.cs:34; Kaldi mirrors indices outside the utterance
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        int idx = start0 + i;
         if (!snip_edges) idx = reflect_index(idx, n);
-        const float v = x[idx] * 32768.0f;
-        tmp[j] = v;
-        sum += v;
+        s_x[padi(i)] = (idx >= 0 && idx < n) ? x[idx] * 32768.0f : 0.0f;
     }
-    sum = warp_sum(sum);
-    const float mean = sum / static_cast<float>(kFrameLen);
-    __syncwarp();
-
-    // 2. remove DC, pre-emphasis 0.97 (x[-1] := x[0]), Hamming; pack even/odd samples into a complex sequence
-    //    stored bit-reversed for the in-place radix-2 DIT FFT.
-    for (int nn = lane; nn < 256; nn += 32) {
-        float re = 0.0f, im = 0.0f;
-        const int j0 = 2 * nn, j1 = 2 * nn + 1;
-        if (j0 < kFrameLen) {
-            const float cur = tmp[j0] - mean;
-            const float prev = (j0 == 0 ? tmp[0] : tmp[j0 - 1]) - mean;
-            re = (cur - 0.97f * prev) * s_win[j0];
-        }
-        if (j1 < kFrameLen) {
-            const float cur = tmp[j1] - mean;
-            const float prev = tmp[j1 - 1] - mean;
-            im = (cur - 0.97f * prev) * s_win[j1];
-        }
-        z[s_rev[nn]] = make_float2(re, im);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tw[i] = tab->tw[i];
+    for (int i = threadIdx.x; i < kFrameLen; i += blockDim.x) s_win[padi(i)] = tab->window[i];
+    for (int i = threadIdx.x; i < kMelNnzSmem; i += blockDim.x) s_melw[i] = tab->mel_w[i];
+    for (int i = threadIdx.x; i < kMel; i += blockDim.x) {
+        s_mst[i] = static_cast<short>(tab->mel_start[i]);
+        s_mln[i] = static_cast<short>(tab->mel_len[i]);
+        s_mof[i] = static_cast<short>(tab->mel_off[i]);
     }
-    __syncwarp();
+    const int dim = lfr_m * kMel;
+    if (feats_out)
+        for (int i = threadIdx.x; i < dim; i += blockDim.x) { s_shift[i] = add_shift[i]; s_scale[i] = rescale[i]; }
+    __syncthreads();
 
-    // 3. 256-point complex FFT, 8 radix-2 stages, 128 butterflies per stage = 4 per lane
-#pragma unroll 1
-    for (int s = 1; s <= 8; ++s) {
-        const int m = 1 << s;
-        const int half = m >> 1;
-        const int tw_stride = 512 >> s;        // index into the 512-th roots table: 2 * pos * (256 / m)
+    // per-lane constants: the 17 consecutive samples behind the lane's 8 bit-reversed positions, and its twiddles
+    constexpr unsigned kFull = 0xffffffffu;
+    const int brl = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);       // rev5(lane)
+    const int jbase = 16 * brl;                                                          // first sample index of the lane
+    float2 tws[5];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = lane + 32 * i;
-            const int grp = j >> (s - 1);
-            const int pos = j & (half - 1);
-            const int i0 = grp * m + pos;
-            const int i1 = i0 + half;
-            const float2 w = s_tw[pos * tw_stride];
-            const float2 a0 = z[i0];
-            const float2 a1 = z[i1];
-            const float tr = w.x * a1.x - w.y * a1.y;
-            const float ti = w.x * a1.y + w.y * a1.x;
-            z[i0] = make_float2(a0.x + tr, a0.y + ti);
-            z[i1] = make_float2(a0.x - tr, a0.y - ti);
-        }
-        __syncwarp();
-    }
+    for (int st = 1; st <= 5; ++st) tws[st - 1] = s_tw[(lane & ((1 << (st - 1)) - 1)) * (512 >> st)];
+    const float2 tw6 = s_tw[lane * 8];
+    const float2 tw7[2] = {s_tw[lane * 4], s_tw[(32 + lane) * 4]};
+    const float2 tw8[4] = {s_tw[lane * 2], s_tw[(32 + lane) * 2], s_tw[(64 + lane) * 2], s_tw[(96 + lane) * 2]};
+    float win[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) win[t] = jbase + t < kFrameLen ? s_win[padi(jbase + t)] : 0.0f;
 
-    // 4. split post-pass -> power spectrum bins 0..255 (Kaldi's mel banks never read the Nyquist bin)
-    float* power = tmp;                         // tmp is free again
-    for (int k = lane; k < 256; k += 32) {
-        const float2 zk = z[k];
-        const float2 zc = z[(256 - k) & 255];   // conj applied below
-        const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);      // E = (Z[k] + conj(Z[N-k])) / 2
-        const float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);      // D = (Z[k] - conj(Z[N-k])) / 2
-        const float orr = di, oi = -dr;                                        // O = D / i
-        const float2 w = s_tw[k];
-        const float xr = er + (w.x * orr - w.y * oi);
-        const float xi = ei + (w.x * oi + w.y * orr);
-        power[k] = xr * xr + xi * xi;
-    }
-    __syncwarp();
-
-    // 5. mel filterbank + log, then scatter into the LFR slots (CMVN on the way out)
     const int Tl = nlfr[b];
     const int left = (lfr_m - 1) / 2;
-    const int p = f + left;                     // index in the left-padded frame sequence
-    // LFR frame i reads padded frames [i*n, i*n + m): i ranges over ceil((p-m+1)/n) .. floor(p/n)
-    int i_hi = p / lfr_n;
-    int i_lo = (p - lfr_m + 1 + lfr_n - 1);
-    i_lo = i_lo <= 0 ? 0 : i_lo / lfr_n;
-    if (i_hi > Tl - 1) i_hi = Tl - 1;
+    float* power = s_p[warp];
 
 #pragma unroll 1
-    for (int mb = lane; mb < kMel; mb += 32) {
-        const int st = tab->mel_start[mb];
-        const int ln = tab->mel_len[mb];
-        const float* w = tab->mel_w + tab->mel_off[mb];
-        float e = 0.0f;
-        for (int k = 0; k < ln; ++k) e += w[k] * power[st + k];
-        const float v = logf(fmaxf(e, 1.1920928955078125e-07f));
-        if (fbank_out) fbank_out[fbank_off[b] + static_cast<long long>(f) * kMel + mb] = v;
-        if (feats_out) {
-            for (int i = i_lo; i <= i_hi; ++i) {
-                const int slot = p - i * lfr_n;
-                const int col = slot * kMel + mb;
-                float o = (v + add_shift[col]) * rescale[col];
-                if (pad_quirk && o == 0.0f) o = pad_value;
-                feats_out[feats_off[b] + static_cast<long long>(i) * (lfr_m * kMel) + col] = o;
+    for (int fl = warp; fl < nfr; fl += kWarps) {
+        const int f = f0 + fl;
+        const int foff = fl * kFrameShift;
+        // 1. the lane's samples j = jbase - 1 .. jbase + 15 (pre-emphasis needs the previous one; x[-1] := x[0])
+        float xs[17];
+#pragma unroll
+        for (int t = 0; t < 17; ++t) {
+            const int jj = jbase - 1 + t;
+            xs[t] = (jj >= 0 && jj < kFrameLen) ? s_x[padi(foff + jj)] : 0.0f;
+        }
+        if (brl == 0) xs[0] = xs[1];
+        float sum = 0.0f;
+#pragma unroll
+        for (int t = 1; t < 17; ++t) sum += xs[t];             // samples past 400 read as 0
+        sum = warp_sum(sum);
+        const float mean = sum / static_cast<float>(kFrameLen);
+        // 2. remove DC, pre-emphasis 0.97, Hamming; even / odd samples packed as re / im at the bit-reversed position
+        float y[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const float cur = xs[t + 1] - mean;
+            const float prev = xs[t] - mean;
+            y[t] = jbase + t < kFrameLen ? (cur - 0.97f * prev) * win[t] : 0.0f;
+        }
+        float2 z[8];                                           // position r*32 + lane holds input n = rev8(position) = 8*brl + rev3(r)
+        z[0] = make_float2(y[0], y[1]);   z[1] = make_float2(y[8], y[9]);
+        z[2] = make_float2(y[4], y[5]);   z[3] = make_float2(y[12], y[13]);
+        z[4] = make_float2(y[2], y[3]);   z[5] = make_float2(y[10], y[11]);
+        z[6] = make_float2(y[6], y[7]);   z[7] = make_float2(y[14], y[15]);
+        // 3. stages 1..5: the partner position differs in a lane bit
+#pragma unroll
+        for (int st = 1; st <= 5; ++st) {
+            const int half = 1 << (st - 1);
+            const bool upper = (lane & half) != 0;
+            const float2 w = tws[st - 1];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                float2 o;
+                o.x = __shfl_xor_sync(kFull, z[r].x, half);
+                o.y = __shfl_xor_sync(kFull, z[r].y, half);
+                const float2 a1 = upper ? z[r] : o;
+                const float2 a0 = upper ? o : z[r];
+                const float2 tt = cmul_tw(w, a1);
+                z[r] = upper ? make_float2(a0.x - tt.x, a0.y - tt.y) : make_float2(a0.x + tt.x, a0.y + tt.y);
             }
         }
-    }
-    // The (m-1)/2 left-pad frames are zeros in the reference (Q1): after CMVN they read shift*scale.
-    if (feats_out && f == 0 && Tl > 0) {
-        for (int pp = 0; pp < left; ++pp) {
-            // padded frame pp belongs to LFR frames i with i*n <= pp < i*n + m
-            for (int i = 0; i * lfr_n <= pp && i < Tl; ++i) {
-                const int slot = pp - i * lfr_n;
-                if (slot >= lfr_m) continue;
-                for (int mb = lane; mb < kMel; mb += 32) {
+        // stages 6..8: the partner is another register of the same lane
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+            const float2 tt = cmul_tw(tw6, z[r + 1]);
+            const float2 a0 = z[r];
+            z[r] = make_float2(a0.x + tt.x, a0.y + tt.y);
+            z[r + 1] = make_float2(a0.x - tt.x, a0.y - tt.y);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; g += 4)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int r = g + q;
+                const float2 tt = cmul_tw(tw7[q], z[r + 2]);
+                const float2 a0 = z[r];
+                z[r] = make_float2(a0.x + tt.x, a0.y + tt.y);
+                z[r + 2] = make_float2(a0.x - tt.x, a0.y - tt.y);
+            }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float2 tt = cmul_tw(tw8[r], z[r + 4]);
+            const float2 a0 = z[r];
+            z[r] = make_float2(a0.x + tt.x, a0.y + tt.y);
+            z[r + 4] = make_float2(a0.x - tt.x, a0.y - tt.y);
+        }
+        // 4. split post-pass -> power spectrum bins k = r*32 + lane (Kaldi's mel banks never read the Nyquist bin);
+        //    Z[256 - k] sits in register 7 - r of lane 32 - L (register (8 - r) & 7 of lane 0 when L = 0)
+        __syncwarp();                                          // the previous frame's mel reads of `power` are done
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float2 mine = lane == 0 ? z[(8 - r) & 7] : z[7 - r];
+            float2 zc;
+            zc.x = __shfl_sync(kFull, mine.x, (32 - lane) & 31);
+            zc.y = __shfl_sync(kFull, mine.y, (32 - lane) & 31);
+            const float2 zk = z[r];
+            const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);      // E = (Z[k] + conj(Z[N-k])) / 2
+            const float dr = 0.5f * (zk.x - zc.x), di = 0.5f * (zk.y + zc.y);      // D = (Z[k] - conj(Z[N-k])) / 2
+            const float orr = di, oi = -dr;                                        // O = D / i
+            const float2 w = s_tw[r * 32 + lane];
+            const float xr = er + (w.x * orr - w.y * oi);
+            const float xi = ei + (w.x * oi + w.y * orr);
+            power[r * 32 + lane] = xr * xr + xi * xi;
+        }
+        __syncwarp();
+
+        // 5. mel filterbank + log, then scatter into the LFR slots (CMVN on the way out)
+        const int p = f + left;                     // index in the left-padded frame sequence
+        // LFR frame i reads padded frames [i*n, i*n + m): i ranges over ceil((p-m+1)/n) .. floor(p/n)
+        int i_hi = p / lfr_n;
+        int i_lo = (p - lfr_m + 1 + lfr_n - 1);
+        i_lo = i_lo <= 0 ? 0 : i_lo / lfr_n;
+        if (i_hi > Tl - 1) i_hi = Tl - 1;
+#pragma unroll 1
+        for (int mb = lane; mb < kMel; mb += 32) {
+            const int st = s_mst[mb];
+            const int ln = s_mln[mb];
+            const float* w = s_melw + s_mof[mb];
+            float e = 0.0f;
+            for (int k = 0; k < ln; ++k) e += w[k] * power[st + k];
+            const float v = logf(fmaxf(e, 1.1920928955078125e-07f));
+            if (fbank_out) fbank_out[fbank_off[b] + static_cast<long long>(f) * kMel + mb] = v;
+            if (feats_out) {
+                for (int i = i_lo; i <= i_hi; ++i) {
+                    const int slot = p - i * lfr_n;
                     const int col = slot * kMel + mb;
-                    float o = (0.0f + add_shift[col]) * rescale[col];
+                    float o = (v + s_shift[col]) * s_scale[col];
                     if (pad_quirk && o == 0.0f) o = pad_value;
-                    feats_out[feats_off[b] + static_cast<long long>(i) * (lfr_m * kMel) + col] = o;
+                    feats_out[feats_off[b] + static_cast<long long>(i) * dim + col] = o;
+                }
+            }
+        }
+        // The (m-1)/2 left-pad frames are zeros in the reference (Q1): after CMVN they read shift*scale.
+        if (feats_out && f == 0 && Tl > 0) {
+            for (int pp = 0; pp < left; ++pp) {
+                // padded frame pp belongs to LFR frames i with i*n <= pp < i*n + m
+                for (int i = 0; i * lfr_n <= pp && i < Tl; ++i) {
+                    const int slot = pp - i * lfr_n;
+                    if (slot >= lfr_m) continue;
+                    for (int mb = lane; mb < kMel; mb += 32) {
+                        const int col = slot * kMel + mb;
+                        float o = (0.0f + s_shift[col]) * s_scale[col];
+                        if (pad_quirk && o == 0.0f) o = pad_value;
+                        feats_out[feats_off[b] + static_cast<long long>(i) * dim + col] = o;
+                    }
                 }
             }
         }
@@ -257,7 +323,7 @@ void* frontend_tables_create() {
         t.mel_start[b] = first < 0 ? 0 : first;
         t.mel_len[b] = first < 0 ? 0 : last - first + 1;
         t.mel_off[b] = off;
-        if (off + static_cast<int>(w.size()) > kMaxMelNnz) throw CudaError{"mel table overflow"};
+        if (off + static_cast<int>(w.size()) > kMelNnzSmem) throw CudaError{"mel table overflow"};
         for (size_t i = 0; i < w.size(); ++i) t.mel_w[off + i] = w[i];
         off += static_cast<int>(w.size());
     }
@@ -273,7 +339,8 @@ void frontend_tables_destroy(void* tables) {
 
 void frontend_launch(const FrontendLaunch& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_frames <= 0) return;
-    dim3 grid(ceil_div(a.max_frames, kWarps), a.batch);
+    if (a.feats_out && a.lfr_m * kMel > kMaxCmvnDim) throw CudaError{"front-end: lfr_m * 80 exceeds the staged CMVN table"};
+    dim3 grid(ceil_div(a.max_frames, kChunkFrames), a.batch);
     launch_k(pf_frontend_fbank_lfr_cmvn, grid, dim3(kWarps * 32), 0, stream,
              static_cast<const FrontendTables*>(a.tables), a.pcm, a.pcm_off, a.nsamp, a.nframes, a.nlfr, a.add_shift, a.rescale,
              a.fbank_out, a.fbank_off, a.feats_out, a.feats_off, a.lfr_m, a.lfr_n, a.snip_edges ? 1 : 0, a.pad_quirk ? 1 : 0,
