@@ -44,16 +44,21 @@ struct GemmOp {
     int throughput = 0;   // prepared under the throughput objective (gemm_set_policy)
     int epi16 = 0;        // sixteen epilogue warps (fp16 output without addends; tile_code bit 22 or PFASR_GEMM_EPI16=1)
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
+    int half_sm = 0; // launched as one 128 x 256 tile per CTA, two CTAs per SM (gemm_half.cu)
     int red_add = 0; // the residual aliases the output: added by a TMA fp32 reduce-add instead of load + add + store
     int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
 
 // Build the TMA descriptors for one GEMM.  lda / ldw are in elements and must be multiples of 8 (16 B).
 // tile_code = 0 picks tile width and pairing from the problem shape; otherwise bn | (cm << 12); bit 22 asks for the
-// sixteen-epilogue-warp variant (fp16 output without addends).
+// sixteen-epilogue-warp variant (fp16 output without addends), bit 23 for the half-SM kernel (256-wide tiles, fp16 output).
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
+// half-SM variant (csrc/gemm_half.cu): fp16 output, 128 x 256 tile per CTA, two CTAs per SM.  PFASR_GEMM_HALFSM = 0 off,
+// 1 (default) for multi-lane handles, 2 always
+bool gemm_half_eligible(const GemmOp& op, bool force = false);
+void gemm_half_launch(const GemmOp& op, cudaStream_t stream);
 // tile-selection objective of the ops this thread prepares from now on: 0 = shortest kernel (one batch at a time),
 // 1 = least SM time (several batches in flight); PFASR_GEMM_POLICY=latency|throughput overrides
 void gemm_set_policy(int throughput);

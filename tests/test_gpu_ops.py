@@ -47,6 +47,24 @@ def test_gemm_f16_sixteen_epilogue_warps(lib, M, N, K, tile):
     assert np.abs(out - ref).max() < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K,relu", [(5312, 1536, 512, 0), (5312, 2048, 512, 1), (5312, 1536, 560, 0), (5312, 16384, 512, 0), (1600, 2048, 512, 1),
+                                        (83, 1536, 512, 0), (300, 1024, 192, 1), (129, 288, 64, 0), (5344, 2048, 2048, 1)])
+def test_gemm_half_sm_kernel(lib, M, N, K, relu):
+    """csrc/gemm_half.cu: one 128 x 256 tile per CTA, two CTAs per SM (tile_code bit 23), fp16 output with bias / ReLU;
+    ragged M and N edges are clipped by the tensor maps."""
+    rng = np.random.default_rng(M + 3 * N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out, _ = dbg_gemm(lib, A, W, bias, relu=relu, out_half=1, tile_n=256 | (1 << 23))
+    ref = half_round(A).astype(np.float64) @ half_round(W).astype(np.float64).T + bias
+    if relu:
+        ref = np.maximum(ref, 0.0)
+    assert np.abs(out - half_round(ref)).max() < 6e-3
+    plain, _ = dbg_gemm(lib, A, W, bias, relu=relu, out_half=1, tile_n=256)
+    assert np.array_equal(out, plain)                  # same MMAs, same epilogue arithmetic as the persistent kernel
+
+
 @pytest.mark.parametrize("out_half,relu", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("adds", [0, 1, 2])
 @pytest.mark.parametrize("N", [520, 517])          # 517: unaligned pitch -> scalar epilogue path
