@@ -799,13 +799,20 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
         make_tmap_any(&op.tmL, epi.ln_out16, false, M, N, epi.ld_ln16, 32, 64);
     }
     if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 31) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA, 8 no TMA store, 16 no staging either
+#ifdef PFASR_EXPERIMENTS
     op.half_sm = gemm_half_eligible(op, ((tile_code >> 23) & 1) != 0) ? 1 : 0;
+#else
+    op.half_sm = 0;
+    if ((tile_code >> 23) & 1) throw CudaError{"gemm: the half-SM kernel needs a PFASR_BUILD_EXPERIMENTS=1 build"};
+#endif
     make_tmap(&op.tmA, A, M, K, lda, BM);           // every CTA stages its own 128 rows of A
     make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and (in a CTA pair) half of the W tile
 }
 
 void gemm_launch(const GemmOp& op, cudaStream_t stream) {
+#ifdef PFASR_EXPERIMENTS
     if (op.half_sm) { gemm_half_launch(op, stream); return; }
+#endif
     if (op.bn <= 128) launch_bn<128>(op, stream);      // 32 KiB stage slots, 6 stages
     else launch_bn<256>(op, stream);                   // 48 KiB stage slots
 }

@@ -55,8 +55,8 @@ struct GemmOp {
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code = 0);
 void gemm_launch(const GemmOp& op, cudaStream_t stream);
-// half-SM variant (csrc/gemm_half.cu): fp16 output, 128 x 256 tile per CTA, two CTAs per SM.  PFASR_GEMM_HALFSM = 0 off,
-// 1 (default) for multi-lane handles, 2 always
+// half-SM variant (csrc/gemm_half.cu, PFASR_BUILD_EXPERIMENTS=1 builds only): fp16 output, 128 x 256 tile per CTA, two CTAs
+// per SM.  PFASR_GEMM_HALFSM = 0 off (default: measured slower), 1 for multi-lane handles, 2 always
 bool gemm_half_eligible(const GemmOp& op, bool force = false);
 void gemm_half_launch(const GemmOp& op, cudaStream_t stream);
 // tile-selection objective of the ops this thread prepares from now on: 0 = shortest kernel (one batch at a time),

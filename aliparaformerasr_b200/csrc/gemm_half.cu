@@ -7,8 +7,14 @@
 // launch in which the SM's tensor pipe idles.  Here those phases of one CTA overlap the main loop of the
 // CTA that shares the SM - a tile of the same launch, the first tile of the NEXT launch (programmatic dependent launch:
 // its CTAs become resident, allocate TMEM and prefetch their weight tiles while this kernel still computes), or another
-// execution lane's tile.  Two stages per CTA are enough because the two co-resident CTAs together keep four operand
-// stages in flight per SM, and their MMAs interleave on the one tensor pipe.
+// execution lane's tile.  The bet: two stages per CTA are enough because the two co-resident CTAs together keep four
+// operand stages in flight per SM, and their MMAs interleave on the one tensor pipe.
+//
+// MEASURED (round 2, A/B on one B200, scripts/quick_bench.py): parity-green and bit-identical to the persistent kernel,
+// but slower - GEMM replay on one stream 484 vs 552 TFLOP/s (256-wide tiles), three lanes concurrently 706 vs 768 TFLOP/s,
+// cfg2 step 3.94 vs 3.79 ms.  Two stages per CTA do not cover the L2 latency: each CTA's pipe stalls after every second
+// k-block and the partner CTA does not fill the gap, so the main loop loses more than the overlapped prologue / epilogue
+// returns.  Kept as an experiment (PFASR_BUILD_EXPERIMENTS=1 builds; PFASR_GEMM_HALFSM=1|2 or tile_code bit 23).
 //
 // Same warp roles and mbarrier protocol as gemm.cu, minus the tile loop: warp 0 = TMA producer, warp 1 = MMA issuer,
 // warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM row -> bias / ReLU -> fp16 -> swizzled 32 x 32 boxes -> TMA store).
@@ -150,8 +156,8 @@ pf_gemm_f16_tn_tcgen05_half(const __grid_constant__ CUtensorMap tmA, const __gri
 }  // namespace
 
 bool gemm_half_eligible(const GemmOp& op, bool force) {
-    // 0 = off, 1 = multi-lane handles only (throughput objective), 2 = always
-    static const int mode = [] { const char* e = getenv("PFASR_GEMM_HALFSM"); return e ? atoi(e) : 1; }();
+    // 0 = off (default: measured slower), 1 = multi-lane handles only (throughput objective), 2 = always
+    static const int mode = [] { const char* e = getenv("PFASR_GEMM_HALFSM"); return e ? atoi(e) : 0; }();
     if (!force && (mode <= 0 || (mode == 1 && !op.throughput))) return false;
     return op.epi.out_f16 != nullptr && op.n_adds == 0 && (op.vec_ok & 2) != 0 && op.bn == kHalfBN && op.cm == 1 && op.cn == 1 &&
            op.ln_cluster == 0 && op.epi.bias != nullptr && (reinterpret_cast<uintptr_t>(op.epi.bias) & 15) == 0 && op.N % 32 == 0 &&
