@@ -110,7 +110,7 @@ class ClockSampler:
 
 def _gemm_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/gemm_traffic_r01_v11.json: launch-weighted mean over the four GEMMs of an encoder layer)."""
+    (profiles/gemm_traffic_r02.json: launch-weighted mean over the four GEMMs of an encoder layer)."""
     path = os.path.join(ROOT, "profiles", "gemm_traffic_r01_v11.json")
     try:
         return int(json.load(open(path))["avg_dram_bytes_per_launch"])
@@ -490,7 +490,7 @@ def main():
             "stage_ms": stage_ms,
             "kernel_ms_profiled_step": kernel_ms,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r01_v11.json)",
+                         "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r02.json)",
                          "kernel": "pf_gemm_f16_tn_tcgen05", "peak_source": peak_src,
                          "method": "all GEMM launches of one step re-launched back to back on the engine's stream (programmatic-launch "
                                    "chained as inside the step, weights streamed from HBM: 0.43 GB per pass), 5 passes between two CUDA events",
