@@ -433,6 +433,7 @@ def main():
             e1.run_pcm(pcm[0])
             e2e.append((time.perf_counter() - t0) * 1e3)
         e1.close()
+        torch.cuda.set_device(local_rank)
         audio = BATCH * SECONDS
         return {"handle": tag, "global_batch": BATCH, "n_gpus": len(devices), "steps": args.steps,
                 "resident_ms_min_median_max": [min(res), statistics.median(res), max(res)],
@@ -452,8 +453,10 @@ def main():
     elif rank == 0:
         strong = dict(latency, handle="1 GPU: identical to latency_single_lane")
 
-    # -------- reduce over ranks (max time)
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # -------- reduce over ranks (max time).  (The multi-device handle of the strong-scaling leg leaves the calling thread on
+    # its last device: go back to this rank's own.)
+    torch.cuda.set_device(local_rank)
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=torch.device("cuda", local_rank))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
