@@ -117,6 +117,28 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
     });
 }
 
+pf_status pf_dbg_gemm_pick(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, int32_t tile_n,
+                           int32_t* tokens) {
+    return guarded([&] {
+        if (!A || !W || !tokens) throw StatusError{PF_ERR_BAD_ARG, "null argument"};
+        Scratch s;
+        __half* dA = s.up_half(A, static_cast<size_t>(M) * K);
+        __half* dW = s.up_half(W, static_cast<size_t>(N) * K);
+        GemmEpi e;
+        if (bias) e.bias = s.up(bias, N);
+        const int slots = gemm_pick_slots(N);
+        e.pick_out = s.alloc<float>(static_cast<size_t>(M) * slots * 3);
+        e.pick_ld = slots;
+        int* dtok = s.alloc<int>(M);
+        GemmOp op;
+        gemm_prepare(op, dA, K, dW, K, M, N, K, e, tile_n);
+        gemm_launch(op, 0);
+        pick_combine_launch(e.pick_out, M, slots, ceil_div(N, op.bn) * 2, dtok, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        PF_CUDA(cudaMemcpy(tokens, dtok, static_cast<size_t>(M) * sizeof(int), cudaMemcpyDeviceToHost));
+    });
+}
+
 pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* x, float* out, float* elapsed_ms, int32_t iters) {
 #ifndef PFASR_EXPERIMENTS

@@ -440,6 +440,8 @@ void DeviceCtx::ensure_workspace(int B, int T) {
     enc32_ = dalloc<float>(M * d, apool_);
     enc16_ = dalloc<__half>(M * d, apool_);
     prompt_ids_ = dalloc<int>(4, apool_);
+    pick_ld_ = gemm_pick_slots(cfg_.vocab);
+    pick_ = dalloc<float>((sv ? M : Md) * pick_ld_ * 3, apool_);
     if (sv) {
         logits_ = dalloc<float>(M * ldv(), apool_);
         tokens_ = dalloc<int>(M, apool_);
@@ -533,6 +535,8 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
     if (cfg_.model_kind == PF_MODEL_SENSEVOICE_SMALL) {
         GemmEpi e; e.bias = b_head_; e.out_f32 = logits_; e.ld_out = ldv();
         gemm_prepare(plan.ctc_head, enc16_, d, w_head_, d, M, cfg_.vocab, d, e);
+        GemmEpi pk; pk.bias = b_head_; pk.pick_out = pick_; pk.pick_ld = pick_ld_;
+        gemm_prepare(plan.ctc_head_pick, enc16_, d, w_head_, d, M, cfg_.vocab, d, pk);
     } else {
         GemmEpi e; e.bias = b_conv_; e.relu = 1; e.out_f32 = mem32_; e.ld_out = d;
         gemm_prepare(plan.pred_conv, qkv16_, 3 * d, w_conv_, 3 * d, M, d, 3 * d, e);   // qkv16_ holds the im2col rows
@@ -576,6 +580,8 @@ DecoderPlan& DeviceCtx::decoder_plan(int B, int T, int L) {
     ffn(dec3_, plan.d3_w1, plan.d3_w2);
     GemmEpi h; h.bias = b_head_; h.out_f32 = logits_; h.ld_out = ldv();
     gemm_prepare(plan.head, ad16_, d, w_head_, d, Md, cfg_.vocab, d, h);
+    GemmEpi pk; pk.bias = b_head_; pk.pick_out = pick_; pk.pick_ld = pick_ld_;
+    gemm_prepare(plan.head_pick, ad16_, d, w_head_, d, Md, cfg_.vocab, d, pk);
     if (cfg_.model_kind == PF_MODEL_SEACO_PARAFORMER) {
         const int sf = cfg_.seaco_ffn;
         auto sffn = [&](const DecFfnW& w, GemmOp& g1, GemmOp& g2) {
@@ -996,9 +1002,15 @@ void DeviceCtx::decoder_forward(int B, int T, int L, bool online) {
     dec_stack(dec_, dec3_, plan.layers, plan.d3_w1, plan.d3_w2, cfg_.dec_ffn, cfg_.dec_kernel, kv16_, cfg_.dec_layers * 2 * d, false, T, B, L, online);
     // after_norm -> fp16 operand of the output layer (+ fp32 copy: the decoder hidden the SeACo branch queries with)
     layernorm_f32_launch(t32_, d, Md, d, dec_after_.g, dec_after_.b, eps, ad16_, d, seaco ? hid32_ : nullptr, d, stream_);
-    gemm(plan.head);
-    // offline model_out is log-softmax; the streaming decoder graph returns raw logits (the pick is the same)
-    logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, online ? 0 : 1, stream_);
+    if (want_logits_ || seaco) {
+        gemm(plan.head);
+        // offline model_out is log-softmax; the streaming decoder graph returns raw logits (the pick is the same)
+        logsoftmax_argmax_launch(logits_, Md, cfg_.vocab, ldv(), tokens_, online ? 0 : 1, stream_);
+    } else {
+        // ids only (the default): the greedy pick rides on the head GEMM's epilogue, the [B*L, V] log-probs are never written
+        gemm(plan.head_pick);
+        pick_combine_launch(pick_, Md, pick_ld_, ceil_div(cfg_.vocab, plan.head_pick.bn) * 2, tokens_, stream_);
+    }
     launches += 2;
     if (seaco) seaco_forward(B, L, plan);
 }
@@ -1148,6 +1160,7 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
     int T = staged_T_;
     launches = 0;
     gemm_flops = 0.0;
+    want_logits_ = (flags & PF_RUN_WANT_LOGITS) != 0;
     if (B <= 0) throw StatusError{PF_ERR_BAD_ARG, "nothing staged"};
     const int din = cfg_.input_size;
     // ---- front-end
@@ -1201,10 +1214,19 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
     ensure_pinned(reinterpret_cast<void**>(&h_token_num), &h_tn_cap_, static_cast<size_t>(B) * sizeof(int32_t));
     if (sv) {
         const int M = B * T;
-        gemm(encoder_plan(B, T).ctc_head);
-        PF_CUDA(cudaEventRecord(ev_[3], stream_));
-        PF_CUDA(cudaEventRecord(ev_[4], stream_));
-        logsoftmax_argmax_launch(logits_, M, cfg_.vocab, ldv(), tokens_, (flags & PF_RUN_WANT_LOGITS) ? 1 : 0, stream_);
+        if (flags & PF_RUN_WANT_LOGITS) {
+            gemm(encoder_plan(B, T).ctc_head);
+            PF_CUDA(cudaEventRecord(ev_[3], stream_));
+            PF_CUDA(cudaEventRecord(ev_[4], stream_));
+            logsoftmax_argmax_launch(logits_, M, cfg_.vocab, ldv(), tokens_, 1, stream_);
+        } else {
+            // per-frame ids only: fused pick in the CTC head's epilogue, the [B, T, 25055] tensor (879 MB at cfg3) is never written
+            EncoderPlan& ep = encoder_plan(B, T);
+            gemm(ep.ctc_head_pick);
+            PF_CUDA(cudaEventRecord(ev_[3], stream_));
+            PF_CUDA(cudaEventRecord(ev_[4], stream_));
+            pick_combine_launch(pick_, M, pick_ld_, ceil_div(cfg_.vocab, ep.ctc_head_pick.bn) * 2, tokens_, stream_);
+        }
         ++launches;
         PF_CUDA(cudaEventRecord(ev_[5], stream_));
         Lmax_ = T; Lpad_ = T;
@@ -1393,6 +1415,7 @@ void DeviceCtx::online_step_impl(const std::vector<int>& slots, uint32_t flags, 
     PF_CUDA(cudaSetDevice(dev_));
     launches = 0;
     gemm_flops = 0.0;
+    want_logits_ = (flags & PF_RUN_WANT_LOGITS) != 0;
     online_working.clear();
     Lmax_ = 0; Lpad_ = 0; B_ = 0; T_ = 0;
     PF_CUDA(cudaEventRecord(ev_[0], stream_));

@@ -89,11 +89,11 @@ struct DecLayerPlan {
 };
 struct EncoderPlan {
     std::vector<EncLayerPlan> layers;            // encoders0 + encoders + tp_encoders
-    GemmOp pred_conv, kv_all, ctc_head;
+    GemmOp pred_conv, kv_all, ctc_head, ctc_head_pick;
 };
 struct DecoderPlan {
     std::vector<DecLayerPlan> layers;
-    GemmOp d3_w1, d3_w2, head;
+    GemmOp d3_w1, d3_w2, head, head_pick;
     std::vector<DecLayerPlan> slayers;           // SeACo bias decoder
     GemmOp s_d3_w1, s_d3_w2, hw_head;
 };
@@ -286,6 +286,8 @@ private:
     float* xd32_ = nullptr; __half* ad16_ = nullptr; float* hd32_ = nullptr; __half* hd16_ = nullptr;
     float* t32_ = nullptr; float* tn32_ = nullptr; __half* q16_ = nullptr; __half* ctxd16_ = nullptr;
     float* logits_ = nullptr; int* tokens_ = nullptr;
+    float* pick_ = nullptr; int pick_ld_ = 0;    // partials of the fused greedy pick (head GEMM epilogue)
+    bool want_logits_ = false;                   // this run returns log-probs: the head GEMM stores them and the pick is a kernel
     int* prompt_ids_ = nullptr;
 #ifdef PFASR_EXPERIMENTS
     FfnChainScratch chain_;                  // dependency flags of the fused feed-forward kernel (this device's compute stream)

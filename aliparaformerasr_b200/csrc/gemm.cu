@@ -244,13 +244,14 @@ __device__ __forceinline__ void epilogue_ln_pass2(const LnFuse& f, uint32_t t_ac
 // tmem_empty barrier (the peer through a mapa-translated shared::cluster address).
 // kEW = epilogue warps: 8 (two column groups per TMEM quadrant) or 16 (four groups: half the chunks per warp; 640
 // threads cap the kernel at 96 registers per thread; opt-in, see launch_cl).
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps, bool kPick = false>
 __global__ void __launch_bounds__(kEpiWarp0 * 32 + kEW * 32, 1)
 pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                        const __grid_constant__ CUtensorMap tmL, const GemmEpi epi, const int M, const int N, const int K,
                        const int bn, const int tiles_n, const int num_tiles, const int vec_ok_flags) {
     static_assert(!kLn || (!kPair && !kOutHalf && kAdds == 1), "fused LayerNorm rides on the fp32 + residual epilogue");
+    static_assert(!kPick || (!kPair && !kOutHalf && kAdds == 0 && !kLn), "the fused greedy pick replaces the plain fp32 epilogue");
     const int vec_ok = vec_ok_flags & 1;
     const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
     using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
@@ -451,7 +452,19 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     ln_gb[BNMAX + i] = ok ? __ldg(epi.ln_beta + n0 + i) : 0.0f;
                 }
             }
-            if (kTmaOk && tma_epi) {
+            if constexpr (kPick) {
+                int nchunks = 0;
+                for (int c = cbase; c < cbase + cpw && c < nch; ++c)
+                    if (n0 + c * 32 < N) ++nchunks;
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                tc_fence_after_sync();
+                epi_bar_sync_n<kEW>();                                   // bias tile visible to all epilogue warps
+                if (m0 < M && !dbg_no_epi) {
+                    const int row = row0 + lane;
+                    float* dst = row < M ? epi.pick_out + (static_cast<size_t>(row) * epi.pick_ld + (t % tiles_n) * kGroups + grp) * 3 : nullptr;
+                    epilogue_pick_f32<kCpwMax>(t_acc + cbase * 32, nchunks, bias_t + cbase * 32, n0 + cbase * 32, N, dst);
+                }
+            } else if (kTmaOk && tma_epi) {
                 int nchunks = 0;
                 for (int c = cbase; c < cbase + cpw && c < nch; ++c)
                     if (n0 + c * 32 < N) ++nchunks;
@@ -575,14 +588,14 @@ int num_sms() {
     return n;
 }
 
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps>
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn = false, int kEW = kEpiWarps, bool kPick = false>
 struct Launcher {
     static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
         using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
         constexpr int CS = kPair ? 2 : 1;
-        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>;
+        auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW, kPick>;
         static std::once_flag once;
         std::call_once(once, [&] {
             int ndev = 0, cur = 0;
@@ -637,8 +650,8 @@ struct Launcher {
         PF_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA, op.tmB, op.tmC, op.tmR, op.tmL, op.epi, op.M, op.N, op.K, op.bn, tiles_n, num_tiles, op.vec_ok));
     }
 };
-template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn, int kEW>
-int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>::max_units = 1;
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn, int kEW, bool kPick>
+int Launcher<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW, kPick>::max_units = 1;
 
 template <int BNMAX, bool kOutHalf, int kAdds>
 void launch_cl(const GemmOp& op, cudaStream_t stream) {
@@ -658,6 +671,7 @@ void launch_cl(const GemmOp& op, cudaStream_t stream) {
 
 template <int BNMAX>
 void launch_bn(const GemmOp& op, cudaStream_t stream) {
+    if (op.pick) { Launcher<BNMAX, false, false, 0, false, kEpiWarps, true>::run(op, stream); return; }
     if (op.ln_cluster > 0) {
 #ifdef PFASR_EXPERIMENTS
         Launcher<BNMAX, false, false, 1, true>::run(op, stream);
@@ -725,7 +739,10 @@ int gemm_num_sms() { return num_sms(); }
 
 void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                   const GemmEpi& epi, int tile_code) {
-    if ((epi.out_f32 != nullptr) == (epi.out_f16 != nullptr)) throw CudaError{"gemm: exactly one output pointer must be set"};
+    const bool pick = epi.pick_out != nullptr;
+    if (!pick && (epi.out_f32 != nullptr) == (epi.out_f16 != nullptr)) throw CudaError{"gemm: exactly one output pointer must be set"};
+    if (pick && (epi.out_f32 || epi.out_f16 || epi.resid || epi.addend || epi.ln_out16 || epi.relu))
+        throw CudaError{"gemm: the fused greedy pick takes bias only and stores nothing else"};
     if (M <= 0 || N <= 0 || K <= 0) throw CudaError{"gemm: empty problem"};
     int bn = tile_code & 0xFFF, cm = (tile_code >> 12) & 0xF, cn = (tile_code >> 16) & 0xF;
     if ((tile_code & 0xFFFFF) == 0) pick_config(M, N, K, bn, cm, cn);
@@ -747,6 +764,12 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if (cm == 2 || ((tile_code >> 22) & 1)) throw CudaError{"gemm: CTA pairs / sixteen epilogue warps need a PFASR_BUILD_EXPERIMENTS=1 build"};
 #endif
     if (cm == 2 && bn % 64 != 0) throw CudaError{"gemm: the CTA-pair MMA needs an N tile that is a multiple of 64"};
+    if (pick) {
+        if (bn < 128) bn = 128;                                      // bounds the partial slots per row (gemm_pick_slots)
+        cm = 1;
+        if (ceil_div(N, bn) * (kEpiWarps / 4) > epi.pick_ld) throw CudaError{"gemm: pick_ld too small for this tile width"};
+    }
+    op.pick = pick ? 1 : 0;
     op.M = M; op.N = N; op.K = K; op.bn = bn; op.cm = cm; op.cn = cn; op.epi = epi;
     op.throughput = g_policy;
     op.epi16 = (tile_code >> 22) & 1;
@@ -775,7 +798,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     // most one; everything 16-byte aligned.  PFASR_GEMM_LEGACY_EPI=1 keeps the smem-transposed epilogue (A/B switch).
     static const bool legacy_epi = [] { const char* e = getenv("PFASR_GEMM_LEGACY_EPI"); return e && *e && *e != '0'; }();
     auto row_ok = [](const void* p, int ld, int esz) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (static_cast<size_t>(ld) * esz) % 16 == 0; };
-    const bool tma_epi = !legacy_epi && op.vec_ok &&
+    const bool tma_epi = !pick && !legacy_epi && op.vec_ok &&
                          (epi.out_f16 ? (op.n_adds == 0 && row_ok(epi.out_f16, epi.ld_out, 2))
                                       : (op.n_adds <= 1 && row_ok(epi.out_f32, epi.ld_out, 4) &&
                                          (op.n_adds == 0 || row_ok(op.epi.add0, op.epi.ld_add0, 4))));
@@ -818,6 +841,7 @@ void gemm_launch(const GemmOp& op, cudaStream_t stream) {
 }
 
 double gemm_flops(const GemmOp& op) { return 2.0 * op.M * static_cast<double>(op.N) * op.K; }
+int gemm_pick_slots(int N) { return ceil_div(N, 128) * (kEpiWarps / 4); }
 
 bool gemm_ln_fusable(int M, int N) {
 #ifndef PFASR_EXPERIMENTS

@@ -24,6 +24,12 @@ struct GemmEpi {
     float ln_eps = 0.0f;
     __half* ln_out16 = nullptr;
     int ld_ln16 = 0;
+    // greedy pick fused into the epilogue (head GEMMs when the caller does not ask for the log-probs): nothing is stored
+    // to out_f32; instead every (row, column group of a tile) writes one partial {best value, best index, last NaN index}
+    // to pick_out [M, pick_ld, 3] in ascending column order, combined by pick_combine_launch (ops.cu) with the reference's
+    // rule "best = x[best] > x[k] ? best : k" (OfflineRecognizer.cs:145-149, Q5)
+    float* pick_out = nullptr;
+    int pick_ld = 0;
     // filled by gemm_prepare: the (up to two) fp32 addends in the order the kernel applies them
     const float* add0 = nullptr;
     const float* add1 = nullptr;
@@ -45,6 +51,7 @@ struct GemmOp {
     int epi16 = 0;        // sixteen epilogue warps (fp16 output without addends; tile_code bit 22 or PFASR_GEMM_EPI16=1)
     int n_adds = 0;  // fp32 tensors added in the epilogue (0..2)
     int half_sm = 0; // launched as one 128 x 256 tile per CTA, two CTAs per SM (gemm_half.cu)
+    int pick = 0;    // epilogue = fused greedy pick (epi.pick_out), no output store
     int red_add = 0; // the residual aliases the output: added by a TMA fp32 reduce-add instead of load + add + store
     int vec_ok = 0;  // bit 0: all epilogue tensors 16-byte aligned with pitches % 4 == 0; bit 1: asynchronous (TMA) epilogue
 };
@@ -63,6 +70,8 @@ void gemm_half_launch(const GemmOp& op, cudaStream_t stream);
 // 1 = least SM time (several batches in flight); PFASR_GEMM_POLICY=latency|throughput overrides
 void gemm_set_policy(int throughput);
 double gemm_flops(const GemmOp& op);
+// partial slots per row a fused-pick GEMM over N columns writes at most (tiles are at least 128 wide, two column groups each)
+int gemm_pick_slots(int N);
 // can a [M, N] fp32 + residual GEMM carry the fused LayerNorm epilogue (row inside one cluster, one wave)?
 bool gemm_ln_fusable(int M, int N);
 // cuTensorMapEncodeTiled entry point (resolved through the runtime, no libcuda link dependency); throws if missing

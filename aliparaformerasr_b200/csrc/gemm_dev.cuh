@@ -117,6 +117,42 @@ __device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, ui
     }
 }
 
+// Fused greedy pick (head GEMMs): this warp's rows x columns [colw, colw + 32*nchunks) are scanned in ascending column
+// order, thread = row, and reduced to one partial per row: the last NaN column (or -1) and the last maximum among the
+// columns after it ("v >= best" keeps the LAST index attaining the maximum: OfflineRecognizer.cs:145-149 walks k upwards
+// with best = x[best] > x[k] ? best : k, and a NaN makes every comparison false, restarting the scan there).
+template <int kMaxChunks>
+__device__ __forceinline__ void epilogue_pick_f32(uint32_t t_acc, int nchunks, const float* bias_w, int colw, int N, float* dst) {
+    uint32_t ra[32], rb[32];
+    float bv = -INFINITY;
+    int bi = -1, ln = -1;
+    if (nchunks > 0) tmem_ld_issue(t_acc, ra);
+#pragma unroll
+    for (int k = 0; k < kMaxChunks; ++k) {
+        if (k < nchunks) {
+            uint32_t (&cur)[32] = (k & 1) ? rb : ra;
+            uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
+            tmem_ld_wait();
+            if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
+            const int col = colw + k * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = __uint_as_float(cur[j]) + bias_w[k * 32 + j];
+                const int c = col + j;
+                if (c < N) {
+                    if (x != x) { ln = c; bv = -INFINITY; bi = -1; }
+                    else if (x >= bv) { bv = x; bi = c; }
+                }
+            }
+        }
+    }
+    if (dst != nullptr) {
+        dst[0] = bv;
+        dst[1] = __int_as_float(bi);
+        dst[2] = __int_as_float(ln);
+    }
+}
+
 // fp32 output (+ optional fp32 residual, TMA-prefetched into the staging boxes): 32 columns per box, two boxes.
 // rbar: the two "residual landed" mbarriers of this warp; rcount: loads issued so far per buffer (phase tracking).
 struct ResidPipe {

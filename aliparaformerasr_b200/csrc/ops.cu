@@ -489,6 +489,28 @@ pf_logsoftmax_argmax(float* __restrict__ logits, int V, int ld, int* __restrict_
     }
 }
 
+// Combine the per-(tile, column group) partials of a fused-pick head GEMM (gemm_dev.cuh: epilogue_pick_f32) into the
+// greedy id of every row.  Slots are in ascending column order; a slot that saw a NaN restarts the scan (its own best is
+// the best among the columns after its last NaN), exactly like the sequential loop of OfflineRecognizer.cs:145-149.
+__global__ void __launch_bounds__(128)
+pf_pick_combine(const float* __restrict__ partials, int M, int ld, int slots, int* __restrict__ tokens) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    const float* p = partials + static_cast<size_t>(row) * ld * 3;
+    float bv = -INFINITY;
+    int bi = -1, last_nan = -1;
+    for (int s = 0; s < slots; ++s) {
+        const float v = p[3 * s];
+        const int i = __float_as_int(p[3 * s + 1]);
+        const int ln = __float_as_int(p[3 * s + 2]);
+        if (ln >= 0) { last_nan = ln; bv = v; bi = i; }
+        else if (i >= 0 && v >= bv) { bv = v; bi = i; }
+    }
+    tokens[row] = bi >= 0 ? bi : (last_nan >= 0 ? last_nan : 0);
+}
+
 __global__ void pf_f32_to_f16(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -680,6 +702,11 @@ void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_
 void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, int write_logp, cudaStream_t s) {
     if (M <= 0) return;
     launch_k(pf_logsoftmax_argmax, dim3(M), dim3(256), 0, s, logits, V, ld, tokens, write_logp);
+}
+
+void pick_combine_launch(const float* partials, int M, int ld, int slots, int* tokens, cudaStream_t s) {
+    if (M <= 0) return;
+    launch_k(pf_pick_combine, dim3(ceil_div(M, 128)), dim3(128), 0, s, partials, M, ld, slots, tokens);
 }
 
 void f32_to_f16_launch(const float* in, __half* out, size_t n, cudaStream_t s) {

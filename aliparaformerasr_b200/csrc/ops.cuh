@@ -44,6 +44,8 @@ void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_
 // In-place log-softmax over [M, V] fp32 (row pitch ld) + greedy pick with the reference's tie rule (last max wins,
 // scan restarts after a NaN; OfflineRecognizer.cs:139-152).  tokens: [M] int32.  write_logp = 0 leaves logits raw.
 void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, int write_logp, cudaStream_t s);
+// greedy ids from the partials of a fused-pick head GEMM ([M, ld, 3] floats, `slots` used per row)
+void pick_combine_launch(const float* partials, int M, int ld, int slots, int* tokens, cudaStream_t s);
 
 // Gather rows: dst[b, l, :] = src[b, l, :] for l < L (compacts [B, Lsrc, W] -> [B, L, W]); int32 / fp32 payloads.
 void compact_rows_launch(const void* src, void* dst, int B, int Lsrc, int L, int width_bytes, cudaStream_t s);

@@ -323,6 +323,9 @@ int32_t pf_build_experiments(void);
 pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                       const float* resid, const float* addend, int32_t relu, int32_t out_half, int32_t tile_n,
                       float* out, float* elapsed_ms, int32_t iters);
+/* greedy ids of the rows of A W^T + bias with the pick fused into the GEMM epilogue (no [M, N] tensor is written) */
+pf_status pf_dbg_gemm_pick(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, int32_t tile_n,
+                           int32_t* tokens);
 /* x = A W^T + bias + resid (fp32) and LN(x) * gamma + beta (fp16) from the fused-LayerNorm GEMM epilogue */
 /* x + relu(a W1^T + b1) W2^T + b2 through the fused feed-forward kernel (csrc/ffn_chain.cu); D, F multiples of 256 */
 pf_status pf_dbg_ffn_chain(int32_t M, int32_t D, int32_t F, const float* a, const float* w1, const float* b1, const float* w2,

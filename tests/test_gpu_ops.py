@@ -67,6 +67,36 @@ def test_gemm_half_sm_kernel(lib, M, N, K, relu):
     assert np.array_equal(out, plain)                  # same MMAs, same epilogue arithmetic as the persistent kernel
 
 
+@pytest.mark.parametrize("M,N,K,tile", [(1600, 8404, 512, 0), (300, 25055, 512, 0), (333, 8404, 512, 128), (129, 1000, 64, 256), (5, 40, 64, 0)])
+def test_gemm_fused_greedy_pick(lib, M, N, K, tile):
+    """K14: the greedy pick in the head GEMM's epilogue + pf_pick_combine == OfflineRecognizer.cs:145-149 on the same logits
+    (last maximum wins on ties; a NaN restarts the scan; a NaN in the last column wins outright), for vocabularies that do
+    not fill the last tile."""
+    rng = np.random.default_rng(M + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    # ties: duplicate weight rows -> bit-identical logits in two columns, made the row maximum through the bias
+    W[N - 3] = W[7]
+    bias[N - 3] = bias[7] = 9.0
+    W[20] = W[N // 2]
+    bias[20] = bias[N // 2]
+    bias_nan = bias.copy()
+    bias_nan[N // 3] = np.nan                          # a NaN column in every row: the scan restarts behind it
+    for b in (bias, bias_nan):
+        logits, _ = dbg_gemm(lib, A, W, b)
+        want = sanm.greedy_pick(logits)
+        got = np.zeros(M, np.int32)
+        _lib.check(lib.pf_dbg_gemm_pick(M, N, K, _lib.fptr(f(A)), _lib.fptr(f(W)), _lib.fptr(f(b)), tile, _lib.iptr(got)))
+        assert np.array_equal(got, want)
+        assert (got == N - 3).mean() > 0.5             # the tie really decides rows
+    last = bias.copy()
+    last[N - 1] = np.nan                               # NaN in the last position wins
+    got = np.zeros(M, np.int32)
+    _lib.check(lib.pf_dbg_gemm_pick(M, N, K, _lib.fptr(f(A)), _lib.fptr(f(W)), _lib.fptr(f(last)), tile, _lib.iptr(got)))
+    assert (got == N - 1).all()
+
+
 @pytest.mark.parametrize("out_half,relu", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("adds", [0, 1, 2])
 @pytest.mark.parametrize("N", [520, 517])          # 517: unaligned pitch -> scalar epilogue path
