@@ -173,7 +173,10 @@ def load() -> C.CDLL:
             f"{path} not found: build it with `python -m aliparaformerasr_b200.build` "
             "(nvcc, sm_100a). aliparaformerasr_b200 has no CPU fallback.")
     lib = C.CDLL(path)
+    variant = "PFASR_LIB" in os.environ            # an A/B build of another revision (scripts/build_variant.py) may lack newer hooks
     for name, (res, args) in SIGNATURES.items():
+        if variant and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
