@@ -147,6 +147,7 @@ SIGNATURES = {
     "pf_last_error": (C.c_char_p, []),
     "pf_abi_version": (C.c_int32, []),
     "pf_dbg_gemm": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, _F, _F, C.c_int32]),
+    "pf_dbg_ln_gemm": (C.c_int32, [C.c_int32, C.c_int32, _F, _F, _F, C.c_float, _F, _F, C.c_int32, _F, _F, C.c_int32]),
     "pf_dbg_gemm_pick": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, C.c_int32, C.POINTER(C.c_int32)]),
     "pf_dbg_ffn_chain": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, _F, _F, _F, C.c_int32]),
     "pf_dbg_gemm_ln": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, _F, _F, _F, _F, _F, _F, C.c_float, _F, _F]),

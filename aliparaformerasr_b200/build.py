@@ -21,7 +21,7 @@ LIB = PKG / "libpfasr.so"
 # sixteen-epilogue-warp GEMM, the fused-LayerNorm GEMM epilogue and the half-SM GEMM (gemm_half.cu: two CTAs per SM).
 # The product library carries only the selected path.
 EXPERIMENTS = os.environ.get("PFASR_BUILD_EXPERIMENTS", "0") == "1"
-SOURCES = ["gemm.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
+SOURCES = ["gemm.cu", "gemm_ln.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

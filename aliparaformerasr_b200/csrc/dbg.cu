@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "engine.cuh"
+#include "gemm_ln.cuh"
 #include "gemm.cuh"
 #include "ops.cuh"
 
@@ -106,6 +107,43 @@ pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const flo
             for (int i = 0; i < 3; ++i) gemm_launch(op, 0);
             PF_CUDA(cudaEventRecord(a, 0));
             for (int i = 0; i < iters; ++i) gemm_launch(op, 0);
+            PF_CUDA(cudaEventRecord(b, 0));
+            PF_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            PF_CUDA(cudaEventElapsedTime(&ms, a, b));
+            *elapsed_ms = ms / iters;
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    });
+}
+
+pf_status pf_dbg_ln_gemm(int32_t M, int32_t N, const float* x, const float* gamma, const float* beta, float eps, const float* W,
+                         const float* bias, int32_t relu, float* out, float* elapsed_ms, int32_t iters) {
+    return guarded([&] {
+        const int K = 512;
+        Scratch s;
+        float* dx = s.up(x, static_cast<size_t>(M) * K);
+        __half* dW = s.up_half(W, static_cast<size_t>(N) * K);
+        float* dg = s.up(gamma, K);
+        float* db = s.up(beta, K);
+        float* dbias = bias ? s.up(bias, N) : nullptr;
+        __half* o16 = s.alloc<__half>(static_cast<size_t>(M) * N);
+        float* o32 = s.alloc<float>(static_cast<size_t>(M) * N);
+        LnGemmOp op;
+        ln_gemm_prepare(op, dx, K, dg, db, eps, dW, K, dbias, o16, N, relu, M, N, K);
+        ln_gemm_launch(op, 0);
+        PF_CUDA(cudaDeviceSynchronize());
+        pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, static_cast<size_t>(M) * N);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemcpy(out, o32, static_cast<size_t>(M) * N * sizeof(float), cudaMemcpyDeviceToHost));
+        if (elapsed_ms && iters > 0) {
+            cudaEvent_t a, b;
+            PF_CUDA(cudaEventCreate(&a));
+            PF_CUDA(cudaEventCreate(&b));
+            for (int i = 0; i < 3; ++i) ln_gemm_launch(op, 0);
+            PF_CUDA(cudaEventRecord(a, 0));
+            for (int i = 0; i < iters; ++i) ln_gemm_launch(op, 0);
             PF_CUDA(cudaEventRecord(b, 0));
             PF_CUDA(cudaEventSynchronize(b));
             float ms = 0;

@@ -512,12 +512,19 @@ EncoderPlan& DeviceCtx::encoder_plan(int B, int T) {
         GemmEpi e;
         e = GemmEpi{}; e.bias = w.b_qkv; e.out_f16 = qkv16_; e.ld_out = 3 * d;
         gemm_prepare(lp.qkv, a16_, w.in_size, w.w_qkv, w.in_size, M, 3 * d, w.in_size, e);
+        // several lanes: LayerNorm + GEMM as one row-tile-stationary kernel (a third less SM time); layer 0 of a
+        // stack keeps the two-kernel form (its norm1 is part of embed_pe_ln / runs on 560 columns)
+        const bool ln_gemm_on = ln_gemm_mode() == 2 || (ln_gemm_mode() == 1 && throughput_mode);
+        if (ln_gemm_on && !fuse && w.in_size == d && ln_gemm_supported(M, 3 * d, d, x32_, d, qkv16_, 3 * d, w.b_qkv))
+            ln_gemm_prepare(lp.qkv_ln, x32_, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, w.w_qkv, d, w.b_qkv, qkv16_, 3 * d, 0, M, 3 * d, d);
         // x32_ already holds residual + FSMN memory (the attention kernel accumulates the memory into it)
         e = GemmEpi{}; e.bias = w.b_out; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
         if (fuse) { e.ln_gamma = w.ln2.g; e.ln_beta = w.ln2.b; e.ln_eps = cfg_.ln_eps; e.ln_out16 = a16_; e.ld_ln16 = d; lp.ln2_fused = true; }
         gemm_prepare(lp.out, ctx16_, d, w.w_out, d, M, d, d, e);
         e = GemmEpi{}; e.bias = w.b_ffn1; e.relu = 1; e.out_f16 = h16_; e.ld_out = f;
         gemm_prepare(lp.ffn1, a16_, d, w.w_ffn1, d, M, f, d, e);
+        if (ln_gemm_on && !fuse && ln_gemm_supported(M, f, d, x32_, d, h16_, f, w.b_ffn1))
+            ln_gemm_prepare(lp.ffn1_ln, x32_, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, w.w_ffn1, d, w.b_ffn1, h16_, f, 1, M, f, d);
         e = GemmEpi{}; e.bias = w.b_ffn2; e.resid = x32_; e.ld_resid = d; e.out_f32 = x32_; e.ld_out = d;
         if (fuse && next != nullptr) {
             e.ln_gamma = next->ln1.g; e.ln_beta = next->ln1.b; e.ln_eps = cfg_.ln_eps; e.ln_out16 = a16_; e.ld_ln16 = d;
@@ -612,10 +619,15 @@ double DeviceCtx::replay_gemms(int iters) {
     cudaEvent_t a, b;
     PF_CUDA(cudaEventCreate(&a));
     PF_CUDA(cudaEventCreate(&b));
-    for (const GemmOp& op : replay_) gemm_launch(op, stream_);            // warm pass
+    auto pass = [&] {
+        for (const ReplayOp& op : replay_) {
+            if (op.fused) ln_gemm_launch(op.l, stream_);
+            else gemm_launch(op.g, stream_);
+        }
+    };
+    pass();                                                               // warm pass
     PF_CUDA(cudaEventRecord(a, stream_));
-    for (int i = 0; i < iters; ++i)
-        for (const GemmOp& op : replay_) gemm_launch(op, stream_);
+    for (int i = 0; i < iters; ++i) pass();
     PF_CUDA(cudaEventRecord(b, stream_));
     PF_CUDA(cudaEventSynchronize(b));
     float ms = 0.0f;
@@ -625,8 +637,27 @@ double DeviceCtx::replay_gemms(int iters) {
     return ms / iters;
 }
 
+void DeviceCtx::ln_gemm(const LnGemmOp& op) {
+    if (profile_ == 1) { ReplayOp r; r.fused = true; r.l = op; replay_.push_back(r); }
+    if (profile_) {
+        ProfRec r{op.M, op.N, op.K, 256 + 1000 * 11, nullptr, nullptr, nullptr};
+        for (cudaEvent_t* e : {&r.a, &r.b}) {
+            if (!prof_pool_.empty()) { *e = prof_pool_.back(); prof_pool_.pop_back(); }
+            else PF_CUDA(cudaEventCreate(e));
+        }
+        PF_CUDA(cudaEventRecord(r.a, stream_));
+        ln_gemm_launch(op, stream_);
+        PF_CUDA(cudaEventRecord(r.b, stream_));
+        prof_.push_back(r);
+    } else {
+        ln_gemm_launch(op, stream_);
+    }
+    ++launches;
+    gemm_flops += ln_gemm_flops(op);
+}
+
 void DeviceCtx::gemm(const GemmOp& op) {
-    if (profile_ == 1) replay_.push_back(op);
+    if (profile_ == 1) { ReplayOp r; r.g = op; replay_.push_back(r); }
     if (profile_) {
         ProfRec r{op.M, op.N, op.K, op.bn + 1000 * (op.cm * 10 + op.cn), nullptr, nullptr, nullptr};
         for (cudaEvent_t* e : {&r.a, &r.b}) {
@@ -881,11 +912,15 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
     });
     ++launches;
     auto layer = [&](const EncLayerW& w, const EncLayerPlan& lp, bool have_ln1) {
-        if (!have_ln1) {
-            if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
-            ++launches;
+        if (!have_ln1 && lp.qkv_ln.valid) {
+            ln_gemm(lp.qkv_ln);                            // norm1 + QKV in one kernel
+        } else {
+            if (!have_ln1) {
+                if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln1.g, w.ln1.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
+                ++launches;
+            }
+            gemm(lp.qkv);
         }
-        gemm(lp.qkv);
         if (!(dbg_skip() & 2)) timed("enc_attention_fsmn", [&] {
             // x += mem (layer with a residual) or x = mem (encoders0: in_size != d_model, no residual); the
             // out-projection then adds ctx W_o + b on top of x32_
@@ -893,6 +928,11 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
                                               x32_, d, w.in_size == d, stream_);
         });
         gemm(lp.out);
+        if (lp.ffn1_ln.valid) {
+            ln_gemm(lp.ffn1_ln);                           // norm2 + FFN1 in one kernel
+            gemm(lp.ffn2);
+            return;
+        }
         if (!lp.ln2_fused) {
             if (!(dbg_skip() & 1)) timed("enc_layernorm", [&] { layernorm_f32_launch(x32_, d, M, d, w.ln2.g, w.ln2.b, cfg_.ln_eps, a16_, d, nullptr, 0, stream_); });
             ++launches;

@@ -17,6 +17,7 @@
 #endif
 #include "frontend.cuh"
 #include "gemm.cuh"
+#include "gemm_ln.cuh"
 #include "online.cuh"
 #include "ops.cuh"
 #include "timestamp.cuh"
@@ -77,6 +78,7 @@ struct DecLayerW {
 
 struct EncLayerPlan {
     GemmOp qkv, out, ffn1, ffn2;
+    LnGemmOp qkv_ln, ffn1_ln;        // valid: norm1 + QKV / norm2 + FFN1 run as one row-tile-stationary kernel (csrc/gemm_ln.cu)
 #ifdef PFASR_EXPERIMENTS
     FfnChainOp chain;                // valid: ffn1 + ffn2 run as one persistent kernel (csrc/ffn_chain.cu)
 #endif
@@ -165,7 +167,8 @@ public:
     // CUDA events: ms per pass.  The per-launch events of set_profile(1) break the programmatic launch chain and add an
     // event round trip to every launch; this measures the kernel's launch duration the way the step experiences it.
     double replay_gemms(int iters);
-    std::vector<GemmOp> replay_;
+    struct ReplayOp { bool fused = false; GemmOp g; LnGemmOp l; };
+    std::vector<ReplayOp> replay_;
     double gemm_ms = 0.0;              // sum of GEMM launch durations of the last profiled run
     std::string profile_json;          // per-shape breakdown of the last profiled run
 
@@ -210,6 +213,7 @@ private:
     EncoderPlan& encoder_plan(int B, int T);
     DecoderPlan& decoder_plan(int B, int T, int L);
     void gemm(const GemmOp& op);
+    void ln_gemm(const LnGemmOp& op);
     void encoder_forward(int B, int T, bool online = false);
     void predictor_forward(int B, int T, bool online = false);
     void decoder_forward(int B, int T, int L, bool online = false);

@@ -1,0 +1,30 @@
+// LayerNorm + fp16-output GEMM as one row-tile-stationary kernel (csrc/gemm_ln.cu): out = relu?(LN(x) W^T + bias).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace pf {
+
+struct LnGemmOp {
+    bool valid = false;
+    const float* x = nullptr;        // fp32 residual stream [M, ld_x], K = 512 columns
+    int ld_x = 0;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    float eps = 0.0f;
+    CUtensorMap tmB;                 // W [N, K] fp16, 256-row boxes
+    const float* bias = nullptr;
+    __half* out = nullptr;
+    int ld_out = 0;
+    int relu = 0;
+    int M = 0, N = 0, K = 0;
+};
+
+int ln_gemm_mode();                  // PFASR_LN_GEMM: 0 off, 1 (default) multi-lane handles, 2 always
+bool ln_gemm_supported(int M, int N, int K, const void* x, int ld_x, const void* out, int ld_out, const void* bias);
+void ln_gemm_prepare(LnGemmOp& op, const float* x, int ld_x, const float* gamma, const float* beta, float eps, const __half* W, int ldw,
+                     const float* bias, __half* out, int ld_out, int relu, int M, int N, int K);
+void ln_gemm_launch(const LnGemmOp& op, cudaStream_t stream);
+double ln_gemm_flops(const LnGemmOp& op);
+
+}  // namespace pf

@@ -323,6 +323,9 @@ int32_t pf_build_experiments(void);
 pf_status pf_dbg_gemm(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias,
                       const float* resid, const float* addend, int32_t relu, int32_t out_half, int32_t tile_n,
                       float* out, float* elapsed_ms, int32_t iters);
+/* relu?(LayerNorm(x [M, 512]) W^T + bias) as fp16 through the row-tile-stationary LayerNorm + GEMM kernel (csrc/gemm_ln.cu) */
+pf_status pf_dbg_ln_gemm(int32_t M, int32_t N, const float* x, const float* gamma, const float* beta, float eps, const float* W,
+                         const float* bias, int32_t relu, float* out, float* elapsed_ms, int32_t iters);
 /* greedy ids of the rows of A W^T + bias with the pick fused into the GEMM epilogue (no [M, N] tensor is written) */
 pf_status pf_dbg_gemm_pick(int32_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, int32_t tile_n,
                            int32_t* tokens);

@@ -67,6 +67,31 @@ def test_gemm_half_sm_kernel(lib, M, N, K, relu):
     assert np.array_equal(out, plain)                  # same MMAs, same epilogue arithmetic as the persistent kernel
 
 
+@pytest.mark.parametrize("M,N,relu", [(5312, 1536, 0), (5312, 2048, 1), (8768, 2048, 1), (83, 1536, 0), (129, 288, 1), (1, 256, 0)])
+def test_layernorm_gemm_rowtile_kernel(lib, M, N, relu):
+    """csrc/gemm_ln.cu: LayerNorm of the fp32 residual rows + fp16-output GEMM in one row-tile-stationary kernel must give
+    exactly what the two kernels it replaces give (same LayerNorm arithmetic, same MMA order, same epilogue rounding)."""
+    rng = np.random.default_rng(M + N)
+    x = (rng.standard_normal((M, 512)) * 3 + 0.7).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(512)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(512)).astype(np.float32)
+    W = (rng.standard_normal((N, 512)) / np.sqrt(512)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    out = np.zeros((M, N), np.float32)
+    ms = C.c_float(0)
+    _lib.check(lib.pf_dbg_ln_gemm(M, N, _lib.fptr(x), _lib.fptr(g), _lib.fptr(b), 1e-12, _lib.fptr(f(W)), _lib.fptr(bias), relu, _lib.fptr(out),
+                                  C.byref(ms), 0))
+    ln = np.zeros((M, 512), np.float32)
+    _lib.check(lib.pf_dbg_layernorm(M, 512, _lib.fptr(x), _lib.fptr(g), _lib.fptr(b), 1e-12, _lib.fptr(ln)))     # fp16-rounded LN output
+    two, _ = dbg_gemm(lib, ln, W, bias, relu=relu, out_half=1, tile_n=256)
+    assert np.array_equal(out, two)
+    ref = torch.nn.functional.layer_norm(torch.from_numpy(x), (512,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
+    ref = half_round(ref).astype(np.float64) @ half_round(W).astype(np.float64).T + bias
+    if relu:
+        ref = np.maximum(ref, 0.0)
+    assert np.abs(out - ref).max() < 2e-2
+
+
 @pytest.mark.parametrize("M,N,K,tile", [(1600, 8404, 512, 0), (300, 25055, 512, 0), (333, 8404, 512, 128), (129, 1000, 64, 256), (5, 40, 64, 0)])
 def test_gemm_fused_greedy_pick(lib, M, N, K, tile):
     """K14: the greedy pick in the head GEMM's epilogue + pf_pick_combine == OfflineRecognizer.cs:145-149 on the same logits
