@@ -5,7 +5,7 @@
 // residual stream into shared memory as the COMPLETE fp16 A operand (8 k-blocks x 16 KiB, 128B-swizzled K-major, the layout
 // tcgen05.mma expects) - same arithmetic, lane ownership and summation order as pf_layernorm (ops.cu), so the operand is
 // bit-identical to what the stand-alone kernel would have written.  Then the CTA walks the N tiles of its row tile: warp 0
-// streams 256-row W tiles through a 3-stage TMA ring, warp 1 issues the MMAs against the resident A (fp32 accumulators
+// streams 128-row W tiles through a 6-stage TMA ring, warp 1 issues the MMAs against the resident A (fp32 accumulators
 // double-buffered in TMEM), warps 4..11 drain tile i (bias, ReLU, fp16, 16-byte stores straight from registers) while the
 // MMAs of tile i+1 run.
 //
@@ -32,11 +32,11 @@ namespace {
 
 constexpr int kK = 512;                               // d_model: the whole row is one A operand
 constexpr int kKb = kK / BK;                          // 8 k-blocks
-constexpr int kBN = 256;
-constexpr int kStages = 3;
+constexpr int kBN = 128;                              // W tile rows: 16 KiB stages, six of them in flight cover the L2 latency
+constexpr int kStages = 6;
 constexpr int kThreadsLn = 384;
 constexpr int kABytesAll = kKb * kABytes;             // 128 KiB
-constexpr int kBStage = kBN * BK * 2;                 // 32 KiB
+constexpr int kBStage = kBN * BK * 2;                 // 16 KiB
 constexpr int kBiasBytes = 2 * kBN * 4;
 constexpr int kBarBytes = 256;
 constexpr int kSmemLn = kABytesAll + kStages * kBStage + kBiasBytes + kBarBytes;   // no alignment slack: the base is checked
@@ -226,7 +226,9 @@ pf_ln_gemm_f16_rowtile(const float* __restrict__ x, const int ld_x, const float*
         // ------------------------------------------------ epilogue: TMEM row -> bias / ReLU -> fp16 -> global
         const int ew = warp - 4;
         const int q = warp & 3;
-        const int grp = ew >> 2;                                          // left / right 128 columns of the tile
+        const int grp = ew >> 2;                                          // left / right half of the tile's columns
+        constexpr int kHalfCols = kBN / 2;
+        constexpr int kChunks = kHalfCols / 32;
         const int row = m0 + q * 32 + lane;
         const float lo = relu ? 0.0f : -INFINITY;
         for (int n = 0; n < tiles_n; ++n) {
@@ -237,18 +239,18 @@ pf_ln_gemm_f16_rowtile(const float* __restrict__ x, const int ld_x, const float*
             mbar_wait(tmem_full_bar(acc), (n >> 1) & 1u);
             tc_fence_after_sync();
             asm volatile("bar.sync 1, 256;" ::: "memory");               // bias tile visible to the eight epilogue warps
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBN + grp * 128;
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kBN + grp * kHalfCols;
             uint32_t ra[32], rb[32];
             tmem_ld_32x32(t_acc, ra);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < kChunks; ++c) {
                 uint32_t (&cur)[32] = (c & 1) ? rb : ra;
                 uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
                 tmem_ld_wait();
-                if (c + 1 < 4) tmem_ld_32x32(t_acc + (c + 1) * 32, nxt);
-                const int col = n0 + grp * 128 + c * 32;
+                if (c + 1 < kChunks) tmem_ld_32x32(t_acc + (c + 1) * 32, nxt);
+                const int col = n0 + grp * kHalfCols + c * 32;
                 if (row < M && col < N)                                   // N is a multiple of 32 (checked on the host)
-                    store_chunk_f16(cur, bias_t + grp * 128 + c * 32, lo, out + static_cast<size_t>(row) * ld_out + col);
+                    store_chunk_f16(cur, bias_t + grp * kHalfCols + c * 32, lo, out + static_cast<size_t>(row) * ld_out + col);
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -263,8 +265,8 @@ pf_ln_gemm_f16_rowtile(const float* __restrict__ x, const int ld_x, const float*
 }  // namespace
 
 int ln_gemm_mode() {
-    // 0 = off, 1 = multi-lane handles only (throughput objective), 2 = always
-    static const int mode = [] { const char* e = getenv("PFASR_LN_GEMM"); return e ? atoi(e) : 1; }();
+    // 0 = off (default until an A/B shows a win), 1 = multi-lane handles only (throughput objective), 2 = always
+    static const int mode = [] { const char* e = getenv("PFASR_LN_GEMM"); return e ? atoi(e) : 0; }();
     return mode;
 }
 

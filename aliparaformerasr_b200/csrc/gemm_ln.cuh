@@ -20,7 +20,7 @@ struct LnGemmOp {
     int M = 0, N = 0, K = 0;
 };
 
-int ln_gemm_mode();                  // PFASR_LN_GEMM: 0 off, 1 (default) multi-lane handles, 2 always
+int ln_gemm_mode();                  // PFASR_LN_GEMM: 0 off (default), 1 multi-lane handles, 2 always
 bool ln_gemm_supported(int M, int N, int K, const void* x, int ld_x, const void* out, int ld_out, const void* bias);
 void ln_gemm_prepare(LnGemmOp& op, const float* x, int ld_x, const float* gamma, const float* beta, float eps, const __half* W, int ldw,
                      const float* bias, __half* out, int ld_out, int relu, int M, int N, int K);
