@@ -29,25 +29,33 @@ namespace {
 // launch parameter, so one instantiation serves every width that shares its shared-memory / TMEM layout.
 constexpr int kLnMaxCluster = 4;       // column tiles (CTAs of one cluster) a fused-LayerNorm row may span
 
-template <int BNMAX, bool kPair, bool kOutHalf, bool kLn = false, int kEW = kEpiWarps>
+// kBoxes = staging boxes per epilogue warp: two (a box is rewritten two chunks after its store was issued) or, for the
+// 256-wide fp32 tiles without a residual load, one - the 32 KiB that frees are the fourth operand stage.
+template <int BNMAX, bool kPair, bool kOutHalf, bool kLn = false, int kEW = kEpiWarps, int kBoxes = 2>
 struct Cfg {
     static constexpr int kThreadsCta = kEpiWarp0 * 32 + kEW * 32;    // producer, MMA, TMEM, spare warp + kEW epilogue warps
     static constexpr int kBRows = kPair ? BNMAX / 2 : BNMAX;        // W-tile rows a stage slot can hold
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     // per-warp staging: fp16 output = two 32 x 32 boxes (2 KiB each); fp32 output = two 32 x 32 boxes (4 KiB each)
-    static constexpr int kWarpStageBytes = kOutHalf ? 4096 : 8192;
+    static constexpr int kWarpStageBytes = kOutHalf ? 4096 : 4096 * kBoxes;
     static constexpr int kEpiBytes = kEW * kWarpStageBytes;
     static constexpr int kBarBytes = 512;
     static constexpr int kBiasBytes = 2 * BNMAX * 4;                 // two tiles' bias columns
     // fused LayerNorm: gamma | beta tiles and the per-row partial sums of every CTA of the cluster
     static constexpr int kLnBytes = kLn ? 2 * BNMAX * 4 + kLnMaxCluster * 2 * BM * 2 * 4 : 0;
-    static constexpr int kFit = (kSmemMax - 1024 - kBarBytes - kBiasBytes - kLnBytes - kEpiBytes) / kStageBytes;
+    // the dynamic shared memory base is 1024-byte aligned (declared so, checked in the kernel): no alignment slack, which
+    // is what lets the 256-wide fp16-output tiles keep FOUR 48 KiB operand stages instead of three
+    static constexpr int kFit = (kSmemMax - kBarBytes - kBiasBytes - kLnBytes - kEpiBytes) / kStageBytes;
     static constexpr int kStages = kFit > 8 ? 8 : kFit;
     static constexpr int kTmemCols = 2 * BNMAX;                      // two accumulator stages (256 / 512 columns)
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + kLnBytes + 1024;  // +1024: alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + kBiasBytes + kLnBytes;
+    static_assert(kSmemBytes <= kSmemMax, "shared memory budget");
     static_assert(kStages >= 3, "operand ring too shallow");
 };
+
+template <int BNMAX, bool kPair, bool kOutHalf, int kAdds, bool kLn, int kEW>
+constexpr int epi_boxes() { return (BNMAX == 256 && !kPair && !kOutHalf && kAdds == 0 && !kLn && kEW == kEpiWarps) ? 1 : 2; }
 
 // One 32x32 accumulator chunk of one warp: registers (thread = row) -> XOR-swizzled smem (conflict-free both ways)
 // -> row-segment layout (fp32 out: 8 lanes x float4 per row, 4 rows per instruction; fp16 out: 4 lanes x 8 halfs per
@@ -254,16 +262,16 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     static_assert(!kPick || (!kPair && !kOutHalf && kAdds == 0 && !kLn), "the fused greedy pick replaces the plain fp32 epilogue");
     const int vec_ok = vec_ok_flags & 1;
     const bool tma_epi = (vec_ok_flags & 2) != 0;                // asynchronous epilogue (tmC / tmR are valid)
-    using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
+    constexpr int kBoxes = epi_boxes<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>();
+    using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW, kBoxes>;
     constexpr int STAGES = C::kStages;
     constexpr int kGroups = kEW / 4;                             // column groups (warps per TMEM quadrant)
     constexpr int CS = kPair ? 2 : 1;
     const int brows = bn / CS;                                   // W rows this CTA stages per k-block
     const uint32_t stage_tx = kABytes + static_cast<uint32_t>(brows) * BK * 2;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    const uint32_t base = (raw_addr + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024 B alignment
-    uint8_t* smem = smem_raw + (base - raw_addr);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw);                    // SWIZZLE_128B tiles need 1024 B alignment (checked below)
+    uint8_t* smem = smem_raw;
 
     constexpr uint32_t kEpiOff = STAGES * C::kStageBytes;
     constexpr uint32_t kBarOff = kEpiOff + C::kEpiBytes;
@@ -295,6 +303,7 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
+        if ((base & 1023u) != 0) { printf("pfasr: gemm needs 1024-byte aligned dynamic shared memory\n"); __trap(); }
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (tma_epi) {
@@ -491,8 +500,8 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if constexpr (kOutHalf && kAdds == 0)
                         epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
                     else if constexpr (!kOutHalf && kAdds == 0)
-                        epilogue_tma_f32<kCpwMax, false>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, 0,
-                                                         nullptr, nullptr, (vec_ok_flags & 0x2000) != 0);
+                        epilogue_tma_f32<kCpwMax, false, false, kBoxes>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw,
+                                                                        lane, 0, nullptr, nullptr, (vec_ok_flags & 0x2000) != 0);
                     else if constexpr (!kOutHalf && kAdds == 1 && !kLn)
                         epilogue_tma_f32<kCpwMax, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
                 }
@@ -596,7 +605,7 @@ struct Launcher {
     static int max_units;   // co-resident CTAs (or CTA pairs: GPC boundaries can make it < sms / 2)
 
     static void run(const GemmOp& op, cudaStream_t stream) {
-        using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW>;
+        using C = Cfg<BNMAX, kPair, kOutHalf, kLn, kEW, epi_boxes<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW>()>;
         constexpr int CS = kPair ? 2 : 1;
         auto kern = pf_gemm_f16_tn_tcgen05<BNMAX, kPair, kOutHalf, kAdds, kLn, kEW, kPick>;
         static std::once_flag once;
@@ -691,14 +700,15 @@ void launch_bn(const GemmOp& op, cudaStream_t stream) {
     }
 }
 
-bool pair_enabled() {
+int pair_mode() {                      // 0 off, 1 the tile picker may choose CTA pairs, 2 pairs wherever the shape allows
 #ifdef PFASR_EXPERIMENTS
-    static const bool on = [] { const char* e = getenv("PFASR_GEMM_PAIR"); return e && *e && *e != '0'; }();
-    return on;
+    static const int mode = [] { const char* e = getenv("PFASR_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+    return mode;
 #else
-    return false;
+    return 0;
 #endif
 }
+bool pair_enabled() { return pair_mode() != 0; }
 
 // Tile width (any multiple of 32 up to 256) and pairing from a wave model fitted to scripts/gemm_probe.py on B200
 // (K = 512, fp16 epilogue, one wave of 128 x bn tiles: 2.96 us @128, 3.63 us @192, 4.56 us @256):
@@ -718,7 +728,8 @@ void pick_config(int M, int N, int K, int& bn_out, int& cm_out, int& cn_out) {
     double best_cost = 1e30;
     for (int bn = 256; bn >= 32; bn -= 32) {
         if (bn > 32 && ceil_div(N, bn) == ceil_div(N, bn - 32)) continue;      // a narrower tile covers N with as many columns
-        for (int cm = 1; cm <= ((pair_enabled() && bn % 64 == 0) ? 2 : 1); ++cm) {
+        const bool pair_ok = pair_enabled() && bn % 64 == 0;
+        for (int cm = (pair_ok && pair_mode() == 2 && mt >= 2) ? 2 : 1; cm <= (pair_ok ? 2 : 1); ++cm) {
             const int tiles = ceil_div(mt, cm) * ceil_div(N, bn);
             const int waves = ceil_div(tiles, sms / cm);
             const double t_wave = 0.3 + 0.004 * bn + kb * (0.13 + 0.0011 * bn) + (cm > 1 ? 0.1 * kb : 0.0);

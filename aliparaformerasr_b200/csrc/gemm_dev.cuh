@@ -166,11 +166,13 @@ __device__ __forceinline__ void resid_issue(ResidPipe& rp, int buf, uint32_t stg
         tma_load_2d(stg_u32 + buf * 4096, tmR, rp.bar[buf], col, row0);
     }
 }
-template <int kMaxChunks, bool kResid, bool kLn = false>
+// kBoxes = 1 (no residual load only): a single staging box, so every chunk waits until the previous store has read it.
+template <int kMaxChunks, bool kResid, bool kLn = false, int kBoxes = 2>
 __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, uint8_t* stg, ResidPipe& rp, const CUtensorMap* tmC,
                                                  const CUtensorMap* tmR, const float* bias_w, float lo, int row0,
                                                  int colw, int lane, int prefetched, float* ln_s1 = nullptr, float* ln_s2 = nullptr,
                                                  bool red_add = false) {
+    static_assert(kBoxes == 2 || (kBoxes == 1 && !kResid && !kLn), "the single-box epilogue has no residual pipeline");
     float s1 = 0.0f, s2 = 0.0f;                                    // kLn: this row's sum / sum of squares over the warp's columns
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t ra[32], rb[32];
@@ -185,12 +187,17 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
         if (k < nchunks) {
             uint32_t (&cur)[32] = (k & 1) ? rb : ra;
             uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
-            const int buf = k & 1;
+            const int buf = kBoxes == 2 ? (k & 1) : 0;
             tmem_ld_wait();
             if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
             if (kResid) {
                 mbar_wait(rp.bar[buf], rp.count[buf] & 1u);
                 rp.count[buf]++;
+            } else if (kBoxes == 1) {
+                if (k >= 1) {                                      // the one box: the previous chunk's store must have read it
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
             } else if (k >= 2) {                                   // buffer reuse without a residual load in between:
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // only the previous chunk's store may be pending
                 __syncwarp();
