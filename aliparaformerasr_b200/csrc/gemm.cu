@@ -482,6 +482,11 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (n0 + c * 32 < N) ++nchunks;
                 const bool work = row0 < M && nchunks > 0 && !dbg_no_epi;
                 const int colw = n0 + cbase * 32;
+                // the CTA's last tile: its MMAs have consumed every operand stage, so the ring serves as staging with one
+                // box per chunk and the chunks never wait for the store engine to release a box (PFASR_GEMM_DBG bit 32 off)
+                const bool wide = !kPair && !kLn && kAdds == 0 && t + num_units >= num_tiles && (vec_ok_flags & 0x8000) == 0;
+                uint8_t* wide_stage = smem + ew * (kCpwMax * (kOutHalf ? 2048 : 4096));
+                static_assert(kPair || kLn || kAdds != 0 || kEW * kCpwMax * (kOutHalf ? 2048 : 4096) <= STAGES * C::kStageBytes, "ring too small for the last tile's boxes");
                 int prefetched = 0;
                 if constexpr (!kOutHalf && kAdds == 1) {
                     // residual boxes of the first two chunks travel while the MMAs of this tile still run
@@ -498,10 +503,12 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 epi_bar_sync_n<kEW>();                                   // bias tile visible to all epilogue warps
                 if (work) {
                     if constexpr (kOutHalf && kAdds == 0)
-                        epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane, (vec_ok_flags >> 11) & 3);
+                        epilogue_tma_f16<kCpwMax>(t_acc + cbase * 32, nchunks, wide ? wide_stage : wstage, &tmC, bias_t + cbase * 32, lo, row0, colw, lane,
+                                                  (vec_ok_flags >> 11) & 3, wide);
                     else if constexpr (!kOutHalf && kAdds == 0)
-                        epilogue_tma_f32<kCpwMax, false, false, kBoxes>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw,
-                                                                        lane, 0, nullptr, nullptr, (vec_ok_flags & 0x2000) != 0);
+                        epilogue_tma_f32<kCpwMax, false, false, kBoxes>(t_acc + cbase * 32, nchunks, wide ? wide_stage : wstage, rp, &tmC, &tmR,
+                                                                        bias_t + cbase * 32, lo, row0, colw, lane, 0, nullptr, nullptr,
+                                                                        (vec_ok_flags & 0x2000) != 0, wide);
                     else if constexpr (!kOutHalf && kAdds == 1 && !kLn)
                         epilogue_tma_f32<kCpwMax, true>(t_acc + cbase * 32, nchunks, wstage, rp, &tmC, &tmR, bias_t + cbase * 32, lo, row0, colw, lane, prefetched);
                 }
@@ -836,6 +843,8 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
         make_tmap_any(&op.tmL, epi.ln_out16, false, M, N, epi.ld_ln16, 32, 64);
     }
     if (const char* e = getenv("PFASR_GEMM_DBG")) op.vec_ok |= (atoi(e) & 31) << 8;   // 1 no epilogue, 2 no TMA, 4 no MMA, 8 no TMA store, 16 no staging either
+    static const bool no_wide = [] { const char* e = getenv("PFASR_GEMM_NO_WIDE_EPI"); return e && *e && *e != '0'; }();
+    if (no_wide) op.vec_ok |= 0x8000;                               // A/B switch: the last tile keeps the two / one staging boxes
 #ifdef PFASR_EXPERIMENTS
     op.half_sm = gemm_half_eligible(op, ((tile_code >> 23) & 1) != 0) ? 1 : 0;
 #else

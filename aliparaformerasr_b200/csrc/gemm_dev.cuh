@@ -70,9 +70,11 @@ __device__ __forceinline__ void epi_bar_sync() { epi_bar_sync_n<kEpiWarps>(); }
 // fp16 output: this warp's rows [row0, row0+32) x columns [colw, colw + 32*nchunks) of the tile.  One 32 x 32 box
 // (64-byte rows, SWIZZLE_64B) per chunk, two alternating 2 KiB staging boxes, so a box is rewritten two chunks after
 // its store was issued.
+// wide: stg holds one box per chunk (the CTA's last tile borrows the idle operand ring), so no box is ever reused and
+// the chunks never wait for the store engine.
 template <int kMaxChunks>
 __device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, uint8_t* stg, const CUtensorMap* tmC,
-                                                 const float* bias_w, float lo, int row0, int colw, int lane, int dbg = 0) {
+                                                 const float* bias_w, float lo, int row0, int colw, int lane, int dbg = 0, bool wide = false) {
     const uint32_t stg_u32 = smem_u32(stg);
     uint32_t ra[32], rb[32];
     tmem_ld_issue(t_acc, ra);
@@ -83,10 +85,10 @@ __device__ __forceinline__ void epilogue_tma_f16(uint32_t t_acc, int nchunks, ui
         if (k < nchunks) {
             uint32_t (&cur)[32] = (k & 1) ? rb : ra;
             uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
-            const int buf = k & 1;
+            const int buf = wide ? k : (k & 1);
             tmem_ld_wait();
             if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
-            if (k >= 2) {                                         // box reuse: at most the previous chunk's store may be pending
+            if (k >= 2 && !wide) {                                // box reuse: at most the previous chunk's store may be pending
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
             }
@@ -171,7 +173,7 @@ template <int kMaxChunks, bool kResid, bool kLn = false, int kBoxes = 2>
 __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, uint8_t* stg, ResidPipe& rp, const CUtensorMap* tmC,
                                                  const CUtensorMap* tmR, const float* bias_w, float lo, int row0,
                                                  int colw, int lane, int prefetched, float* ln_s1 = nullptr, float* ln_s2 = nullptr,
-                                                 bool red_add = false) {
+                                                 bool red_add = false, bool wide = false) {
     static_assert(kBoxes == 2 || (kBoxes == 1 && !kResid && !kLn), "the single-box epilogue has no residual pipeline");
     float s1 = 0.0f, s2 = 0.0f;                                    // kLn: this row's sum / sum of squares over the warp's columns
     const uint32_t stg_u32 = smem_u32(stg);
@@ -187,12 +189,13 @@ __device__ __forceinline__ void epilogue_tma_f32(uint32_t t_acc, int nchunks, ui
         if (k < nchunks) {
             uint32_t (&cur)[32] = (k & 1) ? rb : ra;
             uint32_t (&nxt)[32] = (k & 1) ? ra : rb;
-            const int buf = kBoxes == 2 ? (k & 1) : 0;
+            const int buf = (!kResid && wide) ? k : (kBoxes == 2 ? (k & 1) : 0);
             tmem_ld_wait();
             if (k + 1 < nchunks) tmem_ld_issue(t_acc + static_cast<uint32_t>((k + 1) * 32), nxt);
             if (kResid) {
                 mbar_wait(rp.bar[buf], rp.count[buf] & 1u);
                 rp.count[buf]++;
+            } else if (wide) {                                     // one box per chunk (the idle operand ring): nothing to wait for
             } else if (kBoxes == 1) {
                 if (k >= 1) {                                      // the one box: the previous chunk's store must have read it
                     if (lane == 0) tma_store_wait_read();
