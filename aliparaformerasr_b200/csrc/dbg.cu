@@ -333,7 +333,9 @@ pf_status pf_dbg_embed_pe_ln(int32_t B, int32_t T, int32_t D, const float* feats
         float* dinv = s.up(inv.data(), half);
         __half* o16 = s.alloc<__half>(n);
         float* o32 = s.alloc<float>(n);
-        embed_pe_ln_launch(dx, B * T, T, D, scale, dinv, g, b, eps, o16, 0);
+        float* pe = s.alloc<float>(static_cast<size_t>(T) * D);
+        pe_table_launch(pe, T, D, dinv, 0);
+        embed_pe_ln_launch(dx, B * T, T, D, scale, pe, g, b, eps, o16, 0);
         pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, n);
         PF_CUDA(cudaGetLastError());
         PF_CUDA(cudaMemcpy(out, o32, n * sizeof(float), cudaMemcpyDeviceToHost));

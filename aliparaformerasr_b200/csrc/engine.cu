@@ -150,6 +150,7 @@ DeviceCtx::~DeviceCtx() {
     free_pool(hpool_);
     free_pool(tpool_);
     if (h_us) cudaFreeHost(h_us);
+    if (pe_table_) cudaFree(pe_table_);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
 #ifdef PFASR_EXPERIMENTS
@@ -905,9 +906,16 @@ int DeviceCtx::extract(const float* samples, int nsamp, float* out, int capacity
 void DeviceCtx::encoder_forward(int B, int T, bool online) {
     const int M = B * T, d = cfg_.d_model, H = cfg_.heads;
     EncoderPlan& plan = encoder_plan(B, T);
+    if (!online && T > pe_rows_) {                          // position-encoding table: rows are independent of T, so it only ever grows
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        if (pe_table_) cudaFree(pe_table_);
+        pe_rows_ = std::max(T, capT_);
+        PF_CUDA(cudaMalloc(&pe_table_, static_cast<size_t>(pe_rows_) * cfg_.input_size * sizeof(float)));
+        pe_table_launch(pe_table_, pe_rows_, cfg_.input_size, inv_ts_, stream_);
+    }
     timed("embed_pe_ln", [&] {
         // streaming windows arrive scaled and position-encoded (OnlineStream.cs:203-206): LayerNorm only
-        embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), online ? nullptr : inv_ts_, enc_[0].ln1.g,
+        embed_pe_ln_launch(feats_, M, T, cfg_.input_size, sqrtf(static_cast<float>(d)), online ? nullptr : pe_table_, enc_[0].ln1.g,
                            enc_[0].ln1.b, cfg_.ln_eps, a16_, stream_);
     });
     ++launches;

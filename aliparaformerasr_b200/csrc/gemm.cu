@@ -297,7 +297,6 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool dbg_no_epi = (vec_ok_flags & 0x100) != 0;               // PFASR_GEMM_DBG bottleneck probes (results are garbage)
     const bool dbg_no_tma = (vec_ok_flags & 0x200) != 0;
     const bool dbg_no_mma = (vec_ok_flags & 0x400) != 0;
-    const bool bsplit = (vec_ok_flags & 0x4000) != 0;                  // W tile requested as two boxes of brows / 2 rows
     const int unit = blockIdx.x / CS;                            // CTA (or CTA pair) index = tile scheduler slot
     const int num_units = gridDim.x / CS;
 
@@ -352,7 +351,6 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int kb = 0; kb < num_kb && it < STAGES; ++kb, ++it) {
                 mbar_arrive_expect_tx(full_bar(it), stage_tx);
                 tma_load_2d(base + it * C::kStageBytes + kABytes, &tmB, full_bar(it), kb * BK, n0);
-                if (bsplit) tma_load_2d(base + it * C::kStageBytes + kABytes + (brows / 2) * BK * 2, &tmB, full_bar(it), kb * BK, n0 + brows / 2);
             }
         }
         npre = it;
@@ -381,7 +379,6 @@ pf_gemm_f16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         mbar_arrive_expect_tx(full_bar(s), stage_tx);
                         tma_load_2d(a_s, &tmA, full_bar(s), kb * BK, m0);
                         tma_load_2d(a_s + kABytes, &tmB, full_bar(s), kb * BK, n0);
-                        if (bsplit) tma_load_2d(a_s + kABytes + (brows / 2) * BK * 2, &tmB, full_bar(s), kb * BK, n0 + brows / 2);
                     } else {
                         if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * stage_tx);
                         const uint32_t lead_full = mapa_shared(full_bar(s), 0);
@@ -852,11 +849,7 @@ void gemm_prepare(GemmOp& op, const __half* A, int lda, const __half* W, int ldw
     if ((tile_code >> 23) & 1) throw CudaError{"gemm: the half-SM kernel needs a PFASR_BUILD_EXPERIMENTS=1 build"};
 #endif
     make_tmap(&op.tmA, A, M, K, lda, BM);           // every CTA stages its own 128 rows of A
-    // W tiles wider than 128 rows travel as two boxes (PFASR_GEMM_BSPLIT, A/B switch)
-    static const int bsplit_env = [] { const char* e = getenv("PFASR_GEMM_BSPLIT"); return e ? atoi(e) : 0; }();
-    const bool bsplit = bsplit_env != 0 && cm == 1 && bn > 128 && (bn / 2) % 8 == 0 && op.ln_cluster == 0;
-    if (bsplit) op.vec_ok |= 0x4000;
-    make_tmap(&op.tmB, W, N, K, ldw, bsplit ? bn / 2 : bn / cm);      // ... and (in a CTA pair) half of the W tile
+    make_tmap(&op.tmB, W, N, K, ldw, bn / cm);      // ... and (in a CTA pair) half of the W tile
 }
 
 void gemm_launch(const GemmOp& op, cudaStream_t stream) {

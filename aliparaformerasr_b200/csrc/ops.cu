@@ -13,18 +13,30 @@ namespace pf {
 namespace {
 
 // ------------------------------------------------------------------ embed (scale + PE) + LayerNorm(D) -> fp16
+// The sinusoidal position encoding depends on (t, c) only: it is tabulated once per sequence length (pf_pe_table, same float
+// expressions as before: angle = pos * inv_timescale rounded, then sinf / cosf) and shared by every utterance and step.
+__global__ void __launch_bounds__(256)
+pf_pe_table(float* __restrict__ pe, int T, int D, const float* __restrict__ inv_ts) {
+    const int half = D >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * D; i += gridDim.x * blockDim.x) {
+        const int t = i / D, c = i - t * D;
+        const int ti = c < half ? c : c - half;
+        const float ang = __fmul_rn(static_cast<float>(t + 1), inv_ts[ti]);
+        pe[i] = c < half ? sinf(ang) : cosf(ang);
+    }
+}
+
 // One warp per row.  Statistics in fp64 so rows made of the huge pad constant (Q4) normalise deterministically.
 template <int kMaxPerLane>
 __global__ void __launch_bounds__(256)
-pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale, const float* __restrict__ inv_ts,
+pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale, const float* __restrict__ pe_table,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, __half* __restrict__ out16) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
-    const int half = D >> 1;
-    const float pos = static_cast<float>((row % T) + 1);
+    const float* pe_row = pe_table ? pe_table + static_cast<size_t>(row % T) * D : nullptr;
     const float* x = feats + static_cast<size_t>(row) * D;
     float v[kMaxPerLane];
     double sum = 0.0;
@@ -33,11 +45,8 @@ pf_embed_pe_ln(const float* __restrict__ feats, int M, int T, int D, float scale
         const int c = lane + 32 * i;
         float val = 0.0f;
         if (c < D) {
-            if (inv_ts != nullptr) {
-                const int ti = c < half ? c : c - half;
-                const float ang = __fmul_rn(pos, inv_ts[ti]);
-                const float pe = c < half ? sinf(ang) : cosf(ang);
-                val = __fadd_rn(__fmul_rn(x[c], scale), pe);     // same rounding as torch: (x*s) then (+pe)
+            if (pe_row != nullptr) {
+                val = __fadd_rn(__fmul_rn(x[c], scale), __ldg(pe_row + c));     // same rounding as torch: (x*s) then (+pe)
             } else {
                 val = x[c];                                        // streaming: the host side already scaled and encoded
             }
@@ -615,10 +624,16 @@ void seaco_merge_launch(const int* dha_tok, const float* dha, int nobias, int M,
     launch_k(pf_seaco_merge, dim3(M), dim3(256), 0, s, dha_tok, dha, nobias, V, ld, tokens, logits);
 }
 
-void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
+void pe_table_launch(float* pe, int T, int D, const float* inv_timescales, cudaStream_t s) {
+    if (T <= 0) return;
+    pf_pe_table<<<std::min(ceil_div(T * D, 256), 1024), 256, 0, s>>>(pe, T, D, inv_timescales);
+    PF_CUDA(cudaGetLastError());
+}
+
+void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* pe_table,
                         const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s) {
     if (D > 32 * 20) throw CudaError{"embed_pe_ln: input_size > 640 unsupported"};
-    launch_k(pf_embed_pe_ln<20>, dim3(ceil_div(M, 8)), dim3(256), 0, s, feats, M, T, D, scale, inv_timescales, gamma, beta, eps, out16);
+    launch_k(pf_embed_pe_ln<20>, dim3(ceil_div(M, 8)), dim3(256), 0, s, feats, M, T, D, scale, pe_table, gamma, beta, eps, out16);
 }
 
 void layernorm_f32_launch(const float* in, int ld_in, int M, int D, const float* gamma, const float* beta, float eps,

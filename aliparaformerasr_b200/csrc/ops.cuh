@@ -4,9 +4,11 @@
 
 namespace pf {
 
-// x = feats * scale + PE(pos)  ->  LayerNorm(D = input_size)  -> fp16     (encoder input + encoders0.norm1);
-// inv_timescales == nullptr: x = feats (streaming windows arrive scaled and position-encoded)
-void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* inv_timescales,
+// pe[t, c] = sin / cos((t + 1) * inv_timescales[c mod D/2]) for t < T: the position encoding of every row index, tabulated once
+void pe_table_launch(float* pe, int T, int D, const float* inv_timescales, cudaStream_t s);
+// x = feats * scale + pe_table[row % T]  ->  LayerNorm(D = input_size)  -> fp16     (encoder input + encoders0.norm1);
+// pe_table == nullptr: x = feats (streaming windows arrive scaled and position-encoded)
+void embed_pe_ln_launch(const float* feats, int M, int T, int D, float scale, const float* pe_table,
                         const float* gamma, const float* beta, float eps, __half* out16, cudaStream_t s);
 
 // LayerNorm over the last dim (D in {512, 2048}); input fp32 or fp16; writes fp16 and/or fp32.
