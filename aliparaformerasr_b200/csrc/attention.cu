@@ -191,7 +191,12 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
                       int ldk, int ldv, int ldo, int head_dim, cudaStream_t s) {
     if (head_dim != HD) throw CudaError{"attention: head dim must be 128"};
     if (Tq <= 0 || Tk <= 0 || B <= 0) return;
-    if (attention_tc_eligible(Tq, Tk, head_dim)) {
+    // Up to 64 query rows (the decoder's cross-attention: one row per token) go to the streaming mma.sync kernel below: one 64-row
+    // query tile per CTA, 87 KB of shared memory and 128 threads, so two CTAs share an SM and leave room for other lanes' kernels,
+    // where the tcgen05 kernel holds a whole SM per (b, h) for a quarter-filled 128-row tile (0.239 -> 0.205 ms per 16 layers,
+    // three-lane step 3.69 -> 3.65 ms; PFASR_XATT_SMALLQ=0 restores the tcgen05 path for every length it covers)
+    static const int small_q = [] { const char* e = getenv("PFASR_XATT_SMALLQ"); return e ? atoi(e) : 64; }();
+    if (attention_tc_eligible(Tq, Tk, head_dim) && !(small_q > 0 && Tq <= small_q)) {
         attention_tc_launch(Q, K, V, O, B, H, Tq, Tk, ldq, ldk, ldv, ldo, nullptr, 0, nullptr, 0, false, s);
         return;
     }
