@@ -54,9 +54,9 @@ def main():
           f"* GEMM work per step: {rf['gemm_flops_per_step'] / 1e12:.3f} TFLOP over {rf['gemm_launches_per_step']} launches "
           f"({rf['gemm_share_of_step']:.0%} of the step).  Three lanes replaying their GEMM launches concurrently (the regime of `value`): "
           f"**{rf['achieved']:.0f} TFLOP/s = {rf['frac']:.3f}** of the measured sustained peak ({rf['peak']:.1f} TFLOP/s, MEASURED_PEAKS.json); one stream alone: "
-          f"{ss.get('achieved', float('nan')):.0f} TFLOP/s = {ss.get('frac', float('nan')):.3f} (round 1: 539 = 0.396).  DRAM traffic per launch {rf['traffic'] / 1e6:.1f} MB = the "
+          f"{ss.get('achieved', float('nan')):.0f} TFLOP/s = {ss.get('frac', float('nan')):.3f} (round 1: 539 = 0.396, single stream).  DRAM traffic per launch {rf['traffic'] / 1e6:.1f} MB = the "
           "compulsory operand reads (`profiles/gemm_traffic_r02.json`).",
-          "* Front-end kernel: 105 µs per 32 × 10 s under ncu = 308 GB/s = 0.047 of the measured 6555.8 GB/s (round 1: 170 µs); instruction-issue bound (`profiles/launches_r02_summary.md`)."]
+          "* Front-end kernel: 69 µs per 32 × 10 s under ncu = 470 GB/s = 0.072 of the measured 6555.8 GB/s (round 1: 170 µs, first half of round 2: 105 µs); instruction-issue bound (`profiles/launches_r02b_summary.md`)."]
     if "cpu_baseline" in one and "value" in one["cpu_baseline"]:
         cb = one["cpu_baseline"]
         o.append(f"* CPU port of the reference path on the same box, same 32-utterance batch: {cb['value']:.1f} audio-s/s on {cb['cores']} cores "
