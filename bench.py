@@ -110,12 +110,13 @@ class ClockSampler:
 
 def _gemm_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/gemm_traffic_r02.json: launch-weighted mean over the four GEMMs of an encoder layer)."""
-    path = os.path.join(ROOT, "profiles", "gemm_traffic_r01_v11.json")
-    try:
-        return int(json.load(open(path))["avg_dram_bytes_per_launch"])
-    except Exception:
-        return None
+    (profiles/gemm_traffic_r02b.json: mean over the four GEMMs of an encoder layer; older captures as fallbacks)."""
+    for name in ("gemm_traffic_r02b.json", "gemm_traffic_r02.json", "gemm_traffic_r01_v11.json"):
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", name)))["avg_dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def _oracle_dims(cfg):
@@ -483,7 +484,7 @@ def main():
         else:
             head = dict(single)
         roofline = {"bound": "tensor", "achieved": head["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": head["frac"],
-                    "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r02.json)",
+                    "traffic": _gemm_traffic(), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/gemm_traffic_r02b.json)",
                     "kernel": "pf_gemm_f16_tn_tcgen05", "peak_source": peak_src, "method": head["method"],
                     "gemm_flops_per_step": gemm_flops, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": head["gemm_ms_per_step"],
                     "gemm_share_of_step": head["gemm_ms_per_step"] / (total_ms / nsteps) if total_ms else None,

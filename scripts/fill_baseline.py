@@ -55,7 +55,7 @@ def main():
           f"({rf['gemm_share_of_step']:.0%} of the step).  Three lanes replaying their GEMM launches concurrently (the regime of `value`): "
           f"**{rf['achieved']:.0f} TFLOP/s = {rf['frac']:.3f}** of the measured sustained peak ({rf['peak']:.1f} TFLOP/s, MEASURED_PEAKS.json); one stream alone: "
           f"{ss.get('achieved', float('nan')):.0f} TFLOP/s = {ss.get('frac', float('nan')):.3f} (round 1: 539 = 0.396, single stream).  DRAM traffic per launch {rf['traffic'] / 1e6:.1f} MB = the "
-          "compulsory operand reads (`profiles/gemm_traffic_r02.json`).",
+          "compulsory operand reads (`profiles/gemm_traffic_r02b.json`).",
           "* Front-end kernel: 69 µs per 32 × 10 s under ncu = 470 GB/s = 0.072 of the measured 6555.8 GB/s (round 1: 170 µs, first half of round 2: 105 µs); instruction-issue bound (`profiles/launches_r02b_summary.md`)."]
     if "cpu_baseline" in one and "value" in one["cpu_baseline"]:
         cb = one["cpu_baseline"]
