@@ -29,15 +29,32 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void st_cluster_u128(uint32_t cluster_addr, const uint4& v) {
-    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+// 16 bytes into a peer CTA's shared memory, completing 16 bytes of the transaction count of THAT CTA's mbarrier: data and
+// "it arrived" travel together, so the receiver needs no barrier round trip
+__device__ __forceinline__ void st_async_u128(uint32_t cluster_addr, const uint4& v, uint32_t cluster_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_acq(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) { printf("pfasr: bilstm h exchange timeout (block %d)\n", blockIdx.x); __trap(); }
+    }
 }
 
 // One thread-block cluster (16 CTAs) per direction.  CTA c keeps the 128 rows of W_hh that produce the four gates of
 // hidden units [32c, 32c+32) in shared memory for all T3 steps.  Per step: gates = h_{t-1} W_hh^T (mma.sync, M = 16
 // utterances, N = 128 gate rows, K = 512) + the precomputed input projections; cell update; the CTA's slice of h_t is
-// pushed (fp16) into every peer's shared memory through DSMEM; one hardware cluster barrier.  No global-memory
-// synchronisation, no re-reading of weights.
+// pushed (fp16) into every peer's shared memory with st.async, each 16-byte piece completing the transaction count of the
+// RECEIVER's mbarrier for that step: a CTA starts step t+1 as soon as the 16 slices of h_t have landed in its own buffer - no
+// cluster-wide barrier (2600 of the 6900 cycles of a step with barrier.cluster), and no WAR hazard either: a peer can only run
+// one step ahead, and it writes the buffer this CTA finished reading before it pushed the slice the peer waited for.  No
+// global-memory synchronisation, no re-reading of weights.
 __global__ void __launch_bounds__(256, 1)
 pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh, int B, int T3, float* __restrict__ y) {
     constexpr int H = 512;
@@ -46,6 +63,7 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
     __half* s_h = s_w + kRows * kPitch;                                               // [2][kMb][kPitch]  h_{t-1} (all units), double buffered
     float* s_g = reinterpret_cast<float*>(s_h + 2 * kMb * kPitch);                    // [kMb][kRows] gate pre-activations (recurrent part)
     __half* s_o = reinterpret_cast<__half*>(s_g + kMb * kRows);                       // [kMb][kUnits] this CTA's h_t slice
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_o + kMb * kUnits);                // [2] "h buffer b is complete" (16 KiB of transactions)
     const int rank = static_cast<int>(cluster_ctarank());
     const int dir = blockIdx.x / kClusterCtas;
     const int u0 = rank * kUnits;
@@ -61,8 +79,15 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
     // cell roles: thread -> (utterance cb, units cu, cu + 16)
     const int cb = tid >> 4, cu = tid & 15;
     float cstate[2] = {0.0f, 0.0f};
-    cluster_sync();                                                   // every CTA's buffers are initialised before remote writes
+    const uint32_t bar_u32 = smem_u32(s_bar);
+    if (tid == 0) {
+        mbar_init(bar_u32, 1);
+        mbar_init(bar_u32 + 8, 1);
+        fence_barrier_init();
+    }
+    cluster_sync();                                                   // every CTA's buffers and barriers are initialised before remote writes
     const uint32_t s_w_u32 = smem_u32(s_w), s_h_u32 = smem_u32(s_h);
+    constexpr uint32_t kStepBytes = kClusterCtas * kMb * kUnits * 2;                 // 16 peers x [16 x 32] halfs = 16 KiB per step
     // input projections of my two cells (4 gates each) are fetched ONE STEP AHEAD: gin (130 MB at 16 x 10 s) streams from
     // HBM, and a step is far shorter than a DRAM round trip
     auto load_gi = [&](int step_, float (&dst)[2][4]) {
@@ -84,17 +109,30 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
             for (int g = 0; g < 4; ++g) gi[k][g] = gi_next[k][g];
         load_gi(step + 1, gi_next);
         // gates[16 x 128] = h_{t-1}[16 x 512] * W^T: warp w owns gate rows [16w, 16w + 16) = two n-tiles
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        if (tid == 0) mbar_arrive_expect_tx(bar_u32 + 8 * (cur ^ 1), kStepBytes);    // the buffer this step's h_t will land in
+        // four independent accumulator sets: the K = 512 reduction is a chain of 8 dependent MMAs instead of 32
+        float acc4[4][2][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc4[a][nt][e] = 0.0f;
         const uint32_t a_base = s_h_u32 + static_cast<uint32_t>(((cur * kMb + (lane & 15)) * kPitch + (lane >> 4) * 8) * 2);
         const uint32_t b_base = s_w_u32 + static_cast<uint32_t>(((warp * 16 + (lane >> 4) * 8 + (lane & 7)) * kPitch + ((lane >> 3) & 1) * 8) * 2);
-#pragma unroll 8
+#pragma unroll
         for (int k0 = 0; k0 < H; k0 += 16) {
             uint32_t a[4], b0, b1, b2, b3;
             ldsm_x4(a_base + k0 * 2, a[0], a[1], a[2], a[3]);
             ldsm_x4(b_base + k0 * 2, b0, b1, b2, b3);
-            mma16816(acc[0], a, b0, b1);
-            mma16816(acc[1], a, b2, b3);
+            mma16816(acc4[(k0 >> 4) & 3][0], a, b0, b1);
+            mma16816(acc4[(k0 >> 4) & 3][1], a, b2, b3);
         }
+        float acc[2][4];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = (acc4[0][nt][e] + acc4[1][nt][e]) + (acc4[2][nt][e] + acc4[3][nt][e]);
         {
             const int g = lane >> 2, c2 = (lane & 3) * 2;
 #pragma unroll
@@ -121,37 +159,52 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
             if (cb < B) y[(static_cast<size_t>(cb) * T3 + t) * (2 * H) + dir * H + u0 + u] = h;
         }
         __syncthreads();
-        // push my [16 x 32] fp16 slice of h_t into the next buffer of every CTA of the cluster (64 x 16-byte pieces x 16 peers)
+        // push my [16 x 32] fp16 slice of h_t into the next buffer of every CTA of the cluster (64 x 16-byte pieces x 16 peers,
+        // myself included), then wait until all 16 slices have landed in MY next buffer
         for (int i = tid; i < kMb * (kUnits / 8) * kClusterCtas; i += blockDim.x) {
             const int peer = i / (kMb * (kUnits / 8)), p = i % (kMb * (kUnits / 8));
             const int row = p / (kUnits / 8), c8 = p % (kUnits / 8);
             const uint4 v = *reinterpret_cast<const uint4*>(s_o + row * kUnits + c8 * 8);
             const uint32_t dst = s_h_u32 + static_cast<uint32_t>((((cur ^ 1) * kMb + row) * kPitch + u0 + c8 * 8) * 2);
-            st_cluster_u128(mapa_shared(dst, peer), v);
+            st_async_u128(mapa_shared(dst, peer), v, mapa_shared(bar_u32 + 8 * (cur ^ 1), peer));
         }
-        cluster_sync();                                               // release / acquire: h_t is complete everywhere
+        mbar_wait_cluster_acq(bar_u32 + 8 * (cur ^ 1), (step >> 1) & 1);
     }
+    cluster_sync();                                                   // nobody leaves while a peer's last slices may still be in flight to it
 }
 
-// one CTA per utterance: alphas2 -> rescale -> integrate-and-fire trace
+// alphas2 of the upsampled frames, one warp per (utterance, frame): Linear(1024, 1) -> sigmoid -> relu(a * smooth - noise).
+// (The first version did this inside the per-utterance scan kernel below - 16 CTAs for 7968 dot products of 1024: 480 us.)
 __global__ void __launch_bounds__(256)
-pf_us_alphas_peaks(const float* __restrict__ y, int T3, int D2, const float* __restrict__ w2, const float* __restrict__ b2,
-                   float smooth, float noise, const int* __restrict__ token_num, float thr, float* __restrict__ us_alphas,
-                   float* __restrict__ us_peaks) {
-    extern __shared__ float s_a[];              // [T3]
+pf_us_alphas_raw(const float* __restrict__ y, int rows, int D2, const float* __restrict__ w2, const float* __restrict__ b2,
+                 float smooth, float noise, float* __restrict__ raw) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* r = y + static_cast<size_t>(row) * D2;
+    float acc = 0.0f;
+    for (int c = lane; c < D2; c += 32) acc += r[c] * w2[c];
+    acc = warp_sum(acc);
+    const float sg = 1.0f / (1.0f + expf(-(acc + b2[0])));
+    if (lane == 0) raw[row] = fmaxf(sg * smooth - noise, 0.0f);
+}
+
+// one CTA per utterance: rescale to token_num -> integrate-and-fire trace (a sequential recurrence over 3T frames: one thread, in
+// shared memory; everything around it is parallel).  Summation order of the total as in the first version: eight strided partial
+// sums, then left to right.
+__global__ void __launch_bounds__(256)
+pf_us_alphas_peaks(const float* raw, int T3, const int* __restrict__ token_num, float thr, float* __restrict__ us_alphas,
+                   float* us_peaks) {      // raw may alias us_peaks (read into shared memory before anything is written)
+    extern __shared__ float s_a[];              // [T3] alphas, then [T3] peaks
+    float* s_p = s_a + T3;
     __shared__ float s_red[8];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float part = 0.0f;
-    for (int t = warp; t < T3; t += 8) {
-        const float* row = y + (static_cast<size_t>(b) * T3 + t) * D2;
-        float acc = 0.0f;
-        for (int c = lane; c < D2; c += 32) acc += row[c] * w2[c];
-        acc = warp_sum(acc);
-        const float sg = 1.0f / (1.0f + expf(-(acc + b2[0])));
-        const float a = fmaxf(sg * smooth - noise, 0.0f);
-        if (lane == 0) { s_a[t] = a; part += a; }
+    for (int t = threadIdx.x; t < T3; t += blockDim.x) s_a[t] = raw[static_cast<size_t>(b) * T3 + t];
+    __syncthreads();
+    if (lane == 0) {
+        float part = 0.0f;
+        for (int t = warp; t < T3; t += 8) part += s_a[t];
+        s_red[warp] = part;
     }
-    if (lane == 0) s_red[warp] = part;
     __syncthreads();
     if (threadIdx.x == 0) {
         float tot = 0.0f;
@@ -160,11 +213,16 @@ pf_us_alphas_peaks(const float* __restrict__ y, int T3, int D2, const float* __r
         float integrate = 0.0f;
         for (int t = 0; t < T3; ++t) {
             const float a = s_a[t] * ratio;
-            us_alphas[static_cast<size_t>(b) * T3 + t] = a;
+            s_a[t] = a;
             integrate = __fadd_rn(integrate, a);
-            us_peaks[static_cast<size_t>(b) * T3 + t] = integrate;
+            s_p[t] = integrate;
             if (integrate >= thr) integrate = __fsub_rn(integrate, thr);
         }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T3; t += blockDim.x) {
+        us_alphas[static_cast<size_t>(b) * T3 + t] = s_a[t];
+        us_peaks[static_cast<size_t>(b) * T3 + t] = s_p[t];
     }
 }
 
@@ -174,7 +232,7 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
     (void)hbuf; (void)bar;
     if (H != 512) throw CudaError{"bilstm: hidden size must be 512"};
     if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..16 utterances per launch"};
-    const int smem = kRows * kPitch * 2 + 2 * kMb * kPitch * 2 + kMb * kRows * 4 + kMb * kUnits * 2;
+    const int smem = kRows * kPitch * 2 + 2 * kMb * kPitch * 2 + kMb * kRows * 4 + kMb * kUnits * 2 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
@@ -204,7 +262,11 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
 void us_alphas_peaks_launch(const float* y, int B, int T3, int D2, const float* w2, const float* b2, float smooth, float noise,
                             const int* token_num, float thr, float* us_alphas, float* us_peaks, cudaStream_t s) {
     if (B <= 0 || T3 <= 0) return;
-    pf_us_alphas_peaks<<<B, 256, static_cast<size_t>(T3) * sizeof(float), s>>>(y, T3, D2, w2, b2, smooth, noise, token_num, thr, us_alphas, us_peaks);
+    // us_peaks doubles as the scratch for the un-scaled alphas: the scan kernel reads its row into shared memory before it writes
+    const int rows = B * T3;
+    pf_us_alphas_raw<<<ceil_div(rows, 8), 256, 0, s>>>(y, rows, D2, w2, b2, smooth, noise, us_peaks);
+    PF_CUDA(cudaGetLastError());
+    pf_us_alphas_peaks<<<B, 256, static_cast<size_t>(2 * T3) * sizeof(float), s>>>(us_peaks, T3, token_num, thr, us_alphas, us_peaks);
     PF_CUDA(cudaGetLastError());
 }
 
