@@ -6,9 +6,12 @@
 //
 // The BiLSTM is a 3T-step (498 at 10 s) sequential recurrence over a [B,512] state: as per-step GEMM launches it would cost
 // more than the whole recogniser, so it runs as ONE persistent kernel - a 16-CTA cluster per direction keeps W_hh in
-// shared memory, multiplies with mma.sync, exchanges h_t through distributed shared memory and meets at the hardware
-// cluster barrier once per step (a first version with a global-memory barrier and scalar dot products took 16 us / step).
+// shared memory, multiplies with tcgen05.mma and exchanges h_t through distributed shared memory (st.async + mbarrier
+// transaction counts).  History: global-memory barrier + scalar dot products 16 us / step; mma.sync + barrier.cluster
+// 5.8 us; this version ~2 us.
 #include "timestamp.cuh"
+
+#include "gemm_dev.cuh"
 
 #include <math.h>
 
@@ -16,19 +19,11 @@ namespace pf {
 
 namespace {
 
-constexpr int kPitch = 512 + 8;       // halfs per staged row of W_hh / h (+16 B: ldmatrix rows hit different banks)
 constexpr int kClusterCtas = 16;      // CTAs per direction = one thread-block cluster; each owns 32 hidden units
 constexpr int kUnits = 32;            // hidden units per CTA -> 128 gate rows of W_hh resident in shared memory
 constexpr int kRows = 4 * kUnits;
-constexpr int kMb = 16;               // utterances per launch = M of mma.m16n8k16
+constexpr int kMb = 16;               // utterances per launch = N of the tcgen05 MMA
 
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 // 16 bytes into a peer CTA's shared memory, completing 16 bytes of the transaction count of THAT CTA's mbarrier: data and
 // "it arrived" travel together, so the receiver needs no barrier round trip
 __device__ __forceinline__ void st_async_u128(uint32_t cluster_addr, const uint4& v, uint32_t cluster_bar) {
@@ -48,46 +43,80 @@ __device__ __forceinline__ void mbar_wait_cluster_acq(uint32_t bar, uint32_t par
 }
 
 // One thread-block cluster (16 CTAs) per direction.  CTA c keeps the 128 rows of W_hh that produce the four gates of
-// hidden units [32c, 32c+32) in shared memory for all T3 steps.  Per step: gates = h_{t-1} W_hh^T (mma.sync, M = 16
-// utterances, N = 128 gate rows, K = 512) + the precomputed input projections; cell update; the CTA's slice of h_t is
-// pushed (fp16) into every peer's shared memory with st.async, each 16-byte piece completing the transaction count of the
-// RECEIVER's mbarrier for that step: a CTA starts step t+1 as soon as the 16 slices of h_t have landed in its own buffer - no
-// cluster-wide barrier (2600 of the 6900 cycles of a step with barrier.cluster), and no WAR hazard either: a peer can only run
-// one step ahead, and it writes the buffer this CTA finished reading before it pushed the slice the peer waited for.  No
-// global-memory synchronisation, no re-reading of weights.
+// hidden units [32c, 32c+32) in shared memory for all T3 steps, as the K-major 128B-swizzled A operand of tcgen05.mma.
+// Per step: gates^T [128 gate rows x 16 utterances] = W_hh[128 x 512] h_{t-1}^T - 32 tcgen05.mma (M = 128, N = 16, K = 16)
+// issued by one thread, fp32 accumulator in TMEM (mma.sync is throttled on sm_100: the same product took 2460 of a step's
+// 5700 cycles) - read back by four warps (thread = gate row), transposed through shared memory, + the precomputed input
+// projections; cell update; the CTA's slice of h_t is pushed (fp16) into every peer's h buffer (the B operand, same swizzled
+// layout) with st.async, each 16-byte piece completing the transaction count of the RECEIVER's mbarrier for that step: a CTA
+// starts step t+1 as soon as the 16 slices of h_t have landed in its own buffer - no cluster-wide barrier (2600 cycles per
+// step with barrier.cluster), and no WAR hazard either: a peer can only run one step ahead, and it writes the buffer this
+// CTA finished reading before it pushed the slice the peer waited for.  No global-memory synchronisation, no re-reading of
+// weights.
+constexpr int kWBytes = kRows * 512 * 2;              // 128 KiB: 8 k-blocks x [128 rows x 128 B]
+constexpr int kHBufBytes = kMb * 512 * 2;             // 16 KiB: 8 k-blocks x [16 rows x 128 B]
+constexpr int kLstmSmem = kWBytes + 2 * kHBufBytes + kMb * kRows * 4 + kMb * kUnits * 2 + 64;
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B operand with `rows` rows per 64-wide k-block
+__device__ __forceinline__ uint32_t sw128_elem_off(int rows, int row, int k) {
+    return static_cast<uint32_t>((k >> 6) * (rows * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((((k & 63) >> 3) ^ (row & 7)) << 4) + (k & 7) * 2);
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 __global__ void __launch_bounds__(256, 1)
 pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh, int B, int T3, float* __restrict__ y) {
     constexpr int H = 512;
-    extern __shared__ __align__(16) uint8_t smem_l[];
-    __half* s_w = reinterpret_cast<__half*>(smem_l);                                  // [kRows][kPitch]
-    __half* s_h = s_w + kRows * kPitch;                                               // [2][kMb][kPitch]  h_{t-1} (all units), double buffered
-    float* s_g = reinterpret_cast<float*>(s_h + 2 * kMb * kPitch);                    // [kMb][kRows] gate pre-activations (recurrent part)
+    extern __shared__ __align__(1024) uint8_t smem_l[];
+    uint8_t* s_w = smem_l;                                                            // A operand: W_hh rows of this CTA
+    uint8_t* s_h = s_w + kWBytes;                                                     // [2] B operand: h_{t-1} of all 512 units, 16 utterances
+    float* s_g = reinterpret_cast<float*>(s_h + 2 * kHBufBytes);                      // [kMb][kRows] gate pre-activations (recurrent part)
     __half* s_o = reinterpret_cast<__half*>(s_g + kMb * kRows);                       // [kMb][kUnits] this CTA's h_t slice
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_o + kMb * kUnits);                // [2] "h buffer b is complete" (16 KiB of transactions)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_o + kMb * kUnits);                // [0,1] "h buffer b complete" (16 KiB of transactions), [2] MMAs done
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(s_bar + 3);
     const int rank = static_cast<int>(cluster_ctarank());
     const int dir = blockIdx.x / kClusterCtas;
     const int u0 = rank * kUnits;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // stage W_hh rows: local row r = gate (r / 32) * 32 + unit offset (r % 32)
+    if (tid == 0 && (smem_u32(smem_l) & 1023u) != 0) { printf("pfasr: bilstm needs 1024-byte aligned dynamic shared memory\n"); __trap(); }
+    // stage W_hh rows: local row r = gate (r / 32) * 32 + unit offset (r % 32), 16-byte pieces into the swizzled operand layout
     for (int i = tid; i < kRows * (H / 8); i += blockDim.x) {
         const int r = i / (H / 8), c8 = i % (H / 8);
         const int grow = (r / kUnits) * H + u0 + (r % kUnits);
-        *reinterpret_cast<uint4*>(s_w + r * kPitch + c8 * 8) =
+        *reinterpret_cast<uint4*>(s_w + sw128_elem_off(kRows, r, c8 * 8)) =
             *reinterpret_cast<const uint4*>(w_hh + (static_cast<size_t>(dir) * 4 * H + grow) * H + c8 * 8);
     }
-    for (int i = tid; i < 2 * kMb * kPitch / 8; i += blockDim.x) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);   // h_0 = 0
+    for (int i = tid; i < 2 * kHBufBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);   // h_0 = 0
     // cell roles: thread -> (utterance cb, units cu, cu + 16)
     const int cb = tid >> 4, cu = tid & 15;
     float cstate[2] = {0.0f, 0.0f};
     const uint32_t bar_u32 = smem_u32(s_bar);
+    const uint32_t mma_bar = bar_u32 + 16;
     if (tid == 0) {
         mbar_init(bar_u32, 1);
         mbar_init(bar_u32 + 8, 1);
+        mbar_init(mma_bar, 1);
         fence_barrier_init();
     }
+    if (warp == 5) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 32);
+        tmem_relinquish();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // W_hh and h_0 were written through the generic proxy
+    tc_fence_before_sync();
     cluster_sync();                                                   // every CTA's buffers and barriers are initialised before remote writes
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
     const uint32_t s_w_u32 = smem_u32(s_w), s_h_u32 = smem_u32(s_h);
     constexpr uint32_t kStepBytes = kClusterCtas * kMb * kUnits * 2;                 // 16 peers x [16 x 32] halfs = 16 KiB per step
+    const uint32_t idesc = gemm_dev::make_idesc(kRows, kMb);
     // input projections of my two cells (4 gates each) are fetched ONE STEP AHEAD: gin (130 MB at 16 x 10 s) streams from
     // HBM, and a step is far shorter than a DRAM round trip
     auto load_gi = [&](int step_, float (&dst)[2][4]) {
@@ -108,41 +137,29 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
 #pragma unroll
             for (int g = 0; g < 4; ++g) gi[k][g] = gi_next[k][g];
         load_gi(step + 1, gi_next);
-        // gates[16 x 128] = h_{t-1}[16 x 512] * W^T: warp w owns gate rows [16w, 16w + 16) = two n-tiles
         if (tid == 0) mbar_arrive_expect_tx(bar_u32 + 8 * (cur ^ 1), kStepBytes);    // the buffer this step's h_t will land in
-        // four independent accumulator sets: the K = 512 reduction is a chain of 8 dependent MMAs instead of 32
-        float acc4[4][2][4];
+        // gates^T[128 x 16] = W_hh[128 x 512] * h_{t-1}[16 x 512]^T: one thread issues the 32 K = 16 steps
+        if (tid == 128) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the peers' slices arrived through the generic proxy
+            tc_fence_after_sync();
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int kb = 0; kb < H / 64; ++kb) {
+                const uint64_t adesc0 = gemm_dev::make_sw128_kmajor_desc(s_w_u32 + kb * (kRows * 128));
+                const uint64_t bdesc0 = gemm_dev::make_sw128_kmajor_desc(s_h_u32 + cur * kHBufBytes + kb * (kMb * 128));
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc4[a][nt][e] = 0.0f;
-        const uint32_t a_base = s_h_u32 + static_cast<uint32_t>(((cur * kMb + (lane & 15)) * kPitch + (lane >> 4) * 8) * 2);
-        const uint32_t b_base = s_w_u32 + static_cast<uint32_t>(((warp * 16 + (lane >> 4) * 8 + (lane & 7)) * kPitch + ((lane >> 3) & 1) * 8) * 2);
-#pragma unroll
-        for (int k0 = 0; k0 < H; k0 += 16) {
-            uint32_t a[4], b0, b1, b2, b3;
-            ldsm_x4(a_base + k0 * 2, a[0], a[1], a[2], a[3]);
-            ldsm_x4(b_base + k0 * 2, b0, b1, b2, b3);
-            mma16816(acc4[(k0 >> 4) & 3][0], a, b0, b1);
-            mma16816(acc4[(k0 >> 4) & 3][1], a, b2, b3);
-        }
-        float acc[2][4];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[nt][e] = (acc4[0][nt][e] + acc4[1][nt][e]) + (acc4[2][nt][e] + acc4[3][nt][e]);
-        {
-            const int g = lane >> 2, c2 = (lane & 3) * 2;
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                const int col = warp * 16 + nt * 8 + c2;
-                s_g[g * kRows + col] = acc[nt][0];
-                s_g[g * kRows + col + 1] = acc[nt][1];
-                s_g[(g + 8) * kRows + col] = acc[nt][2];
-                s_g[(g + 8) * kRows + col + 1] = acc[nt][3];
+                for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc0 + 2u * k, bdesc0 + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
+            umma_commit(mma_bar);
+        }
+        if (warp < 4) {                                               // thread = gate row (TMEM lane), 16 utterances in 16 columns
+            mbar_wait(mma_bar, step & 1);
+            tc_fence_after_sync();
+            uint32_t v[16];
+            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < kMb; ++b) s_g[b * kRows + tid] = __uint_as_float(v[b]);
+            tc_fence_before_sync();
         }
         __syncthreads();
 #pragma unroll
@@ -165,12 +182,14 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
             const int peer = i / (kMb * (kUnits / 8)), p = i % (kMb * (kUnits / 8));
             const int row = p / (kUnits / 8), c8 = p % (kUnits / 8);
             const uint4 v = *reinterpret_cast<const uint4*>(s_o + row * kUnits + c8 * 8);
-            const uint32_t dst = s_h_u32 + static_cast<uint32_t>((((cur ^ 1) * kMb + row) * kPitch + u0 + c8 * 8) * 2);
+            const uint32_t dst = s_h_u32 + (cur ^ 1) * kHBufBytes + sw128_elem_off(kMb, row, u0 + c8 * 8);
             st_async_u128(mapa_shared(dst, peer), v, mapa_shared(bar_u32 + 8 * (cur ^ 1), peer));
         }
         mbar_wait_cluster_acq(bar_u32 + 8 * (cur ^ 1), (step >> 1) & 1);
     }
+    tc_fence_before_sync();
     cluster_sync();                                                   // nobody leaves while a peer's last slices may still be in flight to it
+    if (warp == 5) tmem_dealloc(tmem_base, 32);
 }
 
 // alphas2 of the upsampled frames, one warp per (utterance, frame): Linear(1024, 1) -> sigmoid -> relu(a * smooth - noise).
@@ -232,7 +251,7 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
     (void)hbuf; (void)bar;
     if (H != 512) throw CudaError{"bilstm: hidden size must be 512"};
     if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..16 utterances per launch"};
-    const int smem = kRows * kPitch * 2 + 2 * kMb * kPitch * 2 + kMb * kRows * 4 + kMb * kUnits * 2 + 16;
+    const int smem = kLstmSmem;
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
