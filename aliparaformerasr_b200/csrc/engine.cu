@@ -1087,15 +1087,19 @@ void DeviceCtx::timestamp_forward(int B, int T) {
     GemmEpi g; g.bias = b_bi_; g.out_f32 = gin32_; g.ld_out = 8 * d;
     gemm_prepare(gi, qkv16_, d, w_ih_bi16_, d, 3 * M, 8 * d, d, g);          // qkv16_ viewed as [3M, d]
     gemm(gi);
-    for (int b0 = 0; b0 < B; b0 += kLstmMaxBatch) {
-        const int nb = std::min(kLstmMaxBatch, B - b0);
-        bilstm_launch(gin32_ + static_cast<size_t>(b0) * T3 * 8 * d, w_hh_bi16_, nb, T3, d, y32_ + static_cast<size_t>(b0) * T3 * 2 * d, hbuf_,
-                      lstm_bar_, stream_);
-        ++launches;
-    }
-    us_alphas_peaks_launch(y32_, B, T3, 2 * d, w_out2_, b_out2_, cfg_.smooth_factor2, cfg_.noise_threshold2, token_num_,
-                           cfg_.cif_threshold - 1e-4f, us_alphas_, us_peaks_, stream_);
-    ++launches;
+    timed("ts_bilstm", [&] {
+        for (int b0 = 0; b0 < B; b0 += kLstmMaxBatch) {
+            const int nb = std::min(kLstmMaxBatch, B - b0);
+            bilstm_launch(gin32_ + static_cast<size_t>(b0) * T3 * 8 * d, w_hh_bi16_, nb, T3, d, y32_ + static_cast<size_t>(b0) * T3 * 2 * d, hbuf_,
+                          lstm_bar_, stream_);
+            ++launches;
+        }
+    });
+    timed("ts_alphas_peaks", [&] {
+        us_alphas_peaks_launch(y32_, B, T3, 2 * d, w_out2_, b_out2_, cfg_.smooth_factor2, cfg_.noise_threshold2, token_num_,
+                               cfg_.cif_threshold - 1e-4f, us_alphas_, us_peaks_, stream_);
+    });
+    launches += 2;
 }
 
 // SeACo bias branch (FunASR SeacoParaformer export [EXT]): the bias decoder attends the hot-word rows

@@ -214,9 +214,9 @@ class Engine:
         self._staged_keepalive = arrs
         _lib.check(self._lib.pf_offline_stage_pcm(self._handle(), ptrs, _lib.iptr(ns), len(arrs)))
 
-    def run_staged(self, want_logits: bool = False) -> ModelOutput:
+    def run_staged(self, want_logits: bool = False, want_timestamps: bool = False) -> ModelOutput:
         res = _lib.PfResult()
-        flags = _lib.PF_RUN_WANT_LOGITS if want_logits else 0
+        flags = (_lib.PF_RUN_WANT_LOGITS if want_logits else 0) | (_lib.PF_RUN_WANT_TIMESTAMPS if want_timestamps else 0)
         _lib.check(self._lib.pf_offline_run_staged(self._handle(), flags, C.byref(res)))
         return self._collect(res, want_logits, False)
 

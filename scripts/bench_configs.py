@@ -60,7 +60,7 @@ def offline(name, cfg, batch, seconds, steps, hotwords=None, timestamps=False):
         eng.set_hotwords(hotwords)
     pcm = [synth.make_pcm(i, seconds) for i in range(batch)]
     eng.stage_pcm(pcm)
-    run = (lambda: eng.run_pcm(pcm, want_timestamps=True)) if timestamps else eng.run_staged
+    run = (lambda: eng.run_staged(want_timestamps=True)) if timestamps else eng.run_staged      # both with the PCM already resident
     for _ in range(3):
         out = run()
     ms = []
