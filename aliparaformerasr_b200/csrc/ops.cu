@@ -501,23 +501,42 @@ pf_logsoftmax_argmax(float* __restrict__ logits, int V, int ld, int* __restrict_
 // Combine the per-(tile, column group) partials of a fused-pick head GEMM (gemm_dev.cuh: epilogue_pick_f32) into the
 // greedy id of every row.  Slots are in ascending column order; a slot that saw a NaN restarts the scan (its own best is
 // the best among the columns after its last NaN), exactly like the sequential loop of OfflineRecognizer.cs:145-149.
-__global__ void __launch_bounds__(128)
+// One warp per row: lane L scans its contiguous run of slots, then the 32 run summaries are merged in slot order.  A summary is
+// (best value, best index, last NaN index or -1) of a run scanned from an empty state; "A then B" = B if B saw a NaN (the NaN restarts
+// the scan: B's best already is the best after it), else the later-wins maximum of the two with A's NaN - an associative rule, so the
+// tree merge gives exactly what the sequential loop gives.
+struct PickRun { float v; int i; int ln; };
+__device__ __forceinline__ PickRun pick_merge(const PickRun& a, const PickRun& b) {
+    if (b.ln >= 0) return b;
+    PickRun r = a;
+    if (b.i >= 0 && (a.i < 0 || b.v >= a.v)) { r.v = b.v; r.i = b.i; }
+    return r;
+}
+__global__ void __launch_bounds__(256)
 pf_pick_combine(const float* __restrict__ partials, int M, int ld, int slots, int* __restrict__ tokens) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
     const float* p = partials + static_cast<size_t>(row) * ld * 3;
-    float bv = -INFINITY;
-    int bi = -1, last_nan = -1;
-    for (int s = 0; s < slots; ++s) {
+    const int per = (slots + 31) >> 5;
+    PickRun r{-INFINITY, -1, -1};
+    for (int s = lane * per; s < min(slots, (lane + 1) * per); ++s) {
         const float v = p[3 * s];
         const int i = __float_as_int(p[3 * s + 1]);
         const int ln = __float_as_int(p[3 * s + 2]);
-        if (ln >= 0) { last_nan = ln; bv = v; bi = i; }
-        else if (i >= 0 && v >= bv) { bv = v; bi = i; }
+        if (ln >= 0) { r.ln = ln; r.v = v; r.i = i; }
+        else if (i >= 0 && v >= r.v) { r.v = v; r.i = i; }
     }
-    tokens[row] = bi >= 0 ? bi : (last_nan >= 0 ? last_nan : 0);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        PickRun o;
+        o.v = __shfl_down_sync(0xffffffffu, r.v, d);
+        o.i = __shfl_down_sync(0xffffffffu, r.i, d);
+        o.ln = __shfl_down_sync(0xffffffffu, r.ln, d);
+        if ((lane & (2 * d - 1)) == 0 && lane + d < 32) r = pick_merge(r, o);
+    }
+    if (lane == 0) tokens[row] = r.i >= 0 ? r.i : (r.ln >= 0 ? r.ln : 0);
 }
 
 __global__ void pf_f32_to_f16(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
@@ -721,7 +740,7 @@ void logsoftmax_argmax_launch(float* logits, int M, int V, int ld, int* tokens, 
 
 void pick_combine_launch(const float* partials, int M, int ld, int slots, int* tokens, cudaStream_t s) {
     if (M <= 0) return;
-    launch_k(pf_pick_combine, dim3(ceil_div(M, 128)), dim3(128), 0, s, partials, M, ld, slots, tokens);
+    launch_k(pf_pick_combine, dim3(ceil_div(M, 8)), dim3(256), 0, s, partials, M, ld, slots, tokens);
 }
 
 void f32_to_f16_launch(const float* in, __half* out, size_t n, cudaStream_t s) {
