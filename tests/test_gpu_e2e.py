@@ -155,6 +155,19 @@ def test_long_utterance_takes_the_streaming_attention_path(tiny_paraformer):
     _compare(out, refs, cfg)
 
 
+def test_very_long_and_very_short_utterances_in_one_batch(tiny_paraformer):
+    """Extreme raggedness: 45 s (T_lfr = 750: five 128-row GEMM tiles per utterance, streaming attention over 750 keys) next to
+    0.4 s (T_lfr = 6) - the short one is 99 % PadSequence rows (Q4), which the reference does not mask (Q3)."""
+    cfg, w, eng = tiny_paraformer
+    pcm = [synth.make_pcm(40, 45.0), synth.make_pcm(41, 0.4)]
+    speech = _oracle_feats(pcm, cfg)
+    assert speech.shape[1] >= 740
+    refs = _oracle_pair(sanm.paraformer_forward, speech, w, dims_of(cfg))
+    out = eng.run_pcm(pcm, want_logits=True)
+    assert np.array_equal(out.token_num, refs[0]["token_num"])
+    _compare(out, refs, cfg, max_model=0.1)
+
+
 def test_full_size_properties():
     """BASELINE configs[1] size (paraformer-large, 32 x 10 s), checked through size-independent properties: the step is
     deterministic, ids are valid, and an utterance decodes to the same ids alone or inside the batch (equal lengths =>
