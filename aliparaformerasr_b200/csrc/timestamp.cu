@@ -22,7 +22,6 @@ namespace {
 constexpr int kClusterCtas = 16;      // CTAs per direction = one thread-block cluster; each owns 32 hidden units
 constexpr int kUnits = 32;            // hidden units per CTA -> 128 gate rows of W_hh resident in shared memory
 constexpr int kRows = 4 * kUnits;
-constexpr int kMb = 16;               // utterances per launch = N of the tcgen05 MMA
 
 // 16 bytes into a peer CTA's shared memory, completing 16 bytes of the transaction count of THAT CTA's mbarrier: data and
 // "it arrived" travel together, so the receiver needs no barrier round trip
@@ -54,8 +53,9 @@ __device__ __forceinline__ void mbar_wait_cluster_acq(uint32_t bar, uint32_t par
 // CTA finished reading before it pushed the slice the peer waited for.  No global-memory synchronisation, no re-reading of
 // weights.
 constexpr int kWBytes = kRows * 512 * 2;              // 128 KiB: 8 k-blocks x [128 rows x 128 B]
-constexpr int kHBufBytes = kMb * 512 * 2;             // 16 KiB: 8 k-blocks x [16 rows x 128 B]
-constexpr int kLstmSmem = kWBytes + 2 * kHBufBytes + kMb * kRows * 4 + kMb * kUnits * 2 + 64;
+// MB = utterances per launch = N of the tcgen05 MMA (16 or 32: the instruction costs the same ~55 cycles either way)
+template <int MB> constexpr int lstm_hbuf_bytes() { return MB * 512 * 2; }            // 8 k-blocks x [MB rows x 128 B]
+template <int MB> constexpr int lstm_smem_bytes() { return kWBytes + 2 * lstm_hbuf_bytes<MB>() + MB * kRows * 4 + MB * kUnits * 2 + 64; }
 
 // byte offset of element (row, k) inside a K-major SWIZZLE_128B operand with `rows` rows per 64-wide k-block
 __device__ __forceinline__ uint32_t sw128_elem_off(int rows, int row, int k) {
@@ -71,9 +71,13 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 
+template <int MB>
 __global__ void __launch_bounds__(256, 1)
 pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh, int B, int T3, float* __restrict__ y) {
     constexpr int H = 512;
+    constexpr int kMb = MB;
+    constexpr int kHBufBytes = lstm_hbuf_bytes<MB>();
+    constexpr int kNh = MB / 16;                                                      // utterances per thread in the cell update
     extern __shared__ __align__(1024) uint8_t smem_l[];
     uint8_t* s_w = smem_l;                                                            // A operand: W_hh rows of this CTA
     uint8_t* s_h = s_w + kWBytes;                                                     // [2] B operand: h_{t-1} of all 512 units, 16 utterances
@@ -94,9 +98,11 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
             *reinterpret_cast<const uint4*>(w_hh + (static_cast<size_t>(dir) * 4 * H + grow) * H + c8 * 8);
     }
     for (int i = tid; i < 2 * kHBufBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);   // h_0 = 0
-    // cell roles: thread -> (utterance cb, units cu, cu + 16)
-    const int cb = tid >> 4, cu = tid & 15;
-    float cstate[2] = {0.0f, 0.0f};
+    // cell roles: thread -> (utterances cb0 + 16 j, units cu, cu + 16)
+    const int cb0 = tid >> 4, cu = tid & 15;
+    float cstate[kNh][2];
+#pragma unroll
+    for (int j = 0; j < kNh; ++j) cstate[j][0] = cstate[j][1] = 0.0f;
     const uint32_t bar_u32 = smem_u32(s_bar);
     const uint32_t mma_bar = bar_u32 + 16;
     if (tid == 0) {
@@ -119,23 +125,28 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
     const uint32_t idesc = gemm_dev::make_idesc(kRows, kMb);
     // input projections of my two cells (4 gates each) are fetched ONE STEP AHEAD: gin (130 MB at 16 x 10 s) streams from
     // HBM, and a step is far shorter than a DRAM round trip
-    auto load_gi = [&](int step_, float (&dst)[2][4]) {
+    auto load_gi = [&](int step_, float (&dst)[kNh][2][4]) {
         const int t_ = dir == 0 ? step_ : T3 - 1 - step_;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < kNh; ++j)
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                dst[k][g] = (cb < B && step_ < T3) ? __ldg(gin + (static_cast<size_t>(cb) * T3 + t_) * (8 * H) + dir * 4 * H + g * H + u0 + cu + 16 * k) : 0.0f;
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    dst[j][k][g] = (cb0 + 16 * j < B && step_ < T3)
+                                       ? __ldg(gin + (static_cast<size_t>(cb0 + 16 * j) * T3 + t_) * (8 * H) + dir * 4 * H + g * H + u0 + cu + 16 * k) : 0.0f;
     };
-    float gi[2][4], gi_next[2][4];
+    float gi[kNh][2][4], gi_next[kNh][2][4];
     load_gi(0, gi_next);
     for (int step = 0; step < T3; ++step) {
         const int t = dir == 0 ? step : T3 - 1 - step;
         const int cur = step & 1;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < kNh; ++j)
 #pragma unroll
-            for (int g = 0; g < 4; ++g) gi[k][g] = gi_next[k][g];
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) gi[j][k][g] = gi_next[j][k][g];
         load_gi(step + 1, gi_next);
         if (tid == 0) mbar_arrive_expect_tx(bar_u32 + 8 * (cur ^ 1), kStepBytes);    // the buffer this step's h_t will land in
         // gates^T[128 x 16] = W_hh[128 x 512] * h_{t-1}[16 x 512]^T: one thread issues the 32 K = 16 steps
@@ -154,29 +165,41 @@ pf_bilstm_cluster(const float* __restrict__ gin, const __half* __restrict__ w_hh
         if (warp < 4) {                                               // thread = gate row (TMEM lane), 16 utterances in 16 columns
             mbar_wait(mma_bar, step & 1);
             tc_fence_after_sync();
-            uint32_t v[16];
-            tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
-            tmem_ld_wait();
+            uint32_t v[32];
+            if constexpr (MB == 16) {
+                uint32_t v16[16];
+                tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int b = 0; b < 16; ++b) v[b] = v16[b];
+            } else {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), v);
+                tmem_ld_wait();
+            }
 #pragma unroll
             for (int b = 0; b < kMb; ++b) s_g[b * kRows + tid] = __uint_as_float(v[b]);
             tc_fence_before_sync();
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int u = cu + 16 * k;
-            const float* g = s_g + cb * kRows;
-            const float ig = 1.0f / (1.0f + expf(-(g[u] + gi[k][0])));
-            const float fg = 1.0f / (1.0f + expf(-(g[kUnits + u] + gi[k][1])));
-            const float gg = tanhf(g[2 * kUnits + u] + gi[k][2]);
-            const float og = 1.0f / (1.0f + expf(-(g[3 * kUnits + u] + gi[k][3])));
-            cstate[k] = fg * cstate[k] + ig * gg;
-            const float h = og * tanhf(cstate[k]);
-            s_o[cb * kUnits + u] = __float2half_rn(cb < B ? h : 0.0f);
-            if (cb < B) y[(static_cast<size_t>(cb) * T3 + t) * (2 * H) + dir * H + u0 + u] = h;
+        for (int j = 0; j < kNh; ++j) {
+            const int cb = cb0 + 16 * j;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int u = cu + 16 * k;
+                const float* g = s_g + cb * kRows;
+                const float ig = 1.0f / (1.0f + expf(-(g[u] + gi[j][k][0])));
+                const float fg = 1.0f / (1.0f + expf(-(g[kUnits + u] + gi[j][k][1])));
+                const float gg = tanhf(g[2 * kUnits + u] + gi[j][k][2]);
+                const float og = 1.0f / (1.0f + expf(-(g[3 * kUnits + u] + gi[j][k][3])));
+                cstate[j][k] = fg * cstate[j][k] + ig * gg;
+                const float h = og * tanhf(cstate[j][k]);
+                s_o[cb * kUnits + u] = __float2half_rn(cb < B ? h : 0.0f);
+                if (cb < B) y[(static_cast<size_t>(cb) * T3 + t) * (2 * H) + dir * H + u0 + u] = h;
+            }
         }
         __syncthreads();
-        // push my [16 x 32] fp16 slice of h_t into the next buffer of every CTA of the cluster (64 x 16-byte pieces x 16 peers,
+        // push my [MB x 32] fp16 slice of h_t into the next buffer of every CTA of the cluster (4 MB x 16-byte pieces x 16 peers,
         // myself included), then wait until all 16 slices have landed in MY next buffer
         for (int i = tid; i < kMb * (kUnits / 8) * kClusterCtas; i += blockDim.x) {
             const int peer = i / (kMb * (kUnits / 8)), p = i % (kMb * (kUnits / 8));
@@ -247,11 +270,9 @@ pf_us_alphas_peaks(const float* raw, int T3, const int* __restrict__ token_num, 
 
 }  // namespace
 
-void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, float* y, float* hbuf, unsigned int* bar, cudaStream_t s) {
-    (void)hbuf; (void)bar;
-    if (H != 512) throw CudaError{"bilstm: hidden size must be 512"};
-    if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..16 utterances per launch"};
-    const int smem = kLstmSmem;
+template <int MB>
+static void bilstm_launch_t(const float* gin, const __half* w_hh, int B, int T3, float* y, cudaStream_t s) {
+    constexpr int smem = lstm_smem_bytes<MB>();
     static bool attr_set = false;
     if (!attr_set) {
         int ndev = 0, cur = 0;
@@ -259,8 +280,8 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
         PF_CUDA(cudaGetDevice(&cur));
         for (int d = 0; d < ndev; ++d) {
             PF_CUDA(cudaSetDevice(d));
-            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16-CTA clusters
+            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster<MB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16-CTA clusters
         }
         PF_CUDA(cudaSetDevice(cur));
         attr_set = true;
@@ -275,7 +296,15 @@ void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, f
     at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    PF_CUDA(cudaLaunchKernelEx(&cfg, pf_bilstm_cluster, gin, w_hh, B, T3, y));
+    PF_CUDA(cudaLaunchKernelEx(&cfg, pf_bilstm_cluster<MB>, gin, w_hh, B, T3, y));
+}
+
+void bilstm_launch(const float* gin, const __half* w_hh, int B, int T3, int H, float* y, float* hbuf, unsigned int* bar, cudaStream_t s) {
+    (void)hbuf; (void)bar;
+    if (H != 512) throw CudaError{"bilstm: hidden size must be 512"};
+    if (B < 1 || B > kLstmMaxBatch) throw CudaError{"bilstm: 1..32 utterances per launch"};
+    if (B <= 16) bilstm_launch_t<16>(gin, w_hh, B, T3, y, s);
+    else bilstm_launch_t<32>(gin, w_hh, B, T3, y, s);
 }
 
 void us_alphas_peaks_launch(const float* y, int B, int T3, int D2, const float* w2, const float* b2, float smooth, float noise,

@@ -4,7 +4,7 @@
 
 namespace pf {
 
-constexpr int kLstmMaxBatch = 16;        // utterances per launch (= M of the mma.sync tiles)
+constexpr int kLstmMaxBatch = 32;        // utterances per launch (= N of the tcgen05 product: 16- and 32-wide variants)
 
 // y[b, t, dir*H + u] for t in [0, T3): h_t of a single-layer bidirectional LSTM (PyTorch gate order i|f|g|o).
 //   gin  [B*T3, 2*4H] fp32 : W_ih x_t + b_ih + b_hh for both directions (forward gates first)

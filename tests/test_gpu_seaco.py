@@ -99,11 +99,13 @@ def test_timestamp_branch(tiny_seaco):
         assert all(abs(a[0] - b[0]) <= 20 and abs(a[1] - b[1]) <= 20 for a, b in zip(ts, ts_ref))      # <= one upsampled frame
 
 
-def test_timestamp_branch_more_utterances_than_one_cluster_launch(tiny_seaco):
-    """20 utterances: the persistent BiLSTM takes 16 per launch (N of its tcgen05 product), so this runs two launches (16 + 4)."""
+@pytest.mark.parametrize("n", [20, 36])
+def test_timestamp_branch_wide_and_split_launches(tiny_seaco, n):
+    """The persistent BiLSTM takes up to 32 utterances per launch (N of its tcgen05 product: a 16- and a 32-wide variant):
+    20 utterances run the 32-wide kernel once, 36 run it once plus the 16-wide one for the remaining four."""
     cfg, w, eng = tiny_seaco
     eng.set_hotwords([])
-    pcm, speech = _speech(20, seconds=1.5)
+    pcm, speech = _speech(n, seconds=1.5)
     dims = dims_of(cfg)
     ref = sanm.paraformer_forward(speech, w, dims)
     ua, pk = sanm.upsample_timestamp(ref["enc"], ref["token_num"], w, dims)
@@ -111,7 +113,7 @@ def test_timestamp_branch_more_utterances_than_one_cluster_launch(tiny_seaco):
     assert out.us_alphas.shape == ua.shape
     assert np.abs(out.us_alphas - ua).max() < 3e-3
     assert np.allclose(out.us_alphas.sum(1), ref["token_num"], atol=1e-2)
-    for i in range(20):
+    for i in range(n):
         fires_ref = np.nonzero(pk[i] > 1 - 1e-4)[0]
         fires = np.nonzero(out.us_cif_peak[i] > 1 - 1e-4)[0]
         assert len(fires) == len(fires_ref) and (len(fires) == 0 or np.abs(fires - fires_ref).max() <= 1)
