@@ -18,10 +18,11 @@ OBJ = PKG / "_build"
 LIB = PKG / "libpfasr.so"
 # PFASR_BUILD_EXPERIMENTS=1 additionally compiles the variants that were measured SLOWER than the selected path and are kept
 # for A/B work only: the fused FFN1->FFN2 kernel (ffn_chain.cu), the CTA-pair (cta_group::2) GEMM, the
-# sixteen-epilogue-warp GEMM, the fused-LayerNorm GEMM epilogue and the half-SM GEMM (gemm_half.cu: two CTAs per SM).
+# sixteen-epilogue-warp GEMM, the fused-LayerNorm GEMM epilogue, the half-SM GEMM (gemm_half.cu: two CTAs per SM) and the
+# row-tile-stationary LayerNorm + GEMM kernel (gemm_ln.cu).
 # The product library carries only the selected path.
 EXPERIMENTS = os.environ.get("PFASR_BUILD_EXPERIMENTS", "0") == "1"
-SOURCES = ["gemm.cu", "gemm_ln.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
+SOURCES = ["gemm.cu", "frontend.cu", "audio.cu", "ops.cu", "attention.cu", "attention_tc.cu", "online.cu", "timestamp.cu", "text.cu", "engine.cu", "abi.cu", "dbg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -29,6 +30,7 @@ NVCC_FLAGS = [
 ]
 if EXPERIMENTS:
     SOURCES.insert(1, "ffn_chain.cu")
+    SOURCES.insert(1, "gemm_ln.cu")
     SOURCES.insert(1, "gemm_half.cu")
     NVCC_FLAGS.append("-DPFASR_EXPERIMENTS=1")
 

@@ -71,6 +71,8 @@ def test_gemm_half_sm_kernel(lib, M, N, K, relu):
 def test_layernorm_gemm_rowtile_kernel(lib, M, N, relu):
     """csrc/gemm_ln.cu: LayerNorm of the fp32 residual rows + fp16-output GEMM in one row-tile-stationary kernel must give
     exactly what the two kernels it replaces give (same LayerNorm arithmetic, same MMA order, same epilogue rounding)."""
+    if not lib.pf_build_experiments():
+        pytest.skip("gemm_ln.cu is compiled only with PFASR_BUILD_EXPERIMENTS=1 (measured slower than LayerNorm + GEMM)")
     rng = np.random.default_rng(M + N)
     x = (rng.standard_normal((M, 512)) * 3 + 0.7).astype(np.float32)
     g = (1 + 0.1 * rng.standard_normal(512)).astype(np.float32)
