@@ -7,6 +7,11 @@
 #include "attention.cuh"
 
 #include "ops.cuh"
+#include "gemm.cuh"
+
+#include <stdlib.h>
+
+#include <algorithm>
 
 namespace pf {
 
@@ -17,6 +22,7 @@ constexpr int BQ = 64;
 constexpr int BKV = 64;
 constexpr int LDS = HD + 8;            // padded row: 272 B, conflict-free for ldmatrix
 constexpr int kThreads = 128;
+constexpr int kMaxSplits = 4;
 constexpr int kSmemBytes = (BQ + 4 * BKV) * LDS * 2;
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -49,9 +55,13 @@ __device__ __forceinline__ void stage_tile(uint32_t smem_base, const __half* g, 
     }
 }
 
+// splits > 1 (few query tiles against a long memory, e.g. 800 decoder rows x 2010 SeACo hot-word rows = 52 CTAs): the key range is cut
+// into `splits` runs of whole chunks, CTA (q tile, run) leaves its UNNORMALISED fp32 output and (running max, running sum) per row in
+// part_o / part_ml, and pf_sanm_attention_combine merges the runs - the usual flash-decoding split.
 __global__ void __launch_bounds__(kThreads)
 pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
-                  __half* __restrict__ O, int Tq, int Tk, int ldq, int ldk, int ldv, int ldo, float scale_log2e) {
+                  __half* __restrict__ O, int Tq, int Tk, int ldq, int ldk, int ldv, int ldo, float scale_log2e,
+                  int splits, int chunks_per_split, float* __restrict__ part_o, float* __restrict__ part_ml) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) uint8_t smem[];
@@ -60,7 +70,8 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
     const uint32_t sV = sK + 2 * BKV * LDS * 2;
 
     const int b = blockIdx.z, h = blockIdx.y;
-    const int q0 = blockIdx.x * BQ;
+    const int split = blockIdx.x % splits;
+    const int q0 = (blockIdx.x / splits) * BQ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
 
@@ -68,10 +79,12 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
     const __half* Kg = K + static_cast<size_t>(b) * Tk * ldk + h * HD;
     const __half* Vg = V + static_cast<size_t>(b) * Tk * ldv + h * HD;
 
-    const int nchunks = (Tk + BKV - 1) / BKV;
+    const int nchunks_all = (Tk + BKV - 1) / BKV;
+    const int j_begin = split * chunks_per_split;
+    const int nchunks = min(nchunks_all, j_begin + chunks_per_split);      // this CTA walks chunks [j_begin, nchunks)
     stage_tile(sQ, Qg, ldq, min(BQ, Tq - q0), BQ);
-    stage_tile(sK, Kg, ldk, min(BKV, Tk), BKV);
-    stage_tile(sV, Vg, ldv, min(BKV, Tk), BKV);
+    stage_tile(sK, Kg + static_cast<size_t>(j_begin) * BKV * ldk, ldk, min(BKV, Tk - j_begin * BKV), BKV);
+    stage_tile(sV, Vg + static_cast<size_t>(j_begin) * BKV * ldv, ldv, min(BKV, Tk - j_begin * BKV), BKV);
     cp_async_commit();
 
     uint32_t qf[HD / 16][4];
@@ -80,8 +93,8 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
     for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
 
-    for (int j = 0; j < nchunks; ++j) {
-        const int buf = j & 1;
+    for (int j = j_begin; j < nchunks; ++j) {
+        const int buf = (j - j_begin) & 1;
         if (j + 1 < nchunks) {
             const int kv1 = (j + 1) * BKV;
             stage_tile(sK + (buf ^ 1) * BKV * LDS * 2, Kg + static_cast<size_t>(kv1) * ldk, ldk, min(BKV, Tk - kv1), BKV);
@@ -92,7 +105,7 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
             cp_async_wait<0>();
         }
         __syncthreads();
-        if (j == 0) {
+        if (j == j_begin) {
 #pragma unroll
             for (int kk = 0; kk < HD / 16; ++kk) {
                 const uint32_t addr = sQ + ((warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + kk * 16 + (lane >> 4) * 8) * 2;
@@ -173,9 +186,23 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const int r0 = q0 + warp * 16 + g;
     const int r1 = r0 + 8;
+    if (splits > 1) {
+        const size_t base = ((static_cast<size_t>(split) * gridDim.z + b) * gridDim.y + h) * Tq;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            const int col = nt * 8 + 2 * t4;
+            if (r0 < Tq) *reinterpret_cast<float2*>(part_o + (base + r0) * HD + col) = make_float2(o[nt][0], o[nt][1]);
+            if (r1 < Tq) *reinterpret_cast<float2*>(part_o + (base + r1) * HD + col) = make_float2(o[nt][2], o[nt][3]);
+        }
+        if (t4 == 0) {
+            if (r0 < Tq) *reinterpret_cast<float2*>(part_ml + (base + r0) * 2) = make_float2(m0, l0);
+            if (r1 < Tq) *reinterpret_cast<float2*>(part_ml + (base + r1) * 2) = make_float2(m1, l1);
+        }
+        return;
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     __half* Og = O + static_cast<size_t>(b) * Tq * ldo + h * HD;
 #pragma unroll
     for (int nt = 0; nt < HD / 8; ++nt) {
@@ -185,10 +212,41 @@ pf_sanm_attention(const __half* __restrict__ Q, const __half* __restrict__ K, co
     }
 }
 
+// One warp per (b, h, query row): merge the runs' (max, sum, unnormalised output) and write the fp16 context row.
+__global__ void __launch_bounds__(256)
+pf_sanm_attention_combine(const float* __restrict__ part_o, const float* __restrict__ part_ml, int splits, int rows_total, int H, int Tq,
+                          __half* __restrict__ O, int ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;   // row index over (b, h, t)
+    if (row >= rows_total) return;
+    const int t = row % Tq, h = (row / Tq) % H, b = row / (Tq * H);
+    float M = -INFINITY;
+    for (int s = 0; s < splits; ++s) M = fmaxf(M, part_ml[(static_cast<size_t>(s) * rows_total + row) * 2]);
+    float L = 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float2 ml = *reinterpret_cast<const float2*>(part_ml + (static_cast<size_t>(s) * rows_total + row) * 2);
+        const float w = exp2f(ml.x - M);
+        L += w * ml.y;
+        const float4 v = *reinterpret_cast<const float4*>(part_o + (static_cast<size_t>(s) * rows_total + row) * HD + lane * 4);
+        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    }
+    const float inv = 1.0f / L;
+    uint2 pk;
+    pk.x = pack_half2(acc.x * inv, acc.y * inv);
+    pk.y = pack_half2(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(O + (static_cast<size_t>(b) * Tq + t) * ldo + h * HD + lane * 4) = pk;
+}
+
 }  // namespace
 
+size_t attention_split_workspace_bytes(int B, int H, int Tq) {
+    return static_cast<size_t>(kMaxSplits) * B * H * Tq * (HD + 2) * sizeof(float);
+}
+
 void attention_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int Tq, int Tk, int ldq,
-                      int ldk, int ldv, int ldo, int head_dim, cudaStream_t s) {
+                      int ldk, int ldv, int ldo, int head_dim, cudaStream_t s, float* split_ws, size_t split_ws_bytes) {
     if (head_dim != HD) throw CudaError{"attention: head dim must be 128"};
     if (Tq <= 0 || Tk <= 0 || B <= 0) return;
     // Up to 64 query rows (the decoder's cross-attention: one row per token) go to the streaming mma.sync kernel below: one 64-row
@@ -213,8 +271,26 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
         attr_set = true;
     }
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-    dim3 grid(ceil_div(Tq, BQ), H, B);
-    launch_k(pf_sanm_attention, grid, dim3(kThreads), kSmemBytes, s, Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e);
+    const int qtiles = ceil_div(Tq, BQ), nchunks = ceil_div(Tk, BKV);
+    // few CTAs against a long memory: cut the keys into runs so that the grid fills the chip (needs the caller's workspace)
+    int splits = 1;
+    static const bool no_split = [] { const char* e = getenv("PFASR_ATT_NO_SPLIT"); return e && *e && *e != '0'; }();
+    if (!no_split && split_ws != nullptr && qtiles * H * B * 2 <= gemm_num_sms() && nchunks >= 8) {
+        splits = std::min(kMaxSplits, std::max(1, gemm_num_sms() / (qtiles * H * B)));
+        splits = std::min(splits, nchunks / 4);
+        if (attention_split_workspace_bytes(B, H, Tq) > split_ws_bytes) splits = 1;
+    }
+    int per = ceil_div(nchunks, splits);
+    splits = ceil_div(nchunks, per);                                      // every run holds at least one chunk
+    float* part_o = split_ws;
+    float* part_ml = split_ws ? split_ws + static_cast<size_t>(kMaxSplits) * B * H * Tq * HD : nullptr;
+    dim3 grid(qtiles * splits, H, B);
+    launch_k(pf_sanm_attention, grid, dim3(kThreads), kSmemBytes, s, Q, K, V, O, Tq, Tk, ldq, ldk, ldv, ldo, scale_log2e, splits, per, part_o, part_ml);
+    if (splits > 1) {
+        const int rows_total = B * H * Tq;
+        launch_k(pf_sanm_attention_combine, dim3(ceil_div(rows_total, 8)), dim3(256), 0, s, static_cast<const float*>(part_o),
+                 static_cast<const float*>(part_ml), splits, rows_total, H, Tq, O, ldo);
+    }
 }
 
 int attention_fsmn_launch(const __half* Q, const __half* K, const __half* V, __half* O, int B, int H, int T, int ldqkv, int ldo,

@@ -352,7 +352,9 @@ pf_status pf_dbg_attention(int32_t B, int32_t H, int32_t Tq, int32_t Tk, const f
         __half* dv = s.up_half(v, nk);
         __half* o16 = s.alloc<__half>(nq);
         float* o32 = s.alloc<float>(nq);
-        attention_launch(dq, dk, dv, o16, B, H, Tq, Tk, D, D, D, D, 128, 0);
+        const size_t ws_bytes = attention_split_workspace_bytes(B, H, Tq);          // lets the streaming kernel split a long memory
+        float* ws = s.alloc<float>(ws_bytes / sizeof(float));
+        attention_launch(dq, dk, dv, o16, B, H, Tq, Tk, D, D, D, D, 128, 0, ws, ws_bytes);
         pf_dbg_f16_to_f32<<<256, 256>>>(o16, o32, nq);
         PF_CUDA(cudaGetLastError());
         PF_CUDA(cudaMemcpy(out, o32, nq * sizeof(float), cudaMemcpyDeviceToHost));

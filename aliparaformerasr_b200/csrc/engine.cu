@@ -151,6 +151,7 @@ DeviceCtx::~DeviceCtx() {
     free_pool(tpool_);
     if (h_us) cudaFreeHost(h_us);
     if (pe_table_) cudaFree(pe_table_);
+    if (xatt_ws_) cudaFree(xatt_ws_);
     free_pool(tmp_);
     frontend_tables_destroy(fe_tables_);
 #ifdef PFASR_EXPERIMENTS
@@ -1027,7 +1028,8 @@ void DeviceCtx::dec_stack(const std::vector<DecLayerW>& layers, const DecFfnW& d
         }
         gemm(lp.q);
         if (!(dbg_skip() & 16)) timed("dec_cross_attention", [&] {
-            if (kv_shared) attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, 1, H, Md, Tk, d, ldkv, ldkv, d, d / H, stream_);
+            if (kv_shared) attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, 1, H, Md, Tk, d, ldkv, ldkv, d, d / H, stream_,
+                                            xatt_ws_, xatt_ws_bytes_);
             else attention_launch(q16_, kv16 + i * 2 * d, kv16 + i * 2 * d + d, ctxd16_, B, H, L, Tk, d, ldkv, ldkv, d, d / H, stream_);
         });
         gemm(lp.out);
@@ -1107,6 +1109,15 @@ void DeviceCtx::timestamp_forward(int B, int T) {
 // NO_BIAS keep the ASR posterior, the others take dha.
 void DeviceCtx::seaco_forward(int B, int L, DecoderPlan& plan) {
     const int Md = B * L, d = cfg_.d_model;
+    // all B * L queries attend the one hot-word memory: 13 query tiles x 4 heads would walk 2010 keys each; the workspace lets the
+    // streaming attention kernel cut the memory into runs (attention.cu)
+    const size_t ws_need = attention_split_workspace_bytes(1, cfg_.heads, Md);
+    if (ws_need > xatt_ws_bytes_) {
+        PF_CUDA(cudaStreamSynchronize(stream_));
+        if (xatt_ws_) cudaFree(xatt_ws_);
+        PF_CUDA(cudaMalloc(&xatt_ws_, ws_need));
+        xatt_ws_bytes_ = ws_need;
+    }
     const size_t bytes = static_cast<size_t>(Md) * d * sizeof(float);
     const int ldkv = cfg_.seaco_layers * 2 * d;
     const float eps = cfg_.ln_eps;

@@ -276,6 +276,8 @@ private:
     size_t h_us_cap_ = 0;
     float* embed_table_ = nullptr;     // SenseVoice prompt table [16, input_size]
     float* inv_ts_ = nullptr;          // PE inverse timescales [input_size/2]
+    float* xatt_ws_ = nullptr;         // split workspace of the SeACo bias decoder's cross-attention (attention_split_workspace_bytes)
+    size_t xatt_ws_bytes_ = 0;
     float* pe_table_ = nullptr;        // [pe_rows_, input_size] sin | cos((t + 1) * inv_ts): built when a longer batch arrives
     int pe_rows_ = 0;
     float* cmvn_shift_ = nullptr; float* cmvn_scale_ = nullptr;

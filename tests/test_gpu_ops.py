@@ -228,6 +228,22 @@ def test_attention(lib, B, Tq, Tk):
     assert np.abs(out - ref).max() < 5e-3
 
 
+@pytest.mark.parametrize("B,Tq,Tk", [(1, 100, 2010), (1, 800, 2010), (2, 30, 1000), (1, 64, 513)])
+def test_attention_streaming_kernel_split_memory(lib, B, Tq, Tk):
+    """Few query tiles against a long memory (the SeACo bias decoder: 800 rows x 2010 hot-word rows): the streaming kernel cuts the
+    keys into runs and a combine kernel merges their (max, sum, unnormalised output) - same result as one walk over all keys."""
+    rng = np.random.default_rng(Tq + Tk)
+    H, D = 4, 512
+    q = rng.standard_normal((B, Tq, D)).astype(np.float32)
+    k = rng.standard_normal((B, Tk, D)).astype(np.float32)
+    v = rng.standard_normal((B, Tk, D)).astype(np.float32)
+    k[:, Tk - 7, :] = 0.35 * q[:, 0, :] if Tq > 0 else 0          # one row of the LAST run carries real weight for query 0
+    out = np.zeros_like(q)
+    _lib.check(lib.pf_dbg_attention(B, H, Tq, Tk, _lib.fptr(q), _lib.fptr(k), _lib.fptr(v), _lib.fptr(out)))
+    ref = sanm._mha(torch.from_numpy(half_round(q)), torch.from_numpy(half_round(k)), torch.from_numpy(half_round(v)), H).numpy()
+    assert np.abs(out - ref).max() < 5e-3
+
+
 @pytest.mark.parametrize("B,Tq,Tk", [(2, 166, 166), (3, 40, 166), (2, 200, 192), (1, 1, 1), (2, 129, 16)])
 def test_attention_streaming_kernel_matches(lib, B, Tq, Tk):
     """The mma.sync streaming kernel (long sequences) stays covered: force it with PFASR_NO_ATT_TC in a subprocess."""
