@@ -6,6 +6,8 @@
 // masks are all ones; only the chunk tail (kv >= Tk) is masked here.
 #include "attention.cuh"
 
+#include <mutex>
+
 #include "ops.cuh"
 #include "gemm.cuh"
 
@@ -258,8 +260,8 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
         attention_tc_launch(Q, K, V, O, B, H, Tq, Tk, ldq, ldk, ldv, ldo, nullptr, 0, nullptr, 0, false, s);
         return;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;                              // execution lanes call this from several host threads
+    std::call_once(attr_once, [&] {
         int ndev = 0, cur = 0;
         PF_CUDA(cudaGetDeviceCount(&ndev));
         PF_CUDA(cudaGetDevice(&cur));
@@ -268,8 +270,7 @@ void attention_launch(const __half* Q, const __half* K, const __half* V, __half*
             PF_CUDA(cudaFuncSetAttribute(pf_sanm_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         }
         PF_CUDA(cudaSetDevice(cur));
-        attr_set = true;
-    }
+    });
     const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
     const int qtiles = ceil_div(Tq, BQ), nchunks = ceil_div(Tk, BKV);
     // few CTAs against a long memory: cut the keys into runs so that the grid fills the chip (needs the caller's workspace)

@@ -23,6 +23,8 @@
 // instructions; the FFT phase is 46 % of them).
 #include "frontend.cuh"
 
+#include <mutex>
+
 #include <math.h>
 
 #include <vector>
@@ -420,8 +422,8 @@ void frontend_launch(const FrontendLaunch& a, cudaStream_t stream) {
     if (a.batch <= 0 || a.max_frames <= 0) return;
     if (a.feats_out && a.lfr_m * kMel > kMaxCmvnDim) throw CudaError{"front-end: lfr_m * 80 exceeds the staged CMVN table"};
     dim3 grid(ceil_div(a.max_frames, kChunkFrames), a.batch);
-    static bool attr_set = false;                                  // (idempotent; a race between two lanes sets it twice)
-    if (!attr_set) {
+    static std::once_flag attr_once;                              // execution lanes call this from several host threads
+    std::call_once(attr_once, [&] {
         int ndev = 0, cur = 0;
         PF_CUDA(cudaGetDeviceCount(&ndev));
         PF_CUDA(cudaGetDevice(&cur));
@@ -430,8 +432,7 @@ void frontend_launch(const FrontendLaunch& a, cudaStream_t stream) {
             PF_CUDA(cudaFuncSetAttribute(pf_frontend_fbank_lfr_cmvn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontendSmem));
         }
         PF_CUDA(cudaSetDevice(cur));
-        attr_set = true;
-    }
+    });
     launch_k(pf_frontend_fbank_lfr_cmvn, grid, dim3(kWarps * 32), static_cast<size_t>(kFrontendSmem), stream,
              static_cast<const FrontendTables*>(a.tables), a.pcm, a.pcm_off, a.nsamp, a.nframes, a.nlfr, a.add_shift, a.rescale,
              a.fbank_out, a.fbank_off, a.feats_out, a.feats_off, a.lfr_m, a.lfr_n, a.snip_edges ? 1 : 0, a.pad_quirk ? 1 : 0,

@@ -6,6 +6,8 @@
 // OfflineRecognizer.cs:139-152.
 #include "ops.cuh"
 
+#include <mutex>
+
 #include <math.h>
 
 namespace pf {
@@ -687,8 +689,8 @@ template <int K>
 static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2, const float* b2, const float* w, const float* g3,
                                     const float* b3, const int* lens, int B, int L, float eps, __half* out16, cudaStream_t s) {
     constexpr int kSmem = (kDecTT + K - 1 + kDecTT) * 512 * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;                              // execution lanes call this from several host threads
+    std::call_once(attr_once, [&] {
         int ndev = 0, cur = 0;
         PF_CUDA(cudaGetDeviceCount(&ndev));
         PF_CUDA(cudaGetDevice(&cur));
@@ -697,8 +699,7 @@ static void dec_ln_fsmn_ln_launch_t(const float* t32, float* x, const float* g2,
             PF_CUDA(cudaFuncSetAttribute(pf_dec_ln_fsmn_ln<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         }
         PF_CUDA(cudaSetDevice(cur));
-        attr_set = true;
-    }
+    });
     launch_k(pf_dec_ln_fsmn_ln<K>, dim3(ceil_div(L, kDecTT), B), dim3(512), kSmem, s, t32, x, g2, b2, w, g3, b3, lens, L, eps, out16);
 }
 

@@ -11,6 +11,8 @@
 // 5.8 us; this version ~2 us.
 #include "timestamp.cuh"
 
+#include <mutex>
+
 #include "gemm_dev.cuh"
 
 #include <math.h>
@@ -273,8 +275,8 @@ pf_us_alphas_peaks(const float* raw, int T3, const int* __restrict__ token_num, 
 template <int MB>
 static void bilstm_launch_t(const float* gin, const __half* w_hh, int B, int T3, float* y, cudaStream_t s) {
     constexpr int smem = lstm_smem_bytes<MB>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::once_flag attr_once;                              // execution lanes call this from several host threads
+    std::call_once(attr_once, [&] {
         int ndev = 0, cur = 0;
         PF_CUDA(cudaGetDeviceCount(&ndev));
         PF_CUDA(cudaGetDevice(&cur));
@@ -284,8 +286,7 @@ static void bilstm_launch_t(const float* gin, const __half* w_hh, int B, int T3,
             PF_CUDA(cudaFuncSetAttribute(pf_bilstm_cluster<MB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16-CTA clusters
         }
         PF_CUDA(cudaSetDevice(cur));
-        attr_set = true;
-    }
+    });
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * kClusterCtas);
     cfg.blockDim = dim3(256);
