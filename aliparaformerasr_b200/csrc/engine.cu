@@ -971,10 +971,12 @@ void DeviceCtx::encoder_forward(int B, int T, bool online) {
     }
 }
 
-void DeviceCtx::predictor_forward(int B, int T, bool online) {
+void DeviceCtx::predictor_forward(int B, int T, bool online, bool kv_later) {
     const int d = cfg_.d_model;
     EncoderPlan& plan = encoder_plan(B, T);
-    gemm(plan.kv_all);                                  // decoder K/V of all layers; independent of the CIF result
+    // decoder K/V of all layers: independent of the CIF result.  Offline it is enqueued AFTER the token counts are on their way to the
+    // host (kv_later), so that its ~76 us cover the host's wake-up and the first decoder launches instead of preceding an idle gap
+    if (!kv_later) gemm(plan.kv_all);
     im2col3_launch(enc16_, B, T, d, qkv16_, stream_);
     gemm(plan.pred_conv);
     alpha_head_launch(mem32_, B, T, d, w_alpha_, b_alpha_, cfg_.smooth_factor, cfg_.noise_threshold, online ? 0.0f : cfg_.cif_tail,
@@ -1304,12 +1306,13 @@ void DeviceCtx::run_impl(uint32_t flags, SharedRun* shared, int idx) {
         for (int b = 0; b < B; ++b) h_token_num[b] = T;
     } else {
         // ---- predictor + CIF scan; the token count decides the decoder's shape -> one small D2H + sync
-        predictor_forward(B, T);
+        predictor_forward(B, T, false, true);
         PF_CUDA(cudaMemcpyAsync(h_meta_, meta_, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         PF_CUDA(cudaMemcpyAsync(h_token_num, token_num_, static_cast<size_t>(B) * sizeof(int), cudaMemcpyDeviceToHost, stream_));
         PF_CUDA(cudaEventRecord(ev_[3], stream_));
+        gemm(encoder_plan(B, T).kv_all);                                       // runs while the host reads the counts and enqueues the decoder
         timings_ms[6] = static_cast<float>(host_ms_since(host_t0));           // front-end + encoder + predictor enqueued
-        PF_CUDA(cudaStreamSynchronize(stream_));
+        PF_CUDA(cudaEventSynchronize(ev_[3]));
         timings_ms[7] = static_cast<float>(host_ms_since(host_t0));           // ... and finished (token counts on the host)
         int lmax = h_meta_[0];
         if (shared) {

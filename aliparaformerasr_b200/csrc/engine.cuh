@@ -215,7 +215,7 @@ private:
     void gemm(const GemmOp& op);
     void ln_gemm(const LnGemmOp& op);
     void encoder_forward(int B, int T, bool online = false);
-    void predictor_forward(int B, int T, bool online = false);
+    void predictor_forward(int B, int T, bool online = false, bool kv_later = false);
     void decoder_forward(int B, int T, int L, bool online = false);
     void online_step_impl(const std::vector<int>& slots, uint32_t flags, SharedRun* shared, int idx);
     void online_grow(int min_slots);
