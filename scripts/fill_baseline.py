@@ -35,6 +35,13 @@ def main():
         sc = d.get("shard_check")
         o.append(f"| {d['n_gpus']} | {d['value']:,.0f} | {d['ms_per_step']:.2f} | {d['e2e']['value']:,.0f} | {1.0 / d['e2e']['value']:.2e} | {eff:.3f} | "
                  f"{'yes (rank 1 recomputed on rank 0)' if sc and sc['ids_identical'] else ('n/a' if not sc else 'NO')} |")
+    second = os.path.join(ROOT, "profiles", "bench_r02_1gpu_second_box.json")
+    if os.path.exists(second):
+        b2 = json.load(open(second))
+        o += ["", f"Box-to-box spread: the same command on a second box at the end of the round (final commit, SM clock {b2['clocks']['sm_mhz']:.0f} instead of "
+              f"{one['clocks']['sm_mhz']:.0f} MHz under the same 1 kW cap) gave {b2['value']:,.0f} resident / {b2['e2e']['value']:,.0f} end to end, one lane "
+              f"{b2['latency_single_lane']['resident_ms_min_median_max'][1]:.2f} ms (`profiles/bench_r02_1gpu_second_box.json`); kernels are only ever compared on one box "
+              "(`scripts/quick_bench.py`)."]
     o += ["", "### 4.2 cfg 2 — one caller, and strong scaling of ONE batch of 32 over the GPUs of one handle", "",
           "| handle | resident ms / batch (min / median / max) | audio-s/s | e2e ms / batch (median) | e2e audio-s/s |", "|---|---|---|---|---|"]
     lat = one["latency_single_lane"]
