@@ -325,23 +325,24 @@ pf_alpha_head(const float* __restrict__ h, int B, int T, int D, const float* __r
     }
 }
 
-// CIF scalar recurrence (inherently sequential in t).  One CTA per 32 utterances: the alphas of a chunk of frames are
-// staged in shared memory with coalesced loads, 32 threads (one per utterance) run the recurrence on shared memory, and
+// CIF scalar recurrence (inherently sequential in t).  One CTA per `upc` <= 32 utterances (1 for the usual batches: 32 CTAs finish in a
+// third of the time of one CTA that stages 32 rows chunk by chunk): the alphas of a chunk of frames are
+// staged in shared memory with coalesced loads, `upc` threads (one per utterance) run the recurrence on shared memory, and
 // the four per-frame outputs leave coalesced again - a thread walking global memory frame by frame paid an L2 round trip
 // per step (32 us for T = 167; 5 us now).  Same fp32 operation order as before (OnlineRecognizer.cs:149-200).
 constexpr int kCifChunk = 64;      // frames per staged chunk (4 arrays x 32 x 65 x 4 B = 33 KB of static shared memory)
 __global__ void __launch_bounds__(256)
 pf_cif_scan(const float* __restrict__ alphas, int B, int T1, float threshold, float* __restrict__ w_cur,
             float* __restrict__ w_rem, int* __restrict__ fire_idx, float* __restrict__ peaks,
-            int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta) {
+            int* __restrict__ token_num, int* __restrict__ fires, int* __restrict__ meta, int upc) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float s_a[32][kCifChunk + 1];       // in: alpha; out: w_cur          (+1: conflict-free column walks)
     __shared__ float s_rem[32][kCifChunk + 1];
     __shared__ float s_peak[32][kCifChunk + 1];
     __shared__ int s_idx[32][kCifChunk + 1];
-    const int b0 = blockIdx.x * 32;
-    const int nb = min(32, B - b0);
+    const int b0 = blockIdx.x * upc;
+    const int nb = min(upc, B - b0);
     float integrate = 0.0f, total = 0.0f;
     int nf = 0;
     for (int c0 = 0; c0 < T1; c0 += kCifChunk) {
@@ -725,7 +726,8 @@ void alpha_head_launch(const float* h, int B, int T, int D, const float* w, cons
 
 void cif_scan_launch(const float* alphas, int B, int T1, float threshold, float* w_cur, float* w_rem, int* fire_idx,
                      float* peaks, int* token_num, int* fires, int* meta, cudaStream_t s) {
-    launch_k(pf_cif_scan, dim3(ceil_div(B, 32)), dim3(256), 0, s, alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta);
+    const int upc = std::min(32, std::max(1, ceil_div(B, 2 * 148)));          // utterances per CTA: 1 up to 296 utterances
+    launch_k(pf_cif_scan, dim3(ceil_div(B, upc)), dim3(256), 0, s, alphas, B, T1, threshold, w_cur, w_rem, fire_idx, peaks, token_num, fires, meta, upc);
 }
 
 void cif_gather_launch(const float* hidden, int B, int T, int D, const float* w_cur, const float* w_rem,
